@@ -1,0 +1,246 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes bindings for the CPU oracle.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  Nothing under ``object_slam_b200/``
+does: the product path fails loudly when its CUDA library is missing rather than fall
+back to any of this.
+
+Two libraries:
+  * ``liborb_oracle.so``  -- restatement of the reference algorithm (orb_oracle.cpp,
+    match_oracle.cpp), each function citing the reference file:line it follows.
+  * ``_ref/libref_orbextractor.so`` -- the reference's own ``src/ORBextractor.cc`` compiled
+    unmodified against ``cvshim`` (only buildable where /root/reference exists; the built
+    file travels to the GPU box).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liborb_oracle.so")
+REF_PATH = os.path.join(HERE, "_ref", "libref_orbextractor.so")
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")])
+assert KEYPOINT_DTYPE.itemsize == 28
+
+_u8p = C.POINTER(C.c_uint8)
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+
+
+def build(force=False):
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(LIB_PATH) or _stale():
+        subprocess.check_call(["make", "-s", "-C", HERE, "all"])
+
+
+def _stale():
+    t = os.path.getmtime(LIB_PATH)
+    for f in ("orb_oracle.cpp", "match_oracle.cpp", "orc_primitives.h"):
+        if os.path.getmtime(os.path.join(HERE, f)) > t:
+            return True
+    return False
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.orc_extractor_create.restype = C.c_void_p
+        L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_extractor_destroy.argtypes = [C.c_void_p]
+        L.orc_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
+        L.orc_get_keypoints.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_get_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.orc_get_level_dims.argtypes = [C.c_void_p, C.c_int, _i32p, _i32p]
+        L.orc_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_get_level_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
+        L.orc_gaussian7x7_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.orc_fast9_16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_fast9_16_simple.argtypes = L.orc_fast9_16.argtypes
+        L.orc_fast_score_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_fast_atan2_n.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+        L.orc_sincosf_model_n.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+        L.orc_sincosf_libm_n.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+        L.orc_sincosf_sweep.restype = C.c_long
+        L.orc_sincosf_sweep.argtypes = [C.c_float, C.c_float, C.c_long]
+        L.orc_pattern.restype = C.POINTER(C.c_int * 1024)
+        _bind_match(L)
+        _lib = L
+    return _lib
+
+
+def _bind_match(L):
+    if not hasattr(L, "orc_stereo_match"):
+        return
+    L.orc_stereo_match.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 3 + [C.c_void_p] * 3
+    L.orc_stereo_match.restype = C.c_int
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _img(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    assert a.ndim == 2
+    return a
+
+
+# ----------------------------------------------------------------------------- primitives
+def resize_linear(src, dw, dh):
+    src = _img(src)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dw, dh, dw)
+    return dst
+
+
+def gaussian7x7(src):
+    src = _img(src)
+    dst = np.empty_like(src)
+    lib().orc_gaussian7x7_u8(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dst.strides[0])
+    return dst
+
+
+def fast9_16(img, threshold, nms=True, simple=False):
+    img = _img(img)
+    cap = img.size
+    out = np.empty((max(cap, 1), 3), np.int32)
+    fn = lib().orc_fast9_16_simple if simple else lib().orc_fast9_16
+    n = fn(_ptr(img), img.shape[1], img.shape[0], img.strides[0], int(threshold), int(nms), _ptr(out), cap)
+    return out[:n].copy()
+
+
+def fast_score_map(img):
+    img = _img(img)
+    out = np.empty_like(img)
+    lib().orc_fast_score_map(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(out))
+    return out
+
+
+def fast_atan2(y, x):
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(y)
+    lib().orc_fast_atan2_n(_ptr(y), _ptr(x), _ptr(out), y.size)
+    return out
+
+
+def sincosf(a, model=True):
+    a = np.ascontiguousarray(a, np.float32)
+    s = np.empty_like(a)
+    c = np.empty_like(a)
+    (lib().orc_sincosf_model_n if model else lib().orc_sincosf_libm_n)(_ptr(a), _ptr(s), _ptr(c), a.size)
+    return s, c
+
+
+def pattern():
+    return np.array(lib().orc_pattern().contents, dtype=np.int32).reshape(256, 4)
+
+
+# ----------------------------------------------------------------------------- extractor
+class OracleExtractor:
+    """Restated ORBextractor (orb_oracle.cpp); keeps every intermediate of the last call."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self._h = lib().orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_extractor_destroy(self._h)
+            self._h = None
+
+    def tables(self):
+        n = self.nlevels
+        sc, isc, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        fpl = np.empty(n, np.int32)
+        umax = np.empty(16, np.int32)
+        lib().orc_get_tables(self._h, _ptr(sc), _ptr(isc), _ptr(s2), _ptr(is2), _ptr(fpl), _ptr(umax))
+        return dict(scale=sc, inv_scale=isc, sigma2=s2, inv_sigma2=is2, features_per_level=fpl, umax=umax)
+
+    def __call__(self, img):
+        img = _img(img)
+        n = lib().orc_extract(self._h, _ptr(img), img.shape[1], img.shape[0], img.strides[0])
+        kps = np.empty(n, KEYPOINT_DTYPE)
+        desc = np.empty((n, 32), np.uint8)
+        lib().orc_get_keypoints(self._h, _ptr(kps), _ptr(desc), n)
+        return kps, desc
+
+    def level(self, level, blurred=False):
+        w, h = C.c_int32(), C.c_int32()
+        lib().orc_get_level_dims(self._h, level, C.byref(w), C.byref(h))
+        out = np.empty((h.value, w.value), np.uint8)
+        got = lib().orc_get_level(self._h, int(blurred), level, _ptr(out))
+        return out if got else None
+
+    def level_keypoints(self, level, selected):
+        n = lib().orc_get_level_keypoints(self._h, int(selected), level, None, 0)
+        out = np.empty(n, KEYPOINT_DTYPE)
+        lib().orc_get_level_keypoints(self._h, int(selected), level, _ptr(out), n)
+        return out
+
+
+# ----------------------------------------------------------------------------- reference
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(REF_PATH)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not ref_available():
+            build(force=True)
+        R = C.CDLL(REF_PATH)
+        R.ref_extractor_create.restype = C.c_void_p
+        R.ref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        R.ref_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        R.ref_get_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, _i32p, _i32p]
+        R.ref_get_scale_factors.argtypes = [C.c_void_p, C.c_void_p]
+        if hasattr(R, "ref_extract_many"):
+            R.ref_extract_many.restype = C.c_double
+            R.ref_extract_many.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _ref = R
+    return _ref
+
+
+class ReferenceExtractor:
+    """The reference's own ORB_SLAM2::ORBextractor (unmodified source, cv shim, bump allocator).
+
+    Create and call on one thread (the handle's tables live in that thread's arena)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self.cap = nfeatures * 2 + 1024
+        self._h = ref_lib().ref_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def __call__(self, img):
+        img = _img(img)
+        kps = np.empty(self.cap, KEYPOINT_DTYPE)
+        desc = np.empty((self.cap, 32), np.uint8)
+        n = ref_lib().ref_extract(self._h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(kps), _ptr(desc), self.cap)
+        assert n <= self.cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, level):
+        w, h = C.c_int32(), C.c_int32()
+        ref_lib().ref_get_level(self._h, level, None, C.byref(w), C.byref(h))
+        out = np.empty((h.value, w.value), np.uint8)
+        ref_lib().ref_get_level(self._h, level, _ptr(out), C.byref(w), C.byref(h))
+        return out
