@@ -1,0 +1,138 @@
+/* obslam_b200 -- C ABI of the B200-native ORB front end for Object_SLAM.
+ *
+ * This is the drop-in boundary for the data-parallel per-frame path of the reference
+ * (yangliu9527/Object_SLAM, an ORB_SLAM2 fork).  The reference has no FFI layer of its own: its
+ * seam is the C++ class surface compiled into libORB_SLAM2.so.  Each entry point below names the
+ * reference interface it stands behind (file:line relative to the reference tree); the thin C++
+ * classes in object_slam_b200/host/ keep the reference's signatures and forward to these calls
+ * (see INTEGRATION.md).
+ *
+ * Conventions: plain C, opaque handles, caller-owned output buffers, int status returns
+ * (OBS_OK == 0), no exceptions, no exit(), no global mutable state.  A handle owns its device
+ * buffers and one CUDA stream; calls on different handles may run concurrently from different
+ * threads (the reference extracts the two stereo eyes in two threads on two extractor
+ * instances, src/Frame.cc:78-81); calls on one handle must be serialised by the caller.
+ * There is no CPU fallback: every call fails with OBS_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef OBSLAM_B200_H
+#define OBSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum obs_status {
+    OBS_OK = 0,
+    OBS_ERR_INVALID = 1,      /* bad argument (null pointer, size out of range, shape mismatch) */
+    OBS_ERR_CUDA = 2,         /* CUDA runtime error or no usable device; see obs_last_error() */
+    OBS_ERR_CAPACITY = 3,     /* caller buffer / handle capacity too small */
+    OBS_ERR_STATE = 4         /* call order violated (e.g. stereo match before extraction) */
+} obs_status;
+
+/* ORBextractor constructor arguments, include/ORBextractor.h:51, src/ORBextractor.cc:410. */
+typedef struct obs_orb_params {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+} obs_orb_params;
+
+/* Binary layout of cv::KeyPoint (28 bytes), so the C++ wrapper can write straight into
+ * std::vector<cv::KeyPoint>::data(). */
+typedef struct obs_keypoint {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} obs_keypoint;
+
+typedef struct obs_extractor obs_extractor;
+
+/* Thread-local description of the last failure on the calling thread. */
+const char* obs_last_error(void);
+/* Library / build identification ("obslam_b200 <version> sm_100a"). */
+const char* obs_version(void);
+/* Number of CUDA devices visible, or a negative obs_status. */
+int obs_device_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Extractor.  Replaces ORB_SLAM2::ORBextractor (include/ORBextractor.h:45-111).
+ * --------------------------------------------------------------------------------------- */
+
+/* ORBextractor::ORBextractor, src/ORBextractor.cc:410-470.  max_w/max_h bound the image size,
+ * max_batch the number of images one obs_extract_batch* call may carry. */
+int obs_extractor_create(const obs_orb_params* params, int max_w, int max_h, int max_batch,
+                         int device, obs_extractor** out);
+int obs_extractor_destroy(obs_extractor* e);
+
+/* Getters, include/ORBextractor.h:63-83.  Each array receives nlevels floats. */
+int obs_extractor_levels(const obs_extractor* e);
+int obs_extractor_max_keypoints(const obs_extractor* e);   /* per-image capacity the handle was sized for */
+int obs_extractor_tables(const obs_extractor* e, float* scale_factors, float* inv_scale_factors,
+                         float* level_sigma2, float* inv_level_sigma2, int32_t* features_per_level);
+
+/* ORBextractor::operator(), src/ORBextractor.cc:1043-1105, on one 8-bit single-channel host
+ * image (stride in bytes).  Writes up to `cap` keypoints (level-major order, as the reference)
+ * and cap x 32 descriptor bytes; *n_out is the number found.  An empty image (w or h == 0)
+ * returns OBS_OK with *n_out = 0, like the reference's early return at :1046. */
+int obs_extract(obs_extractor* e, const uint8_t* image, int w, int h, size_t stride,
+                obs_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
+
+/* The same over n_images host images of one shape (images[i] = first byte of image i).
+ * keypoints: n_images x cap records, descriptors: n_images x cap x 32 bytes, n_out: n_images. */
+int obs_extract_batch(obs_extractor* e, const uint8_t* const* images, int n_images, int w, int h,
+                      size_t stride, obs_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
+
+/* Device-resident form: images already in HBM (base and stride 16-byte aligned; image i starts at
+ * d_images + i*image_stride).  Results stay on the device until fetched.  `stream` is a
+ * cudaStream_t the work is ordered on (NULL = the handle's own stream). */
+int obs_extract_batch_device(obs_extractor* e, const uint8_t* d_images, int n_images, int w, int h,
+                             size_t stride, size_t image_stride, void* stream);
+/* Copy the results of the last extraction to host buffers (synchronises the stream used). */
+int obs_extractor_fetch(obs_extractor* e, obs_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out);
+/* Only the per-image keypoint counts (n_images ints). */
+int obs_extractor_fetch_counts(obs_extractor* e, int* n_out);
+/* Device pointers of the last results: per image a record of `record_bytes`, laid out as
+ * int32 header[16] (header[0] = n, header[1..nlevels] = per-level counts), then cap x 28-byte
+ * keypoints, then cap x 32-byte descriptors.  Valid until the next call on the handle. */
+int obs_extractor_results_device(obs_extractor* e, const void** d_records, size_t* record_bytes, int* cap);
+
+/* ORBextractor::mvImagePyramid[level] (include/ORBextractor.h:85) of image `image_index` of the
+ * last call, without the 19-px border the reference keeps around it (that border is never read
+ * on this path).  which = 0: pyramid level; 1: its 7x7 sigma-2 Gaussian blur (:1085-1086).
+ * dst may be NULL to query the size only. */
+int obs_extractor_get_level(obs_extractor* e, int image_index, int level, int which,
+                            uint8_t* dst, size_t dst_stride, int* w, int* h);
+
+/* Stage outputs of the last call, for parity tests: FAST candidates of a level in the order
+ * ComputeKeyPointsOctTree (:765-829) hands them to DistributeOctTree (x, y relative to the
+ * 16-px border, response), and the keypoints DistributeOctTree (:539-763) selected, in list
+ * order.  xyr receives 3 ints per entry; returns the count via *n_out. */
+int obs_extractor_get_candidates(obs_extractor* e, int image_index, int level, int32_t* xyr, int cap, int* n_out);
+int obs_extractor_get_selected(obs_extractor* e, int image_index, int level, int32_t* xyr, int cap, int* n_out);
+
+/* ---------------------------------------------------------------------------------------
+ * Stereo.  Replaces Frame::ComputeStereoMatches (include/Frame.h:103, src/Frame.cc:706-880).
+ * Uses the device-resident pyramids, keypoints and descriptors of the last extraction on the
+ * two handles; image i of `left` is matched against image i of `right`.
+ * min_d / max_d are the disparity limits (the reference derives them from members it has not
+ * initialised yet, Frame.cc:736; the intended values are 0 and fx).
+ * u_right / depth: n_images x cap floats (-1 = no match), cap >= keypoints of each left image.
+ * --------------------------------------------------------------------------------------- */
+int obs_stereo_match(obs_extractor* left, obs_extractor* right, float mbf, float min_d, float max_d,
+                     float* u_right, float* depth, int cap);
+/* Device-resident form: results stay in HBM (n_images x cap floats each, cap =
+ * obs_extractor_max_keypoints(left)); pointers valid until the next call. */
+int obs_stereo_match_device(obs_extractor* left, obs_extractor* right, float mbf, float min_d, float max_d,
+                            void* stream, const float** d_u_right, const float** d_depth);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBSLAM_B200_H */

@@ -1,0 +1,579 @@
+// C ABI of the library (include/obslam_b200.h): handle management, geometry tables, stream
+// orchestration.  All image work happens in the kernels of this directory; this file holds no
+// CPU implementation of any stage.
+#include "../../include/obslam_b200.h"
+#include "kernels.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(OBS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline int cv_round_f(float v) { return (int)nearbyintf(v); }      // cvRound: round half to even
+inline int cv_round_d(double v) { return (int)nearbyint(v); }
+inline int cv_floor_d(double v) { int i = (int)v; return i - (i > v); }
+inline int cv_ceil_d(double v) { int i = (int)v; return i + (i < v); }
+inline short sat_short(float v) { int i = cv_round_f(v); return (short)(i < -32768 ? -32768 : i > 32767 ? 32767 : i); }
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+template <typename T> struct PinBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMallocHost((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct obs_extractor {
+    obs_orb_params prm;
+    int device = 0;
+    int maxW = 0, maxH = 0, maxBatch = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+
+    // tables of the constructor (src/ORBextractor.cc:410-470)
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> featPerLevel;
+    int umax[OBS_HALF_PATCH + 1];
+
+    // geometry of the current image shape
+    Geom g;
+    int nodeCap = 0;
+    bool geomValid = false;
+    std::vector<ResizeTap> hXtab, hYtab;
+    DevBuf<ResizeTap> dXtab, dYtab;
+
+    // device state of the last batch
+    DevBuf<uint8_t> pyr, blur, records;
+    DevBuf<uint32_t> cand, keyScratch, sel;
+    DevBuf<uint16_t> nodeScratch;
+    DevBuf<int> cellCount, selCount;
+    DevBuf<float> uRight, depth;
+    DevBuf<int> sad;
+    PinBuf<uint8_t> stageIn, stageOut;
+    size_t recordBytes = 0;
+    PyrPtrs ptrs{};
+    int lastN = 0;                 // images in the last batch (0 = nothing extracted yet)
+    cudaStream_t lastStream = nullptr;
+};
+
+namespace {
+
+void build_tables(obs_extractor* e) {
+    const obs_orb_params& P = e->prm;
+    const int nl = P.nlevels;
+    const double sf = (double)P.scale_factor;          // the reference keeps the float argument in a double member
+    e->scale.assign(nl, 1.f); e->sigma2.assign(nl, 1.f);
+    e->invScale.assign(nl, 1.f); e->invSigma2.assign(nl, 1.f);
+    for (int i = 1; i < nl; i++) {
+        e->scale[i] = (float)(e->scale[i - 1] * sf);
+        e->sigma2[i] = e->scale[i] * e->scale[i];
+    }
+    for (int i = 0; i < nl; i++) {
+        e->invScale[i] = 1.0f / e->scale[i];
+        e->invSigma2[i] = 1.0f / e->sigma2[i];
+    }
+    e->featPerLevel.assign(nl, 0);
+    const float factor = (float)(1.0f / sf);
+    float nDesired = (float)(P.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl)));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; l++) {
+        e->featPerLevel[l] = cv_round_f(nDesired);
+        sum += e->featPerLevel[l];
+        nDesired *= factor;
+    }
+    e->featPerLevel[nl - 1] = std::max(P.nfeatures - sum, 0);
+    // circular patch half-widths (:454-469)
+    const int HP = OBS_HALF_PATCH;
+    int v, v0;
+    const int vmax = cv_floor_d(HP * sqrt(2.f) / 2 + 1);
+    const int vmin = cv_ceil_d(HP * sqrt(2.f) / 2);
+    const double hp2 = HP * HP;
+    for (v = 0; v <= vmax; ++v) e->umax[v] = cv_round_d(sqrt(hp2 - v * v));
+    for (v = HP, v0 = 0; v >= vmin; --v) {
+        while (e->umax[v0] == e->umax[v0 + 1]) ++v0;
+        e->umax[v] = v0;
+        ++v0;
+    }
+}
+
+// OpenCV resize(INTER_LINEAR, 8U) tap table of one axis: source index and 11-bit weights.
+void resize_taps(int ssize, int dsize, bool isX, ResizeTap* out) {
+    const double scale = 1.0 / ((double)dsize / ssize);
+    for (int d = 0; d < dsize; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = cv_floor_d(f);
+        f -= s;
+        if (isX) {
+            if (s < 0) { f = 0; s = 0; }
+            if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+        }
+        out[d].ofs = s;
+        out[d].a0 = sat_short((1.f - f) * 2048.f);
+        out[d].a1 = sat_short(f * 2048.f);
+    }
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Level sizes, FAST cell grid, slot layout for an image shape.
+void build_geometry(obs_extractor* e, int w, int h) {
+    Geom& g = e->g;
+    memset(&g, 0, sizeof(g));
+    const int nl = e->prm.nlevels;
+    g.nlevels = nl; g.w = w; g.h = h;
+    g.iniTh = e->prm.ini_th_fast; g.minTh = e->prm.min_th_fast;
+    memcpy(g.umax, e->umax, sizeof(g.umax));
+    unsigned off = 0, slot = 0;
+    int cells = 0, xt = 0, yt = 0, tiles = 0, maxFeat = 0, nodeCap = 0;
+    for (int l = 0; l < nl; l++) {
+        LevelGeom& L = g.lv[l];
+        L.w = cv_round_f((float)w * e->invScale[l]);
+        L.h = cv_round_f((float)h * e->invScale[l]);
+        L.pitch = round_up(std::max(L.w, 1), 128);
+        L.off = off;
+        off += (unsigned)L.pitch * (unsigned)std::max(L.h, 1);
+        off = (off + 255u) & ~255u;
+        const int width = L.w - 2 * OBS_BORDER, height = L.h - 2 * OBS_BORDER;
+        L.nCols = width > 0 ? (int)((float)width / 30.f) : 0;
+        L.nRows = height > 0 ? (int)((float)height / 30.f) : 0;
+        if (L.nCols <= 0 || L.nRows <= 0) { L.nCols = L.nRows = 0; L.wCell = L.hCell = 1; }
+        else {
+            L.wCell = (int)ceilf((float)width / L.nCols);
+            L.hCell = (int)ceilf((float)height / L.nRows);
+        }
+        L.cellBase = cells;
+        L.cellCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
+        L.slotBase = slot;
+        cells += L.nCols * L.nRows;
+        slot += (unsigned)(L.nCols * L.nRows) * (unsigned)L.cellCap;
+        L.nfeat = e->featPerLevel[l];
+        L.xtab = xt; L.ytab = yt;
+        if (l > 0) { xt += L.w; yt += L.h; }
+        L.blurTilesX = (L.w + 127) / 128;
+        L.blurTileBase = tiles;
+        tiles += L.blurTilesX * ((L.h + 31) / 32);
+        L.scale = e->scale[l];
+        L.invScale = e->invScale[l];
+        L.patchSize = (float)(int)(31 * e->scale[l]);
+        maxFeat = std::max(maxFeat, L.nfeat);
+        int nIni = 0;
+        if (width > 0 && height > 0) nIni = (int)roundf((float)width / (float)height);
+        nodeCap = std::max(nodeCap, std::max(L.nfeat + 4, 4 * nIni + 4));
+    }
+    g.nCellsTotal = cells;
+    g.slotTotal = std::max(slot, 1u);
+    g.slabBytes = off;
+    g.selCap = round_up(nodeCap, 4);
+    g.kpCap = round_up(e->prm.nfeatures + 4 * nl, 32);
+    g.blurTilesTotal = tiles;
+    e->nodeCap = g.selCap;
+    e->hXtab.assign(std::max(xt, 1), ResizeTap{0, 0, 0});
+    e->hYtab.assign(std::max(yt, 1), ResizeTap{0, 0, 0});
+    for (int l = 1; l < nl; l++) {
+        resize_taps(g.lv[l - 1].w, g.lv[l].w, true, e->hXtab.data() + g.lv[l].xtab);
+        resize_taps(g.lv[l - 1].h, g.lv[l].h, false, e->hYtab.data() + g.lv[l].ytab);
+    }
+}
+
+int set_shape(obs_extractor* e, int w, int h, int nimg, cudaStream_t st) {
+    if (!e->geomValid || e->g.w != w || e->g.h != h) {
+        build_geometry(e, w, h);
+        if (e->g.lv[e->g.nlevels - 1].w < 1 || e->g.lv[e->g.nlevels - 1].h < 1)
+            return fail(OBS_ERR_INVALID, "image %dx%d too small for %d levels", w, h, e->g.nlevels);
+        if (e->nodeCap > 16383 || quadtree_smem_bytes(e->nodeCap) > 200 * 1024)
+            return fail(OBS_ERR_INVALID, "nfeatures too large for the quadtree kernel (node capacity %d)", e->nodeCap);
+        for (int l = 0; l < e->g.nlevels; l++)
+            if (e->g.lv[l].w > 4095 + 2 * OBS_BORDER || e->g.lv[l].h > 4095 + 2 * OBS_BORDER)
+                return fail(OBS_ERR_INVALID, "image %dx%d exceeds the 12-bit key coordinate range", w, h);
+        CU(quadtree_prepare(e->nodeCap));
+        CU(e->dXtab.ensure(e->hXtab.size()));
+        CU(e->dYtab.ensure(e->hYtab.size()));
+        // tables are tiny; a synchronous copy keeps the host vectors free to change on the next shape
+        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpy(e->dXtab.p, e->hXtab.data(), e->hXtab.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(e->dYtab.p, e->hYtab.data(), e->hYtab.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+        e->geomValid = true;
+    }
+    const Geom& g = e->g;
+    const size_t B = (size_t)nimg;
+    e->recordBytes = (size_t)OBS_HDR_INTS * 4 + (size_t)g.kpCap * 60;
+    e->recordBytes = (e->recordBytes + 255) & ~(size_t)255;
+    CU(e->pyr.ensure(B * g.slabBytes));
+    CU(e->blur.ensure(B * g.slabBytes));
+    CU(e->cand.ensure(B * g.slotTotal));
+    CU(e->keyScratch.ensure(B * g.slotTotal));
+    CU(e->nodeScratch.ensure(B * g.slotTotal));
+    CU(e->cellCount.ensure(B * std::max(g.nCellsTotal, 1)));
+    CU(e->sel.ensure(B * g.nlevels * g.selCap));
+    CU(e->selCount.ensure(B * g.nlevels));
+    CU(e->records.ensure(B * e->recordBytes));
+    return OBS_OK;
+}
+
+// Enqueue the whole extraction of `nimg` images on `st`.
+int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st) {
+    const Geom& g = e->g;
+    CU(launch_pyramid(g, e->ptrs, e->dXtab.p, e->dYtab.p, nimg, st));
+    CU(launch_fast(g, e->ptrs, e->cand.p, e->cellCount.p, nimg, st));
+    CU(launch_quadtree(g, e->nodeCap, e->cand.p, e->cellCount.p, e->keyScratch.p, e->nodeScratch.p, e->sel.p, e->selCount.p, nimg, st));
+    CU(launch_blur(g, e->ptrs, e->blur.p, g.slabBytes, nimg, st));
+    CU(launch_describe(g, e->ptrs, e->blur.p, g.slabBytes, e->sel.p, e->selCount.p, e->records.p, e->recordBytes, nimg, st));
+    e->lastN = nimg;
+    e->lastStream = st;
+    return OBS_OK;
+}
+
+int check_handle(const obs_extractor* e) {
+    if (!e) return fail(OBS_ERR_INVALID, "null extractor handle");
+    cudaError_t ce = cudaSetDevice(e->device);
+    if (ce != cudaSuccess) return fail(OBS_ERR_CUDA, "cudaSetDevice(%d): %s", e->device, cudaGetErrorString(ce));
+    return OBS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* obs_last_error(void) { return g_err; }
+const char* obs_version(void) { return "obslam_b200 0.1 sm_100a"; }
+
+int obs_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return -fail(OBS_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int obs_extractor_create(const obs_orb_params* params, int max_w, int max_h, int max_batch, int device, obs_extractor** out) {
+    if (!params || !out) return fail(OBS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (params->nlevels < 1 || params->nlevels > OBS_MAX_LEVELS) return fail(OBS_ERR_INVALID, "nlevels must be in [1,%d]", OBS_MAX_LEVELS);
+    if (params->nfeatures < 1 || params->nfeatures > 60000) return fail(OBS_ERR_INVALID, "nfeatures out of range");
+    if (!(params->scale_factor > 1.0f) || params->scale_factor > 4.0f) return fail(OBS_ERR_INVALID, "scale_factor must be in (1,4]");
+    if (params->ini_th_fast < 0 || params->ini_th_fast > 255 || params->min_th_fast < 0 || params->min_th_fast > 255)
+        return fail(OBS_ERR_INVALID, "FAST thresholds must be in [0,255]");
+    if (max_w < 1 || max_h < 1 || max_batch < 1) return fail(OBS_ERR_INVALID, "max_w, max_h, max_batch must be positive");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(OBS_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(OBS_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(OBS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+    obs_extractor* e = new (std::nothrow) obs_extractor;
+    if (!e) return fail(OBS_ERR_INVALID, "out of host memory");
+    e->prm = *params;
+    e->device = device;
+    e->maxW = max_w; e->maxH = max_h; e->maxBatch = max_batch;
+    build_tables(e);
+    cudaError_t se = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming);
+    if (se != cudaSuccess) { delete e; return fail(OBS_ERR_CUDA, "stream/event creation: %s", cudaGetErrorString(se)); }
+    int rc = set_shape(e, max_w, max_h, max_batch, e->stream);
+    if (rc != OBS_OK) { obs_extractor_destroy(e); return rc; }
+    *out = e;
+    return OBS_OK;
+}
+
+int obs_extractor_destroy(obs_extractor* e) {
+    if (!e) return OBS_OK;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    e->pyr.release(); e->blur.release(); e->records.release(); e->cand.release(); e->keyScratch.release();
+    e->sel.release(); e->nodeScratch.release(); e->cellCount.release(); e->selCount.release();
+    e->uRight.release(); e->depth.release(); e->sad.release(); e->dXtab.release(); e->dYtab.release();
+    e->stageIn.release(); e->stageOut.release();
+    if (e->done) cudaEventDestroy(e->done);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return OBS_OK;
+}
+
+int obs_extractor_levels(const obs_extractor* e) { return e ? e->prm.nlevels : -1; }
+int obs_extractor_max_keypoints(const obs_extractor* e) { return e ? e->g.kpCap : -1; }
+
+int obs_extractor_tables(const obs_extractor* e, float* sc, float* isc, float* s2, float* is2, int32_t* fpl) {
+    if (!e) return fail(OBS_ERR_INVALID, "null extractor handle");
+    for (int i = 0; i < e->prm.nlevels; i++) {
+        if (sc) sc[i] = e->scale[i];
+        if (isc) isc[i] = e->invScale[i];
+        if (s2) s2[i] = e->sigma2[i];
+        if (is2) is2[i] = e->invSigma2[i];
+        if (fpl) fpl[i] = e->featPerLevel[i];
+    }
+    return OBS_OK;
+}
+
+int obs_extract_batch_device(obs_extractor* e, const uint8_t* d_images, int n_images, int w, int h,
+                             size_t stride, size_t image_stride, void* stream) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (!d_images || n_images < 1) return fail(OBS_ERR_INVALID, "no images");
+    if (n_images > e->maxBatch) return fail(OBS_ERR_CAPACITY, "batch of %d exceeds max_batch %d", n_images, e->maxBatch);
+    if (w < 1 || h < 1 || w > e->maxW || h > e->maxH) return fail(OBS_ERR_INVALID, "image %dx%d outside [1,%d]x[1,%d]", w, h, e->maxW, e->maxH);
+    if (((uintptr_t)d_images & 15) || (stride & 15) || (image_stride & 15) || stride < (size_t)w)
+        return fail(OBS_ERR_INVALID, "device images need a 16-byte aligned base, stride and image stride");
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    rc = set_shape(e, w, h, n_images, st);
+    if (rc) return rc;
+    e->ptrs.l0 = d_images;
+    e->ptrs.l0ImgStride = image_stride;
+    e->ptrs.l0Pitch = (int)stride;
+    e->ptrs.slab = e->pyr.p;
+    e->ptrs.slabStride = e->g.slabBytes;
+    return run_pipeline(e, n_images, st);
+}
+
+int obs_extract_batch(obs_extractor* e, const uint8_t* const* images, int n_images, int w, int h,
+                      size_t stride, obs_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (!images || !n_out || n_images < 1) return fail(OBS_ERR_INVALID, "null argument");
+    if (n_images > e->maxBatch) return fail(OBS_ERR_CAPACITY, "batch of %d exceeds max_batch %d", n_images, e->maxBatch);
+    if (w == 0 || h == 0) {                      // empty image: the reference returns without touching its outputs (:1046)
+        for (int i = 0; i < n_images; i++) n_out[i] = 0;
+        e->lastN = 0;
+        return OBS_OK;
+    }
+    if (w < 1 || h < 1 || w > e->maxW || h > e->maxH) return fail(OBS_ERR_INVALID, "image %dx%d outside [1,%d]x[1,%d]", w, h, e->maxW, e->maxH);
+    if (stride < (size_t)w) return fail(OBS_ERR_INVALID, "stride smaller than width");
+    cudaStream_t st = e->stream;
+    rc = set_shape(e, w, h, n_images, st);
+    if (rc) return rc;
+    const Geom& g = e->g;
+    const size_t p0 = (size_t)g.lv[0].pitch, l0Bytes = p0 * h;
+    CU(e->stageIn.ensure((size_t)n_images * l0Bytes));
+    for (int i = 0; i < n_images; i++) {
+        if (!images[i]) return fail(OBS_ERR_INVALID, "image %d is null", i);
+        uint8_t* dstp = e->stageIn.p + (size_t)i * l0Bytes;
+        for (int y = 0; y < h; y++) memcpy(dstp + (size_t)y * p0, images[i] + (size_t)y * stride, w);
+        CU(cudaMemcpyAsync(e->pyr.p + (size_t)i * g.slabBytes, dstp, l0Bytes, cudaMemcpyHostToDevice, st));
+    }
+    e->ptrs.l0 = e->pyr.p;
+    e->ptrs.l0ImgStride = g.slabBytes;
+    e->ptrs.l0Pitch = g.lv[0].pitch;
+    e->ptrs.slab = e->pyr.p;
+    e->ptrs.slabStride = g.slabBytes;
+    rc = run_pipeline(e, n_images, st);
+    if (rc) return rc;
+    return obs_extractor_fetch(e, keypoints, descriptors, cap, n_out);
+}
+
+int obs_extract(obs_extractor* e, const uint8_t* image, int w, int h, size_t stride,
+                obs_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out) {
+    if (!n_out) return fail(OBS_ERR_INVALID, "null argument");
+    if (!image || w == 0 || h == 0) { *n_out = 0; if (e) e->lastN = 0; return OBS_OK; }
+    const uint8_t* one[1] = {image};
+    return obs_extract_batch(e, one, 1, w, h, stride, keypoints, descriptors, cap, n_out);
+}
+
+int obs_extractor_fetch(obs_extractor* e, obs_keypoint* keypoints, uint8_t* descriptors, int cap, int* n_out) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (e->lastN < 1) return fail(OBS_ERR_STATE, "no extraction to fetch");
+    if (!n_out || cap < 0) return fail(OBS_ERR_INVALID, "null argument");
+    const int n = e->lastN;
+    const Geom& g = e->g;
+    CU(e->stageOut.ensure((size_t)n * e->recordBytes));
+    CU(cudaMemcpyAsync(e->stageOut.p, e->records.p, (size_t)n * e->recordBytes, cudaMemcpyDeviceToHost, e->lastStream));
+    CU(cudaStreamSynchronize(e->lastStream));
+    int status = OBS_OK;
+    for (int i = 0; i < n; i++) {
+        const uint8_t* rec = e->stageOut.p + (size_t)i * e->recordBytes;
+        const int cnt = *reinterpret_cast<const int*>(rec);
+        n_out[i] = cnt;
+        const int m = cnt < cap ? cnt : cap;
+        if (cnt > cap && (keypoints || descriptors)) status = OBS_ERR_CAPACITY;
+        if (keypoints) memcpy(keypoints + (size_t)i * cap, rec + OBS_HDR_INTS * 4, (size_t)m * 28);
+        if (descriptors) memcpy(descriptors + (size_t)i * cap * 32, rec + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28, (size_t)m * 32);
+    }
+    if (status) return fail(status, "caller capacity %d smaller than the keypoint count", cap);
+    return OBS_OK;
+}
+
+int obs_extractor_fetch_counts(obs_extractor* e, int* n_out) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (e->lastN < 1) return fail(OBS_ERR_STATE, "no extraction to fetch");
+    if (!n_out) return fail(OBS_ERR_INVALID, "null argument");
+    CU(e->stageOut.ensure((size_t)e->lastN * e->recordBytes));
+    int* tmp = reinterpret_cast<int*>(e->stageOut.p);
+    CU(cudaMemcpy2DAsync(tmp, sizeof(int), e->records.p, e->recordBytes, sizeof(int), e->lastN, cudaMemcpyDeviceToHost, e->lastStream));
+    CU(cudaStreamSynchronize(e->lastStream));
+    for (int i = 0; i < e->lastN; i++) n_out[i] = tmp[i];
+    return OBS_OK;
+}
+
+int obs_extractor_results_device(obs_extractor* e, const void** d_records, size_t* record_bytes, int* cap) {
+    if (!e) return fail(OBS_ERR_INVALID, "null extractor handle");
+    if (e->lastN < 1) return fail(OBS_ERR_STATE, "no extraction yet");
+    if (d_records) *d_records = e->records.p;
+    if (record_bytes) *record_bytes = e->recordBytes;
+    if (cap) *cap = e->g.kpCap;
+    return OBS_OK;
+}
+
+int obs_extractor_get_level(obs_extractor* e, int image_index, int level, int which, uint8_t* dst, size_t dst_stride, int* w, int* h) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (e->lastN < 1) return fail(OBS_ERR_STATE, "no extraction yet");
+    if (image_index < 0 || image_index >= e->lastN || level < 0 || level >= e->g.nlevels) return fail(OBS_ERR_INVALID, "index out of range");
+    const LevelGeom& L = e->g.lv[level];
+    if (w) *w = L.w;
+    if (h) *h = L.h;
+    if (!dst) return OBS_OK;
+    if (dst_stride < (size_t)L.w) return fail(OBS_ERR_INVALID, "dst_stride smaller than the level width");
+    const uint8_t* src;
+    size_t pitch;
+    if (which == 1) { src = e->blur.p + (size_t)image_index * e->g.slabBytes + L.off; pitch = L.pitch; }
+    else if (level == 0) { src = e->ptrs.l0 + (size_t)image_index * e->ptrs.l0ImgStride; pitch = e->ptrs.l0Pitch; }
+    else { src = e->pyr.p + (size_t)image_index * e->g.slabBytes + L.off; pitch = L.pitch; }
+    CU(cudaStreamSynchronize(e->lastStream));
+    CU(cudaMemcpy2D(dst, dst_stride, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return OBS_OK;
+}
+
+static int fetch_keys(obs_extractor* e, int image_index, int level, bool selected, int32_t* xyr, int cap, int* n_out) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (e->lastN < 1) return fail(OBS_ERR_STATE, "no extraction yet");
+    if (!n_out) return fail(OBS_ERR_INVALID, "null argument");
+    if (image_index < 0 || image_index >= e->lastN || level < 0 || level >= e->g.nlevels) return fail(OBS_ERR_INVALID, "index out of range");
+    const Geom& g = e->g;
+    const LevelGeom& L = g.lv[level];
+    CU(cudaStreamSynchronize(e->lastStream));
+    std::vector<uint32_t> keys;
+    if (selected) {
+        int cnt = 0;
+        CU(cudaMemcpy(&cnt, e->selCount.p + (size_t)image_index * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+        keys.resize(cnt);
+        if (cnt) CU(cudaMemcpy(keys.data(), e->sel.p + ((size_t)image_index * g.nlevels + level) * g.selCap, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    } else {
+        const int nCells = L.nCols * L.nRows;
+        std::vector<int> cc(std::max(nCells, 1));
+        if (nCells) CU(cudaMemcpy(cc.data(), e->cellCount.p + (size_t)image_index * g.nCellsTotal + L.cellBase, (size_t)nCells * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> slots((size_t)nCells * L.cellCap);
+        if (nCells) CU(cudaMemcpy(slots.data(), e->cand.p + (size_t)image_index * g.slotTotal + L.slotBase, slots.size() * 4, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < nCells; c++)
+            for (int i = 0; i < cc[c]; i++) keys.push_back(slots[(size_t)c * L.cellCap + i]);
+    }
+    *n_out = (int)keys.size();
+    if (xyr) {
+        const int m = std::min((int)keys.size(), cap);
+        for (int i = 0; i < m; i++) {
+            xyr[3 * i] = (int)(keys[i] & 0xfffu);
+            xyr[3 * i + 1] = (int)((keys[i] >> 12) & 0xfffu);
+            xyr[3 * i + 2] = (int)(keys[i] >> 24);
+        }
+    }
+    return OBS_OK;
+}
+
+int obs_extractor_get_candidates(obs_extractor* e, int image_index, int level, int32_t* xyr, int cap, int* n_out) {
+    return fetch_keys(e, image_index, level, false, xyr, cap, n_out);
+}
+int obs_extractor_get_selected(obs_extractor* e, int image_index, int level, int32_t* xyr, int cap, int* n_out) {
+    return fetch_keys(e, image_index, level, true, xyr, cap, n_out);
+}
+
+int obs_stereo_match_device(obs_extractor* L, obs_extractor* R, float mbf, float min_d, float max_d,
+                            void* stream, const float** d_u_right, const float** d_depth) {
+    int rc = check_handle(L);
+    if (rc) return rc;
+    if (!R) return fail(OBS_ERR_INVALID, "null right extractor");
+    if (L->lastN < 1 || R->lastN < 1) return fail(OBS_ERR_STATE, "stereo matching needs an extraction on both handles first");
+    if (L->device != R->device) return fail(OBS_ERR_INVALID, "both eyes must live on one device");
+    if (L->lastN != R->lastN || L->g.w != R->g.w || L->g.h != R->g.h || L->g.nlevels != R->g.nlevels ||
+        L->g.kpCap != R->g.kpCap || L->prm.scale_factor != R->prm.scale_factor)
+        return fail(OBS_ERR_INVALID, "left and right extractions differ in shape, batch or parameters");
+    cudaStream_t st = stream ? (cudaStream_t)stream : L->stream;
+    const int n = L->lastN;
+    const size_t cnt = (size_t)n * L->g.kpCap;
+    CU(L->uRight.ensure(cnt));
+    CU(L->depth.ensure(cnt));
+    CU(L->sad.ensure(cnt));
+    // order after both extractions
+    if (R->lastStream != st) { CU(cudaEventRecord(R->done, R->lastStream)); CU(cudaStreamWaitEvent(st, R->done, 0)); }
+    if (L->lastStream != st) { CU(cudaEventRecord(L->done, L->lastStream)); CU(cudaStreamWaitEvent(st, L->done, 0)); }
+    StereoArgs a;
+    a.g = L->g;
+    a.left = L->ptrs; a.right = R->ptrs;
+    a.recL = L->records.p; a.recR = R->records.p; a.recordBytes = L->recordBytes;
+    a.mbf = mbf; a.minD = min_d; a.maxD = max_d;
+    a.uRight = L->uRight.p; a.depth = L->depth.p; a.sad = L->sad.p;
+    CU(launch_stereo(a, n, st));
+    // later work on either handle must not overwrite the inputs while the match runs
+    CU(cudaEventRecord(L->done, st));
+    if (R->stream != st) CU(cudaStreamWaitEvent(R->stream, L->done, 0));
+    if (L->stream != st) CU(cudaStreamWaitEvent(L->stream, L->done, 0));
+    L->lastStream = st;
+    if (d_u_right) *d_u_right = L->uRight.p;
+    if (d_depth) *d_depth = L->depth.p;
+    return OBS_OK;
+}
+
+int obs_stereo_match(obs_extractor* L, obs_extractor* R, float mbf, float min_d, float max_d,
+                     float* u_right, float* depth, int cap) {
+    if (!u_right || !depth) return fail(OBS_ERR_INVALID, "null output");
+    int rc = obs_stereo_match_device(L, R, mbf, min_d, max_d, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    const int n = L->lastN, kc = L->g.kpCap;
+    std::vector<float> hu((size_t)n * kc), hd((size_t)n * kc);
+    CU(cudaMemcpyAsync(hu.data(), L->uRight.p, hu.size() * 4, cudaMemcpyDeviceToHost, L->stream));
+    CU(cudaMemcpyAsync(hd.data(), L->depth.p, hd.size() * 4, cudaMemcpyDeviceToHost, L->stream));
+    CU(cudaStreamSynchronize(L->stream));
+    const int m = std::min(cap, kc);
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < cap; j++) { u_right[(size_t)i * cap + j] = -1.f; depth[(size_t)i * cap + j] = -1.f; }
+        memcpy(u_right + (size_t)i * cap, hu.data() + (size_t)i * kc, (size_t)m * 4);
+        memcpy(depth + (size_t)i * cap, hd.data() + (size_t)i * kc, (size_t)m * 4);
+    }
+    return OBS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// K4 + K6 + K7 -- orientation, rBRIEF descriptor and keypoint finalisation, one warp per keypoint.
+// Replaces IC_Angle / computeOrientation (src/ORBextractor.cc:77-104, :472-479),
+// computeOrbDescriptor / computeDescriptors (:108-147, :1034-1041) and the keypoint bookkeeping of
+// ComputeKeyPointsOctTree (:837-847) and operator() (:1094-1103).
+//
+// Float semantics are part of the contract (descriptor bits depend on them): cv::fastAtan2's
+// polynomial and the pattern rotation are evaluated with individually rounded binary32 operations
+// (no FMA contraction), cvRound is round-half-to-even, and cosf/sinf are glibc's sincosf algorithm
+// evaluated in binary64 -- CUDA's cosf/sinf round differently and are not used.
+#include "kernels.h"
+#include <float.h>
+
+namespace {
+
+__device__ const int8_t d_pattern[256 * 4] = {
+#include "orb_pattern.inc"
+};
+
+constexpr int DESC_WARPS = 8;
+
+// cv::fastAtan2 (OpenCV core, atanImpl scalar path): degrees in [0, 360).
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale;
+    const float p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale;
+    const float p7 = -0.04432655554792128f * scale;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+// glibc >= 2.28 sincosf (ARM optimized-routines), |y| < 120, every binary64 op rounded on its own.
+__device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp) {
+    const double c0 = 1.0, c1 = -0x1.ffffffd0c621cp-2, c2c = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10,
+                 c4 = 0x1.99343027bf8c3p-16, s1c = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    double x = (double)y;
+    const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ff;
+    const uint32_t top_pio4 = (__float_as_uint(0x1.921FB6p-1f) >> 20) & 0x7ff;
+    const uint32_t top_tiny = (__float_as_uint(0x1p-12f) >> 20) & 0x7ff;
+    int n = 0;
+    double x2;
+    if (top < top_pio4) {
+        if (top < top_tiny) { *sinp = y; *cosp = 1.0f; return; }
+        x2 = __dmul_rn(x, x);
+    } else {
+        const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+        n = (__double2int_rz(r) + 0x800000) >> 24;
+        x = __dsub_rn(x, __dmul_rn((double)n, 0x1.921FB54442D18p0));
+        x2 = __dmul_rn(x, x);                        // squared before the sign is applied
+        if ((n & 3) == 1 || (n & 3) == 2) x = -x;    // sign table {1,-1,-1,1}
+    }
+    const double sg = (n & 2) ? -1.0 : 1.0;          // second table = first with the cosine coefficients negated
+    const double x4 = __dmul_rn(x2, x2), x3 = __dmul_rn(x2, x);
+    const double pc2 = __dadd_rn(sg * c3, __dmul_rn(x2, sg * c4));
+    const double ps1 = __dadd_rn(s2, __dmul_rn(x2, s3));
+    const double pc1 = __dadd_rn(sg * c0, __dmul_rn(x2, sg * c1));
+    const double x5 = __dmul_rn(x3, x2), x6 = __dmul_rn(x4, x2);
+    const double Sv = __dadd_rn(x, __dmul_rn(x3, s1c));
+    const double Cv = __dadd_rn(pc1, __dmul_rn(x4, sg * c2c));
+    const float sv = (float)__dadd_rn(Sv, __dmul_rn(x5, ps1));
+    const float cv = (float)__dadd_rn(Cv, __dmul_rn(x6, pc2));
+    if (n & 1) { *sinp = cv; *cosp = sv; } else { *sinp = sv; *cosp = cv; }
+}
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Geom g, const PyrPtrs p,
+                                                              const uint8_t* __restrict__ blurSlab, size_t blurStride,
+                                                              const uint32_t* __restrict__ sel, const int* __restrict__ selCount,
+                                                              uint8_t* __restrict__ records, size_t recordBytes) {
+    __shared__ int8_t pat[256 * 4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 256; i += DESC_WARPS * 32) reinterpret_cast<int32_t*>(pat)[i] = reinterpret_cast<const int32_t*>(d_pattern)[i];
+    __syncthreads();
+
+    const int img = blockIdx.y;
+    const int j = blockIdx.x * DESC_WARPS + warp;              // output index of this warp's keypoint (level-major)
+    const int* cnt = selCount + (size_t)img * g.nlevels;
+    int level = -1, local = 0, total = 0;
+#pragma unroll 1
+    for (int l = 0; l < g.nlevels; l++) {
+        const int c = cnt[l];
+        if (level < 0 && j < total + c) { level = l; local = j - total; }
+        total += c;
+    }
+    uint8_t* rec = records + (size_t)img * recordBytes;
+    if (j == 0 && lane == 0) {
+        int32_t* hdr = reinterpret_cast<int32_t*>(rec);
+        hdr[0] = total;
+        for (int l = 0; l < g.nlevels; l++) hdr[1 + l] = cnt[l];
+    }
+    if (level < 0) return;
+
+    const LevelGeom& lg = g.lv[level];
+    const uint32_t key = sel[((size_t)img * g.nlevels + level) * g.selCap + local];
+    const int cx = key_x(key) + OBS_BORDER, cy = key_y(key) + OBS_BORDER;       // :837-838
+
+    // ---- IC_Angle on the unblurred level (:77-104): integer moments over the circular patch
+    int pitch;
+    const uint8_t* im = level_ptr(p, g, img, level, pitch);
+    const uint8_t* c = im + (size_t)cy * pitch + cx;
+    const int u = lane - OBS_HALF_PATCH;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int au = abs(u);
+#pragma unroll 1
+        for (int v = -OBS_HALF_PATCH; v <= OBS_HALF_PATCH; v++) {
+            if (au <= g.umax[abs(v)]) {
+                const int val = c[v * pitch + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- rBRIEF on the blurred level (:108-147): lane i produces descriptor byte i
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    float a, b;
+    sincosf_glibc(__fmul_rn(angle, factorPI), &b, &a);
+    const uint8_t* cb = blurSlab + (size_t)img * blurStride + lg.off + (size_t)cy * lg.pitch + cx;
+    const int bp = lg.pitch;
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int8_t* pp = pat + (lane * 8 + k) * 4;
+        const float x0 = (float)pp[0], y0 = (float)pp[1], x1 = (float)pp[2], y1 = (float)pp[3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = cb[r0 * bp + q0], t1 = cb[r1 * bp + q1];
+        val |= (t0 < t1) << k;
+    }
+    uint8_t* kpOut = rec + OBS_HDR_INTS * 4;
+    uint8_t* descOut = kpOut + (size_t)g.kpCap * 28;
+    descOut[(size_t)j * 32 + lane] = (uint8_t)val;
+
+    // ---- keypoint record (cv::KeyPoint layout); pt scaled to level-0 coordinates (:1094-1101)
+    if (lane < 7) {
+        float fx = (float)cx, fy = (float)cy;
+        if (level != 0) { fx = __fmul_rn(fx, lg.scale); fy = __fmul_rn(fy, lg.scale); }
+        uint32_t w;
+        switch (lane) {
+            case 0: w = __float_as_uint(fx); break;
+            case 1: w = __float_as_uint(fy); break;
+            case 2: w = __float_as_uint(lg.patchSize); break;
+            case 3: w = __float_as_uint(angle); break;
+            case 4: w = __float_as_uint((float)key_r(key)); break;
+            case 5: w = (uint32_t)level; break;
+            default: w = 0xffffffffu; break;     // class_id = -1
+        }
+        reinterpret_cast<uint32_t*>(kpOut + (size_t)j * 28)[lane] = w;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_describe(const Geom& g, PyrPtrs p, const uint8_t* blurSlab, size_t blurStride,
+                            const uint32_t* sel, const int* selCount, uint8_t* records, size_t recordBytes,
+                            int nimg, cudaStream_t st) {
+    dim3 grid((g.kpCap + DESC_WARPS - 1) / DESC_WARPS, nimg);
+    k_describe<<<grid, DESC_WARPS * 32, 0, st>>>(g, p, blurSlab, blurStride, sel, selCount, records, recordBytes);
+    return cudaGetLastError();
+}

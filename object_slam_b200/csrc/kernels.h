@@ -1,0 +1,37 @@
+// Launchers of the sm_100a kernels (one translation unit per stage).  All of them enqueue on
+// `st` and return the launch status; none synchronises.
+#pragma once
+#include "common.cuh"
+
+// K1  pyramid.cu   -- ComputePyramid (src/ORBextractor.cc:1107-1132), levels 1..n-1
+cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, const ResizeTap* ytab, int nimg, cudaStream_t st);
+
+// K2  fast.cu      -- per-cell FAST with threshold fallback (:765-829, cv::FAST :809/:814)
+cudaError_t launch_fast(const Geom& g, PyrPtrs p, uint32_t* cand, int* cellCount, int nimg, cudaStream_t st);
+
+// K3  quadtree.cu  -- DistributeOctTree (:539-763) for every (image, level)
+size_t quadtree_smem_bytes(int nodeCap);
+cudaError_t quadtree_prepare(int nodeCap);
+cudaError_t launch_quadtree(const Geom& g, int nodeCap, const uint32_t* cand, const int* cellCount,
+                            uint32_t* keyScratch, uint16_t* nodeScratch, uint32_t* sel, int* selCount,
+                            int nimg, cudaStream_t st);
+
+// K5  blur.cu      -- GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101 (:1085-1086), all levels
+cudaError_t launch_blur(const Geom& g, PyrPtrs p, uint8_t* blurSlab, size_t blurStride, int nimg, cudaStream_t st);
+
+// K4+K6+K7 describe.cu -- IC_Angle (:77-104), computeOrbDescriptor (:108-147), keypoint
+// finalisation (:837-847, :1094-1103) into the per-image result record
+cudaError_t launch_describe(const Geom& g, PyrPtrs p, const uint8_t* blurSlab, size_t blurStride,
+                            const uint32_t* sel, const int* selCount, uint8_t* records, size_t recordBytes,
+                            int nimg, cudaStream_t st);
+
+// K8  stereo.cu    -- Frame::ComputeStereoMatches (src/Frame.cc:706-880)
+struct StereoArgs {
+    Geom g;                  // geometry shared by both eyes
+    PyrPtrs left, right;
+    const uint8_t* recL; const uint8_t* recR; size_t recordBytes;
+    float mbf, minD, maxD;
+    float* uRight; float* depth;     // nimg x kpCap
+    int* sad;                        // nimg x kpCap scratch (best SAD of accepted matches, -1 otherwise)
+};
+cudaError_t launch_stereo(const StereoArgs& a, int nimg, cudaStream_t st);

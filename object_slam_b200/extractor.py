@@ -1,0 +1,175 @@
+"""Host-side mirror of the reference's ``ORB_SLAM2::ORBextractor`` (include/ORBextractor.h:45-111)
+over the C ABI.  Same constructor arguments, same call semantics, same getters; the work runs in
+the CUDA kernels of ``csrc/`` -- there is no CPU implementation behind this class.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import KEYPOINT_DTYPE, OrbParams, check, lib, ptr
+
+
+class ORBextractor:
+    """``ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)`` -- ORBextractor.h:51.
+
+    ``max_size`` = (width, height) upper bound of the images, ``max_batch`` = images per batched
+    call; both only size the device buffers.
+    """
+
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST,
+                 max_size=(1241, 376), max_batch=1, device=0):
+        self._h = C.c_void_p()
+        self.nfeatures, self.scaleFactor, self.nlevels = int(nfeatures), float(scaleFactor), int(nlevels)
+        self.iniThFAST, self.minThFAST = int(iniThFAST), int(minThFAST)
+        self.max_batch = int(max_batch)
+        prm = OrbParams(self.nfeatures, self.scaleFactor, self.nlevels, self.iniThFAST, self.minThFAST)
+        check(lib().obs_extractor_create(C.byref(prm), int(max_size[0]), int(max_size[1]), self.max_batch,
+                                         int(device), C.byref(self._h)))
+        n = self.nlevels
+        self._scale, self._inv, self._s2, self._is2 = (np.empty(n, np.float32) for _ in range(4))
+        self._fpl = np.empty(n, np.int32)
+        check(lib().obs_extractor_tables(self._h, ptr(self._scale), ptr(self._inv), ptr(self._s2), ptr(self._is2), ptr(self._fpl)))
+        self._last_n = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().obs_extractor_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # ---- getters, ORBextractor.h:63-83
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return np.float32(self.scaleFactor)
+
+    def GetScaleFactors(self):
+        return self._scale.copy()
+
+    def GetInverseScaleFactors(self):
+        return self._inv.copy()
+
+    def GetScaleSigmaSquares(self):
+        return self._s2.copy()
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._is2.copy()
+
+    @property
+    def mnFeaturesPerLevel(self):
+        return self._fpl.copy()
+
+    @property
+    def capacity(self):
+        return lib().obs_extractor_max_keypoints(self._h)
+
+    # ---- operator(), ORBextractor.cc:1043-1105
+    def __call__(self, image, mask=None):
+        """Returns (keypoints, descriptors): a KEYPOINT_DTYPE array (cv::KeyPoint layout, level-major
+        order) and an N x 32 uint8 array.  The mask is ignored, as in the reference.  An empty image
+        gives empty outputs; zero keypoints give a 0 x 32 descriptor array (the reference releases it)."""
+        image = np.asarray(image)
+        if image.size == 0:
+            self._last_n = 0
+            return np.empty(0, KEYPOINT_DTYPE), np.empty((0, 32), np.uint8)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise ValueError("image must be 8-bit single channel (the reference asserts CV_8UC1, ORBextractor.cc:1050)")
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        cap = self.capacity
+        kps = np.empty(cap, KEYPOINT_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0)
+        check(lib().obs_extract(self._h, ptr(image), image.shape[1], image.shape[0], image.strides[0],
+                                ptr(kps), ptr(desc), cap, C.byref(n)))
+        self._last_n = 1
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images):
+        """operator() over a list of equally shaped host images in one call."""
+        images = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        h, w = images[0].shape
+        assert all(im.shape == (h, w) for im in images)
+        nimg = len(images)
+        cap = self.capacity
+        kps = np.empty((nimg, cap), KEYPOINT_DTYPE)
+        desc = np.empty((nimg, cap, 32), np.uint8)
+        counts = np.zeros(nimg, np.int32)
+        arr = (C.c_void_p * nimg)(*[im.ctypes.data for im in images])
+        check(lib().obs_extract_batch(self._h, arr, nimg, w, h, w, ptr(kps), ptr(desc), cap, ptr(counts)))
+        self._last_n = nimg
+        return [(kps[i, :counts[i]].copy(), desc[i, :counts[i]].copy()) for i in range(nimg)]
+
+    def extract_device(self, d_images, n_images, w, h, stride, image_stride, stream=None):
+        """Images already resident in HBM (``d_images`` = device address); results stay on the device."""
+        check(lib().obs_extract_batch_device(self._h, C.c_void_p(int(d_images)), int(n_images), int(w), int(h),
+                                             int(stride), int(image_stride), C.c_void_p(int(stream) if stream else 0)))
+        self._last_n = int(n_images)
+
+    def fetch(self):
+        nimg, cap = self._last_n, self.capacity
+        kps = np.empty((nimg, cap), KEYPOINT_DTYPE)
+        desc = np.empty((nimg, cap, 32), np.uint8)
+        counts = np.zeros(nimg, np.int32)
+        check(lib().obs_extractor_fetch(self._h, ptr(kps), ptr(desc), cap, ptr(counts)))
+        return [(kps[i, :counts[i]].copy(), desc[i, :counts[i]].copy()) for i in range(nimg)]
+
+    def fetch_counts(self):
+        counts = np.zeros(self._last_n, np.int32)
+        check(lib().obs_extractor_fetch_counts(self._h, ptr(counts)))
+        return counts
+
+    def results_device(self):
+        p, rb, cap = C.c_void_p(), C.c_size_t(), C.c_int()
+        check(lib().obs_extractor_results_device(self._h, C.byref(p), C.byref(rb), C.byref(cap)))
+        return p.value, rb.value, cap.value
+
+    # ---- mvImagePyramid, ORBextractor.h:85 (downloaded on demand; border-less)
+    def level(self, level, image_index=0, blurred=False):
+        w, h = C.c_int(), C.c_int()
+        check(lib().obs_extractor_get_level(self._h, image_index, level, int(blurred), None, 0, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.uint8)
+        check(lib().obs_extractor_get_level(self._h, image_index, level, int(blurred), ptr(out), out.strides[0], C.byref(w), C.byref(h)))
+        return out
+
+    @property
+    def mvImagePyramid(self):
+        return [self.level(l) for l in range(self.nlevels)]
+
+    # ---- stage outputs for parity tests
+    def _keys(self, fn, level, image_index):
+        n = C.c_int()
+        check(fn(self._h, image_index, level, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 3), np.int32)
+        check(fn(self._h, image_index, level, ptr(out), n.value, C.byref(n)))
+        return out[:n.value]
+
+    def candidates(self, level, image_index=0):
+        return self._keys(lib().obs_extractor_get_candidates, level, image_index)
+
+    def selected(self, level, image_index=0):
+        return self._keys(lib().obs_extractor_get_selected, level, image_index)
+
+
+def ComputeStereoMatches(left, right, mbf, minD, maxD):
+    """Frame::ComputeStereoMatches (src/Frame.cc:706-880) on the last extraction of two extractors.
+    Returns (mvuRight, mvDepth): per image of the batch, float32 arrays over the left keypoints."""
+    cap = left.capacity
+    nimg = left._last_n
+    ur = np.empty((nimg, cap), np.float32)
+    dp = np.empty((nimg, cap), np.float32)
+    check(lib().obs_stereo_match(left._h, right._h, float(mbf), float(minD), float(maxD), ptr(ur), ptr(dp), cap))
+    counts = left.fetch_counts()
+    return [(ur[i, :counts[i]].copy(), dp[i, :counts[i]].copy()) for i in range(nimg)]
+
+
+def stereo_match_device(left, right, mbf, minD, maxD, stream=None):
+    pu, pd = C.c_void_p(), C.c_void_p()
+    check(lib().obs_stereo_match_device(left._h, right._h, float(mbf), float(minD), float(maxD),
+                                        C.c_void_p(int(stream) if stream else 0), C.byref(pu), C.byref(pd)))
+    return pu.value, pd.value

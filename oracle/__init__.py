@@ -82,11 +82,11 @@ def lib():
 
 
 def _bind_match(L):
-    if not hasattr(L, "orc_stereo_match"):
-        return
-    L.orc_stereo_match.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
-        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 3 + [C.c_void_p] * 3
-    L.orc_stereo_match.restype = C.c_int
+    L.orc_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
 
 
 def _ptr(a):
@@ -244,3 +244,33 @@ class ReferenceExtractor:
         out = np.empty((h.value, w.value), np.uint8)
         ref_lib().ref_get_level(self._h, level, _ptr(out), C.byref(w), C.byref(h))
         return out
+
+
+# ----------------------------------------------------------------------------- matching
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_ptr(a), _ptr(b))
+
+
+def stereo_match(kpsL, descL, kpsR, descR, pyrL, pyrR, scale, inv_scale, mbf, minD, maxD):
+    """Frame::ComputeStereoMatches restated (match_oracle.cpp).  pyrL/pyrR: lists of border-less
+    level images.  Returns (uRight, depth, sad) over the left keypoints (sad = -1 where the
+    sub-pixel stage did not accept the match; it is not reset by the median cut)."""
+    kpsL = np.ascontiguousarray(kpsL); kpsR = np.ascontiguousarray(kpsR)
+    descL = np.ascontiguousarray(descL, np.uint8); descR = np.ascontiguousarray(descR, np.uint8)
+    pl = [_img(p) for p in pyrL]
+    pr = [_img(p) for p in pyrR]
+    n = len(pl)
+    arrL = (C.c_void_p * n)(*[p.ctypes.data for p in pl])
+    arrR = (C.c_void_p * n)(*[p.ctypes.data for p in pr])
+    lw = np.array([p.shape[1] for p in pl], np.int32)
+    lh = np.array([p.shape[0] for p in pl], np.int32)
+    scale = np.ascontiguousarray(scale, np.float32)
+    inv_scale = np.ascontiguousarray(inv_scale, np.float32)
+    nL = len(kpsL)
+    ur = np.empty(max(nL, 1), np.float32); dp = np.empty(max(nL, 1), np.float32); sad = np.empty(max(nL, 1), np.int32)
+    lib().orc_stereo_match(_ptr(kpsL), _ptr(descL), nL, _ptr(kpsR), _ptr(descR), len(kpsR),
+                           arrL, arrR, _ptr(lw), _ptr(lh), n, _ptr(scale), _ptr(inv_scale),
+                           float(mbf), float(minD), float(maxD), _ptr(ur), _ptr(dp), _ptr(sad))
+    return ur[:nL], dp[:nL], sad[:nL]
