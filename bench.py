@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the north-star path: ORB extraction of both eyes + Frame::ComputeStereoMatches on
+KITTI-shape (1241x376, nFeatures=2000) synthetic stereo frames.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
+
+One "step" = one batch of F stereo frames through the whole hot path.  `value` is stereo frames/s
+with the images already resident in HBM (CUDA-event timed on the launching stream); `e2e` is the same
+through the host-buffer C ABI (host images in, keypoints/descriptors/uRight/depth out), wall clock
+around synchronous calls.  Multi-GPU: one process per GPU (torchrun), frames sharded by rank, no
+data-path collective; timing is the max over ranks.
+
+Only the `cpu_baseline` leg and `--impl reference` touch oracle/ (the reference's own
+ORBextractor.cc compiled in place + the restated stereo matcher) -- as the thing timed beside the
+product, never inside it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from object_slam_b200 import synth  # noqa: E402
+
+W, H, NFEAT = 1241, 376, 2000
+PITCH = 1280
+METRIC = "stereo frames/s, ORB extract (both eyes) + stereo match, KITTI 1241x376, 2000 kp"
+LEVEL_PX = [1241 * 376, 1034 * 313, 862 * 261, 718 * 218, 598 * 181, 499 * 151, 416 * 126, 346 * 105]
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference's own ORBextractor.cc (oracle/_ref) + the restated stereo matcher
+# --------------------------------------------------------------------------------------------
+def cpu_stereo_frames(pairs, cores):
+    """Runs extraction of both eyes + stereo matching for every pair on `cores` host threads.
+    Returns (seconds, kind)."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    use_ref = oracle.ref_available()
+    tl = threading.local()
+
+    def eye(img):
+        if not hasattr(tl, "ex"):
+            tl.ex = oracle.ReferenceExtractor(NFEAT) if use_ref else oracle.OracleExtractor(NFEAT)
+        k, d = tl.ex(img)
+        return k, d, [tl.ex.level(l) for l in range(8)]
+
+    tables = oracle.OracleExtractor(NFEAT).tables()
+
+    def stereo(lr):
+        (kL, dL, pL), (kR, dR, pR) = lr
+        return oracle.stereo_match(kL, dL, kR, dR, pL, pR, tables["scale"], tables["inv_scale"],
+                                   synth.KITTI_BF, 0.0, synth.KITTI_FX)
+
+    with ThreadPoolExecutor(cores) as pool:
+        list(pool.map(eye, [pairs[0][0]] * cores))            # per-thread extractor construction, untimed
+        t0 = time.perf_counter()
+        eyes = list(pool.map(eye, [im for p in pairs for im in p]))
+        list(pool.map(stereo, [(eyes[2 * i], eyes[2 * i + 1]) for i in range(len(pairs))]))
+        dt = time.perf_counter() - t0
+    return dt, ("reference" if use_ref else "port")
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nper = max(cores // 2, 1) * 2          # frames per step: one bounded sample, two eyes per core pair
+    pairs = [synth.stereo_pair((H, W), i) for i in range(nper)]
+    for _ in range(args.warmup):
+        cpu_stereo_frames(pairs[:max(cores // 2, 1)], cores)
+    total = 0.0
+    kind = "port"
+    for _ in range(args.steps):
+        dt, kind = cpu_stereo_frames(pairs, cores)
+        total += dt
+    fps = nper * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1]: KITTI-shape 1241x376 synthetic stereo pairs, nFeatures=2000, "
+                               "ORB extraction of both eyes + ComputeStereoMatches", "frames_per_step": nper},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": f"{nper} stereo frames per step x {args.steps} steps; reference src/ORBextractor.cc compiled "
+                                   f"in place (oracle/_ref) per eye + restated ComputeStereoMatches, {cores} host threads"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=64, help="stereo frames per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=48, help="stereo frames of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from object_slam_b200.extractor import ORBextractor, ComputeStereoMatches, stereo_match_device
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: object_slam_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    F = args.frames
+    # synthetic stereo frames, distinct per rank and per slot (seed = global frame index)
+    pairs = [synth.stereo_pair((H, W), rank * F + i) for i in range(F)]
+    hostL = np.zeros((F, H, PITCH), np.uint8)
+    hostR = np.zeros((F, H, PITCH), np.uint8)
+    for i, (l, r) in enumerate(pairs):
+        hostL[i, :, :W] = l
+        hostR[i, :, :W] = r
+    dL = torch.from_numpy(hostL).cuda()
+    dR = torch.from_numpy(hostR).cuda()
+
+    exL = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_size=(W, H), max_batch=F, device=local_rank)
+    exR = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_size=(W, H), max_batch=F, device=local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        exL.extract_device(dL.data_ptr(), F, W, H, PITCH, H * PITCH, stream)
+        exR.extract_device(dR.data_ptr(), F, W, H, PITCH, H * PITCH, stream)
+        stereo_match_device(exL, exR, synth.KITTI_BF, 0.0, synth.KITTI_FX, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        step_device()
+    exL.set_profiling(True)
+    exR.set_profiling(True)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    stL, ncL, nsL = exL.stage_ms()
+    stR, ncR, _ = exR.stage_ms()
+    exL.set_profiling(False)
+    exR.set_profiling(False)
+    counts = exL.fetch_counts()
+    countsR = exR.fetch_counts()
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * F * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI (two threads for the two eyes, like Frame.cc:78-81)
+    listL = [p[0] for p in pairs]
+    listR = [p[1] for p in pairs]
+
+    def step_host():
+        res = [None, None]
+        th = threading.Thread(target=lambda: res.__setitem__(1, exR.extract_batch(listR)))
+        th.start()
+        res[0] = exL.extract_batch(listL)
+        th.join()
+        return res, ComputeStereoMatches(exL, exR, synth.KITTI_BF, 0.0, synth.KITTI_FX)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * F * e2e_steps / float(t.item())
+    _, rec_bytes, kp_cap = exL.results_device()
+    h2d = 2 * F * H * PITCH
+    d2h = 2 * F * rec_bytes + 2 * F * kp_cap * 4 + F * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per-launch CUDA-event time from the timed region above)
+    peak, peak_src = measured_peaks()
+    nkp = float(counts.mean())
+    alg = {   # algorithmic bytes per launch (one eye, F images): each stage reads its input once, writes its output once
+        "pyramid": F * (sum(LEVEL_PX[:-1]) + sum(LEVEL_PX[1:])),
+        "fast": F * sum(LEVEL_PX),
+        "quadtree": None,
+        "blur": F * 2 * sum(LEVEL_PX),
+        "describe": F * nkp * (749 + 512 + 60),
+        "stereo": F * (2 * nkp * 32 + nkp * (121 + 11 * 21) + nkp * 8),
+    }
+    per_launch_ms = {k: (stL[k] + stR[k]) / max(ncL + ncR, 1) for k in ORBextractor.STAGES}
+    per_launch_ms["stereo"] = stL["stereo"] / max(nsL, 1)
+    step_ms = ms_total / args.steps
+    shares = {k: (2 * v if k != "stereo" else v) / step_ms for k, v in per_launch_ms.items()}
+    dominant = max(shares, key=shares.get)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dominant)
+    except Exception:
+        pass
+    if alg[dominant] is not None:
+        achieved = alg[dominant] / (per_launch_ms[dominant] * 1e-3) / 1e9
+    else:
+        achieved = 0.0
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "per_launch_ms": per_launch_ms, "share_of_step": shares,
+                "whole_step": {"algorithmic_bytes": F * 19.5e6, "achieved": F * 19.5e6 / (step_ms * 1e-3) / 1e9,
+                               "frac": F * 19.5e6 / (step_ms * 1e-3) / 1e9 / peak}}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        sample = pairs[:min(args.cpu_frames, F)]
+        dt, kind = cpu_stereo_frames(sample, cores)
+        cpu_baseline = {"value": len(sample) / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+                        "sample": f"{len(sample)} of the step's stereo frames; reference src/ORBextractor.cc compiled in place "
+                                  f"(oracle/_ref) per eye + restated ComputeStereoMatches on {cores} host threads, {dt:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1]: KITTI-shape 1241x376 synthetic stereo pairs, nFeatures=2000, nLevels=8, scale 1.2, "
+                               "FAST 20/7: ORB extraction of both eyes + Frame::ComputeStereoMatches",
+                   "frames_per_step_per_gpu": F, "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                   "l2": f"working set per step {2 * F * 7.3:.0f} MB (> 126 MB L2): inputs and intermediates larger than L2",
+                   "mean_keypoints_left": nkp, "mean_keypoints_right": float(countsR.mean())},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "obs_extract_batch x2 (two host threads) + obs_stereo_match, host buffers"},
+        "gpu_launches": 24 * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,8 @@ _PROTOS = {
     "obs_extractor_get_level": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "obs_extractor_get_candidates": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
     "obs_extractor_get_selected": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(C.c_int)]),
+    "obs_extractor_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "obs_extractor_stage_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "obs_stereo_match": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_float, _vp, _vp, C.c_int]),
     "obs_stereo_match_device": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_float, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
 }

@@ -35,6 +35,8 @@ inline int cv_floor_d(double v) { int i = (int)v; return i - (i > v); }
 inline int cv_ceil_d(double v) { int i = (int)v; return i + (i < v); }
 inline short sat_short(float v) { int i = cv_round_f(v); return (short)(i < -32768 ? -32768 : i > 32767 ? 32767 : i); }
 
+constexpr int PROF_SLOTS = 128;
+
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
@@ -96,6 +98,13 @@ struct obs_extractor {
     PyrPtrs ptrs{};
     int lastN = 0;                 // images in the last batch (0 = nothing extracted yet)
     cudaStream_t lastStream = nullptr;
+
+    // optional per-stage CUDA-event timing (obs_extractor_set_profiling)
+    bool prof = false;
+    std::vector<cudaEvent_t> pev;  // ring of PROF_SLOTS x (OBS_NUM_STAGES + 1) events
+    int profCalls = 0;
+    std::vector<cudaEvent_t> sev;  // stereo: ring of PROF_SLOTS x 2 events (owned by the left handle)
+    int stereoCalls = 0;
 };
 
 namespace {
@@ -255,11 +264,19 @@ int set_shape(obs_extractor* e, int w, int h, int nimg, cudaStream_t st) {
 // Enqueue the whole extraction of `nimg` images on `st`.
 int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st) {
     const Geom& g = e->g;
+    cudaEvent_t* ev = nullptr;
+    if (e->prof && e->profCalls < PROF_SLOTS) ev = e->pev.data() + (size_t)e->profCalls * (OBS_NUM_STAGES + 1);
+    if (ev) CU(cudaEventRecord(ev[0], st));
     CU(launch_pyramid(g, e->ptrs, e->dXtab.p, e->dYtab.p, nimg, st));
+    if (ev) CU(cudaEventRecord(ev[1], st));
     CU(launch_fast(g, e->ptrs, e->cand.p, e->cellCount.p, nimg, st));
+    if (ev) CU(cudaEventRecord(ev[2], st));
     CU(launch_quadtree(g, e->nodeCap, e->cand.p, e->cellCount.p, e->keyScratch.p, e->nodeScratch.p, e->sel.p, e->selCount.p, nimg, st));
+    if (ev) CU(cudaEventRecord(ev[3], st));
     CU(launch_blur(g, e->ptrs, e->blur.p, g.slabBytes, nimg, st));
+    if (ev) CU(cudaEventRecord(ev[4], st));
     CU(launch_describe(g, e->ptrs, e->blur.p, g.slabBytes, e->sel.p, e->selCount.p, e->records.p, e->recordBytes, nimg, st));
+    if (ev) { CU(cudaEventRecord(ev[5], st)); e->profCalls++; }
     e->lastN = nimg;
     e->lastStream = st;
     return OBS_OK;
@@ -328,6 +345,8 @@ int obs_extractor_destroy(obs_extractor* e) {
     e->sel.release(); e->nodeScratch.release(); e->cellCount.release(); e->selCount.release();
     e->uRight.release(); e->depth.release(); e->sad.release(); e->dXtab.release(); e->dYtab.release();
     e->stageIn.release(); e->stageOut.release();
+    for (cudaEvent_t ev : e->pev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->sev) cudaEventDestroy(ev);
     if (e->done) cudaEventDestroy(e->done);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -346,6 +365,47 @@ int obs_extractor_tables(const obs_extractor* e, float* sc, float* isc, float* s
         if (is2) is2[i] = e->invSigma2[i];
         if (fpl) fpl[i] = e->featPerLevel[i];
     }
+    return OBS_OK;
+}
+
+int obs_extractor_set_profiling(obs_extractor* e, int on) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (on && e->pev.empty()) {
+        e->pev.resize((size_t)PROF_SLOTS * (OBS_NUM_STAGES + 1));
+        for (cudaEvent_t& ev : e->pev) CU(cudaEventCreate(&ev));
+        e->sev.resize((size_t)PROF_SLOTS * 2);
+        for (cudaEvent_t& ev : e->sev) CU(cudaEventCreate(&ev));
+    }
+    e->prof = on != 0;
+    e->profCalls = 0;
+    e->stereoCalls = 0;
+    return OBS_OK;
+}
+
+int obs_extractor_stage_ms(obs_extractor* e, float* stage_ms, float* stereo_ms, int* n_calls, int* n_stereo_calls) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    CU(cudaDeviceSynchronize());
+    for (int s = 0; s < OBS_NUM_STAGES; s++) {
+        float sum = 0.f;
+        for (int c = 0; c < e->profCalls; c++) {
+            float ms = 0.f;
+            const cudaEvent_t* ev = e->pev.data() + (size_t)c * (OBS_NUM_STAGES + 1);
+            CU(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+            sum += ms;
+        }
+        if (stage_ms) stage_ms[s] = sum;
+    }
+    float ssum = 0.f;
+    for (int c = 0; c < e->stereoCalls; c++) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e->sev[2 * c], e->sev[2 * c + 1]));
+        ssum += ms;
+    }
+    if (stereo_ms) *stereo_ms = ssum;
+    if (n_calls) *n_calls = e->profCalls;
+    if (n_stereo_calls) *n_stereo_calls = e->stereoCalls;
     return OBS_OK;
 }
 
@@ -546,7 +606,11 @@ int obs_stereo_match_device(obs_extractor* L, obs_extractor* R, float mbf, float
     a.recL = L->records.p; a.recR = R->records.p; a.recordBytes = L->recordBytes;
     a.mbf = mbf; a.minD = min_d; a.maxD = max_d;
     a.uRight = L->uRight.p; a.depth = L->depth.p; a.sad = L->sad.p;
+    cudaEvent_t* sev = nullptr;
+    if (L->prof && L->stereoCalls < PROF_SLOTS) sev = L->sev.data() + (size_t)L->stereoCalls * 2;
+    if (sev) CU(cudaEventRecord(sev[0], st));
     CU(launch_stereo(a, n, st));
+    if (sev) { CU(cudaEventRecord(sev[1], st)); L->stereoCalls++; }
     // later work on either handle must not overwrite the inputs while the match runs
     CU(cudaEventRecord(L->done, st));
     if (R->stream != st) CU(cudaStreamWaitEvent(R->stream, L->done, 0));

@@ -129,6 +129,20 @@ class ORBextractor:
         check(lib().obs_extractor_results_device(self._h, C.byref(p), C.byref(rb), C.byref(cap)))
         return p.value, rb.value, cap.value
 
+    STAGES = ("pyramid", "fast", "quadtree", "blur", "describe")
+
+    def set_profiling(self, on):
+        check(lib().obs_extractor_set_profiling(self._h, int(bool(on))))
+
+    def stage_ms(self):
+        """Summed per-stage device time (ms) over the calls recorded since set_profiling(True)."""
+        ms = np.zeros(len(self.STAGES), np.float32)
+        st, nc, ns = C.c_float(), C.c_int(), C.c_int()
+        check(lib().obs_extractor_stage_ms(self._h, ptr(ms), C.byref(st), C.byref(nc), C.byref(ns)))
+        out = {k: float(v) for k, v in zip(self.STAGES, ms)}
+        out["stereo"] = float(st.value)
+        return out, nc.value, ns.value
+
     # ---- mvImagePyramid, ORBextractor.h:85 (downloaded on demand; border-less)
     def level(self, level, image_index=0, blurred=False):
         w, h = C.c_int(), C.c_int()
