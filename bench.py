@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=64, help="stereo frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-frames", type=int, default=48, help="stereo frames of the cpu_baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=256, help="stereo frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -193,7 +193,10 @@ def main():
 
     exL = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_size=(W, H), max_batch=F, device=local_rank)
     exR = ORBextractor(NFEAT, 1.2, 8, 20, 7, max_size=(W, H), max_batch=F, device=local_rank)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a side stream of torch's: the ABI treats a NULL stream as "the handle's own stream"
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     def step_device():
         exL.extract_device(dL.data_ptr(), F, W, H, PITCH, H * PITCH, stream)
@@ -303,10 +306,10 @@ def main():
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        sample = pairs[:min(args.cpu_frames, F)]
+        sample = [pairs[i % F] for i in range(args.cpu_frames)]
         dt, kind = cpu_stereo_frames(sample, cores)
         cpu_baseline = {"value": len(sample) / dt, "unit": "frames/s", "cores": cores, "kind": kind,
-                        "sample": f"{len(sample)} of the step's stereo frames; reference src/ORBextractor.cc compiled in place "
+                        "sample": f"{len(sample)} stereo frames (the step's {F}, cycled); reference src/ORBextractor.cc compiled in place "
                                   f"(oracle/_ref) per eye + restated ComputeStereoMatches on {cores} host threads, {dt:.1f} s"}
 
     line = {
