@@ -175,7 +175,7 @@ void build_geometry(obs_extractor* e, int w, int h) {
     g.iniTh = e->prm.ini_th_fast; g.minTh = e->prm.min_th_fast;
     memcpy(g.umax, e->umax, sizeof(g.umax));
     unsigned off = 0, slot = 0;
-    int cells = 0, xt = 0, yt = 0, tiles = 0, maxFeat = 0, nodeCap = 0;
+    int cells = 0, xt = 0, yt = 0, tiles = 0, maxFeat = 0, nodeCap = 0, fastCtas = 0, edgeItems = 0;
     for (int l = 0; l < nl; l++) {
         LevelGeom& L = g.lv[l];
         L.w = cv_round_f((float)w * e->invScale[l]);
@@ -197,12 +197,22 @@ void build_geometry(obs_extractor* e, int w, int h) {
         L.slotBase = slot;
         cells += L.nCols * L.nRows;
         slot += (unsigned)(L.nCols * L.nRows) * (unsigned)L.cellCap;
+        L.fastCellsPerCta = fast_cells_per_cta_host(L.wCell, L.hCell);
+        L.fastCtaBase = fastCtas;
+        if (L.nCols > 0) fastCtas += ((L.nCols + L.fastCellsPerCta - 1) / L.fastCellsPerCta) * L.nRows;
         L.nfeat = e->featPerLevel[l];
         L.xtab = xt; L.ytab = yt;
         if (l > 0) { xt += L.w; yt += L.h; }
         L.blurTilesX = (L.w + 127) / 128;
         L.blurTileBase = tiles;
-        tiles += L.blurTilesX * ((L.h + 31) / 32);
+        tiles += L.blurTilesX * ((L.h + 127) / 128);
+        {   // border strips: strip 0 and the strips whose 8-byte look-ahead crosses the right border, per 32-row band
+            const int nStrips = (L.w + 3) >> 2;
+            const int firstRight = std::max(1, (L.w - 8 + 4) >> 2);
+            const int perBand = 1 + std::max(0, nStrips - firstRight);
+            L.blurEdgeBase = edgeItems;
+            edgeItems += perBand * ((L.h + 31) / 32);
+        }
         L.scale = e->scale[l];
         L.invScale = e->invScale[l];
         L.patchSize = (float)(int)(31 * e->scale[l]);
@@ -217,6 +227,8 @@ void build_geometry(obs_extractor* e, int w, int h) {
     g.selCap = round_up(nodeCap, 4);
     g.kpCap = round_up(e->prm.nfeatures + 4 * nl, 32);
     g.blurTilesTotal = tiles;
+    g.blurEdgeCtas = (edgeItems + 127) / 128;
+    g.fastCtasTotal = fastCtas;
     e->nodeCap = g.selCap;
     e->hXtab.assign(std::max(xt, 1), ResizeTap{0, 0, 0});
     e->hYtab.assign(std::max(yt, 1), ResizeTap{0, 0, 0});
@@ -237,6 +249,7 @@ int set_shape(obs_extractor* e, int w, int h, int nimg, cudaStream_t st) {
             if (e->g.lv[l].w > 4095 + 2 * OBS_BORDER || e->g.lv[l].h > 4095 + 2 * OBS_BORDER)
                 return fail(OBS_ERR_INVALID, "image %dx%d exceeds the 12-bit key coordinate range", w, h);
         CU(quadtree_prepare(e->nodeCap));
+        CU(fast_prepare());
         CU(e->dXtab.ensure(e->hXtab.size()));
         CU(e->dYtab.ensure(e->hYtab.size()));
         // tables are tiny; a synchronous copy keeps the host vectors free to change on the next shape

@@ -23,8 +23,11 @@ struct LevelGeom {
                          // the compact key array and the node-id scratch of the level start here too
     int nfeat;           // mnFeaturesPerLevel[level] (:435-446)
     int xtab, ytab;      // first entry of the level's resize coefficient tables (level >= 1)
+    int fastCellsPerCta; // cells of one cell row handled by one FAST CTA
+    int fastCtaBase;     // first CTA of this level in the FAST grid
     int blurTileBase;    // first CTA of this level in the blur grid
     int blurTilesX;      // tiles per row of the blur grid
+    int blurEdgeBase;    // first border-strip work item of this level
     float scale;         // mvScaleFactor[level]
     float invScale;      // mvInvScaleFactor[level]
     float patchSize;     // (float)(int)(31 * scale), :838
@@ -40,6 +43,8 @@ struct Geom {
     int selCap;              // per-level capacity of the selected-keypoint list (max nfeat + 4)
     int kpCap;               // per-image keypoint capacity of the result record
     int blurTilesTotal;
+    int blurEdgeCtas;        // CTAs appended to the blur grid for the border strips
+    int fastCtasTotal;
     int umax[OBS_HALF_PATCH + 1];
     LevelGeom lv[OBS_MAX_LEVELS];
 };

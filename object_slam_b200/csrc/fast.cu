@@ -2,196 +2,286 @@
 // ORBextractor::ComputeKeyPointsOctTree (src/ORBextractor.cc:765-829) and the two cv::FAST
 // calls inside it (:809, :814).
 //
-// One CTA owns one 30x30-ish cell of one level of one image: it stages the cell's sub-image
-// (cell + 6 overlap px, the window the reference hands to cv::FAST) in shared memory, computes
-// the exact FAST score (max over the sixteen 9-arcs of the min contrast, minus 1) of every
-// interior pixel once -- one score map serves both thresholds, a pixel being a corner at t iff
-// score >= t -- then applies OpenCV's strict 3x3 non-max suppression inside the cell at iniThFAST,
-// falls back to minThFAST when nothing survives (the decision is made after suppression, as in
-// the reference), and emits the survivors in row-major order into the cell's slot.  Interiors
-// of neighbouring cells tile the level without overlap, so every pixel is scored exactly once.
+// Semantics kept from the reference: cv::FAST runs on each 30x30-ish cell window (cell + 6 overlap
+// px); corners live in the window's interior (3-px margin), the interiors of neighbouring cells
+// tile the level without overlap; OpenCV's score of a corner is (max over the sixteen 9-arcs of
+// the min |contrast|) - 1, so one score map serves both thresholds (corner at t  <=>  score >= t);
+// the 3x3 non-max suppression is strict and sees only the cell's own interior; a cell whose
+// suppressed result at iniThFAST is empty is redone at minThFAST (decided after suppression);
+// output order is row-major inside the cell.  Because a score >= iniThFAST beats every neighbour
+// below iniThFAST anyway, "local maximum at T" == "score >= T and local maximum of the raw map",
+// so one suppression pass serves both thresholds.
+//
+// Shape of the kernel (issue-bound work, so it is organised around instructions per pixel):
+//   * one CTA owns a run of up to 8 cells of one cell row and stages their window with 128-bit loads;
+//   * pass 1 tests 4 pixels per instruction group with byte-SIMD |a-b| (VABSDIFF4) against the four
+//     compass ring pixels -- every 9-arc contains one of ring {0,8} and one of {4,12}, so
+//     "(|d0|>t or |d8|>t) and (|d4|>t or |d12|>t)" is a necessary condition -- and queues the few
+//     survivors;
+//   * pass 2 gives each queued pixel to one lane: exact score with both polarities packed as
+//     s16x2 (v-r, r-v) through a min/max network of VIMNMX(3).S16x2;
+//   * pass 3 suppresses non-maxima among the scored pixels only; pass 4: one warp per cell emits the
+//     survivors in row-major order with ballots.
 #include "kernels.h"
 
 namespace {
 
-constexpr int TILE_PITCH = 80;       // bytes per staged row (sub-image <= 66 px + <= 3 px alignment slack, word padded)
-constexpr int TILE_ROWS = 66;
-constexpr int SC_PITCH = 64;         // score rows: interior <= 60 px + 1-px zero apron each side
-constexpr int SC_ROWS = 62;
-constexpr int FAST_THREADS = 128;
+constexpr int FT_PITCH = 256;          // bytes per staged row
+constexpr int FT_ROWS = 66;            // hCell <= 60, + 6
+constexpr int FT_THREADS = 256;
+constexpr int FT_LIST = 8192;          // queue capacity == max interior pixels per CTA (host enforces)
+constexpr int FT_MAXCELLS = 8;
 
-// Exact FAST-9/16 score of the pixel at c (shared memory, row pitch TILE_PITCH):
-// 0 if the pixel is not a corner at threshold t, else (corner contrast - 1) >= t.
-__device__ __forceinline__ int fast_score(const uint8_t* c, int t) {
-    const int v = c[0];
-    const int lo = v - t, hi = v + t;
-    const int r0 = c[3 * TILE_PITCH], r8 = c[-3 * TILE_PITCH], r4 = c[3], r12 = c[-3];
-    // every 9-arc holds one of ring pixels {0,8} and one of {4,12}
-    const bool dk = ((r0 < lo) | (r8 < lo)) & ((r4 < lo) | (r12 < lo));
-    const bool br = ((r0 > hi) | (r8 > hi)) & ((r4 > hi) | (r12 > hi));
-    if (!(dk | br)) return 0;
-    int d[16];
-    d[0] = v - r0;
-    d[1] = v - c[3 * TILE_PITCH + 1];
-    d[2] = v - c[2 * TILE_PITCH + 2];
-    d[3] = v - c[1 * TILE_PITCH + 3];
-    d[4] = v - r4;
-    d[5] = v - c[-1 * TILE_PITCH + 3];
-    d[6] = v - c[-2 * TILE_PITCH + 2];
-    d[7] = v - c[-3 * TILE_PITCH + 1];
-    d[8] = v - r8;
-    d[9] = v - c[-3 * TILE_PITCH - 1];
-    d[10] = v - c[-2 * TILE_PITCH - 2];
-    d[11] = v - c[-1 * TILE_PITCH - 3];
-    d[12] = v - r12;
-    d[13] = v - c[1 * TILE_PITCH - 3];
-    d[14] = v - c[2 * TILE_PITCH - 2];
-    d[15] = v - c[3 * TILE_PITCH - 1];
-    // sliding minimum / maximum over 9 consecutive ring positions by doubling (2,4,8,+1)
-    int lo2[16], hi2[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) { lo2[i] = min(d[i], d[(i + 1) & 15]); hi2[i] = max(d[i], d[(i + 1) & 15]); }
-    int lo4[16], hi4[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) { lo4[i] = min(lo2[i], lo2[(i + 2) & 15]); hi4[i] = max(hi2[i], hi2[(i + 2) & 15]); }
-    int a = -256, b = 256;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int m9 = min(min(lo4[i], lo4[(i + 4) & 15]), d[(i + 8) & 15]);
-        const int x9 = max(max(hi4[i], hi4[(i + 4) & 15]), d[(i + 8) & 15]);
-        a = max(a, m9);        // ring darker than the centre
-        b = min(b, x9);        // ring brighter than the centre
-    }
-    const int contrast = max(a, -b);
-    return contrast > t ? contrast - 1 : 0;
+__host__ __device__ inline int fast_cells_per_cta(int wCell, int hCell) {
+    int cg = (FT_PITCH - 15 - 6) / wCell;
+    const int byList = FT_LIST / (wCell * hCell);
+    if (cg > byList) cg = byList;
+    if (cg > FT_MAXCELLS) cg = FT_MAXCELLS;
+    return cg < 1 ? 1 : cg;
 }
 
-__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ Geom g, const PyrPtrs p,
-                                                             uint32_t* __restrict__ cand, int* __restrict__ cellCount) {
-    __shared__ __align__(16) uint8_t tile[TILE_ROWS * TILE_PITCH];
-    __shared__ __align__(16) uint8_t score[SC_ROWS * SC_PITCH];
-    __shared__ uint8_t flags[60 * 60 + 32];
-    __shared__ int chunkOfs[128];
-    __shared__ int sAny;
+// Exact FAST-9/16 corner contrast of the pixel at c (staged tile): max over the 16 arcs of 9
+// contiguous ring pixels of the minimum of (v - r) [ring darker] and of (r - v) [ring brighter].
+// Both polarities ride in one register as two 16-bit lanes, biased by +255 so that one IMAD per
+// ring pixel builds the pair: r * 0xFFFF + (v + 255 | (255 - v) << 16) = (v - r + 255, r - v + 255).
+__device__ __forceinline__ int fast_contrast(const uint8_t* c) {
+    const unsigned v = c[0];
+    const unsigned Vc = (v + 255u) | ((255u - v) << 16);
+    unsigned P[16];
+#define RING(k, dx, dy) P[k] = (unsigned)c[(dy) * FT_PITCH + (dx)] * 0xFFFFu + Vc
+    RING(0, 0, 3); RING(1, 1, 3); RING(2, 2, 2); RING(3, 3, 1); RING(4, 3, 0); RING(5, 3, -1); RING(6, 2, -2); RING(7, 1, -3);
+    RING(8, 0, -3); RING(9, -1, -3); RING(10, -2, -2); RING(11, -3, -1); RING(12, -3, 0); RING(13, -3, 1); RING(14, -2, 2); RING(15, -1, 3);
+#undef RING
+    unsigned m2[16], m4[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) m2[i] = __vminu2(P[i], P[(i + 1) & 15]);
+#pragma unroll
+    for (int i = 0; i < 16; i++) m4[i] = __vminu2(m2[i], m2[(i + 2) & 15]);
+    unsigned best = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        const unsigned a = __vimin3_u16x2(m4[i], m4[(i + 4) & 15], P[(i + 8) & 15]);
+        const unsigned b = __vimin3_u16x2(m4[i + 1], m4[(i + 5) & 15], P[(i + 9) & 15]);
+        best = __vimax3_u16x2(best, a, b);
+    }
+    return (int)max(best & 0xffffu, best >> 16) - 255;
+}
 
-    const int tid = threadIdx.x;
+// number of set bits of a 256-bit row bitmap (8 words) inside columns [a, b)
+__device__ __forceinline__ int row_bits(const uint32_t* bm, int a, int b) {
+    int n = 0;
+    for (int w = a >> 5; w <= (b - 1) >> 5; w++) {
+        uint32_t m = bm[w];
+        if (w == (a >> 5)) m &= 0xffffffffu << (a & 31);
+        if (w == ((b - 1) >> 5)) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
+        n += __popc(m);
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant__ Geom g, const PyrPtrs p,
+                                                           uint32_t* __restrict__ cand, int* __restrict__ cellCount) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    uint8_t* tile = sm;                                   // FT_ROWS x FT_PITCH pixels
+    uint8_t* score = sm + FT_ROWS * FT_PITCH;             // same geometry, 0 = not a corner
+    uint16_t* list = reinterpret_cast<uint16_t*>(sm + 2 * FT_ROWS * FT_PITCH);     // queued pixels: row << 8 | col
+    __shared__ uint32_t bitmap[FT_ROWS][8];               // emitted keypoints, one bit per tile pixel
+    __shared__ uint16_t rowOfs[FT_MAXCELLS][FT_ROWS];     // per cell: keypoints in the rows above
+    __shared__ uint8_t colCell[FT_PITCH], colIn[FT_PITCH];   // tile column -> cell of the run, column inside the cell
+    __shared__ int sCount;
+    __shared__ int sCellAny[FT_MAXCELLS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.y;
-    int cell = blockIdx.x;
-    int level = 0;
+    int blk = blockIdx.x, level = 0;
 #pragma unroll 1
-    for (int l = 1; l < g.nlevels; l++) if (cell >= g.lv[l].cellBase) level = l;
+    for (int l = 1; l < g.nlevels; l++) if (blk >= g.lv[l].fastCtaBase) level = l;
     const LevelGeom& lg = g.lv[level];
-    cell -= lg.cellBase;
-    const int ci = cell / lg.nCols, cj = cell - ci * lg.nCols;
-    int* countOut = cellCount + (size_t)img * g.nCellsTotal + lg.cellBase + cell;
+    blk -= lg.fastCtaBase;
+    const int cg = lg.fastCellsPerCta;
+    const int ctasPerRow = (lg.nCols + cg - 1) / cg;
+    const int ci = blk / ctasPerRow;
+    const int j0 = (blk - ci * ctasPerRow) * cg;
+    const int j1 = min(j0 + cg, lg.nCols);
+    const int nCellsHere = j1 - j0;
+    int* countOut = cellCount + (size_t)img * g.nCellsTotal + lg.cellBase + ci * lg.nCols + j0;
 
-    // cell window, :789-806 (all values are small integers, so the reference's float arithmetic is exact)
+    // window of the cell run (:789-806): interiors tile [19, maxB-3) in both axes
     const int maxBX = lg.w - OBS_BORDER, maxBY = lg.h - OBS_BORDER;
-    const int X0 = OBS_BORDER + cj * lg.wCell, Y0 = OBS_BORDER + ci * lg.hCell;
-    const int X1 = min(X0 + lg.wCell + 6, maxBX), Y1 = min(Y0 + lg.hCell + 6, maxBY);
+    const int wCell = lg.wCell, hCell = lg.hCell;
+    const int X0 = OBS_BORDER + j0 * wCell, Y0 = OBS_BORDER + ci * hCell;
+    const int X1 = min(X0 + nCellsHere * wCell + 6, maxBX), Y1 = min(Y0 + hCell + 6, maxBY);
     const int sw = X1 - X0, sh = Y1 - Y0;
-    if (Y0 >= maxBY - 3 || X0 >= maxBX - 6 || sw < 7 || sh < 7) {     // skipped cell, or too small for FAST
-        if (tid == 0) *countOut = 0;
+    if (sw < 7 || sh < 7) {                               // no interior pixel: every cell of the run is empty
+        if (tid < nCellsHere) countOut[tid] = 0;
         return;
     }
-    const int wInt = sw - 6, hInt = sh - 6;
+    const int xa = X0 & ~15;                              // tile column 0 <-> level column xa
+    const int cLo = X0 + 3 - xa, cHi = X1 - 3 - xa;       // interior columns in tile coordinates
+    const int rLo = 3, rHi = sh - 3;                      // interior rows
 
-    // stage the window with aligned 32-bit loads
-    int pitch;
-    const uint8_t* base = level_ptr(p, g, img, level, pitch);
-    const int xa = X0 & ~3;                       // aligned start column
-    const int shift = X0 - xa;
-    const int nWords = (shift + sw + 3) >> 2;     // <= 18
-    for (int i = tid; i < sh * nWords; i += FAST_THREADS) {
-        const int r = i / nWords, wv = i - r * nWords;
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)(Y0 + r) * pitch + xa) + wv);
-        *reinterpret_cast<uint32_t*>(tile + r * TILE_PITCH + 4 * wv) = v;
+    // ---- stage the window (128-bit loads), clear the score map and the bitmap, build the column tables
+    {
+        int pitch;
+        const uint8_t* base = level_ptr(p, g, img, level, pitch);
+        const int nVec = (X1 - xa + 15) >> 4;             // <= 16
+        for (int i = tid; i < sh * 16; i += FT_THREADS) {
+            const int r = i >> 4, v = i & 15;
+            if (v < nVec) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(Y0 + r) * pitch + xa) + v);
+                *reinterpret_cast<uint4*>(tile + r * FT_PITCH + 16 * v) = q;
+            }
+            *reinterpret_cast<uint4*>(score + r * FT_PITCH + 16 * v) = make_uint4(0, 0, 0, 0);
+        }
+        for (int i = tid; i < FT_ROWS * 8; i += FT_THREADS) (&bitmap[0][0])[i] = 0;
+        const int xr = max(tid + xa - OBS_EDGE, 0);       // column relative to the level's first interior column
+        const int cc = xr / wCell;
+        colCell[tid] = (uint8_t)min(max(cc - j0, 0), FT_MAXCELLS - 1);
+        colIn[tid] = (uint8_t)(xr - cc * wCell);
+        if (tid == 0) sCount = 0;
+        if (tid < FT_MAXCELLS) sCellAny[tid] = 0;
     }
-    for (int i = tid; i < SC_ROWS * SC_PITCH / 4; i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0;
-    if (tid == 0) sAny = 0;
     __syncthreads();
 
+    // ---- pass 1: compass-point rejection, 8 pixels per lane, one row per warp iteration
     const int tLow = min(g.iniTh, g.minTh);
-    const int nInt = wInt * hInt;
-    for (int i = tid; i < nInt; i += FAST_THREADS) {
-        const int iy = i / wInt, ix = i - iy * wInt;
-        const int s = fast_score(tile + (iy + 3) * TILE_PITCH + shift + ix + 3, tLow);
-        score[(iy + 1) * SC_PITCH + ix + 1] = (uint8_t)s;
-    }
-    __syncthreads();
-
-    // 3x3 strict non-max suppression at both thresholds (pixels outside the interior count 0)
-    const int tIni = g.iniTh, tMin = g.minTh;
-    int anyIni = 0;
-    for (int i = tid; i < nInt; i += FAST_THREADS) {
-        const int iy = i / wInt, ix = i - iy * wInt;
-        const uint8_t* sc = score + (iy + 1) * SC_PITCH + ix + 1;
-        const int s = sc[0];
-        int f = 0;
-        if (s > 0) {
-            int mIni = 0, mMin = 0;      // max neighbour score among corners at the initial / the minimum threshold
+    {
+        const int w0 = cLo >> 2, w1 = (cHi + 3) >> 2;     // word range covering the interior columns (w1 - w0 <= 64)
+        const unsigned K = (unsigned)(127 - min(tLow, 127)) * 0x01010101u;
+        const int wA = w0 + 2 * lane;
+        for (int r = rLo + warp; r < rHi; r += FT_THREADS / 32) {
+            unsigned f[2] = {0, 0};
+            if (wA < w1) {
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + r * FT_PITCH);
+                const unsigned L = row[wA - 1], C0 = row[wA], C1 = row[wA + 1], R = row[wA + 2];
 #pragma unroll
-            for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                for (int dx = -1; dx <= 1; dx++) {
-                    if (dx == 0 && dy == 0) continue;
-                    const int n = sc[dy * SC_PITCH + dx];
-                    mIni = max(mIni, n >= tIni ? n : 0);
-                    mMin = max(mMin, n >= tMin ? n : 0);
+                for (int h = 0; h < 2; h++) {
+                    const unsigned C = h ? C1 : C0;
+                    const unsigned up = row[wA + h + 3 * (FT_PITCH / 4)], dn = row[wA + h - 3 * (FT_PITCH / 4)];
+                    const unsigned lf = __byte_perm(h ? C0 : L, C, 0x4321), rt = __byte_perm(C, h ? R : C1, 0x6543);
+                    unsigned ff;
+                    if (tLow < 128) {
+                        // per byte: |d| > t  <=>  bit 7 of ((|d| & 0x7f) + (127 - t)) | |d|
+                        const unsigned a0 = __vabsdiffu4(C, up), a8 = __vabsdiffu4(C, dn);
+                        const unsigned a4 = __vabsdiffu4(C, rt), a12 = __vabsdiffu4(C, lf);
+                        const unsigned v08 = ((a0 & 0x7f7f7f7fu) + K) | ((a8 & 0x7f7f7f7fu) + K) | a0 | a8;
+                        const unsigned v412 = ((a4 & 0x7f7f7f7fu) + K) | ((a12 & 0x7f7f7f7fu) + K) | a4 | a12;
+                        ff = v08 & v412 & 0x80808080u;
+                    } else {
+                        ff = 0x80808080u;                  // thresholds >= 128: no cheap rejection, score everything
+                    }
+                    const int c0 = (wA + h) * 4;
+                    if (c0 < cLo) ff &= 0xffffffffu << (8 * (cLo - c0));
+                    if (c0 + 4 > cHi) ff &= (c0 >= cHi) ? 0u : (0xffffffffu >> (8 * (c0 + 4 - cHi)));
+                    f[h] = ff;
                 }
-            if (s >= tIni && s > mIni) f |= 1;
-            if (s >= tMin && s > mMin) f |= 2;
+            }
+            // warp-aggregated append of the flagged pixels to the queue
+            const int cnt = __popc(f[0]) + __popc(f[1]);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            int base = 0;
+            if (lane == 31 && incl) base = atomicAdd(&sCount, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            int pos = base + incl - cnt;
+            const int e0 = (r << 8) | (wA * 4);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (f[k >> 2] & (0x80u << (8 * (k & 3)))) list[pos++] = (uint16_t)(e0 + k);
+            }
         }
-        flags[i] = (uint8_t)f;
-        anyIni |= f & 1;
     }
-    if (anyIni) sAny = 1;
     __syncthreads();
-    const int useBit = sAny ? 1 : 2;
+    const int nList = sCount;
 
-    // ordered compaction (row-major inside the cell, like cv::FAST's output)
-    const int lane = tid & 31, warp = tid >> 5;
-    const int nChunks = (nInt + 31) >> 5;            // <= 113
-    for (int c = warp; c < nChunks; c += FAST_THREADS / 32) {
-        const int i = c * 32 + lane;
-        const bool on = i < nInt && (flags[i] & useBit);
-        const unsigned b = __ballot_sync(0xffffffffu, on);
-        if (lane == 0) chunkOfs[c] = __popc(b);
+    // ---- pass 2: exact score of the queued pixels, one lane each
+    for (int i = tid; i < nList; i += FT_THREADS) {
+        const int e = list[i];
+        const int r = e >> 8, c = e & 255;
+        const int contrast = fast_contrast(tile + r * FT_PITCH + c);
+        if (contrast > tLow && contrast > 1) score[r * FT_PITCH + c] = (uint8_t)(contrast - 1);   // OpenCV: score = contrast - 1
+        else list[i] = 0xffffu;
     }
     __syncthreads();
-    if (warp == 0) {                                  // exclusive scan of <= 128 chunk counts
-        int v[4], s = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const int c = lane * 4 + k; v[k] = c < nChunks ? chunkOfs[c] : 0; s += v[k]; }
-        int incl = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
-        int run = incl - s;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const int c = lane * 4 + k; if (c < nChunks) chunkOfs[c] = run; run += v[k]; }
-        if (lane == 31) *countOut = incl;
-    }
-    __syncthreads();
-    uint32_t* slot = cand + (size_t)img * g.slotTotal + lg.slotBase + (size_t)cell * lg.cellCap;
-    for (int c = warp; c < nChunks; c += FAST_THREADS / 32) {
-        const int i = c * 32 + lane;
-        const bool on = i < nInt && (flags[i] & useBit);
-        const unsigned b = __ballot_sync(0xffffffffu, on);
-        if (on) {
-            const int iy = i / wInt, ix = i - iy * wInt;
-            const int s = score[(iy + 1) * SC_PITCH + ix + 1];
-            const int o = chunkOfs[c] + __popc(b & ((1u << lane) - 1));
-            // coordinates relative to the border origin: (X0 - 16) + (ix + 3), :820-825
-            slot[o] = pack_key(X0 - OBS_BORDER + ix + 3, Y0 - OBS_BORDER + iy + 3, s);
+
+    // ---- pass 3: strict 3x3 non-max suppression inside each cell, over the scored pixels only
+    const int lastCol = maxBX - 4 - xa;                    // tile column of the level's last interior column
+    for (int i = tid; i < nList; i += FT_THREADS) {
+        const int e = list[i];
+        if (e == 0xffff) continue;
+        const int r = e >> 8, c = e & 255;
+        const uint8_t* sc = score + r * FT_PITCH + c;
+        const int s = sc[0];
+        const int inCell = colIn[c];
+        const bool hasL = inCell > 0, hasR = inCell < wCell - 1 && c < lastCol;
+        int m = max(sc[-FT_PITCH], sc[FT_PITCH]);
+        if (hasL) m = max(m, max(max(sc[-FT_PITCH - 1], sc[-1]), sc[FT_PITCH - 1]));
+        if (hasR) m = max(m, max(max(sc[-FT_PITCH + 1], sc[1]), sc[FT_PITCH + 1]));
+        if (s > m) {
+            if (s >= g.iniTh) sCellAny[colCell[c]] = 1;
+        } else {
+            list[i] = 0xffffu;
         }
+    }
+    __syncthreads();
+
+    // ---- pass 4: threshold fallback per cell (:809-816); mark what is emitted
+    for (int i = tid; i < nList; i += FT_THREADS) {
+        const int e = list[i];
+        if (e == 0xffff) continue;
+        const int r = e >> 8, c = e & 255;
+        const int T = sCellAny[colCell[c]] ? g.iniTh : g.minTh;
+        if (score[r * FT_PITCH + c] >= T) atomicOr(&bitmap[r][c >> 5], 1u << (c & 31));
+        else list[i] = 0xffffu;
+    }
+    __syncthreads();
+
+    // ---- pass 5: per cell, keypoints per row -> exclusive prefix over the rows (one warp per cell)
+    for (int cl = warp; cl < nCellsHere; cl += FT_THREADS / 32) {
+        const int cx0 = OBS_EDGE + (j0 + cl) * wCell - xa; // first interior tile column of the cell
+        const int cx1 = min(cx0 + wCell, cHi);
+        int carry = 0;
+        for (int rb = rLo; rb < rHi; rb += 32) {
+            const int r = rb + lane;
+            const int n = (r < rHi && cx1 > cx0) ? row_bits(bitmap[r], cx0, cx1) : 0;
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (r < rHi) rowOfs[cl][r] = (uint16_t)(carry + incl - n);
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) countOut[cl] = carry;
+    }
+    __syncthreads();
+
+    // ---- pass 6: write the keypoints in row-major order inside each cell (cv::FAST's order)
+    for (int i = tid; i < nList; i += FT_THREADS) {
+        const int e = list[i];
+        if (e == 0xffff) continue;
+        const int r = e >> 8, c = e & 255;
+        const int cl = colCell[c];
+        const int cx0 = OBS_EDGE + (j0 + cl) * wCell - xa;
+        const int pos = rowOfs[cl][r] + (c > cx0 ? row_bits(bitmap[r], cx0, c) : 0);
+        uint32_t* slot = cand + (size_t)img * g.slotTotal + lg.slotBase + (size_t)(ci * lg.nCols + j0 + cl) * lg.cellCap;
+        // coordinates relative to the 16-px border origin, :820-825
+        slot[pos] = pack_key(xa + c - OBS_BORDER, Y0 + r - OBS_BORDER, score[r * FT_PITCH + c]);
     }
 }
 
 }  // namespace
 
+size_t fast_smem_bytes() { return (size_t)2 * FT_ROWS * FT_PITCH + (size_t)FT_LIST * 2; }
+
+cudaError_t fast_prepare() {
+    return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes());
+}
+
+int fast_cells_per_cta_host(int wCell, int hCell) { return fast_cells_per_cta(wCell, hCell); }
+
 cudaError_t launch_fast(const Geom& g, PyrPtrs p, uint32_t* cand, int* cellCount, int nimg, cudaStream_t st) {
-    if (g.nCellsTotal == 0) return cudaSuccess;
-    dim3 grid(g.nCellsTotal, nimg);
-    k_fast_cells<<<grid, FAST_THREADS, 0, st>>>(g, p, cand, cellCount);
+    if (g.fastCtasTotal == 0) return cudaSuccess;
+    dim3 grid(g.fastCtasTotal, nimg);
+    k_fast_cells<<<grid, FT_THREADS, fast_smem_bytes(), st>>>(g, p, cand, cellCount);
     return cudaGetLastError();
 }

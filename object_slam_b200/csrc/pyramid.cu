@@ -1,58 +1,128 @@
 // K1 -- image pyramid.  Replaces ORBextractor::ComputePyramid (src/ORBextractor.cc:1107-1132):
 // level l = cv::resize(level l-1, INTER_LINEAR) on 8-bit pixels.  OpenCV's 8U bilinear path is
-// fixed point (11-bit weights, two-stage shifts); the weights come from the host-built tap
-// tables so that every output byte equals the reference's.  The 19-px reflect border the
-// reference adds around each level is never read on this path and is not materialised.
+// fixed point: 11-bit weights per axis, horizontal sums kept at full precision, then
+// out = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2.  The weights come from
+// host-built tap tables so that every output byte equals the reference's.  The 19-px reflect
+// border the reference adds around each level is never read on this path and is not materialised.
+//
+// A thread owns four consecutive output columns and walks down the output rows: its x taps, byte
+// selectors and weights live in registers; per source row it loads the (at most) 12 bytes under
+// its taps as three aligned words, forms each horizontal sum with one PRMT + one IDP.2A
+// (a0*S[x] + a1*S[x+1]) and reuses the lower source row of one output row as the upper row of the
+// next when the vertical taps allow; the vertical blend is two IMAD.HI per pixel.
 #include "kernels.h"
 
 namespace {
 
-// 128 x 8 output pixels per CTA, 4 consecutive pixels per thread (one 32-bit store).
-__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Geom g, const PyrPtrs p,
-                                                const ResizeTap* __restrict__ xtab,
-                                                const ResizeTap* __restrict__ ytab, int level) {
+constexpr int RS_ROWS = 8;           // output rows per thread
+constexpr int RS_BANDS = 4;          // row bands per CTA (CTA tile: 128 x 32 output pixels)
+
+struct XTaps {
+    unsigned w[4];       // a0 | a1 << 16
+    unsigned sel[4];     // PRMT selector picking (S[sx], S[sx+1]) out of the 8-byte shifted window
+    int word0;           // first source word of the window
+    int shift;           // bit shift aligning the window to the first tap
+    bool fast;           // all four taps fit the 8-byte window
+    int ofs[4];
+};
+
+__device__ __forceinline__ void hrow(const uint8_t* __restrict__ row, int lastWord, int srcW, const XTaps& t, unsigned hs[4]) {
+    if (t.fast) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(row);
+        const unsigned W0 = __ldg(q + t.word0), W1 = __ldg(q + min(t.word0 + 1, lastWord)), W2 = __ldg(q + min(t.word0 + 2, lastWord));
+        const unsigned U0 = __funnelshift_r(W0, W1, t.shift), U1 = __funnelshift_r(W1, W2, t.shift);
+#pragma unroll
+        for (int i = 0; i < 4; i++) hs[i] = __dp2a_lo(t.w[i], __byte_perm(U0, U1, t.sel[i]), 0u) >> 4;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int sx = t.ofs[i];
+            const unsigned s0 = row[sx], s1 = row[min(sx + 1, srcW - 1)];
+            hs[i] = (s0 * (t.w[i] & 0xffffu) + s1 * (t.w[i] >> 16)) >> 4;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * RS_BANDS) k_resize(const __grid_constant__ Geom g, const PyrPtrs p,
+                                                          const ResizeTap* __restrict__ xtab,
+                                                          const ResizeTap* __restrict__ ytab, int level) {
     const LevelGeom& D = g.lv[level];
     const LevelGeom& S = g.lv[level - 1];
     const int img = blockIdx.z;
+    const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int dy0 = (blockIdx.y * RS_BANDS + threadIdx.y) * RS_ROWS;
+    if (dx0 >= D.w || dy0 >= D.h) return;
     int spitch, dpitch;
     const uint8_t* src = level_ptr(p, g, img, level - 1, spitch);
-    uint8_t* dst = const_cast<uint8_t*>(level_ptr(p, g, img, level, dpitch));
-    const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int dy = blockIdx.y * 8 + threadIdx.y;
-    if (dx0 >= D.w || dy >= D.h) return;
+    uint8_t* dst = const_cast<uint8_t*>(level_ptr(p, g, img, level, dpitch)) + dx0;
+    const int lastWord = (spitch >> 2) - 1;
 
-    const ResizeTap ty = ytab[D.ytab + dy];
-    const int y0 = min(max(ty.ofs, 0), S.h - 1);
-    const int y1 = min(max(ty.ofs + 1, 0), S.h - 1);
-    const uint8_t* __restrict__ r0 = src + (size_t)y0 * spitch;
-    const uint8_t* __restrict__ r1 = src + (size_t)y1 * spitch;
-    const int b0 = ty.a0, b1 = ty.a1;
-
-    uint32_t out = 0;
+    XTaps t;
+    {
+        int ofs[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int dx = dx0 + i;
-        if (dx < D.w) {
-            const ResizeTap tx = xtab[D.xtab + dx];
-            const int sx = tx.ofs;
-            const int sx1 = min(sx + 1, S.w - 1);
-            const int h0 = (int)r0[sx] * tx.a0 + (int)r0[sx1] * tx.a1;
-            const int h1 = (int)r1[sx] * tx.a0 + (int)r1[sx1] * tx.a1;
-            int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            v = min(max(v, 0), 255);
-            out |= (uint32_t)v << (8 * i);
+        for (int i = 0; i < 4; i++) {
+            const ResizeTap tx = xtab[D.xtab + min(dx0 + i, D.w - 1)];
+            ofs[i] = tx.ofs;
+            t.ofs[i] = tx.ofs;
+            t.w[i] = (unsigned)(unsigned short)tx.a0 | ((unsigned)(unsigned short)tx.a1 << 16);
+        }
+        t.word0 = ofs[0] >> 2;
+        t.shift = 8 * (ofs[0] & 3);
+        t.fast = true;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int o = ofs[i] - ofs[0];
+            if (o < 0 || o > 6) t.fast = false;
+            t.sel[i] = (unsigned)(o & 7) | ((unsigned)((o + 1) & 7) << 4);
         }
     }
-    // rows are padded to the pitch, so the full word may be written
-    *reinterpret_cast<uint32_t*>(dst + (size_t)dy * dpitch + dx0) = out;
+
+    unsigned ha[4], hb[4];                  // horizontal sums (>> 4) of source rows rowA, rowB
+    int rowA = -1, rowB = -1;
+    const int nOut = min(RS_ROWS, D.h - dy0);
+#pragma unroll 1
+    for (int r = 0; r < nOut; r++) {
+        const int dy = dy0 + r;
+        const ResizeTap ty = ytab[D.ytab + dy];
+        const int y0 = min(max(ty.ofs, 0), S.h - 1);
+        const int y1 = min(max(ty.ofs + 1, 0), S.h - 1);
+        if (y0 != rowA) {
+            if (y0 == rowB) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) ha[i] = hb[i];
+            } else {
+                hrow(src + (size_t)y0 * spitch, lastWord, S.w, t, ha);
+            }
+            rowA = y0;
+        }
+        if (y1 != rowB) {
+            if (y1 == rowA) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) hb[i] = ha[i];
+            } else {
+                hrow(src + (size_t)y1 * spitch, lastWord, S.w, t, hb);
+            }
+            rowB = y1;
+        }
+        const unsigned b0 = (unsigned)ty.a0 << 16, b1 = (unsigned)ty.a1 << 16;      // (b * h) >> 16 == umulhi(b << 16, h)
+        unsigned o = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            unsigned v = (__umulhi(b0, ha[i]) + __umulhi(b1, hb[i]) + 2u) >> 2;
+            v = min(v, 255u);
+            o |= v << (8 * i);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)dy * dpitch) = o;      // rows are padded to the pitch
+    }
 }
 
 }  // namespace
 
 cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, const ResizeTap* ytab, int nimg, cudaStream_t st) {
     for (int l = 1; l < g.nlevels; l++) {
-        dim3 block(32, 8);
-        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 7) / 8, nimg);
+        dim3 block(32, RS_BANDS);
+        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + RS_ROWS * RS_BANDS - 1) / (RS_ROWS * RS_BANDS), nimg);
         k_resize<<<grid, block, 0, st>>>(g, p, xtab, ytab, l);
     }
     return cudaGetLastError();
