@@ -85,6 +85,8 @@ struct obs_extractor {
     bool geomValid = false;
     std::vector<ResizeTap> hXtab, hYtab;
     DevBuf<ResizeTap> dXtab, dYtab;
+    std::vector<FastCta> hFastCtas;
+    DevBuf<FastCta> dFastCtas;
 
     // device state of the last batch
     DevBuf<uint8_t> pyr, blur, records;
@@ -199,7 +201,12 @@ void build_geometry(obs_extractor* e, int w, int h) {
         slot += (unsigned)(L.nCols * L.nRows) * (unsigned)L.cellCap;
         L.fastCellsPerCta = fast_cells_per_cta_host(L.wCell, L.hCell);
         L.fastCtaBase = fastCtas;
-        if (L.nCols > 0) fastCtas += ((L.nCols + L.fastCellsPerCta - 1) / L.fastCellsPerCta) * L.nRows;
+        if (l == 0) e->hFastCtas.clear();
+        for (int ci = 0; ci < L.nRows; ci++)
+            for (int j0 = 0; j0 < L.nCols; j0 += L.fastCellsPerCta) {
+                e->hFastCtas.push_back(FastCta{(short)l, (short)ci, (short)j0, (short)std::min(L.fastCellsPerCta, L.nCols - j0)});
+                fastCtas++;
+            }
         L.nfeat = e->featPerLevel[l];
         L.xtab = xt; L.ytab = yt;
         if (l > 0) { xt += L.w; yt += L.h; }
@@ -252,10 +259,13 @@ int set_shape(obs_extractor* e, int w, int h, int nimg, cudaStream_t st) {
         CU(fast_prepare());
         CU(e->dXtab.ensure(e->hXtab.size()));
         CU(e->dYtab.ensure(e->hYtab.size()));
+        CU(e->dFastCtas.ensure(std::max<size_t>(e->hFastCtas.size(), 1)));
         // tables are tiny; a synchronous copy keeps the host vectors free to change on the next shape
         CU(cudaStreamSynchronize(st));
         CU(cudaMemcpy(e->dXtab.p, e->hXtab.data(), e->hXtab.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(e->dYtab.p, e->hYtab.data(), e->hYtab.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+        if (!e->hFastCtas.empty())
+            CU(cudaMemcpy(e->dFastCtas.p, e->hFastCtas.data(), e->hFastCtas.size() * sizeof(FastCta), cudaMemcpyHostToDevice));
         e->geomValid = true;
     }
     const Geom& g = e->g;
@@ -282,7 +292,7 @@ int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st) {
     if (ev) CU(cudaEventRecord(ev[0], st));
     CU(launch_pyramid(g, e->ptrs, e->dXtab.p, e->dYtab.p, nimg, st));
     if (ev) CU(cudaEventRecord(ev[1], st));
-    CU(launch_fast(g, e->ptrs, e->cand.p, e->cellCount.p, nimg, st));
+    CU(launch_fast(g, e->ptrs, e->dFastCtas.p, e->cand.p, e->cellCount.p, nimg, st));
     if (ev) CU(cudaEventRecord(ev[2], st));
     CU(launch_quadtree(g, e->nodeCap, e->cand.p, e->cellCount.p, e->keyScratch.p, e->nodeScratch.p, e->sel.p, e->selCount.p, nimg, st));
     if (ev) CU(cudaEventRecord(ev[3], st));
@@ -356,7 +366,7 @@ int obs_extractor_destroy(obs_extractor* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->pyr.release(); e->blur.release(); e->records.release(); e->cand.release(); e->keyScratch.release();
     e->sel.release(); e->nodeScratch.release(); e->cellCount.release(); e->selCount.release();
-    e->uRight.release(); e->depth.release(); e->sad.release(); e->dXtab.release(); e->dYtab.release();
+    e->uRight.release(); e->depth.release(); e->sad.release(); e->dXtab.release(); e->dYtab.release(); e->dFastCtas.release();
     e->stageIn.release(); e->stageOut.release();
     for (cudaEvent_t ev : e->pev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->sev) cudaEventDestroy(ev);

@@ -71,6 +71,10 @@ __device__ __forceinline__ int key_x(uint32_t k) { return (int)(k & 0xfffu); }
 __device__ __forceinline__ int key_y(uint32_t k) { return (int)((k >> 12) & 0xfffu); }
 __device__ __forceinline__ int key_r(uint32_t k) { return (int)(k >> 24); }
 
+struct FastCta {                // one CTA of the FAST grid: a run of cells of one cell row
+    short level, ci, j0, n;
+};
+
 struct alignas(4) ResizeTap {   // one destination index of one axis
     int32_t ofs;                // source index
     int16_t a0, a1;             // 11-bit fixed-point weights of source[ofs], source[ofs+1]

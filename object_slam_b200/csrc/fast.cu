@@ -14,14 +14,14 @@
 //
 // Shape of the kernel (issue-bound work, so it is organised around instructions per pixel):
 //   * one CTA owns a run of up to 8 cells of one cell row and stages their window with 128-bit loads;
-//   * pass 1 tests 4 pixels per instruction group with byte-SIMD |a-b| (VABSDIFF4) against the four
-//     compass ring pixels -- every 9-arc contains one of ring {0,8} and one of {4,12}, so
-//     "(|d0|>t or |d8|>t) and (|d4|>t or |d12|>t)" is a necessary condition -- and queues the few
-//     survivors;
-//   * pass 2 gives each queued pixel to one lane: exact score with both polarities packed as
-//     s16x2 (v-r, r-v) through a min/max network of VIMNMX(3).S16x2;
-//   * pass 3 suppresses non-maxima among the scored pixels only; pass 4: one warp per cell emits the
-//     survivors in row-major order with ballots.
+//   * pass 1 tests 8 pixels per lane with byte-SIMD |a-b| (VABSDIFF4) against the four compass ring
+//     pixels (a necessary condition for a 9-arc), leaves one bit per pixel in a bitmap, and pass 1b
+//     expands the bitmap into a dense queue of pixels;
+//   * pass 2 gives each queued pixel to one lane: exact score with both polarities packed as u16x2
+//     (v-r+255, r-v+255) through a min/max network of VIMNMX(3).U16x2; corners are re-queued densely;
+//   * pass 3 suppresses non-maxima among the corners only and re-queues the survivors; passes 4-6
+//     apply the per-cell threshold fallback and write the survivors in row-major order per cell,
+//     positions coming from popcounts over a bitmap of the emitted pixels.
 #include "kernels.h"
 
 namespace {
@@ -67,43 +67,39 @@ __device__ __forceinline__ int fast_contrast(const uint8_t* c) {
     return (int)max(best & 0xffffu, best >> 16) - 255;
 }
 
-// number of set bits of a 256-bit row bitmap (8 words) inside columns [a, b)
+// number of set bits of a 256-bit row bitmap (8 words) inside columns [a, b), a < b
 __device__ __forceinline__ int row_bits(const uint32_t* bm, int a, int b) {
-    int n = 0;
-    for (int w = a >> 5; w <= (b - 1) >> 5; w++) {
-        uint32_t m = bm[w];
-        if (w == (a >> 5)) m &= 0xffffffffu << (a & 31);
-        if (w == ((b - 1) >> 5)) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
-        n += __popc(m);
-    }
+    const int wa = a >> 5, wb = (b - 1) >> 5;
+    const uint32_t ma = 0xffffffffu << (a & 31), mb = 0xffffffffu >> (31 - ((b - 1) & 31));
+    if (wa == wb) return __popc(bm[wa] & ma & mb);
+    int n = __popc(bm[wa] & ma) + __popc(bm[wb] & mb);
+    for (int w = wa + 1; w < wb; w++) n += __popc(bm[w]);
     return n;
 }
 
+// per byte: 0x80 where the byte of y exceeds t (t < 128, K = (127 - t) * 0x01010101)
+__device__ __forceinline__ unsigned over_threshold(unsigned y, unsigned K) { return ((y & 0x7f7f7f7fu) + K) | y; }
+
 __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant__ Geom g, const PyrPtrs p,
+                                                           const FastCta* __restrict__ ctaTab,
                                                            uint32_t* __restrict__ cand, int* __restrict__ cellCount) {
     extern __shared__ __align__(16) uint8_t sm[];
     uint8_t* tile = sm;                                   // FT_ROWS x FT_PITCH pixels
     uint8_t* score = sm + FT_ROWS * FT_PITCH;             // same geometry, 0 = not a corner
-    uint16_t* list = reinterpret_cast<uint16_t*>(sm + 2 * FT_ROWS * FT_PITCH);     // queued pixels: row << 8 | col
+    uint16_t* listA = reinterpret_cast<uint16_t*>(sm + 2 * FT_ROWS * FT_PITCH);    // pixel queues: row << 8 | col
+    uint16_t* listB = listA + FT_LIST;
+    __shared__ uint32_t flagmap[FT_ROWS][8];              // pass-1 survivors, one bit per tile pixel
     __shared__ uint32_t bitmap[FT_ROWS][8];               // emitted keypoints, one bit per tile pixel
     __shared__ uint16_t rowOfs[FT_MAXCELLS][FT_ROWS];     // per cell: keypoints in the rows above
     __shared__ uint8_t colCell[FT_PITCH], colIn[FT_PITCH];   // tile column -> cell of the run, column inside the cell
-    __shared__ int sCount;
+    __shared__ int sCount[4];
     __shared__ int sCellAny[FT_MAXCELLS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.y;
-    int blk = blockIdx.x, level = 0;
-#pragma unroll 1
-    for (int l = 1; l < g.nlevels; l++) if (blk >= g.lv[l].fastCtaBase) level = l;
+    const FastCta cta = ctaTab[blockIdx.x];
+    const int level = cta.level, ci = cta.ci, j0 = cta.j0, nCellsHere = cta.n;
     const LevelGeom& lg = g.lv[level];
-    blk -= lg.fastCtaBase;
-    const int cg = lg.fastCellsPerCta;
-    const int ctasPerRow = (lg.nCols + cg - 1) / cg;
-    const int ci = blk / ctasPerRow;
-    const int j0 = (blk - ci * ctasPerRow) * cg;
-    const int j1 = min(j0 + cg, lg.nCols);
-    const int nCellsHere = j1 - j0;
     int* countOut = cellCount + (size_t)img * g.nCellsTotal + lg.cellBase + ci * lg.nCols + j0;
 
     // window of the cell run (:789-806): interiors tile [19, maxB-3) in both axes
@@ -120,7 +116,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
     const int cLo = X0 + 3 - xa, cHi = X1 - 3 - xa;       // interior columns in tile coordinates
     const int rLo = 3, rHi = sh - 3;                      // interior rows
 
-    // ---- stage the window (128-bit loads), clear the score map and the bitmap, build the column tables
+    // ---- stage the window (128-bit loads), clear the maps, build the column tables
     {
         int pitch;
         const uint8_t* base = level_ptr(p, g, img, level, pitch);
@@ -133,107 +129,135 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
             }
             *reinterpret_cast<uint4*>(score + r * FT_PITCH + 16 * v) = make_uint4(0, 0, 0, 0);
         }
-        for (int i = tid; i < FT_ROWS * 8; i += FT_THREADS) (&bitmap[0][0])[i] = 0;
+        for (int i = tid; i < FT_ROWS * 8; i += FT_THREADS) { (&flagmap[0][0])[i] = 0; (&bitmap[0][0])[i] = 0; }
         const int xr = max(tid + xa - OBS_EDGE, 0);       // column relative to the level's first interior column
         const int cc = xr / wCell;
         colCell[tid] = (uint8_t)min(max(cc - j0, 0), FT_MAXCELLS - 1);
         colIn[tid] = (uint8_t)(xr - cc * wCell);
-        if (tid == 0) sCount = 0;
+        if (tid < 4) sCount[tid] = 0;
         if (tid < FT_MAXCELLS) sCellAny[tid] = 0;
     }
     __syncthreads();
 
-    // ---- pass 1: compass-point rejection, 8 pixels per lane, one row per warp iteration
+    // ---- pass 1: compass-point rejection, 8 pixels per lane, one row per warp iteration.
+    // Every 9-arc holds one of ring pixels {0,8} and one of {4,12}; (|d0| | |d8|) > t is implied by
+    // |d0| > t or |d8| > t, so "(|d0| | |d8|) > t and (|d4| | |d12|) > t" is a necessary condition.
     const int tLow = min(g.iniTh, g.minTh);
     {
-        const int w0 = cLo >> 2, w1 = (cHi + 3) >> 2;     // word range covering the interior columns (w1 - w0 <= 64)
+        const int w0 = (cLo >> 2) & ~1, w1 = (cHi + 3) >> 2;     // even-aligned word range covering the interior columns
         const unsigned K = (unsigned)(127 - min(tLow, 127)) * 0x01010101u;
         const int wA = w0 + 2 * lane;
-        for (int r = rLo + warp; r < rHi; r += FT_THREADS / 32) {
-            unsigned f[2] = {0, 0};
-            if (wA < w1) {
+        if (wA < w1) {
+            for (int r = rLo + warp; r < rHi; r += FT_THREADS / 32) {
                 const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + r * FT_PITCH);
-                const unsigned L = row[wA - 1], C0 = row[wA], C1 = row[wA + 1], R = row[wA + 2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const unsigned C = h ? C1 : C0;
-                    const unsigned up = row[wA + h + 3 * (FT_PITCH / 4)], dn = row[wA + h - 3 * (FT_PITCH / 4)];
-                    const unsigned lf = __byte_perm(h ? C0 : L, C, 0x4321), rt = __byte_perm(C, h ? R : C1, 0x6543);
-                    unsigned ff;
-                    if (tLow < 128) {
-                        // per byte: |d| > t  <=>  bit 7 of ((|d| & 0x7f) + (127 - t)) | |d|
-                        const unsigned a0 = __vabsdiffu4(C, up), a8 = __vabsdiffu4(C, dn);
-                        const unsigned a4 = __vabsdiffu4(C, rt), a12 = __vabsdiffu4(C, lf);
-                        const unsigned v08 = ((a0 & 0x7f7f7f7fu) + K) | ((a8 & 0x7f7f7f7fu) + K) | a0 | a8;
-                        const unsigned v412 = ((a4 & 0x7f7f7f7fu) + K) | ((a12 & 0x7f7f7f7fu) + K) | a4 | a12;
-                        ff = v08 & v412 & 0x80808080u;
-                    } else {
-                        ff = 0x80808080u;                  // thresholds >= 128: no cheap rejection, score everything
-                    }
-                    const int c0 = (wA + h) * 4;
-                    if (c0 < cLo) ff &= 0xffffffffu << (8 * (cLo - c0));
-                    if (c0 + 4 > cHi) ff &= (c0 >= cHi) ? 0u : (0xffffffffu >> (8 * (c0 + 4 - cHi)));
-                    f[h] = ff;
+                const uint2 C = *reinterpret_cast<const uint2*>(row + wA);
+                const uint2 up = *reinterpret_cast<const uint2*>(row + wA + 3 * (FT_PITCH / 4));
+                const uint2 dn = *reinterpret_cast<const uint2*>(row + wA - 3 * (FT_PITCH / 4));
+                const unsigned L = row[wA - 1], R = row[wA + 2];
+                unsigned f0, f1;
+                if (tLow < 128) {
+                    const unsigned y0 = __vabsdiffu4(C.x, up.x) | __vabsdiffu4(C.x, dn.x);
+                    const unsigned z0 = __vabsdiffu4(C.x, __byte_perm(L, C.x, 0x4321)) | __vabsdiffu4(C.x, __byte_perm(C.x, C.y, 0x6543));
+                    const unsigned y1 = __vabsdiffu4(C.y, up.y) | __vabsdiffu4(C.y, dn.y);
+                    const unsigned z1 = __vabsdiffu4(C.y, __byte_perm(C.x, C.y, 0x4321)) | __vabsdiffu4(C.y, __byte_perm(C.y, R, 0x6543));
+                    f0 = over_threshold(y0, K) & over_threshold(z0, K) & 0x80808080u;
+                    f1 = over_threshold(y1, K) & over_threshold(z1, K) & 0x80808080u;
+                } else {
+                    f0 = f1 = 0x80808080u;                 // thresholds >= 128: no cheap rejection, score everything
                 }
+                // gather the 8 flag bits (bit 7 of each byte) into one byte of the row's bitmap
+                unsigned m8 = (((f0 >> 7) * 0x00204081u) >> 21 & 0xfu) | (((f1 >> 7) * 0x00204081u) >> 17 & 0xf0u);
+                const int c0 = wA * 4;
+                if (c0 < cLo) m8 &= 0xffu << (cLo - c0);
+                if (c0 + 8 > cHi) m8 &= 0xffu >> (c0 + 8 - cHi);
+                reinterpret_cast<uint8_t*>(flagmap[r])[wA >> 1] = (uint8_t)m8;
             }
-            // warp-aggregated append of the flagged pixels to the queue
-            const int cnt = __popc(f[0]) + __popc(f[1]);
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 1b: expand the bitmap into a queue of pixels (order is irrelevant)
+    {
+        const int nWords = (rHi - rLo) * 8;
+        for (int i0 = warp * 32; i0 < nWords; i0 += FT_THREADS) {
+            const int i = i0 + lane;
+            const int r = rLo + (i >> 3), w = i & 7;
+            unsigned bits = i < nWords ? flagmap[r][w] : 0u;
+            const int cnt = __popc(bits);
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
             int base = 0;
-            if (lane == 31 && incl) base = atomicAdd(&sCount, incl);
+            if (lane == 31 && incl) base = atomicAdd(&sCount[0], incl);
             base = __shfl_sync(0xffffffffu, base, 31);
-            int pos = base + incl - cnt;
-            const int e0 = (r << 8) | (wA * 4);
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (f[k >> 2] & (0x80u << (8 * (k & 3)))) list[pos++] = (uint16_t)(e0 + k);
+            uint16_t* out = listA + base + incl - cnt;
+            const int e0 = (r << 8) | (w << 5);
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                *out++ = (uint16_t)(e0 + b);
             }
         }
     }
     __syncthreads();
-    const int nList = sCount;
+    const int nA = sCount[0];
 
-    // ---- pass 2: exact score of the queued pixels, one lane each
-    for (int i = tid; i < nList; i += FT_THREADS) {
-        const int e = list[i];
-        const int r = e >> 8, c = e & 255;
-        const int contrast = fast_contrast(tile + r * FT_PITCH + c);
-        if (contrast > tLow && contrast > 1) score[r * FT_PITCH + c] = (uint8_t)(contrast - 1);   // OpenCV: score = contrast - 1
-        else list[i] = 0xffffu;
-    }
-    __syncthreads();
-
-    // ---- pass 3: strict 3x3 non-max suppression inside each cell, over the scored pixels only
-    const int lastCol = maxBX - 4 - xa;                    // tile column of the level's last interior column
-    for (int i = tid; i < nList; i += FT_THREADS) {
-        const int e = list[i];
-        if (e == 0xffff) continue;
-        const int r = e >> 8, c = e & 255;
-        const uint8_t* sc = score + r * FT_PITCH + c;
-        const int s = sc[0];
-        const int inCell = colIn[c];
-        const bool hasL = inCell > 0, hasR = inCell < wCell - 1 && c < lastCol;
-        int m = max(sc[-FT_PITCH], sc[FT_PITCH]);
-        if (hasL) m = max(m, max(max(sc[-FT_PITCH - 1], sc[-1]), sc[FT_PITCH - 1]));
-        if (hasR) m = max(m, max(max(sc[-FT_PITCH + 1], sc[1]), sc[FT_PITCH + 1]));
-        if (s > m) {
-            if (s >= g.iniTh) sCellAny[colCell[c]] = 1;
-        } else {
-            list[i] = 0xffffu;
+    // ---- pass 2: exact score of the queued pixels, one lane each; corners go on to queue B
+    for (int i0 = warp * 32; i0 < nA; i0 += FT_THREADS) {
+        const int i = i0 + lane;
+        int e = 0, s = 0;
+        if (i < nA) {
+            e = listA[i];
+            const int contrast = fast_contrast(tile + (e >> 8) * FT_PITCH + (e & 255));
+            if (contrast > tLow && contrast > 1) s = contrast - 1;            // OpenCV: score = corner contrast - 1
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, s > 0);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&sCount[1], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (s > 0) {
+            score[(e >> 8) * FT_PITCH + (e & 255)] = (uint8_t)s;
+            listB[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)e;
         }
     }
     __syncthreads();
+    const int nB = sCount[1];
+
+    // ---- pass 3: strict 3x3 non-max suppression inside each cell, over the corners only; survivors go to queue A
+    const int lastCol = maxBX - 4 - xa;                    // tile column of the level's last interior column
+    for (int i0 = warp * 32; i0 < nB; i0 += FT_THREADS) {
+        const int i = i0 + lane;
+        bool keep = false;
+        int e = 0;
+        if (i < nB) {
+            e = listB[i];
+            const int c = e & 255;
+            const uint8_t* sc = score + (e >> 8) * FT_PITCH + c;
+            const int s = sc[0];
+            const int inCell = colIn[c];
+            const bool hasL = inCell > 0, hasR = inCell < wCell - 1 && c < lastCol;
+            int m = max(sc[-FT_PITCH], sc[FT_PITCH]);
+            if (hasL) m = max(m, max(max(sc[-FT_PITCH - 1], sc[-1]), sc[FT_PITCH - 1]));
+            if (hasR) m = max(m, max(max(sc[-FT_PITCH + 1], sc[1]), sc[FT_PITCH + 1]));
+            keep = s > m;
+            if (keep && s >= g.iniTh) sCellAny[colCell[c]] = 1;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&sCount[2], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) listA[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)e;
+    }
+    __syncthreads();
+    const int nS = sCount[2];
 
     // ---- pass 4: threshold fallback per cell (:809-816); mark what is emitted
-    for (int i = tid; i < nList; i += FT_THREADS) {
-        const int e = list[i];
-        if (e == 0xffff) continue;
+    for (int i = tid; i < nS; i += FT_THREADS) {
+        const int e = listA[i];
         const int r = e >> 8, c = e & 255;
         const int T = sCellAny[colCell[c]] ? g.iniTh : g.minTh;
         if (score[r * FT_PITCH + c] >= T) atomicOr(&bitmap[r][c >> 5], 1u << (c & 31));
-        else list[i] = 0xffffu;
+        else listA[i] = 0xffffu;
     }
     __syncthreads();
 
@@ -256,8 +280,8 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
     __syncthreads();
 
     // ---- pass 6: write the keypoints in row-major order inside each cell (cv::FAST's order)
-    for (int i = tid; i < nList; i += FT_THREADS) {
-        const int e = list[i];
+    for (int i = tid; i < nS; i += FT_THREADS) {
+        const int e = listA[i];
         if (e == 0xffff) continue;
         const int r = e >> 8, c = e & 255;
         const int cl = colCell[c];
@@ -271,7 +295,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
 
 }  // namespace
 
-size_t fast_smem_bytes() { return (size_t)2 * FT_ROWS * FT_PITCH + (size_t)FT_LIST * 2; }
+size_t fast_smem_bytes() { return (size_t)2 * FT_ROWS * FT_PITCH + (size_t)FT_LIST * 4; }
 
 cudaError_t fast_prepare() {
     return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes());
@@ -279,9 +303,9 @@ cudaError_t fast_prepare() {
 
 int fast_cells_per_cta_host(int wCell, int hCell) { return fast_cells_per_cta(wCell, hCell); }
 
-cudaError_t launch_fast(const Geom& g, PyrPtrs p, uint32_t* cand, int* cellCount, int nimg, cudaStream_t st) {
+cudaError_t launch_fast(const Geom& g, PyrPtrs p, const FastCta* ctaTab, uint32_t* cand, int* cellCount, int nimg, cudaStream_t st) {
     if (g.fastCtasTotal == 0) return cudaSuccess;
     dim3 grid(g.fastCtasTotal, nimg);
-    k_fast_cells<<<grid, FT_THREADS, fast_smem_bytes(), st>>>(g, p, cand, cellCount);
+    k_fast_cells<<<grid, FT_THREADS, fast_smem_bytes(), st>>>(g, p, ctaTab, cand, cellCount);
     return cudaGetLastError();
 }

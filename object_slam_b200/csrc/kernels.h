@@ -10,7 +10,7 @@ cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, cons
 size_t fast_smem_bytes();
 cudaError_t fast_prepare();
 int fast_cells_per_cta_host(int wCell, int hCell);
-cudaError_t launch_fast(const Geom& g, PyrPtrs p, uint32_t* cand, int* cellCount, int nimg, cudaStream_t st);
+cudaError_t launch_fast(const Geom& g, PyrPtrs p, const FastCta* ctaTab, uint32_t* cand, int* cellCount, int nimg, cudaStream_t st);
 
 // K3  quadtree.cu  -- DistributeOctTree (:539-763) for every (image, level)
 size_t quadtree_smem_bytes(int nodeCap);
