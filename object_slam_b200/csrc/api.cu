@@ -236,6 +236,8 @@ void build_geometry(obs_extractor* e, int w, int h) {
     g.blurTilesTotal = tiles;
     g.blurEdgeCtas = (edgeItems + 127) / 128;
     g.fastCtasTotal = fastCtas;
+    g.fastTileRows = 7;
+    for (int l = 0; l < nl; l++) if (g.lv[l].nCols > 0) g.fastTileRows = std::max(g.fastTileRows, g.lv[l].hCell + 6);
     e->nodeCap = g.selCap;
     e->hXtab.assign(std::max(xt, 1), ResizeTap{0, 0, 0});
     e->hYtab.assign(std::max(yt, 1), ResizeTap{0, 0, 0});
@@ -256,7 +258,7 @@ int set_shape(obs_extractor* e, int w, int h, int nimg, cudaStream_t st) {
             if (e->g.lv[l].w > 4095 + 2 * OBS_BORDER || e->g.lv[l].h > 4095 + 2 * OBS_BORDER)
                 return fail(OBS_ERR_INVALID, "image %dx%d exceeds the 12-bit key coordinate range", w, h);
         CU(quadtree_prepare(e->nodeCap));
-        CU(fast_prepare());
+        CU(fast_prepare(e->g.fastTileRows));
         CU(e->dXtab.ensure(e->hXtab.size()));
         CU(e->dYtab.ensure(e->hYtab.size()));
         CU(e->dFastCtas.ensure(std::max<size_t>(e->hFastCtas.size(), 1)));

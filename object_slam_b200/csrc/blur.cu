@@ -59,13 +59,18 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
 #pragma unroll 1
     for (int jb = 0; jb < BL_ROWS + 8; jb += 8) {
         if (jb >= nOut + 6) break;
+        // issue the loads of all 8 rows of the block first: 24 independent words in flight per thread
+        unsigned Aw[8], Bw[8], Cw[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            int sy = y0 - 3 + jb + jj;
+            if (!yInside) sy = reflect101(sy, H);
+            load_window(src + (size_t)sy * pitch, x, W, INTERIOR, Aw[jj], Bw[jj], Cw[jj]);
+        }
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
             const int j = jb + jj;                             // staged row j <-> level row y0 - 3 + j
-            int sy = y0 - 3 + j;
-            if (!yInside) sy = reflect101(sy, H);
-            unsigned A, B, C;
-            load_window(src + (size_t)sy * pitch, x, W, INTERIOR, A, B, C);
+            const unsigned A = Aw[jj], B = Bw[jj], C = Cw[jj];
             // horizontal pass: output k needs bytes k+1 .. k+7 of the 12-byte window
             unsigned hs[4];
             hs[0] = __dp4a(__byte_perm(B, C, 0x4321), WB, __dp4a(__byte_perm(A, B, 0x4321), WA, 0u));

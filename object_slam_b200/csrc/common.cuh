@@ -45,6 +45,7 @@ struct Geom {
     int blurTilesTotal;
     int blurEdgeCtas;        // CTAs appended to the blur grid for the border strips
     int fastCtasTotal;
+    int fastTileRows;        // rows of the FAST window tile: max hCell over the levels + 6
     int umax[OBS_HALF_PATCH + 1];
     LevelGeom lv[OBS_MAX_LEVELS];
 };

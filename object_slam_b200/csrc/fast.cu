@@ -31,6 +31,7 @@ constexpr int FT_ROWS = 66;            // hCell <= 60, + 6
 constexpr int FT_THREADS = 256;
 constexpr int FT_LIST = 8192;          // queue capacity == max interior pixels per CTA (host enforces)
 constexpr int FT_MAXCELLS = 8;
+constexpr int FT_SEG = FT_LIST / 8 + FT_PITCH;   // capacity of one warp's queue: its share of the rows, rounded up by one row
 
 __host__ __device__ inline int fast_cells_per_cta(int wCell, int hCell) {
     int cg = (FT_PITCH - 15 - 6) / wCell;
@@ -81,21 +82,19 @@ __device__ __forceinline__ int row_bits(const uint32_t* bm, int a, int b) {
 __device__ __forceinline__ unsigned over_threshold(unsigned y, unsigned K) { return ((y & 0x7f7f7f7fu) + K) | y; }
 
 __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant__ Geom g, const PyrPtrs p,
-                                                           const FastCta* __restrict__ ctaTab,
+                                                           const FastCta* __restrict__ ctaTab, int tileRows,
                                                            uint32_t* __restrict__ cand, int* __restrict__ cellCount) {
     extern __shared__ __align__(16) uint8_t sm[];
-    uint8_t* tile = sm;                                   // FT_ROWS x FT_PITCH pixels
-    uint8_t* score = sm + FT_ROWS * FT_PITCH;             // same geometry, 0 = not a corner
-    uint16_t* listA = reinterpret_cast<uint16_t*>(sm + 2 * FT_ROWS * FT_PITCH);    // pixel queues: row << 8 | col
-    uint16_t* listB = listA + FT_LIST;
-    __shared__ uint32_t flagmap[FT_ROWS][8];              // pass-1 survivors, one bit per tile pixel
+    uint8_t* tile = sm;                                   // tileRows x FT_PITCH pixels
+    uint8_t* score = sm + tileRows * FT_PITCH;            // same geometry, 0 = not a corner
+    uint16_t* list = reinterpret_cast<uint16_t*>(sm + 2 * tileRows * FT_PITCH);    // 8 warp-private pixel queues: row << 8 | col
     __shared__ uint32_t bitmap[FT_ROWS][8];               // emitted keypoints, one bit per tile pixel
     __shared__ uint16_t rowOfs[FT_MAXCELLS][FT_ROWS];     // per cell: keypoints in the rows above
     __shared__ uint8_t colCell[FT_PITCH], colIn[FT_PITCH];   // tile column -> cell of the run, column inside the cell
-    __shared__ int sCount[4];
     __shared__ int sCellAny[FT_MAXCELLS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned ltMask = (1u << lane) - 1;
     const int img = blockIdx.y;
     const FastCta cta = ctaTab[blockIdx.x];
     const int level = cta.level, ci = cta.ci, j0 = cta.j0, nCellsHere = cta.n;
@@ -129,26 +128,35 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
             }
             *reinterpret_cast<uint4*>(score + r * FT_PITCH + 16 * v) = make_uint4(0, 0, 0, 0);
         }
-        for (int i = tid; i < FT_ROWS * 8; i += FT_THREADS) { (&flagmap[0][0])[i] = 0; (&bitmap[0][0])[i] = 0; }
+        for (int i = tid; i < FT_ROWS * 8; i += FT_THREADS) (&bitmap[0][0])[i] = 0;
         const int xr = max(tid + xa - OBS_EDGE, 0);       // column relative to the level's first interior column
         const int cc = xr / wCell;
         colCell[tid] = (uint8_t)min(max(cc - j0, 0), FT_MAXCELLS - 1);
         colIn[tid] = (uint8_t)(xr - cc * wCell);
-        if (tid < 4) sCount[tid] = 0;
         if (tid < FT_MAXCELLS) sCellAny[tid] = 0;
     }
     __syncthreads();
 
-    // ---- pass 1: compass-point rejection, 8 pixels per lane, one row per warp iteration.
+    // Each warp owns the interior rows rLo + warp, + 8, ... and a private queue: no atomics, and
+    // every later filtering step compacts the queue in place.
+    uint16_t* seg = list + warp * FT_SEG;
+
+    // ---- pass 1: compass-point rejection, 8 pixels per lane, one row per iteration, survivors queued.
     // Every 9-arc holds one of ring pixels {0,8} and one of {4,12}; (|d0| | |d8|) > t is implied by
     // |d0| > t or |d8| > t, so "(|d0| | |d8|) > t and (|d4| | |d12|) > t" is a necessary condition.
     const int tLow = min(g.iniTh, g.minTh);
+    int nQ = 0;
     {
         const int w0 = (cLo >> 2) & ~1, w1 = (cHi + 3) >> 2;     // even-aligned word range covering the interior columns
         const unsigned K = (unsigned)(127 - min(tLow, 127)) * 0x01010101u;
         const int wA = w0 + 2 * lane;
-        if (wA < w1) {
-            for (int r = rLo + warp; r < rHi; r += FT_THREADS / 32) {
+        const int c0 = wA * 4;
+        unsigned edgeMask = wA < w1 ? 0xffu : 0u;
+        if (c0 < cLo) edgeMask &= 0xffu << (cLo - c0);
+        if (c0 + 8 > cHi && c0 < cHi) edgeMask &= 0xffu >> (c0 + 8 - cHi);
+        for (int r = rLo + warp; r < rHi; r += FT_THREADS / 32) {
+            unsigned m8 = 0;
+            if (edgeMask) {
                 const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + r * FT_PITCH);
                 const uint2 C = *reinterpret_cast<const uint2*>(row + wA);
                 const uint2 up = *reinterpret_cast<const uint2*>(row + wA + 3 * (FT_PITCH / 4));
@@ -165,72 +173,53 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
                 } else {
                     f0 = f1 = 0x80808080u;                 // thresholds >= 128: no cheap rejection, score everything
                 }
-                // gather the 8 flag bits (bit 7 of each byte) into one byte of the row's bitmap
-                unsigned m8 = (((f0 >> 7) * 0x00204081u) >> 21 & 0xfu) | (((f1 >> 7) * 0x00204081u) >> 17 & 0xf0u);
-                const int c0 = wA * 4;
-                if (c0 < cLo) m8 &= 0xffu << (cLo - c0);
-                if (c0 + 8 > cHi) m8 &= 0xffu >> (c0 + 8 - cHi);
-                reinterpret_cast<uint8_t*>(flagmap[r])[wA >> 1] = (uint8_t)m8;
+                // gather the 8 flag bits (bit 7 of each byte)
+                m8 = ((((f0 >> 7) * 0x00204081u) >> 21 & 0xfu) | (((f1 >> 7) * 0x00204081u) >> 17 & 0xf0u)) & edgeMask;
             }
-        }
-    }
-    __syncthreads();
-
-    // ---- pass 1b: expand the bitmap into a queue of pixels (order is irrelevant)
-    {
-        const int nWords = (rHi - rLo) * 8;
-        for (int i0 = warp * 32; i0 < nWords; i0 += FT_THREADS) {
-            const int i = i0 + lane;
-            const int r = rLo + (i >> 3), w = i & 7;
-            unsigned bits = i < nWords ? flagmap[r][w] : 0u;
-            const int cnt = __popc(bits);
-            int incl = cnt;
+            const int n = __popc(m8);
+            int incl = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            int base = 0;
-            if (lane == 31 && incl) base = atomicAdd(&sCount[0], incl);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            uint16_t* out = listA + base + incl - cnt;
-            const int e0 = (r << 8) | (w << 5);
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
+            uint16_t* out = seg + nQ + incl - n;
+            const int e0 = (r << 8) | c0;
+            while (m8) {
+                const int b = __ffs(m8) - 1;
+                m8 &= m8 - 1;
                 *out++ = (uint16_t)(e0 + b);
             }
+            nQ += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
-    __syncthreads();
-    const int nA = sCount[0];
+    __syncwarp();
 
-    // ---- pass 2: exact score of the queued pixels, one lane each; corners go on to queue B
-    for (int i0 = warp * 32; i0 < nA; i0 += FT_THREADS) {
+    // ---- pass 2: exact score of the queued pixels, one lane each; corners stay queued
+    int nC = 0;
+    for (int i0 = 0; i0 < nQ; i0 += 32) {
         const int i = i0 + lane;
         int e = 0, s = 0;
-        if (i < nA) {
-            e = listA[i];
+        if (i < nQ) {
+            e = seg[i];
             const int contrast = fast_contrast(tile + (e >> 8) * FT_PITCH + (e & 255));
             if (contrast > tLow && contrast > 1) s = contrast - 1;            // OpenCV: score = corner contrast - 1
         }
         const unsigned bal = __ballot_sync(0xffffffffu, s > 0);
-        int base = 0;
-        if (lane == 0 && bal) base = atomicAdd(&sCount[1], __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
         if (s > 0) {
             score[(e >> 8) * FT_PITCH + (e & 255)] = (uint8_t)s;
-            listB[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)e;
+            seg[nC + __popc(bal & ltMask)] = (uint16_t)e;
         }
+        nC += __popc(bal);
     }
     __syncthreads();
-    const int nB = sCount[1];
 
-    // ---- pass 3: strict 3x3 non-max suppression inside each cell, over the corners only; survivors go to queue A
+    // ---- pass 3: strict 3x3 non-max suppression inside each cell, over the corners only; survivors stay queued
     const int lastCol = maxBX - 4 - xa;                    // tile column of the level's last interior column
-    for (int i0 = warp * 32; i0 < nB; i0 += FT_THREADS) {
+    int nS = 0;
+    for (int i0 = 0; i0 < nC; i0 += 32) {
         const int i = i0 + lane;
         bool keep = false;
         int e = 0;
-        if (i < nB) {
-            e = listB[i];
+        if (i < nC) {
+            e = seg[i];
             const int c = e & 255;
             const uint8_t* sc = score + (e >> 8) * FT_PITCH + c;
             const int s = sc[0];
@@ -243,21 +232,27 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
             if (keep && s >= g.iniTh) sCellAny[colCell[c]] = 1;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        int base = 0;
-        if (lane == 0 && bal) base = atomicAdd(&sCount[2], __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) listA[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)e;
+        if (keep) seg[nS + __popc(bal & ltMask)] = (uint16_t)e;
+        nS += __popc(bal);
     }
     __syncthreads();
-    const int nS = sCount[2];
 
     // ---- pass 4: threshold fallback per cell (:809-816); mark what is emitted
-    for (int i = tid; i < nS; i += FT_THREADS) {
-        const int e = listA[i];
-        const int r = e >> 8, c = e & 255;
-        const int T = sCellAny[colCell[c]] ? g.iniTh : g.minTh;
-        if (score[r * FT_PITCH + c] >= T) atomicOr(&bitmap[r][c >> 5], 1u << (c & 31));
-        else listA[i] = 0xffffu;
+    int nE = 0;
+    for (int i0 = 0; i0 < nS; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false;
+        int e = 0;
+        if (i < nS) {
+            e = seg[i];
+            const int r = e >> 8, c = e & 255;
+            const int T = sCellAny[colCell[c]] ? g.iniTh : g.minTh;
+            keep = score[r * FT_PITCH + c] >= T;
+            if (keep) atomicOr(&bitmap[r][c >> 5], 1u << (c & 31));
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) seg[nE + __popc(bal & ltMask)] = (uint16_t)e;
+        nE += __popc(bal);
     }
     __syncthreads();
 
@@ -280,9 +275,8 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
     __syncthreads();
 
     // ---- pass 6: write the keypoints in row-major order inside each cell (cv::FAST's order)
-    for (int i = tid; i < nS; i += FT_THREADS) {
-        const int e = listA[i];
-        if (e == 0xffff) continue;
+    for (int i = lane; i < nE; i += 32) {
+        const int e = seg[i];
         const int r = e >> 8, c = e & 255;
         const int cl = colCell[c];
         const int cx0 = OBS_EDGE + (j0 + cl) * wCell - xa;
@@ -295,10 +289,10 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
 
 }  // namespace
 
-size_t fast_smem_bytes() { return (size_t)2 * FT_ROWS * FT_PITCH + (size_t)FT_LIST * 4; }
+size_t fast_smem_bytes(int tileRows) { return (size_t)2 * tileRows * FT_PITCH + (size_t)8 * FT_SEG * 2; }
 
-cudaError_t fast_prepare() {
-    return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes());
+cudaError_t fast_prepare(int tileRows) {
+    return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(tileRows));
 }
 
 int fast_cells_per_cta_host(int wCell, int hCell) { return fast_cells_per_cta(wCell, hCell); }
@@ -306,6 +300,6 @@ int fast_cells_per_cta_host(int wCell, int hCell) { return fast_cells_per_cta(wC
 cudaError_t launch_fast(const Geom& g, PyrPtrs p, const FastCta* ctaTab, uint32_t* cand, int* cellCount, int nimg, cudaStream_t st) {
     if (g.fastCtasTotal == 0) return cudaSuccess;
     dim3 grid(g.fastCtasTotal, nimg);
-    k_fast_cells<<<grid, FT_THREADS, fast_smem_bytes(), st>>>(g, p, ctaTab, cand, cellCount);
+    k_fast_cells<<<grid, FT_THREADS, fast_smem_bytes(g.fastTileRows), st>>>(g, p, ctaTab, g.fastTileRows, cand, cellCount);
     return cudaGetLastError();
 }

@@ -7,8 +7,8 @@
 cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, const ResizeTap* ytab, int nimg, cudaStream_t st);
 
 // K2  fast.cu      -- per-cell FAST with threshold fallback (:765-829, cv::FAST :809/:814)
-size_t fast_smem_bytes();
-cudaError_t fast_prepare();
+size_t fast_smem_bytes(int tileRows);
+cudaError_t fast_prepare(int tileRows);
 int fast_cells_per_cta_host(int wCell, int hCell);
 cudaError_t launch_fast(const Geom& g, PyrPtrs p, const FastCta* ctaTab, uint32_t* cand, int* cellCount, int nimg, cudaStream_t st);
 

@@ -26,11 +26,22 @@ struct XTaps {
     int ofs[4];
 };
 
-__device__ __forceinline__ void hrow(const uint8_t* __restrict__ row, int lastWord, int srcW, const XTaps& t, unsigned hs[4]) {
+struct RowWords { unsigned w0, w1, w2; };
+
+__device__ __forceinline__ RowWords load_row(const uint8_t* __restrict__ row, int lastWord, const XTaps& t) {
+    RowWords r;
     if (t.fast) {
         const uint32_t* q = reinterpret_cast<const uint32_t*>(row);
-        const unsigned W0 = __ldg(q + t.word0), W1 = __ldg(q + min(t.word0 + 1, lastWord)), W2 = __ldg(q + min(t.word0 + 2, lastWord));
-        const unsigned U0 = __funnelshift_r(W0, W1, t.shift), U1 = __funnelshift_r(W1, W2, t.shift);
+        r.w0 = __ldg(q + t.word0); r.w1 = __ldg(q + min(t.word0 + 1, lastWord)); r.w2 = __ldg(q + min(t.word0 + 2, lastWord));
+    } else {
+        r.w0 = r.w1 = r.w2 = 0;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void hrow(const RowWords& rw, const uint8_t* __restrict__ row, int srcW, const XTaps& t, unsigned hs[4]) {
+    if (t.fast) {
+        const unsigned U0 = __funnelshift_r(rw.w0, rw.w1, t.shift), U1 = __funnelshift_r(rw.w1, rw.w2, t.shift);
 #pragma unroll
         for (int i = 0; i < 4; i++) hs[i] = __dp2a_lo(t.w[i], __byte_perm(U0, U1, t.sel[i]), 0u) >> 4;
     } else {
@@ -78,42 +89,41 @@ __global__ void __launch_bounds__(32 * RS_BANDS) k_resize(const __grid_constant_
         }
     }
 
-    unsigned ha[4], hb[4];                  // horizontal sums (>> 4) of source rows rowA, rowB
-    int rowA = -1, rowB = -1;
+    // Walk the source rows the band needs, two rows of loads ahead of the arithmetic; an output row is
+    // produced when its lower source row arrives (the vertical taps advance by >= 1 source row per output row).
     const int nOut = min(RS_ROWS, D.h - dy0);
+    const ResizeTap* yt = ytab + D.ytab + dy0;
+    const int sA = min(max(yt[0].ofs, 0), S.h - 1);
+    const int sB = min(max(yt[nOut - 1].ofs + 1, 0), S.h - 1);
+    RowWords wa = load_row(src + (size_t)sA * spitch, lastWord, t);
+    RowWords wb = load_row(src + (size_t)min(sA + 1, sB) * spitch, lastWord, t);
+    unsigned hprev[4] = {0, 0, 0, 0}, hcur[4];
+    int r = 0;
+    ResizeTap ty = yt[0];
 #pragma unroll 1
-    for (int r = 0; r < nOut; r++) {
-        const int dy = dy0 + r;
-        const ResizeTap ty = ytab[D.ytab + dy];
-        const int y0 = min(max(ty.ofs, 0), S.h - 1);
-        const int y1 = min(max(ty.ofs + 1, 0), S.h - 1);
-        if (y0 != rowA) {
-            if (y0 == rowB) {
+    for (int s = sA; s <= sB; s++) {
+        const RowWords wc = load_row(src + (size_t)min(s + 2, sB) * spitch, lastWord, t);
+        hrow(wa, src + (size_t)s * spitch, S.w, t, hcur);
+        while (r < nOut) {
+            const int y0 = min(max(ty.ofs, 0), S.h - 1);
+            const int y1 = min(max(ty.ofs + 1, 0), S.h - 1);
+            if (y1 != s) break;
+            const unsigned b0 = (unsigned)ty.a0 << 16, b1 = (unsigned)ty.a1 << 16;      // (b * h) >> 16 == umulhi(b << 16, h)
+            unsigned o = 0;
 #pragma unroll
-                for (int i = 0; i < 4; i++) ha[i] = hb[i];
-            } else {
-                hrow(src + (size_t)y0 * spitch, lastWord, S.w, t, ha);
+            for (int i = 0; i < 4; i++) {
+                const unsigned h0 = (y0 == s) ? hcur[i] : hprev[i];
+                unsigned v = (__umulhi(b0, h0) + __umulhi(b1, hcur[i]) + 2u) >> 2;
+                v = min(v, 255u);
+                o |= v << (8 * i);
             }
-            rowA = y0;
+            *reinterpret_cast<uint32_t*>(dst + (size_t)(dy0 + r) * dpitch) = o;      // rows are padded to the pitch
+            r++;
+            if (r < nOut) ty = yt[r];
         }
-        if (y1 != rowB) {
-            if (y1 == rowA) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) hb[i] = ha[i];
-            } else {
-                hrow(src + (size_t)y1 * spitch, lastWord, S.w, t, hb);
-            }
-            rowB = y1;
-        }
-        const unsigned b0 = (unsigned)ty.a0 << 16, b1 = (unsigned)ty.a1 << 16;      // (b * h) >> 16 == umulhi(b << 16, h)
-        unsigned o = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            unsigned v = (__umulhi(b0, ha[i]) + __umulhi(b1, hb[i]) + 2u) >> 2;
-            v = min(v, 255u);
-            o |= v << (8 * i);
-        }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)dy * dpitch) = o;      // rows are padded to the pitch
+        for (int i = 0; i < 4; i++) hprev[i] = hcur[i];
+        wa = wb; wb = wc;
     }
 }
 
