@@ -78,51 +78,52 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
                                                               const uint8_t* __restrict__ blurSlab, size_t blurStride,
                                                               const uint32_t* __restrict__ sel, const int* __restrict__ selCount,
                                                               uint8_t* __restrict__ records, size_t recordBytes) {
-    __shared__ int8_t pat[256 * 4];
+    __shared__ float4 pat[256];                 // (x0, y0, x1, y1) of point pair 8*lane + k at [k * 32 + lane] (conflict-free)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 256; i += DESC_WARPS * 32) reinterpret_cast<int32_t*>(pat)[i] = reinterpret_cast<const int32_t*>(d_pattern)[i];
+    for (int i = tid; i < 256; i += DESC_WARPS * 32) {
+        const int pr = (i & 31) * 8 + (i >> 5);
+        pat[i] = make_float4((float)d_pattern[4 * pr], (float)d_pattern[4 * pr + 1], (float)d_pattern[4 * pr + 2], (float)d_pattern[4 * pr + 3]);
+    }
     __syncthreads();
 
     const int img = blockIdx.y;
     const int j = blockIdx.x * DESC_WARPS + warp;              // output index of this warp's keypoint (level-major)
+    // level of keypoint j: lanes 0..nlevels-1 hold the per-level counts, a warp scan gives the offsets
     const int* cnt = selCount + (size_t)img * g.nlevels;
-    int level = -1, local = 0, total = 0;
-#pragma unroll 1
-    for (int l = 0; l < g.nlevels; l++) {
-        const int c = cnt[l];
-        if (level < 0 && j < total + c) { level = l; local = j - total; }
-        total += c;
-    }
+    const int myCnt = lane < g.nlevels ? cnt[lane] : 0;
+    int incl = myCnt;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, OBS_MAX_LEVELS - 1);
+    const unsigned owner = __ballot_sync(0xffffffffu, lane < g.nlevels && j >= incl - myCnt && j < incl);
     uint8_t* rec = records + (size_t)img * recordBytes;
-    if (j == 0 && lane == 0) {
-        int32_t* hdr = reinterpret_cast<int32_t*>(rec);
-        hdr[0] = total;
-        for (int l = 0; l < g.nlevels; l++) hdr[1 + l] = cnt[l];
-    }
-    if (level < 0) return;
+    const int prevCnt = __shfl_up_sync(0xffffffffu, myCnt, 1);
+    if (j == 0 && lane <= g.nlevels) reinterpret_cast<int32_t*>(rec)[lane] = lane == 0 ? total : prevCnt;   // header: n, per-level counts
+    if (owner == 0) return;
+    const int level = __ffs(owner) - 1;
+    const int local = j - (__shfl_sync(0xffffffffu, incl, level) - __shfl_sync(0xffffffffu, myCnt, level));
 
     const LevelGeom& lg = g.lv[level];
     const uint32_t key = sel[((size_t)img * g.nlevels + level) * g.selCap + local];
     const int cx = key_x(key) + OBS_BORDER, cy = key_y(key) + OBS_BORDER;       // :837-838
 
-    // ---- IC_Angle on the unblurred level (:77-104): integer moments over the circular patch
+    // ---- IC_Angle on the unblurred level (:77-104): integer moments over the circular patch.
+    // Lane = column u of the patch; the patch is symmetric, so column u spans rows |v| <= umax[|u|].
     int pitch;
     const uint8_t* im = level_ptr(p, g, img, level, pitch);
     const uint8_t* c = im + (size_t)cy * pitch + cx;
     const int u = lane - OBS_HALF_PATCH;
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int au = abs(u);
-#pragma unroll 1
-        for (int v = -OBS_HALF_PATCH; v <= OBS_HALF_PATCH; v++) {
-            if (au <= g.umax[abs(v)]) {
-                const int val = c[v * pitch + u];
-                m10 += u * val;
-                m01 += v * val;
-            }
-        }
+    const int vm = lane < 31 ? g.umax[abs(u)] : -1;
+    int colSum = 0, m01 = 0;
+#pragma unroll
+    for (int v = -OBS_HALF_PATCH; v <= OBS_HALF_PATCH; v++) {
+        const int a = v < 0 ? -v : v;
+        int val = 0;
+        if (a <= vm) val = c[v * pitch + u];
+        colSum += val;
+        m01 += v * val;
     }
-    m10 = __reduce_add_sync(0xffffffffu, m10);
+    const int m10 = __reduce_add_sync(0xffffffffu, u * colSum);
     m01 = __reduce_add_sync(0xffffffffu, m01);
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
@@ -132,18 +133,20 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
     sincosf_glibc(__fmul_rn(angle, factorPI), &b, &a);
     const uint8_t* cb = blurSlab + (size_t)img * blurStride + lg.off + (size_t)cy * lg.pitch + cx;
     const int bp = lg.pitch;
-    int val = 0;
+    int t0[8], t1[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const int8_t* pp = pat + (lane * 8 + k) * 4;
-        const float x0 = (float)pp[0], y0 = (float)pp[1], x1 = (float)pp[2], y1 = (float)pp[3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = cb[r0 * bp + q0], t1 = cb[r1 * bp + q1];
-        val |= (t0 < t1) << k;
+        const float4 q = pat[k * 32 + lane];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)));
+        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, b), __fmul_rn(q.w, a)));
+        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(q.z, a), __fmul_rn(q.w, b)));
+        t0[k] = cb[r0 * bp + q0];
+        t1[k] = cb[r1 * bp + q1];
     }
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) val |= (t0[k] < t1[k]) << k;
     uint8_t* kpOut = rec + OBS_HDR_INTS * 4;
     uint8_t* descOut = kpOut + (size_t)g.kpCap * 28;
     descOut[(size_t)j * 32 + lane] = (uint8_t)val;

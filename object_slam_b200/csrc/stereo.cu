@@ -1,11 +1,11 @@
 // K8 -- stereo matching.  Replaces Frame::ComputeStereoMatches (src/Frame.cc:706-880).
 //
-//   k_stereo_match : one warp per left keypoint.  The CTA first stages, for every right keypoint,
-//     its row band [floor(y-r), ceil(y+r)] (r = 2*scale[octave], :723-733), x and octave in shared
-//     memory; a warp then scans the right keypoints in index order -- the order of the reference's
-//     row table -- keeps those whose band holds int(vL), whose octave is within +-1 and whose x lies
-//     in [uL-maxD, uL-minD] (:773-778), and takes the smallest 256-bit Hamming distance below
-//     TH_HIGH, the lowest index winning ties (:781-787; key = dist<<16 | index, warp min).  If that
+//   k_stereo_rows  : one CTA per frame builds the reference's row table (:716-733) as a CSR in HBM:
+//     right keypoint i is listed under every row of its band [floor(y-r), ceil(y+r)], r = 2*scale[octave].
+//   k_stereo_match : one warp per left keypoint scans the candidates of row int(vL), keeps those whose
+//     octave is within +-1 and whose x lies in [uL-maxD, uL-minD] (:773-778), and takes the smallest
+//     256-bit Hamming distance below TH_HIGH, the lowest index winning ties like the reference's
+//     in-order scan with a strict < (:781-787; key = dist<<16 | index, warp min).  If that
 //     distance is < 75 the warp refines it with the 11x11 centre-subtracted SAD slid over +-5 px on
 //     the keypoint's pyramid level (:802-832), fits the parabola (:838-845) and converts to
 //     disparity / depth (:848-862).
@@ -17,151 +17,200 @@
 namespace {
 
 constexpr int ST_WARPS = 8;
-constexpr int ST_KP_PER_WARP = 8;
 constexpr int TH_HIGH = 100, TH_LOW = 50;
-
-struct RightKp {
-    float x;
-    short minr, maxr;
-    int octave;
-};
 
 __device__ __forceinline__ int hamming256(const uint32_t* a, const uint4 b0, const uint4 b1) {
     return __popc(a[0] ^ b0.x) + __popc(a[1] ^ b0.y) + __popc(a[2] ^ b0.z) + __popc(a[3] ^ b0.w) +
            __popc(a[4] ^ b1.x) + __popc(a[5] ^ b1.y) + __popc(a[6] ^ b1.z) + __popc(a[7] ^ b1.w);
 }
 
-__global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_constant__ StereoArgs A) {
-    extern __shared__ __align__(16) uint8_t smraw[];
-    RightKp* rk = reinterpret_cast<RightKp*>(smraw);
+// Row table of the right keypoints (:716-733) as a CSR: rowStart[H+1], rowIdx[...].  One CTA per frame.
+// The order inside a row does not matter here: ties are broken by the keypoint index in the match kernel.
+__global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ StereoArgs A) {
+    extern __shared__ int sRow[];                 // H + 1 counters, then cursors
+    __shared__ int sWarp[9];
     const Geom& g = A.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int img = blockIdx.y;
-    const uint8_t* recL = A.recL + (size_t)img * A.recordBytes;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.x;
+    const int H = g.lv[0].h;
     const uint8_t* recR = A.recR + (size_t)img * A.recordBytes;
-    const int nL = *reinterpret_cast<const int*>(recL);
-    const int nR = *reinterpret_cast<const int*>(recR);
-    const float* kpL = reinterpret_cast<const float*>(recL + OBS_HDR_INTS * 4);
+    const int nR = min(*reinterpret_cast<const int*>(recR), g.kpCap);
     const float* kpR = reinterpret_cast<const float*>(recR + OBS_HDR_INTS * 4);
-    const uint8_t* descL = recL + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28;
-    const uint8_t* descR = recR + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28;
-    float* uRightOut = A.uRight + (size_t)img * g.kpCap;
-    float* depthOut = A.depth + (size_t)img * g.kpCap;
-    int* sadOut = A.sad + (size_t)img * g.kpCap;
+    int* rowStart = A.rowStart + (size_t)img * (g.h + 1);
+    uint16_t* rowIdx = A.rowIdx + (size_t)img * A.rowIdxCap;
+    float2* rk = A.rightXO + (size_t)img * g.kpCap;
 
-    for (int i = tid; i < nR; i += ST_WARPS * 32) {
+    for (int i = tid; i <= H; i += 256) sRow[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < nR; i += 256) {
         const float y = kpR[i * 7 + 1];
         const int oct = reinterpret_cast<const int*>(kpR)[i * 7 + 5];
         const float r = __fmul_rn(2.0f, g.lv[oct].scale);
-        RightKp k;
-        k.x = kpR[i * 7];
-        k.maxr = (short)(int)ceilf(__fadd_rn(y, r));
-        k.minr = (short)(int)floorf(__fsub_rn(y, r));
-        k.octave = oct;
-        rk[i] = k;
+        const int maxr = min((int)ceilf(__fadd_rn(y, r)), H - 1);
+        const int minr = max((int)floorf(__fsub_rn(y, r)), 0);
+        for (int yi = minr; yi <= maxr; yi++) atomicAdd(&sRow[yi], 1);
+        rk[i] = make_float2(kpR[i * 7], __int_as_float(oct));
     }
     __syncthreads();
+    // exclusive scan of the H row counts (chunks of 256)
+    int carry = 0;
+    for (int base = 0; base < H; base += 256) {
+        const int i = base + tid;
+        const int v = i < H ? sRow[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) sWarp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = lane < 8 ? sWarp[lane] : 0;
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            if (lane < 8) sWarp[lane] = wi - w;
+            if (lane == 7) sWarp[8] = wi;
+        }
+        __syncthreads();
+        if (i < H) {
+            const int ex = carry + sWarp[warp] + incl - v;
+            sRow[i] = ex;                           // becomes the fill cursor
+            rowStart[i] = ex;
+        }
+        carry += sWarp[8];
+        __syncthreads();
+    }
+    if (tid == 0) rowStart[H] = carry;
+    __syncthreads();
+    for (int i = tid; i < nR; i += 256) {
+        const float y = kpR[i * 7 + 1];
+        const int oct = reinterpret_cast<const int*>(kpR)[i * 7 + 5];
+        const float r = __fmul_rn(2.0f, g.lv[oct].scale);
+        const int maxr = min((int)ceilf(__fadd_rn(y, r)), H - 1);
+        const int minr = max((int)floorf(__fsub_rn(y, r)), 0);
+        for (int yi = minr; yi <= maxr; yi++) {
+            const int pos = atomicAdd(&sRow[yi], 1);
+            if (pos < A.rowIdxCap) rowIdx[pos] = (uint16_t)i;
+        }
+    }
+}
 
-    const int first = (blockIdx.x * ST_WARPS + warp) * ST_KP_PER_WARP;
-#pragma unroll 1
-    for (int iL = first; iL < first + ST_KP_PER_WARP && iL < g.kpCap; iL++) {
-        float outU = -1.0f, outD = -1.0f;
-        int outSad = -1;
-        if (iL < nL) {
-            const float uL = kpL[iL * 7], vL = kpL[iL * 7 + 1];
-            const int levelL = reinterpret_cast<const int*>(kpL)[iL * 7 + 5];
-            const int row = (int)vL;                                  // vRowIndices[vL], :758
-            const float minU = __fsub_rn(uL, A.maxD), maxU = __fsub_rn(uL, A.minD);
+__global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_constant__ StereoArgs A) {
+    const Geom& g = A.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int img = blockIdx.y;
+    const int iL = blockIdx.x * ST_WARPS + warp;
+    if (iL >= g.kpCap) return;
+    const uint8_t* recL = A.recL + (size_t)img * A.recordBytes;
+    const uint8_t* recR = A.recR + (size_t)img * A.recordBytes;
+    const int nL = *reinterpret_cast<const int*>(recL);
+    const float* kpL = reinterpret_cast<const float*>(recL + OBS_HDR_INTS * 4);
+    const uint8_t* descL = recL + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28;
+    const uint8_t* descR = recR + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28;
+    const int* rowStart = A.rowStart + (size_t)img * (g.h + 1);
+    const uint16_t* rowIdx = A.rowIdx + (size_t)img * A.rowIdxCap;
+    const float2* rk = A.rightXO + (size_t)img * g.kpCap;
+
+    float outU = -1.0f, outD = -1.0f;
+    int outSad = -1;
+    if (iL < nL) {
+        const float uL = kpL[iL * 7], vL = kpL[iL * 7 + 1];
+        const int levelL = reinterpret_cast<const int*>(kpL)[iL * 7 + 5];
+        const int row = (int)vL;                                  // vRowIndices[vL], :758
+        const float minU = __fsub_rn(uL, A.maxD), maxU = __fsub_rn(uL, A.minD);
+        uint32_t best = ((uint32_t)TH_HIGH << 16);                // dist << 16 | iR ; only dist < TH_HIGH can win
+        if (!(maxU < 0) && row >= 0 && row < g.lv[0].h) {
             uint32_t dl[8];
             {
                 const uint4 d0 = *reinterpret_cast<const uint4*>(descL + (size_t)iL * 32);
                 const uint4 d1 = *reinterpret_cast<const uint4*>(descL + (size_t)iL * 32 + 16);
                 dl[0] = d0.x; dl[1] = d0.y; dl[2] = d0.z; dl[3] = d0.w; dl[4] = d1.x; dl[5] = d1.y; dl[6] = d1.z; dl[7] = d1.w;
             }
-            uint32_t best = ((uint32_t)TH_HIGH << 16);                // dist << 16 | iR ; only dist < TH_HIGH can win
-            if (!(maxU < 0)) {
-                for (int iR = lane; iR < nR; iR += 32) {
-                    const RightKp k = rk[iR];
-                    if (row < k.minr || row > k.maxr) continue;
-                    if (k.octave < levelL - 1 || k.octave > levelL + 1) continue;
-                    if (!(k.x >= minU && k.x <= maxU)) continue;
-                    const uint4 b0 = *reinterpret_cast<const uint4*>(descR + (size_t)iR * 32);
-                    const uint4 b1 = *reinterpret_cast<const uint4*>(descR + (size_t)iR * 32 + 16);
-                    const uint32_t key = ((uint32_t)hamming256(dl, b0, b1) << 16) | (uint32_t)iR;
-                    best = min(best, key);
-                }
+            const int c0 = rowStart[row], c1 = min(rowStart[row + 1], A.rowIdxCap);
+            for (int ci = c0 + lane; ci < c1; ci += 32) {
+                const int iR = rowIdx[ci];
+                const float2 k = rk[iR];
+                const int octR = __float_as_int(k.y);
+                if (octR < levelL - 1 || octR > levelL + 1) continue;
+                if (!(k.x >= minU && k.x <= maxU)) continue;
+                const uint4 b0 = *reinterpret_cast<const uint4*>(descR + (size_t)iR * 32);
+                const uint4 b1 = *reinterpret_cast<const uint4*>(descR + (size_t)iR * 32 + 16);
+                best = min(best, ((uint32_t)hamming256(dl, b0, b1) << 16) | (uint32_t)iR);
             }
-            best = __reduce_min_sync(0xffffffffu, best);
-            const int bestDist = (int)(best >> 16);
-            const int bestIdxR = (int)(best & 0xffffu);
-            if (bestDist < (TH_HIGH + TH_LOW) / 2) {
-                // ---- sub-pixel refinement by correlation on level `levelL` (:794-862)
-                const float uR0 = rk[bestIdxR].x;
-                const float sf = g.lv[levelL].invScale;
-                const float scaleduL = roundf(__fmul_rn(uL, sf));
-                const float scaledvL = roundf(__fmul_rn(vL, sf));
-                const float scaleduR0 = roundf(__fmul_rn(uR0, sf));
-                const int w = 5, Ls = 5;
-                const LevelGeom& lg = g.lv[levelL];
-                const float iniu = scaleduR0 + Ls - w, endu = scaleduR0 + Ls + w + 1;
-                const int cxL = (int)scaleduL, cy = (int)scaledvL, cxR = (int)scaleduR0;
-                // the reference would throw inside cv::Mat::rowRange/colRange for windows that leave the level
-                const bool inside = cy - w >= 0 && cy + w < lg.h && cxL - w >= 0 && cxL + w < lg.w &&
-                                    cxR - Ls - w >= 0 && cxR + Ls + w < lg.w;
-                if (!(iniu < 0 || endu >= (float)lg.w) && inside) {
-                    int pl, pr;
-                    const uint8_t* imL = level_ptr(A.left, g, img, levelL, pl);
-                    const uint8_t* imR = level_ptr(A.right, g, img, levelL, pr);
-                    const uint8_t* cL = imL + (size_t)cy * pl + cxL;
-                    const uint8_t* cR = imR + (size_t)cy * pr + cxR;
-                    const int centreL = cL[0];
-                    int lv[4], offR[4];
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        const int bestDist = (int)(best >> 16);
+        const int bestIdxR = (int)(best & 0xffffu);
+        if (bestDist < (TH_HIGH + TH_LOW) / 2) {
+            // ---- sub-pixel refinement by correlation on level `levelL` (:794-862)
+            const float uR0 = rk[bestIdxR].x;
+            const float sf = g.lv[levelL].invScale;
+            const float scaleduL = roundf(__fmul_rn(uL, sf));
+            const float scaledvL = roundf(__fmul_rn(vL, sf));
+            const float scaleduR0 = roundf(__fmul_rn(uR0, sf));
+            const int w = 5, Ls = 5;
+            const LevelGeom& lg = g.lv[levelL];
+            const float iniu = scaleduR0 + Ls - w, endu = scaleduR0 + Ls + w + 1;
+            const int cxL = (int)scaleduL, cy = (int)scaledvL, cxR = (int)scaleduR0;
+            // the reference would throw inside cv::Mat::rowRange/colRange for windows that leave the level
+            const bool inside = cy - w >= 0 && cy + w < lg.h && cxL - w >= 0 && cxL + w < lg.w &&
+                                cxR - Ls - w >= 0 && cxR + Ls + w < lg.w;
+            if (!(iniu < 0 || endu >= (float)lg.w) && inside) {
+                int pl, pr;
+                const uint8_t* imL = level_ptr(A.left, g, img, levelL, pl);
+                const uint8_t* imR = level_ptr(A.right, g, img, levelL, pr);
+                const uint8_t* cL = imL + (size_t)cy * pl + cxL;
+                const uint8_t* cR = imR + (size_t)cy * pr + cxR;
+                const int centreL = cL[0];
+                int lv[4], offR[4];
 #pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const int e = lane + 32 * t;
-                        const int py = e / 11, px = e - py * 11;
-                        const bool on = e < 121;
-                        lv[t] = on ? (int)cL[(py - w) * pl + (px - w)] - centreL : 0;
-                        offR[t] = on ? (py - w) * pr + (px - w) : 0x7fffffff;
-                    }
-                    int bestSad = 0x7fffffff, bestInc = 0;
-                    int sads[11];
+                for (int t = 0; t < 4; t++) {
+                    const int e = lane + 32 * t;
+                    const int py = e / 11, px = e - py * 11;
+                    const bool on = e < 121;
+                    lv[t] = on ? (int)cL[(py - w) * pl + (px - w)] - centreL : 0;
+                    offR[t] = on ? (py - w) * pr + (px - w) : 0x7fffffff;
+                }
+                // the right strip: lane's pixels at the 11 shifts (offsets offR[t] - 5 .. offR[t] + 5)
+                int bestSad = 0x7fffffff, bestInc = 0;
+                int sads[11];
 #pragma unroll
-                    for (int inc = -Ls; inc <= Ls; inc++) {
-                        const int centreR = cR[inc];
-                        int s = 0;
+                for (int inc = -Ls; inc <= Ls; inc++) {
+                    const int centreR = cR[inc];
+                    int s = 0;
 #pragma unroll
-                        for (int t = 0; t < 4; t++)
-                            if (offR[t] != 0x7fffffff) s += abs(lv[t] - ((int)cR[offR[t] + inc] - centreR));
-                        s = __reduce_add_sync(0xffffffffu, s);
-                        sads[inc + Ls] = s;
-                        if (s < bestSad) { bestSad = s; bestInc = inc; }
-                    }
-                    if (bestInc != -Ls && bestInc != Ls) {
-                        float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                    for (int t = 0; t < 4; t++)
+                        if (offR[t] != 0x7fffffff) s += abs(lv[t] - ((int)cR[offR[t] + inc] - centreR));
+                    s = __reduce_add_sync(0xffffffffu, s);
+                    sads[inc + Ls] = s;
+                    if (s < bestSad) { bestSad = s; bestInc = inc; }
+                }
+                if (bestInc != -Ls && bestInc != Ls) {
+                    float d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-                        for (int k = 1; k < 10; k++)
-                            if (k == bestInc + Ls) { d1 = (float)sads[k - 1]; d2 = (float)sads[k]; d3 = (float)sads[k + 1]; }
-                        const float deltaR = __fdiv_rn(__fsub_rn(d1, d3),
-                                                       __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
-                        if (!(deltaR < -1 || deltaR > 1)) {
-                            float bestuR = __fmul_rn(lg.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestInc), deltaR));
-                            float disparity = __fsub_rn(uL, bestuR);
-                            if (disparity >= A.minD && disparity < A.maxD) {
-                                if (disparity <= 0) {
-                                    disparity = 0.01f;
-                                    bestuR = (float)__dsub_rn((double)uL, 0.01);
-                                }
-                                outD = __fdiv_rn(A.mbf, disparity);
-                                outU = bestuR;
-                                outSad = bestSad;
+                    for (int k = 1; k < 10; k++)
+                        if (k == bestInc + Ls) { d1 = (float)sads[k - 1]; d2 = (float)sads[k]; d3 = (float)sads[k + 1]; }
+                    const float deltaR = __fdiv_rn(__fsub_rn(d1, d3),
+                                                   __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+                    if (!(deltaR < -1 || deltaR > 1)) {
+                        float bestuR = __fmul_rn(lg.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestInc), deltaR));
+                        float disparity = __fsub_rn(uL, bestuR);
+                        if (disparity >= A.minD && disparity < A.maxD) {
+                            if (disparity <= 0) {
+                                disparity = 0.01f;
+                                bestuR = (float)__dsub_rn((double)uL, 0.01);
                             }
+                            outD = __fdiv_rn(A.mbf, disparity);
+                            outU = bestuR;
+                            outSad = bestSad;
                         }
                     }
                 }
             }
         }
-        if (lane == 0) { uRightOut[iL] = outU; depthOut[iL] = outD; sadOut[iL] = outSad; }
+    }
+    if (lane == 0) {
+        A.uRight[(size_t)img * g.kpCap + iL] = outU;
+        A.depth[(size_t)img * g.kpCap + iL] = outD;
+        A.sad[(size_t)img * g.kpCap + iL] = outSad;
     }
 }
 
@@ -211,16 +260,16 @@ __global__ void __launch_bounds__(256) k_stereo_filter(const __grid_constant__ S
 }  // namespace
 
 cudaError_t launch_stereo(const StereoArgs& a, int nimg, cudaStream_t st) {
-    const int perCta = ST_WARPS * ST_KP_PER_WARP;
-    dim3 grid((a.g.kpCap + perCta - 1) / perCta, nimg);
-    const size_t smem = (size_t)a.g.kpCap * sizeof(RightKp);
+    const size_t smemRows = (size_t)(a.g.lv[0].h + 1) * sizeof(int);
     static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smemRows > 48 * 1024 && smemRows > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRows);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured = smemRows;
     }
-    k_stereo_match<<<grid, ST_WARPS * 32, smem, st>>>(a);
+    k_stereo_rows<<<nimg, 256, smemRows, st>>>(a);
+    dim3 grid((a.g.kpCap + ST_WARPS - 1) / ST_WARPS, nimg);
+    k_stereo_match<<<grid, ST_WARPS * 32, 0, st>>>(a);
     k_stereo_filter<<<nimg, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
