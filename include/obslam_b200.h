@@ -61,6 +61,12 @@ const char* obs_version(void);
 /* Number of CUDA devices visible, or a negative obs_status. */
 int obs_device_count(void);
 
+/* Page-locked host memory.  Host buffers handed to obs_extract*, obs_extractor_fetch and
+ * obs_stereo_match that were allocated here (or with cudaMallocHost / cudaHostRegister) are moved by
+ * DMA directly; any other host pointer goes through a staging copy inside the library. */
+int obs_host_alloc(size_t bytes, void** out);
+int obs_host_free(void* p);
+
 /* ---------------------------------------------------------------------------------------
  * Extractor.  Replaces ORB_SLAM2::ORBextractor (include/ORBextractor.h:45-111).
  * --------------------------------------------------------------------------------------- */

@@ -38,6 +38,8 @@ _PROTOS = {
     "obs_last_error": (C.c_char_p, []),
     "obs_version": (C.c_char_p, []),
     "obs_device_count": (C.c_int, []),
+    "obs_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "obs_host_free": (C.c_int, [_vp]),
     "obs_extractor_create": (C.c_int, [C.POINTER(OrbParams), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "obs_extractor_destroy": (C.c_int, [_vp]),
     "obs_extractor_levels": (C.c_int, [_vp]),
@@ -89,3 +91,25 @@ def check(rc):
 
 def ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class _PinnedOwner:
+    def __init__(self, p):
+        self.p = p
+
+    def __del__(self):
+        try:
+            lib().obs_host_free(self.p)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (obs_host_alloc): moved by DMA without a staging copy."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = C.c_void_p()
+    check(lib().obs_host_alloc(max(n, 1), C.byref(p)))
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    buf._owner = _PinnedOwner(p)      # numpy keeps `buf` alive through .base; the allocation dies with it
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)

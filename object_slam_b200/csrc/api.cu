@@ -89,7 +89,7 @@ struct obs_extractor {
     DevBuf<FastCta> dFastCtas;
 
     // device state of the last batch
-    DevBuf<uint8_t> pyr, blur, records;
+    DevBuf<uint8_t> pyr, blur, records, rawIn;
     DevBuf<uint32_t> cand, keyScratch, sel;
     DevBuf<uint16_t> nodeScratch;
     DevBuf<int> cellCount, selCount;
@@ -309,6 +309,13 @@ int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st) {
     return OBS_OK;
 }
 
+// true for cudaMallocHost / cudaHostRegister memory: such buffers are DMA-ed directly, without the staging copy
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 int check_handle(const obs_extractor* e) {
     if (!e) return fail(OBS_ERR_INVALID, "null extractor handle");
     cudaError_t ce = cudaSetDevice(e->device);
@@ -368,7 +375,7 @@ int obs_extractor_destroy(obs_extractor* e) {
     if (!e) return OBS_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->pyr.release(); e->blur.release(); e->records.release(); e->cand.release(); e->keyScratch.release();
+    e->pyr.release(); e->blur.release(); e->records.release(); e->rawIn.release(); e->cand.release(); e->keyScratch.release();
     e->sel.release(); e->nodeScratch.release(); e->cellCount.release(); e->selCount.release();
     e->uRight.release(); e->depth.release(); e->sad.release(); e->rowStart.release(); e->rowIdx.release(); e->rightXO.release(); e->dXtab.release(); e->dYtab.release(); e->dFastCtas.release();
     e->stageIn.release(); e->stageOut.release();
@@ -474,12 +481,28 @@ int obs_extract_batch(obs_extractor* e, const uint8_t* const* images, int n_imag
     if (rc) return rc;
     const Geom& g = e->g;
     const size_t p0 = (size_t)g.lv[0].pitch, l0Bytes = p0 * h;
-    CU(e->stageIn.ensure((size_t)n_images * l0Bytes));
-    for (int i = 0; i < n_images; i++) {
+    for (int i = 0; i < n_images; i++)
         if (!images[i]) return fail(OBS_ERR_INVALID, "image %d is null", i);
-        uint8_t* dstp = e->stageIn.p + (size_t)i * l0Bytes;
-        for (int y = 0; y < h; y++) memcpy(dstp + (size_t)y * p0, images[i] + (size_t)y * stride, w);
-        CU(cudaMemcpyAsync(e->pyr.p + (size_t)i * g.slabBytes, dstp, l0Bytes, cudaMemcpyHostToDevice, st));
+    // page-locked images that follow each other in memory: one DMA for the whole batch, repacked to the
+    // pitched level-0 slab on the device
+    bool oneBlock = is_pinned(images[0]);
+    const size_t imgBytes = stride * (size_t)h;
+    for (int i = 1; oneBlock && i < n_images; i++) oneBlock = images[i] == images[i - 1] + imgBytes;
+    if (oneBlock) {
+        CU(e->rawIn.ensure((size_t)e->maxBatch * imgBytes + 16));
+        CU(cudaMemcpyAsync(e->rawIn.p, images[0], (size_t)n_images * imgBytes, cudaMemcpyHostToDevice, st));
+        CU(launch_repack(e->rawIn.p, imgBytes, stride, e->pyr.p, g.slabBytes, (int)p0, w, h, n_images, st));
+    } else {
+        for (int i = 0; i < n_images; i++) {
+            if (is_pinned(images[i])) {           // page-locked caller memory: DMA straight into the pitched level-0 slab
+                CU(cudaMemcpy2DAsync(e->pyr.p + (size_t)i * g.slabBytes, p0, images[i], stride, w, h, cudaMemcpyHostToDevice, st));
+            } else {
+                CU(e->stageIn.ensure((size_t)e->maxBatch * l0Bytes));
+                uint8_t* dstp = e->stageIn.p + (size_t)i * l0Bytes;
+                for (int y = 0; y < h; y++) memcpy(dstp + (size_t)y * p0, images[i] + (size_t)y * stride, w);
+                CU(cudaMemcpyAsync(e->pyr.p + (size_t)i * g.slabBytes, dstp, l0Bytes, cudaMemcpyHostToDevice, st));
+            }
+        }
     }
     e->ptrs.l0 = e->pyr.p;
     e->ptrs.l0ImgStride = g.slabBytes;
@@ -506,18 +529,35 @@ int obs_extractor_fetch(obs_extractor* e, obs_keypoint* keypoints, uint8_t* desc
     if (!n_out || cap < 0) return fail(OBS_ERR_INVALID, "null argument");
     const int n = e->lastN;
     const Geom& g = e->g;
-    CU(e->stageOut.ensure((size_t)n * e->recordBytes));
-    CU(cudaMemcpyAsync(e->stageOut.p, e->records.p, (size_t)n * e->recordBytes, cudaMemcpyDeviceToHost, e->lastStream));
-    CU(cudaStreamSynchronize(e->lastStream));
+    const uint8_t* kpSrc = e->records.p + OBS_HDR_INTS * 4;
+    const uint8_t* descSrc = kpSrc + (size_t)g.kpCap * 28;
+    const int m = cap < g.kpCap ? cap : g.kpCap;
     int status = OBS_OK;
-    for (int i = 0; i < n; i++) {
-        const uint8_t* rec = e->stageOut.p + (size_t)i * e->recordBytes;
-        const int cnt = *reinterpret_cast<const int*>(rec);
-        n_out[i] = cnt;
-        const int m = cnt < cap ? cnt : cap;
-        if (cnt > cap && (keypoints || descriptors)) status = OBS_ERR_CAPACITY;
-        if (keypoints) memcpy(keypoints + (size_t)i * cap, rec + OBS_HDR_INTS * 4, (size_t)m * 28);
-        if (descriptors) memcpy(descriptors + (size_t)i * cap * 32, rec + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28, (size_t)m * 32);
+    if ((!keypoints || is_pinned(keypoints)) && (!descriptors || is_pinned(descriptors)) && m > 0) {
+        // page-locked outputs: strided DMA from the result records, no staging
+        CU(e->stageOut.ensure((size_t)e->maxBatch * sizeof(int)));
+        int* cnts = reinterpret_cast<int*>(e->stageOut.p);
+        CU(cudaMemcpy2DAsync(cnts, sizeof(int), e->records.p, e->recordBytes, sizeof(int), n, cudaMemcpyDeviceToHost, e->lastStream));
+        if (keypoints) CU(cudaMemcpy2DAsync(keypoints, (size_t)cap * 28, kpSrc, e->recordBytes, (size_t)m * 28, n, cudaMemcpyDeviceToHost, e->lastStream));
+        if (descriptors) CU(cudaMemcpy2DAsync(descriptors, (size_t)cap * 32, descSrc, e->recordBytes, (size_t)m * 32, n, cudaMemcpyDeviceToHost, e->lastStream));
+        CU(cudaStreamSynchronize(e->lastStream));
+        for (int i = 0; i < n; i++) {
+            n_out[i] = cnts[i];
+            if (cnts[i] > cap && (keypoints || descriptors)) status = OBS_ERR_CAPACITY;
+        }
+    } else {
+        CU(e->stageOut.ensure((size_t)e->maxBatch * e->recordBytes));
+        CU(cudaMemcpyAsync(e->stageOut.p, e->records.p, (size_t)n * e->recordBytes, cudaMemcpyDeviceToHost, e->lastStream));
+        CU(cudaStreamSynchronize(e->lastStream));
+        for (int i = 0; i < n; i++) {
+            const uint8_t* rec = e->stageOut.p + (size_t)i * e->recordBytes;
+            const int cnt = *reinterpret_cast<const int*>(rec);
+            n_out[i] = cnt;
+            const int mm = cnt < cap ? cnt : cap;
+            if (cnt > cap && (keypoints || descriptors)) status = OBS_ERR_CAPACITY;
+            if (keypoints) memcpy(keypoints + (size_t)i * cap, rec + OBS_HDR_INTS * 4, (size_t)mm * 28);
+            if (descriptors) memcpy(descriptors + (size_t)i * cap * 32, rec + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28, (size_t)mm * 32);
+        }
     }
     if (status) return fail(status, "caller capacity %d smaller than the keypoint count", cap);
     return OBS_OK;
@@ -661,16 +701,34 @@ int obs_stereo_match(obs_extractor* L, obs_extractor* R, float mbf, float min_d,
     int rc = obs_stereo_match_device(L, R, mbf, min_d, max_d, nullptr, nullptr, nullptr);
     if (rc) return rc;
     const int n = L->lastN, kc = L->g.kpCap;
+    const int m = std::min(cap, kc);
+    if (is_pinned(u_right) && is_pinned(depth) && cap <= kc) {
+        CU(cudaMemcpy2DAsync(u_right, (size_t)cap * 4, L->uRight.p, (size_t)kc * 4, (size_t)m * 4, n, cudaMemcpyDeviceToHost, L->stream));
+        CU(cudaMemcpy2DAsync(depth, (size_t)cap * 4, L->depth.p, (size_t)kc * 4, (size_t)m * 4, n, cudaMemcpyDeviceToHost, L->stream));
+        CU(cudaStreamSynchronize(L->stream));
+        return OBS_OK;
+    }
     std::vector<float> hu((size_t)n * kc), hd((size_t)n * kc);
     CU(cudaMemcpyAsync(hu.data(), L->uRight.p, hu.size() * 4, cudaMemcpyDeviceToHost, L->stream));
     CU(cudaMemcpyAsync(hd.data(), L->depth.p, hd.size() * 4, cudaMemcpyDeviceToHost, L->stream));
     CU(cudaStreamSynchronize(L->stream));
-    const int m = std::min(cap, kc);
     for (int i = 0; i < n; i++) {
         for (int j = 0; j < cap; j++) { u_right[(size_t)i * cap + j] = -1.f; depth[(size_t)i * cap + j] = -1.f; }
         memcpy(u_right + (size_t)i * cap, hu.data() + (size_t)i * kc, (size_t)m * 4);
         memcpy(depth + (size_t)i * cap, hd.data() + (size_t)i * kc, (size_t)m * 4);
     }
+    return OBS_OK;
+}
+
+int obs_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(OBS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return OBS_OK;
+}
+
+int obs_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
     return OBS_OK;
 }
 

@@ -6,6 +6,9 @@
 // K1  pyramid.cu   -- ComputePyramid (src/ORBextractor.cc:1107-1132), levels 1..n-1
 cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, const ResizeTap* ytab, int nimg, cudaStream_t st);
 
+cudaError_t launch_repack(const uint8_t* src, size_t srcImgStride, size_t srcPitch, uint8_t* dst, size_t dstImgStride,
+                          int dstPitch, int w, int h, int nimg, cudaStream_t st);
+
 // K2  fast.cu      -- per-cell FAST with threshold fallback (:765-829, cv::FAST :809/:814)
 size_t fast_smem_bytes(int tileRows);
 cudaError_t fast_prepare(int tileRows);

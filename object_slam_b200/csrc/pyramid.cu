@@ -127,7 +127,42 @@ __global__ void __launch_bounds__(32 * RS_BANDS) k_resize(const __grid_constant_
     }
 }
 
+// Host uploads arrive as one contiguous block (rows of w bytes); level 0 lives in the slab with a
+// 128-byte row pitch so that every later stage can use aligned vector loads.
+__global__ void __launch_bounds__(256) k_repack(const uint8_t* __restrict__ src, size_t srcImgStride, size_t srcPitch,
+                                                uint8_t* __restrict__ dst, size_t dstImgStride, int dstPitch, int w, int h) {
+    const int img = blockIdx.z;
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (y >= h) return;
+    const uint8_t* s = src + (size_t)img * srcImgStride + (size_t)y * srcPitch;
+    uint8_t* d = dst + (size_t)img * dstImgStride + (size_t)y * dstPitch;
+    const int lane = threadIdx.x & 31;
+    // destination words are aligned; source bytes are fetched individually only at unaligned rows
+    const int nWords = (w + 3) >> 2;
+    const uintptr_t mis = reinterpret_cast<uintptr_t>(s) & 3;
+    for (int i = blockIdx.x * 32 + lane; i < nWords; i += gridDim.x * 32) {
+        uint32_t v;
+        if (mis == 0 && 4 * i + 3 < w) {
+            v = __ldg(reinterpret_cast<const uint32_t*>(s) + i);
+        } else if (4 * i + 3 < w) {
+            const uint32_t* a = reinterpret_cast<const uint32_t*>(s - mis) + i;      // aligned pair straddling the word
+            v = __funnelshift_r(__ldg(a), __ldg(a + 1), 8 * (int)mis);
+        } else {
+            v = 0;
+            for (int b = 0; b < 4; b++) if (4 * i + b < w) v |= (uint32_t)s[4 * i + b] << (8 * b);
+        }
+        reinterpret_cast<uint32_t*>(d)[i] = v;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_repack(const uint8_t* src, size_t srcImgStride, size_t srcPitch, uint8_t* dst, size_t dstImgStride,
+                          int dstPitch, int w, int h, int nimg, cudaStream_t st) {
+    dim3 grid((w + 4 * 32 * 4 - 1) / (4 * 32 * 4), (h + 7) / 8, nimg);
+    k_repack<<<grid, 256, 0, st>>>(src, srcImgStride, srcPitch, dst, dstImgStride, dstPitch, w, h);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, const ResizeTap* ytab, int nimg, cudaStream_t st) {
     for (int l = 1; l < g.nlevels; l++) {

@@ -90,20 +90,32 @@ class ORBextractor:
         self._last_n = 1
         return kps[:n.value].copy(), desc[:n.value].copy()
 
-    def extract_batch(self, images):
-        """operator() over a list of equally shaped host images in one call."""
-        images = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
-        h, w = images[0].shape
-        assert all(im.shape == (h, w) for im in images)
-        nimg = len(images)
+    def extract_batch(self, images, out=None, copy=True):
+        """operator() over equally shaped host images in one call.  `images`: a list of 2-D arrays or one
+        (n, h, w) array; page-locked arrays (``_capi.pinned_empty``) are DMA-ed without staging.
+        `out` = (keypoints[n, cap], descriptors[n, cap, 32], counts[n]) reuses caller (ideally pinned) buffers;
+        with copy=False the per-image results are views into them."""
+        if isinstance(images, np.ndarray) and images.ndim == 3:
+            assert images.dtype == np.uint8 and images.strides[2] == 1
+            nimg, h, w = images.shape
+            stride = images.strides[1]
+            ptrs = [images.ctypes.data + i * images.strides[0] for i in range(nimg)]
+        else:
+            images = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+            h, w = images[0].shape
+            assert all(im.shape == (h, w) for im in images)
+            nimg, stride = len(images), w
+            ptrs = [im.ctypes.data for im in images]
         cap = self.capacity
-        kps = np.empty((nimg, cap), KEYPOINT_DTYPE)
-        desc = np.empty((nimg, cap, 32), np.uint8)
-        counts = np.zeros(nimg, np.int32)
-        arr = (C.c_void_p * nimg)(*[im.ctypes.data for im in images])
-        check(lib().obs_extract_batch(self._h, arr, nimg, w, h, w, ptr(kps), ptr(desc), cap, ptr(counts)))
+        if out is None:
+            out = (np.empty((nimg, cap), KEYPOINT_DTYPE), np.empty((nimg, cap, 32), np.uint8), np.zeros(nimg, np.int32))
+        kps, desc, counts = out
+        arr = (C.c_void_p * nimg)(*ptrs)
+        check(lib().obs_extract_batch(self._h, arr, nimg, w, h, stride, ptr(kps), ptr(desc), kps.shape[1], ptr(counts)))
         self._last_n = nimg
-        return [(kps[i, :counts[i]].copy(), desc[i, :counts[i]].copy()) for i in range(nimg)]
+        if copy:
+            return [(kps[i, :counts[i]].copy(), desc[i, :counts[i]].copy()) for i in range(nimg)]
+        return [(kps[i, :counts[i]], desc[i, :counts[i]]) for i in range(nimg)]
 
     def extract_device(self, d_images, n_images, w, h, stride, image_stride, stream=None):
         """Images already resident in HBM (``d_images`` = device address); results stay on the device."""
@@ -170,16 +182,22 @@ class ORBextractor:
         return self._keys(lib().obs_extractor_get_selected, level, image_index)
 
 
-def ComputeStereoMatches(left, right, mbf, minD, maxD):
+def ComputeStereoMatches(left, right, mbf, minD, maxD, out=None):
     """Frame::ComputeStereoMatches (src/Frame.cc:706-880) on the last extraction of two extractors.
-    Returns (mvuRight, mvDepth): per image of the batch, float32 arrays over the left keypoints."""
+    Returns (mvuRight, mvDepth) per image of the batch: float32 arrays over the left keypoints
+    (views into `out` = (uRight[n, cap], depth[n, cap]) when given)."""
     cap = left.capacity
     nimg = left._last_n
-    ur = np.empty((nimg, cap), np.float32)
-    dp = np.empty((nimg, cap), np.float32)
-    check(lib().obs_stereo_match(left._h, right._h, float(mbf), float(minD), float(maxD), ptr(ur), ptr(dp), cap))
+    if out is None:
+        ur = np.empty((nimg, cap), np.float32)
+        dp = np.empty((nimg, cap), np.float32)
+    else:
+        ur, dp = out
+    check(lib().obs_stereo_match(left._h, right._h, float(mbf), float(minD), float(maxD), ptr(ur), ptr(dp), ur.shape[1]))
     counts = left.fetch_counts()
-    return [(ur[i, :counts[i]].copy(), dp[i, :counts[i]].copy()) for i in range(nimg)]
+    if out is None:
+        return [(ur[i, :counts[i]].copy(), dp[i, :counts[i]].copy()) for i in range(nimg)]
+    return [(ur[i, :counts[i]], dp[i, :counts[i]]) for i in range(nimg)]
 
 
 def stereo_match_device(left, right, mbf, minD, maxD, stream=None):

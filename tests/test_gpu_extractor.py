@@ -182,3 +182,27 @@ def test_concurrent_handles_two_threads(gpu):
         for key, im in (("L", L), ("R", R)):
             ok, od = oracle.OracleExtractor(2000)(im)
             assert out[key][0].tobytes() == ok.tobytes() and np.array_equal(out[key][1], od)
+
+
+def test_pinned_host_buffers_take_the_dma_path(gpu):
+    """Page-locked inputs/outputs (obs_host_alloc) must give the same bytes as pageable ones."""
+    from object_slam_b200._capi import pinned_empty, KEYPOINT_DTYPE
+    from object_slam_b200.extractor import ComputeStereoMatches
+    shape = synth.KITTI_SHAPE
+    pairs = [synth.stereo_pair(shape, s) for s in (60, 61, 62)]
+    eL, eR = _ex(2000, shape, max_batch=3), _ex(2000, shape, max_batch=3)
+    want = eL.extract_batch([p[0] for p in pairs]); eR.extract_batch([p[1] for p in pairs])
+    wantS = ComputeStereoMatches(eL, eR, synth.KITTI_BF, 0.0, synth.KITTI_FX)
+    cap = eL.capacity
+    pinL, pinR = pinned_empty((3,) + shape, np.uint8), pinned_empty((3,) + shape, np.uint8)
+    for i, (l, r) in enumerate(pairs):
+        pinL[i] = l; pinR[i] = r
+    out = (pinned_empty((3, cap), KEYPOINT_DTYPE), pinned_empty((3, cap, 32), np.uint8), pinned_empty((3,), np.int32))
+    outR = (pinned_empty((3, cap), KEYPOINT_DTYPE), pinned_empty((3, cap, 32), np.uint8), pinned_empty((3,), np.int32))
+    got = eL.extract_batch(pinL, out=out, copy=False); eR.extract_batch(pinR, out=outR, copy=False)
+    outS = (pinned_empty((3, cap), np.float32), pinned_empty((3, cap), np.float32))
+    gotS = ComputeStereoMatches(eL, eR, synth.KITTI_BF, 0.0, synth.KITTI_FX, out=outS)
+    for (k, d), (wk, wd) in zip(got, want):
+        assert k.tobytes() == wk.tobytes() and np.array_equal(d, wd)
+    for (u, z), (wu, wz) in zip(gotS, wantS):
+        assert np.array_equal(u, wu) and np.array_equal(z, wz)
