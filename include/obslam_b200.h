@@ -147,6 +147,138 @@ int obs_stereo_match(obs_extractor* left, obs_extractor* right, float mbf, float
 int obs_stereo_match_device(obs_extractor* left, obs_extractor* right, float mbf, float min_d, float max_d,
                             void* stream, const float** d_u_right, const float** d_depth);
 
+
+/* ---------------------------------------------------------------------------------------
+ * Matchers.  Replace the Hamming searches of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:37-102)
+ * that Tracking runs on every frame.  The reference walks pointer graphs (Frame, MapPoint); the
+ * entry points below take the same quantities as flat arrays, named after the members they are
+ * read from.  EVERY array pointer below may be host memory or device memory (the library looks the
+ * pointer up; host arrays are staged, device arrays are used in place, device outputs are written
+ * in place without a synchronisation).
+ *
+ * An obs_matcher owns one stream and its workspace; calls on different matchers may run
+ * concurrently from different threads (the reference's matchers are stack-local objects used from
+ * the Tracking, LocalMapping and LoopClosing threads).
+ * --------------------------------------------------------------------------------------- */
+typedef struct obs_matcher obs_matcher;
+typedef struct obs_frame_set obs_frame_set;
+
+int obs_matcher_create(int device, obs_matcher** out);
+int obs_matcher_destroy(obs_matcher* m);
+/* cudaStream_t the matcher's work is ordered on. */
+void* obs_matcher_stream(obs_matcher* m);
+/* Wait for everything queued on the matcher's stream (needed only after calls with device outputs). */
+int obs_matcher_sync(obs_matcher* m);
+
+/* Static members of Frame and the camera (src/Frame.cc:33-35, :93-114, :691-702). */
+typedef struct obs_frame_params {
+    float min_x, max_x, min_y, max_y;       /* mnMinX, mnMaxX, mnMinY, mnMaxY */
+    float fx, fy, cx, cy, mbf, mb;
+    int32_t nlevels;
+    float scale_factors[12];                /* mvScaleFactors */
+} obs_frame_params;
+
+/* What the matchers read of one Frame. */
+typedef struct obs_frame_view {
+    int32_t n;                              /* N */
+    const obs_keypoint* keys_un;            /* mvKeysUn (x, y, angle, octave are read) */
+    const uint8_t* descriptors;             /* mDescriptors, n x 32 */
+    const float* u_right;                   /* mvuRight, or NULL for a monocular frame (all -1) */
+} obs_frame_view;
+
+/* A batch of up to max_frames frames of up to max_keypoints keypoints each, resident in HBM together
+ * with the 64x48 keypoint grid of each frame (Frame::AssignFeaturesToGrid, src/Frame.cc:455-470,
+ * PosInGrid :622-632), which is built on the device. */
+int obs_frame_set_create(obs_matcher* m, const obs_frame_params* params, int max_frames, int max_keypoints,
+                         obs_frame_set** out);
+int obs_frame_set_destroy(obs_frame_set* fs);
+int obs_frame_set_upload(obs_frame_set* fs, const obs_frame_view* frames, int n_frames);
+/* The same from the results of the last extraction on `e` (no host round trip): frame i = image i;
+ * the keypoints are taken as undistorted (the reference copies mvKeys to mvKeysUn when the camera has
+ * no distortion, src/Frame.cc:646-650).  d_u_right: device array n_images x obs_extractor_max_keypoints
+ * (e.g. from obs_stereo_match_device) or NULL. */
+int obs_frame_set_from_extractor(obs_frame_set* fs, obs_extractor* e, const float* d_u_right);
+int obs_frame_set_count(const obs_frame_set* fs);
+/* Grid of frame `frame` as a CSR in mGrid[ix][iy] order (cell = ix*48 + iy): cell_start receives
+ * 64*48+1 ints, cell_idx the keypoint indices (ascending inside a cell, like the reference's push_back). */
+int obs_frame_set_grid(obs_frame_set* fs, int frame, int32_t* cell_start, int32_t* cell_idx, int cap);
+
+/* Fields of MapPoint read by SearchByProjection(Frame&, const vector<MapPoint*>&, th); arrays of n
+ * entries per frame.  per_frame = 0: one list shared by all frames of the set; 1: n_frames lists
+ * stored one after the other. */
+typedef struct obs_mappoint_view {
+    int32_t n;
+    int32_t per_frame;
+    const uint8_t* in_view;                 /* mbTrackInView && !isBad() */
+    const float* proj_x;                    /* mTrackProjX */
+    const float* proj_y;                    /* mTrackProjY */
+    const float* proj_xr;                   /* mTrackProjXR */
+    const int32_t* scale_level;             /* mnTrackScaleLevel */
+    const float* view_cos;                  /* mTrackViewCos */
+    const uint8_t* descriptors;             /* GetDescriptor(), n x 32 */
+    const int32_t* observations;            /* Observations() */
+} obs_mappoint_view;
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:45-129,
+ * for every frame of the set.  F.mvpMapPoints is modelled by two arrays over the keypoints
+ * (n_frames x max_keypoints each): kp_observations (in, may be NULL = all free) holds Observations()
+ * of the point a keypoint already carries (0 = none); kp_match (out) receives -1 where the call
+ * left the keypoint alone, else the index of the map point assigned last.  n_matches: per frame,
+ * the function's return value.  The result equals the reference's sequential first-come-first-served
+ * loop exactly. */
+int obs_search_by_projection(obs_matcher* m, obs_frame_set* frames, const obs_mappoint_view* points,
+                             float th, float nnratio, const int32_t* kp_observations,
+                             int32_t* kp_match, int32_t* n_matches);
+
+/* Fields of the last Frame read by SearchByProjection(Frame& Current, const Frame& Last, th, bMono);
+ * n entries per frame (per_frame as above). */
+typedef struct obs_lastframe_view {
+    int32_t n;                              /* LastFrame.N */
+    int32_t per_frame;
+    const uint8_t* has_point;               /* mvpMapPoints[i] && !mvbOutlier[i] */
+    const float* world_pos;                 /* GetWorldPos(), n x 3 */
+    const int32_t* octave;                  /* mvKeys[i].octave */
+    const float* angle;                     /* mvKeysUn[i].angle */
+    const uint8_t* descriptors;             /* pMP->GetDescriptor(), n x 32 */
+    const int32_t* observations;            /* pMP->Observations() */
+    const float* tcw_last;                  /* LastFrame.mTcw rows 0..2, 12 floats per frame */
+    const float* tcw_current;               /* CurrentFrame.mTcw rows 0..2, 12 floats per frame */
+} obs_lastframe_view;
+
+/* src/ORBmatcher.cc:1328-1470 incl. the rotation-histogram check (:1431-1467) with
+ * ComputeThreeMaxima (:1601-1642).  kp_match additionally uses -2 = reset to NULL by that check. */
+int obs_search_by_projection_last(obs_matcher* m, obs_frame_set* current, const obs_lastframe_view* last,
+                                  float th, int mono, int check_orientation, const int32_t* kp_observations,
+                                  int32_t* kp_match, int32_t* n_matches);
+
+/* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:405-520: frame i of f1 against frame i of f2.
+ * prev_matched: n_frames x max_keypoints(f1) x 2 floats, in/out (vbPrevMatched); matches12:
+ * n_frames x max_keypoints(f1) (vnMatches12). */
+int obs_search_for_initialization(obs_matcher* m, obs_frame_set* f1, obs_frame_set* f2, float* prev_matched,
+                                  int32_t* matches12, int window_size, float nnratio, int check_orientation,
+                                  int32_t* n_matches);
+
+/* Diagnostics: resolution rounds each frame of the last projection search with host outputs took
+ * (see csrc/matcher.cu); returns the number of frames. */
+int obs_matcher_last_rounds(obs_matcher* m, int32_t* rounds, int cap);
+
+/* ORBmatcher::ComputeThreeMaxima, src/ORBmatcher.cc:1601-1642, over n_hist histograms of `length`
+ * bin sizes each; ind receives 3 ints per histogram. */
+int obs_compute_three_maxima(obs_matcher* m, const int32_t* bin_sizes, int n_hist, int length, int32_t* ind);
+
+/* ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1647-1663, over n pairs of 32-byte descriptors. */
+int obs_descriptor_distance(obs_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
+
+/* Brute-force best / second-best Hamming search with the ratio test (the candidate loop of
+ * ORBmatcher::SearchByBoW, src/ORBmatcher.cc:200-229, over whole keyframes): `descriptors` holds
+ * n_keyframes x n_desc x 32 bytes; pairs holds n_pairs x 2 ints (query keyframe, database keyframe).
+ * Per pair and query descriptor: best_dist, second_dist (256 = none) and best_idx = index of the
+ * nearest database descriptor if best_dist <= th_low and best_dist < nnratio * second_dist, else -1
+ * (lowest index wins ties).  Outputs are n_pairs x n_desc ints each; best_dist / second_dist may be NULL. */
+int obs_hamming_knn2(obs_matcher* m, const uint8_t* descriptors, int n_keyframes, int n_desc,
+                     const int32_t* pairs, int n_pairs, int th_low, float nnratio,
+                     int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
+
 #ifdef __cplusplus
 }
 #endif

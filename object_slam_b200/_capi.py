@@ -26,6 +26,28 @@ class OrbParams(C.Structure):
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
 
 
+class FrameParams(C.Structure):
+    _fields_ = [("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("mbf", C.c_float), ("mb", C.c_float), ("nlevels", C.c_int32), ("scale_factors", C.c_float * 12)]
+
+
+class FrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("descriptors", C.c_void_p), ("u_right", C.c_void_p)]
+
+
+class MapPointView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("per_frame", C.c_int32), ("in_view", C.c_void_p), ("proj_x", C.c_void_p),
+                ("proj_y", C.c_void_p), ("proj_xr", C.c_void_p), ("scale_level", C.c_void_p), ("view_cos", C.c_void_p),
+                ("descriptors", C.c_void_p), ("observations", C.c_void_p)]
+
+
+class LastFrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("per_frame", C.c_int32), ("has_point", C.c_void_p), ("world_pos", C.c_void_p),
+                ("octave", C.c_void_p), ("angle", C.c_void_p), ("descriptors", C.c_void_p), ("observations", C.c_void_p),
+                ("tcw_last", C.c_void_p), ("tcw_current", C.c_void_p)]
+
+
 class ObsError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"obslam_b200 error {code}: {msg}")
@@ -58,6 +80,23 @@ _PROTOS = {
     "obs_extractor_stage_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "obs_stereo_match": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_float, _vp, _vp, C.c_int]),
     "obs_stereo_match_device": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_float, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "obs_matcher_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "obs_matcher_destroy": (C.c_int, [_vp]),
+    "obs_matcher_stream": (_vp, [_vp]),
+    "obs_matcher_sync": (C.c_int, [_vp]),
+    "obs_matcher_last_rounds": (C.c_int, [_vp, _vp, C.c_int]),
+    "obs_frame_set_create": (C.c_int, [_vp, C.POINTER(FrameParams), C.c_int, C.c_int, C.POINTER(_vp)]),
+    "obs_frame_set_destroy": (C.c_int, [_vp]),
+    "obs_frame_set_upload": (C.c_int, [_vp, C.POINTER(FrameView), C.c_int]),
+    "obs_frame_set_from_extractor": (C.c_int, [_vp, _vp, _vp]),
+    "obs_frame_set_count": (C.c_int, [_vp]),
+    "obs_frame_set_grid": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
+    "obs_search_by_projection": (C.c_int, [_vp, _vp, C.POINTER(MapPointView), C.c_float, C.c_float, _vp, _vp, _vp]),
+    "obs_search_by_projection_last": (C.c_int, [_vp, _vp, C.POINTER(LastFrameView), C.c_float, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "obs_search_for_initialization": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int, _vp]),
+    "obs_compute_three_maxima": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
+    "obs_descriptor_distance": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    "obs_hamming_knn2": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -90,7 +129,21 @@ def check(rc):
 
 
 def ptr(a):
-    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+    """Address of a numpy array; ints pass through as raw (host or device) addresses."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def addr(a):
+    """The same as an integer (0 for None), for ctypes.Structure fields."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    return a.ctypes.data
 
 
 class _PinnedOwner:

@@ -3,6 +3,8 @@
 // CPU implementation of any stage.
 #include "../../include/obslam_b200.h"
 #include "kernels.h"
+#include "host_util.h"
+#include "matcher_api.h"
 
 #include <cmath>
 #include <cstdarg>
@@ -11,7 +13,7 @@
 #include <new>
 #include <vector>
 
-namespace {
+namespace obsdetail {
 
 thread_local char g_err[512] = "";
 
@@ -23,11 +25,22 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail(OBS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
+// true for cudaMallocHost / cudaHostRegister memory: such buffers are DMA-ed directly, without the staging copy
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+bool is_device(const void* p) {
+    cudaPointerAttributes at;
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace obsdetail
+
+namespace {
 
 inline int cv_round_f(float v) { return (int)nearbyintf(v); }      // cvRound: round half to even
 inline int cv_round_d(double v) { return (int)nearbyint(v); }
@@ -36,34 +49,6 @@ inline int cv_ceil_d(double v) { int i = (int)v; return i + (i < v); }
 inline short sat_short(float v) { int i = cv_round_f(v); return (short)(i < -32768 ? -32768 : i > 32767 ? 32767 : i); }
 
 constexpr int PROF_SLOTS = 128;
-
-template <typename T> struct DevBuf {
-    T* p = nullptr;
-    size_t n = 0;
-    cudaError_t ensure(size_t count) {
-        if (count <= n) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; n = 0;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-};
-
-template <typename T> struct PinBuf {
-    T* p = nullptr;
-    size_t n = 0;
-    cudaError_t ensure(size_t count) {
-        if (count <= n) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; n = 0;
-        cudaError_t e = cudaMallocHost((void**)&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
-};
 
 }  // namespace
 
@@ -309,13 +294,6 @@ int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st) {
     return OBS_OK;
 }
 
-// true for cudaMallocHost / cudaHostRegister memory: such buffers are DMA-ed directly, without the staging copy
-bool is_pinned(const void* p) {
-    cudaPointerAttributes at;
-    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
-}
-
 int check_handle(const obs_extractor* e) {
     if (!e) return fail(OBS_ERR_INVALID, "null extractor handle");
     cudaError_t ce = cudaSetDevice(e->device);
@@ -327,7 +305,7 @@ int check_handle(const obs_extractor* e) {
 
 extern "C" {
 
-const char* obs_last_error(void) { return g_err; }
+const char* obs_last_error(void) { return obsdetail::g_err; }
 const char* obs_version(void) { return "obslam_b200 0.1 sm_100a"; }
 
 int obs_device_count(void) {
@@ -718,6 +696,20 @@ int obs_stereo_match(obs_extractor* L, obs_extractor* R, float mbf, float min_d,
         memcpy(depth + (size_t)i * cap, hd.data() + (size_t)i * kc, (size_t)m * 4);
     }
     return OBS_OK;
+}
+
+int obs_frame_set_from_extractor(obs_frame_set* fs, obs_extractor* e, const float* d_u_right) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (!fs) return fail(OBS_ERR_INVALID, "null frame set");
+    if (e->lastN < 1) return fail(OBS_ERR_STATE, "no extraction yet");
+    if (obs_frame_set_capacity(fs) < e->g.kpCap)
+        return fail(OBS_ERR_CAPACITY, "frame set keypoint capacity %d < extractor capacity %d", obs_frame_set_capacity(fs), e->g.kpCap);
+    if (d_u_right && !is_device(d_u_right)) return fail(OBS_ERR_INVALID, "d_u_right must be device memory");
+    const uint8_t* rec = e->records.p;
+    return obs_frame_set_build_device(fs, rec + OBS_HDR_INTS * 4, e->recordBytes, rec + OBS_HDR_INTS * 4 + (size_t)e->g.kpCap * 28,
+                                      e->recordBytes, d_u_right, (size_t)e->g.kpCap, reinterpret_cast<const int*>(rec),
+                                      e->recordBytes / 4, e->lastN, e->lastStream);
 }
 
 int obs_host_alloc(size_t bytes, void** out) {

@@ -1,0 +1,49 @@
+// Host-side helpers shared by the C-ABI translation units (api.cu, matcher_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+
+namespace obsdetail {
+int fail(int code, const char* fmt, ...);     // records the thread-local message of obs_last_error(), returns code
+bool is_pinned(const void* p);                // page-locked host memory
+bool is_device(const void* p);                // device (or managed) memory
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+template <typename T> struct PinBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMallocHost((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+}  // namespace obsdetail
+using obsdetail::fail;
+using obsdetail::is_pinned;
+using obsdetail::is_device;
+using obsdetail::DevBuf;
+using obsdetail::PinBuf;
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(OBS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)

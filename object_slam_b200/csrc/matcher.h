@@ -1,0 +1,89 @@
+// Device-side argument blocks and launchers of the matcher kernels (matcher.cu).
+#pragma once
+#include "common.cuh"
+
+#define OBS_GRID_COLS 64          // FRAME_GRID_COLS, include/Frame.h:41
+#define OBS_GRID_ROWS 48          // FRAME_GRID_ROWS, include/Frame.h:42
+#define OBS_GRID_CELLS (OBS_GRID_COLS * OBS_GRID_ROWS)
+#define OBS_HISTO_LENGTH 30       // src/ORBmatcher.cc:39
+#define OBS_CAND_SLOTS 8          // cached candidates per projected point (more -> traversal on demand)
+
+struct FrameParamsDev {
+    float minX, maxX, minY, maxY, invW, invH;
+    float fx, fy, cx, cy, mbf, mb;
+    int nlevels;
+    float scale[OBS_MAX_LEVELS];
+};
+
+// B frames, `cap` keypoint slots each.
+struct FrameSetDev {
+    int cap;
+    int* n;                  // [B]
+    float4* kp;              // [B][cap]   x, y, uRight, octave (int bits)
+    float* angle;            // [B][cap]
+    uint4* desc;             // [B][cap][2]
+    int* cellStart;          // [B][OBS_GRID_CELLS + 1]   CSR of mGrid[ix][iy], cell = ix*48 + iy
+    uint16_t* cellIdx;       // [B][cap]
+    FrameParamsDev P;
+};
+
+// Source of a frame-set build: AoS keypoints (28-byte cv::KeyPoint records) + descriptors + uRight.
+struct FrameBuildArgs {
+    FrameSetDev F;
+    const uint8_t* keys;  size_t keysFrameStride;     // bytes between frames
+    const uint8_t* desc;  size_t descFrameStride;     // bytes
+    const float* uRight;  size_t uRightFrameStride;   // floats; uRight may be null
+    const int* count;     size_t countStrideInts;     // keypoints of frame b = count[b * countStrideInts]
+};
+cudaError_t launch_frame_build(const FrameBuildArgs& a, int nFrames, cudaStream_t st);
+
+struct MapPointDev {          // SearchByProjection(Frame&, vector<MapPoint*>, th)
+    int n; size_t stride;     // stride (entries) between frames, 0 = shared
+    const uint8_t* inView; const float* projX; const float* projY; const float* projXR;
+    const int* level; const float* viewCos; const uint4* desc; const int* obs;
+};
+struct LastFrameDev {         // SearchByProjection(Frame& Current, const Frame& Last, th, bMono)
+    int n; size_t stride;
+    const uint8_t* hasPoint; const float* pos; const int* octave; const float* angle;
+    const uint4* desc; const int* obs;
+    const float* tcwLast; const float* tcwCur;      // [B][12]
+    int mono, checkOri;
+};
+struct ProjSearchArgs {
+    FrameSetDev F;
+    MapPointDev mp;
+    LastFrameDev lf;
+    float th, nnratio;
+    const int* kpObs;         // [B][cap] or null
+    uint32_t* cand;           // [B][M][OBS_CAND_SLOTS]
+    int* choice;              // [B][M]
+    int* kpMatch;             // [B][cap]
+    int* nMatches;            // [B]
+    int* rounds;              // [B] resolution rounds (diagnostics)
+};
+// variant 0: map points (ORBmatcher.cc:45-129); 1: last frame (:1328-1470)
+cudaError_t launch_proj_search(const ProjSearchArgs& a, int variant, int nFrames, cudaStream_t st);
+
+struct InitSearchArgs {       // SearchForInitialization (:405-520)
+    FrameSetDev F1, F2;
+    float* prevMatched;       // [B][cap1][2]
+    int* matches12;           // [B][cap1]
+    int* nMatches;            // [B]
+    uint32_t* list;           // [B][cap1][listCap]  dist << 16 | i2, in GetFeaturesInArea order
+    int* listCount;           // [B][cap1]
+    int listCap;
+    int window; float nnratio; int checkOri;
+};
+cudaError_t launch_init_search(const InitSearchArgs& a, int nFrames, cudaStream_t st);
+
+cudaError_t launch_three_maxima(const int* binSizes, int nHist, int length, int* ind, cudaStream_t st);
+cudaError_t launch_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int* dist, cudaStream_t st);
+
+struct Knn2Args {
+    const uint4* desc;        // [K][n][2]
+    int n;
+    const int2* pairs; int nPairs;
+    int thLow; float nnratio;
+    int* bestIdx; int* bestDist; int* secondDist;   // [P][n]; the last two may be null
+};
+cudaError_t launch_knn2(const Knn2Args& a, cudaStream_t st);

@@ -1,0 +1,443 @@
+// C ABI of the matchers (include/obslam_b200.h, "Matchers"): handles, staging of host arrays,
+// launches.  No matching arithmetic happens on the host.
+#include "../../include/obslam_b200.h"
+#include "matcher.h"
+#include "matcher_api.h"
+#include "host_util.h"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+struct obs_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    // staging slots for host inputs / device copies of host outputs
+    static constexpr int SLOTS = 24;
+    DevBuf<uint8_t> slot[SLOTS];
+    DevBuf<uint32_t> cand;
+    DevBuf<int> choice, rounds;
+    DevBuf<uint32_t> initList;
+    DevBuf<int> initCount;
+    std::vector<int> lastRounds;
+};
+
+struct obs_frame_set {
+    obs_matcher* m = nullptr;
+    obs_frame_params prm;
+    int maxFrames = 0, cap = 0;
+    int nFrames = 0;
+    FrameSetDev d{};
+    DevBuf<int> n, cellStart;
+    DevBuf<float4> kp;
+    DevBuf<float> angle;
+    DevBuf<uint4> desc;
+    DevBuf<uint16_t> cellIdx;
+    // upload staging
+    PinBuf<uint8_t> hStage;
+    DevBuf<uint8_t> dStage;
+};
+
+namespace {
+
+int check_matcher(const obs_matcher* m) {
+    if (!m) return fail(OBS_ERR_INVALID, "null matcher handle");
+    cudaError_t ce = cudaSetDevice(m->device);
+    if (ce != cudaSuccess) return fail(OBS_ERR_CUDA, "cudaSetDevice(%d): %s", m->device, cudaGetErrorString(ce));
+    return OBS_OK;
+}
+
+// Device view of an input array: device pointers pass through, host arrays are copied into staging slot `s`.
+template <typename T> int dev_in(obs_matcher* m, int s, const T* p, size_t count, const T** out) {
+    *out = nullptr;
+    if (!p || count == 0) return OBS_OK;
+    if (is_device(p)) { *out = p; return OBS_OK; }
+    const size_t bytes = count * sizeof(T);
+    CU(m->slot[s].ensure((bytes + 15) & ~(size_t)15));
+    CU(cudaMemcpyAsync(m->slot[s].p, p, bytes, cudaMemcpyHostToDevice, m->stream));
+    *out = reinterpret_cast<const T*>(m->slot[s].p);
+    return OBS_OK;
+}
+
+// Device buffer an output is produced in: the caller's own array if it is device memory, else slot `s`.
+template <typename T> int dev_out(obs_matcher* m, int s, T* p, size_t count, T** out) {
+    *out = nullptr;
+    if (!p || count == 0) return OBS_OK;
+    if (is_device(p)) { *out = p; return OBS_OK; }
+    CU(m->slot[s].ensure((count * sizeof(T) + 15) & ~(size_t)15));
+    *out = reinterpret_cast<T*>(m->slot[s].p);
+    return OBS_OK;
+}
+
+// Copy a staged output back to a host array (no-op for device outputs).  Returns whether a copy was queued.
+template <typename T> int host_back(obs_matcher* m, T* hostp, const T* devp, size_t count, bool* queued) {
+    if (!hostp || !devp || count == 0 || (const void*)hostp == (const void*)devp) return OBS_OK;
+    CU(cudaMemcpyAsync(hostp, devp, count * sizeof(T), cudaMemcpyDeviceToHost, m->stream));
+    *queued = true;
+    return OBS_OK;
+}
+
+FrameParamsDev to_dev(const obs_frame_params& p) {
+    FrameParamsDev d;
+    memset(&d, 0, sizeof(d));
+    d.minX = p.min_x; d.maxX = p.max_x; d.minY = p.min_y; d.maxY = p.max_y;
+    d.invW = (float)OBS_GRID_COLS / (p.max_x - p.min_x);       // Frame.cc:101-102
+    d.invH = (float)OBS_GRID_ROWS / (p.max_y - p.min_y);
+    d.fx = p.fx; d.fy = p.fy; d.cx = p.cx; d.cy = p.cy; d.mbf = p.mbf; d.mb = p.mb;
+    d.nlevels = p.nlevels;
+    for (int i = 0; i < p.nlevels && i < OBS_MAX_LEVELS; i++) d.scale[i] = p.scale_factors[i];
+    return d;
+}
+
+}  // namespace
+
+int obs_frame_set_build_device(obs_frame_set* fs, const uint8_t* keys, size_t keysFrameStride, const uint8_t* desc,
+                               size_t descFrameStride, const float* uRight, size_t uRightFrameStride, const int* count,
+                               size_t countStrideInts, int nFrames, cudaStream_t producer) {
+    int rc = check_matcher(fs ? fs->m : nullptr);
+    if (rc) return rc;
+    if (nFrames < 1 || nFrames > fs->maxFrames) return fail(OBS_ERR_CAPACITY, "%d frames exceed the set's capacity %d", nFrames, fs->maxFrames);
+    obs_matcher* m = fs->m;
+    if (producer && producer != m->stream) {
+        CU(cudaEventRecord(m->ev, producer));
+        CU(cudaStreamWaitEvent(m->stream, m->ev, 0));
+    }
+    FrameBuildArgs a;
+    a.F = fs->d;
+    a.keys = keys; a.keysFrameStride = keysFrameStride;
+    a.desc = desc; a.descFrameStride = descFrameStride;
+    a.uRight = uRight; a.uRightFrameStride = uRightFrameStride;
+    a.count = count; a.countStrideInts = countStrideInts;
+    CU(launch_frame_build(a, nFrames, m->stream));
+    fs->nFrames = nFrames;
+    return OBS_OK;
+}
+
+extern "C" {
+
+int obs_matcher_create(int device, obs_matcher** out) {
+    if (!out) return fail(OBS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(OBS_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(OBS_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(OBS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    obs_matcher* m = new (std::nothrow) obs_matcher;
+    if (!m) return fail(OBS_ERR_INVALID, "out of host memory");
+    m->device = device;
+    cudaError_t se = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&m->ev, cudaEventDisableTiming);
+    if (se != cudaSuccess) { delete m; return fail(OBS_ERR_CUDA, "stream/event creation: %s", cudaGetErrorString(se)); }
+    *out = m;
+    return OBS_OK;
+}
+
+int obs_matcher_destroy(obs_matcher* m) {
+    if (!m) return OBS_OK;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (auto& s : m->slot) s.release();
+    m->cand.release(); m->choice.release(); m->rounds.release(); m->initList.release(); m->initCount.release();
+    if (m->ev) cudaEventDestroy(m->ev);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return OBS_OK;
+}
+
+void* obs_matcher_stream(obs_matcher* m) { return m ? (void*)m->stream : nullptr; }
+
+int obs_matcher_sync(obs_matcher* m) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
+int obs_matcher_last_rounds(obs_matcher* m, int32_t* rounds, int cap) {
+    if (!m || !rounds) return fail(OBS_ERR_INVALID, "null argument");
+    const int n = (int)m->lastRounds.size();
+    for (int i = 0; i < n && i < cap; i++) rounds[i] = m->lastRounds[i];
+    return n;
+}
+
+int obs_frame_set_create(obs_matcher* m, const obs_frame_params* params, int max_frames, int max_keypoints, obs_frame_set** out) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!params || !out) return fail(OBS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (max_frames < 1 || max_keypoints < 1 || max_keypoints > 65535) return fail(OBS_ERR_INVALID, "max_frames >= 1 and 1 <= max_keypoints <= 65535 required");
+    if (params->nlevels < 1 || params->nlevels > OBS_MAX_LEVELS) return fail(OBS_ERR_INVALID, "nlevels must be in [1,%d]", OBS_MAX_LEVELS);
+    if (!(params->max_x > params->min_x) || !(params->max_y > params->min_y)) return fail(OBS_ERR_INVALID, "empty image bounds");
+    obs_frame_set* fs = new (std::nothrow) obs_frame_set;
+    if (!fs) return fail(OBS_ERR_INVALID, "out of host memory");
+    fs->m = m;
+    fs->prm = *params;
+    fs->maxFrames = max_frames;
+    fs->cap = (max_keypoints + 31) & ~31;
+    const size_t B = (size_t)max_frames, cap = (size_t)fs->cap;
+    cudaError_t e = fs->n.ensure(B);
+    if (e == cudaSuccess) e = fs->kp.ensure(B * cap);
+    if (e == cudaSuccess) e = fs->angle.ensure(B * cap);
+    if (e == cudaSuccess) e = fs->desc.ensure(B * cap * 2);
+    if (e == cudaSuccess) e = fs->cellStart.ensure(B * (OBS_GRID_CELLS + 1));
+    if (e == cudaSuccess) e = fs->cellIdx.ensure(B * cap);
+    if (e != cudaSuccess) { obs_frame_set_destroy(fs); return fail(OBS_ERR_CUDA, "frame set allocation: %s", cudaGetErrorString(e)); }
+    fs->d.cap = fs->cap;
+    fs->d.n = fs->n.p; fs->d.kp = fs->kp.p; fs->d.angle = fs->angle.p; fs->d.desc = fs->desc.p;
+    fs->d.cellStart = fs->cellStart.p; fs->d.cellIdx = fs->cellIdx.p;
+    fs->d.P = to_dev(*params);
+    *out = fs;
+    return OBS_OK;
+}
+
+int obs_frame_set_destroy(obs_frame_set* fs) {
+    if (!fs) return OBS_OK;
+    if (fs->m) { cudaSetDevice(fs->m->device); cudaStreamSynchronize(fs->m->stream); }
+    fs->n.release(); fs->kp.release(); fs->angle.release(); fs->desc.release(); fs->cellStart.release(); fs->cellIdx.release();
+    fs->hStage.release(); fs->dStage.release();
+    delete fs;
+    return OBS_OK;
+}
+
+int obs_frame_set_count(const obs_frame_set* fs) { return fs ? fs->nFrames : -1; }
+}
+int obs_frame_set_capacity(const obs_frame_set* fs) { return fs ? fs->cap : -1; }
+extern "C" {
+
+int obs_frame_set_upload(obs_frame_set* fs, const obs_frame_view* frames, int n_frames) {
+    int rc = check_matcher(fs ? fs->m : nullptr);
+    if (rc) return rc;
+    if (!frames || n_frames < 1) return fail(OBS_ERR_INVALID, "no frames");
+    if (n_frames > fs->maxFrames) return fail(OBS_ERR_CAPACITY, "%d frames exceed the set's capacity %d", n_frames, fs->maxFrames);
+    obs_matcher* m = fs->m;
+    const size_t cap = (size_t)fs->cap;
+    // staging record per frame: count (16 bytes) | keys cap x 28 | desc cap x 32 | uRight cap x 4
+    const size_t keysOff = 16, descOff = keysOff + cap * 28, urOff = descOff + cap * 32, frameBytes = urOff + cap * 4;
+    CU(fs->dStage.ensure((size_t)fs->maxFrames * frameBytes));
+    CU(cudaStreamSynchronize(m->stream));         // the previous upload may still read the host staging buffer
+    CU(fs->hStage.ensure((size_t)fs->maxFrames * frameBytes));
+    bool anyUr = false;
+    for (int b = 0; b < n_frames; b++) anyUr |= frames[b].u_right != nullptr;
+    for (int b = 0; b < n_frames; b++) {
+        const obs_frame_view& f = frames[b];
+        if (f.n < 0 || f.n > fs->cap) return fail(OBS_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d", b, f.n, fs->cap);
+        if (f.n > 0 && (!f.keys_un || !f.descriptors)) return fail(OBS_ERR_INVALID, "frame %d: null keypoints or descriptors", b);
+        uint8_t* rec = fs->hStage.p + (size_t)b * frameBytes;
+        *reinterpret_cast<int*>(rec) = f.n;
+        if (f.n > 0 && (is_device(f.keys_un) || is_device(f.descriptors) || (f.u_right && is_device(f.u_right))))
+            return fail(OBS_ERR_INVALID, "obs_frame_set_upload takes host arrays (use obs_frame_set_from_extractor for device data)");
+        memcpy(rec + keysOff, f.keys_un, (size_t)f.n * 28);
+        memcpy(rec + descOff, f.descriptors, (size_t)f.n * 32);
+        float* ur = reinterpret_cast<float*>(rec + urOff);
+        if (f.u_right) memcpy(ur, f.u_right, (size_t)f.n * 4);
+        else if (anyUr) for (int i = 0; i < f.n; i++) ur[i] = -1.0f;
+    }
+    CU(cudaMemcpyAsync(fs->dStage.p, fs->hStage.p, (size_t)n_frames * frameBytes, cudaMemcpyHostToDevice, m->stream));
+    return obs_frame_set_build_device(fs, fs->dStage.p + keysOff, frameBytes, fs->dStage.p + descOff, frameBytes,
+                                      anyUr ? reinterpret_cast<const float*>(fs->dStage.p + urOff) : nullptr, frameBytes / 4,
+                                      reinterpret_cast<const int*>(fs->dStage.p), frameBytes / 4, n_frames, nullptr);
+}
+
+int obs_frame_set_grid(obs_frame_set* fs, int frame, int32_t* cell_start, int32_t* cell_idx, int cap) {
+    int rc = check_matcher(fs ? fs->m : nullptr);
+    if (rc) return rc;
+    if (frame < 0 || frame >= fs->nFrames || !cell_start) return fail(OBS_ERR_INVALID, "bad frame index or null output");
+    CU(cudaStreamSynchronize(fs->m->stream));
+    CU(cudaMemcpy(cell_start, fs->cellStart.p + (size_t)frame * (OBS_GRID_CELLS + 1), (OBS_GRID_CELLS + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    if (cell_idx) {
+        const int total = cell_start[OBS_GRID_CELLS];
+        if (total > cap) return fail(OBS_ERR_CAPACITY, "cell_idx capacity %d < %d", cap, total);
+        std::vector<uint16_t> tmp((size_t)std::max(total, 1));
+        if (total) CU(cudaMemcpy(tmp.data(), fs->cellIdx.p + (size_t)frame * fs->cap, (size_t)total * 2, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < total; i++) cell_idx[i] = tmp[i];
+    }
+    return OBS_OK;
+}
+
+static int run_proj(obs_matcher* m, obs_frame_set* fs, ProjSearchArgs& a, int variant, int M, const int32_t* kp_observations,
+                    int32_t* kp_match, int32_t* n_matches) {
+    const int B = fs->nFrames;
+    const size_t kc = (size_t)B * fs->cap;
+    int rc;
+    if ((rc = dev_in(m, 20, kp_observations, kp_observations ? kc : 0, &a.kpObs))) return rc;
+    int *dMatch = nullptr, *dN = nullptr;
+    if ((rc = dev_out(m, 21, kp_match, kc, &dMatch))) return rc;
+    if ((rc = dev_out(m, 22, n_matches, (size_t)B, &dN))) return rc;
+    CU(m->cand.ensure((size_t)B * std::max(M, 1) * OBS_CAND_SLOTS));
+    CU(m->choice.ensure((size_t)B * std::max(M, 1)));
+    CU(m->rounds.ensure((size_t)B));
+    a.F = fs->d;
+    a.cand = m->cand.p; a.choice = m->choice.p; a.kpMatch = dMatch; a.nMatches = dN; a.rounds = m->rounds.p;
+    CU(launch_proj_search(a, variant, B, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, kp_match, dMatch, kc, &queued))) return rc;
+    if ((rc = host_back(m, n_matches, dN, (size_t)B, &queued))) return rc;
+    if (queued) {
+        m->lastRounds.resize(B);
+        CU(cudaMemcpyAsync(m->lastRounds.data(), m->rounds.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+    }
+    return OBS_OK;
+}
+
+int obs_search_by_projection(obs_matcher* m, obs_frame_set* frames, const obs_mappoint_view* pts, float th, float nnratio,
+                             const int32_t* kp_observations, int32_t* kp_match, int32_t* n_matches) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!frames || !pts || !kp_match || !n_matches) return fail(OBS_ERR_INVALID, "null argument");
+    if (frames->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if (frames->nFrames < 1) return fail(OBS_ERR_STATE, "frame set is empty");
+    if (pts->n < 0) return fail(OBS_ERR_INVALID, "negative point count");
+    if (pts->n > 0 && (!pts->in_view || !pts->proj_x || !pts->proj_y || !pts->proj_xr || !pts->scale_level || !pts->view_cos ||
+                       !pts->descriptors || !pts->observations))
+        return fail(OBS_ERR_INVALID, "null map point array");
+    const int B = frames->nFrames, M = pts->n;
+    const size_t cnt = (size_t)M * (pts->per_frame ? B : 1);
+    ProjSearchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mp.n = M; a.mp.stride = pts->per_frame ? (size_t)M : 0;
+    const uint8_t* dsc = nullptr;
+    if ((rc = dev_in(m, 0, pts->in_view, cnt, &a.mp.inView))) return rc;
+    if ((rc = dev_in(m, 1, pts->proj_x, cnt, &a.mp.projX))) return rc;
+    if ((rc = dev_in(m, 2, pts->proj_y, cnt, &a.mp.projY))) return rc;
+    if ((rc = dev_in(m, 3, pts->proj_xr, cnt, &a.mp.projXR))) return rc;
+    if ((rc = dev_in(m, 4, pts->scale_level, cnt, &a.mp.level))) return rc;
+    if ((rc = dev_in(m, 5, pts->view_cos, cnt, &a.mp.viewCos))) return rc;
+    if ((rc = dev_in(m, 6, pts->descriptors, cnt * 32, &dsc))) return rc;
+    if ((rc = dev_in(m, 7, pts->observations, cnt, &a.mp.obs))) return rc;
+    if ((uintptr_t)dsc & 15) return fail(OBS_ERR_INVALID, "device descriptors must be 16-byte aligned");
+    a.mp.desc = reinterpret_cast<const uint4*>(dsc);
+    a.th = th; a.nnratio = nnratio;
+    return run_proj(m, frames, a, 0, M, kp_observations, kp_match, n_matches);
+}
+
+int obs_search_by_projection_last(obs_matcher* m, obs_frame_set* cur, const obs_lastframe_view* last, float th, int mono,
+                                  int check_orientation, const int32_t* kp_observations, int32_t* kp_match, int32_t* n_matches) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!cur || !last || !kp_match || !n_matches) return fail(OBS_ERR_INVALID, "null argument");
+    if (cur->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if (cur->nFrames < 1) return fail(OBS_ERR_STATE, "frame set is empty");
+    if (last->n < 0) return fail(OBS_ERR_INVALID, "negative point count");
+    if (!last->tcw_last || !last->tcw_current) return fail(OBS_ERR_INVALID, "null pose");
+    if (last->n > 0 && (!last->has_point || !last->world_pos || !last->octave || !last->angle || !last->descriptors || !last->observations))
+        return fail(OBS_ERR_INVALID, "null last-frame array");
+    const int B = cur->nFrames, M = last->n;
+    const size_t cnt = (size_t)M * (last->per_frame ? B : 1);
+    ProjSearchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.lf.n = M; a.lf.stride = last->per_frame ? (size_t)M : 0;
+    const uint8_t* dsc = nullptr;
+    if ((rc = dev_in(m, 0, last->has_point, cnt, &a.lf.hasPoint))) return rc;
+    if ((rc = dev_in(m, 1, last->world_pos, cnt * 3, &a.lf.pos))) return rc;
+    if ((rc = dev_in(m, 2, last->octave, cnt, &a.lf.octave))) return rc;
+    if ((rc = dev_in(m, 3, last->angle, cnt, &a.lf.angle))) return rc;
+    if ((rc = dev_in(m, 4, last->descriptors, cnt * 32, &dsc))) return rc;
+    if ((rc = dev_in(m, 5, last->observations, cnt, &a.lf.obs))) return rc;
+    if ((rc = dev_in(m, 6, last->tcw_last, (size_t)B * 12, &a.lf.tcwLast))) return rc;
+    if ((rc = dev_in(m, 7, last->tcw_current, (size_t)B * 12, &a.lf.tcwCur))) return rc;
+    if ((uintptr_t)dsc & 15) return fail(OBS_ERR_INVALID, "device descriptors must be 16-byte aligned");
+    a.lf.desc = reinterpret_cast<const uint4*>(dsc);
+    a.lf.mono = mono != 0; a.lf.checkOri = check_orientation != 0;
+    a.th = th; a.nnratio = 0.f;
+    return run_proj(m, cur, a, 1, M, kp_observations, kp_match, n_matches);
+}
+
+int obs_search_for_initialization(obs_matcher* m, obs_frame_set* f1, obs_frame_set* f2, float* prev_matched, int32_t* matches12,
+                                  int window_size, float nnratio, int check_orientation, int32_t* n_matches) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!f1 || !f2 || !prev_matched || !matches12 || !n_matches) return fail(OBS_ERR_INVALID, "null argument");
+    if (f1->m != m || f2->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if (f1->nFrames < 1 || f1->nFrames != f2->nFrames) return fail(OBS_ERR_STATE, "both frame sets must hold the same number (>= 1) of frames");
+    const int B = f1->nFrames;
+    const size_t c1 = (size_t)B * f1->cap;
+    InitSearchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.F1 = f1->d; a.F2 = f2->d;
+    const float* pmIn = nullptr;
+    if ((rc = dev_in(m, 0, (const float*)prev_matched, c1 * 2, &pmIn))) return rc;
+    a.prevMatched = const_cast<float*>(pmIn);
+    if ((rc = dev_out(m, 1, matches12, c1, &a.matches12))) return rc;
+    if ((rc = dev_out(m, 2, n_matches, (size_t)B, &a.nMatches))) return rc;
+    a.listCap = f2->cap;
+    CU(m->initList.ensure(c1 * (size_t)a.listCap));
+    CU(m->initCount.ensure(c1));
+    a.list = m->initList.p; a.listCount = m->initCount.p;
+    a.window = window_size; a.nnratio = nnratio; a.checkOri = check_orientation != 0;
+    CU(launch_init_search(a, B, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, prev_matched, a.prevMatched, c1 * 2, &queued))) return rc;
+    if ((rc = host_back(m, matches12, a.matches12, c1, &queued))) return rc;
+    if ((rc = host_back(m, n_matches, a.nMatches, (size_t)B, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
+int obs_compute_three_maxima(obs_matcher* m, const int32_t* bin_sizes, int n_hist, int length, int32_t* ind) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!bin_sizes || !ind || n_hist < 1 || length < 1) return fail(OBS_ERR_INVALID, "bad argument");
+    const int* dIn = nullptr; int* dOut = nullptr;
+    if ((rc = dev_in(m, 0, bin_sizes, (size_t)n_hist * length, &dIn))) return rc;
+    if ((rc = dev_out(m, 1, ind, (size_t)n_hist * 3, &dOut))) return rc;
+    CU(launch_three_maxima(dIn, n_hist, length, dOut, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, ind, dOut, (size_t)n_hist * 3, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
+int obs_descriptor_distance(obs_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!a || !b || !dist || n < 1) return fail(OBS_ERR_INVALID, "bad argument");
+    const uint8_t *da = nullptr, *db = nullptr; int* dd = nullptr;
+    if ((rc = dev_in(m, 0, a, (size_t)n * 32, &da))) return rc;
+    if ((rc = dev_in(m, 1, b, (size_t)n * 32, &db))) return rc;
+    if (((uintptr_t)da | (uintptr_t)db) & 3) return fail(OBS_ERR_INVALID, "device descriptors must be 4-byte aligned");
+    if ((rc = dev_out(m, 2, dist, (size_t)n, &dd))) return rc;
+    CU(launch_descriptor_distance(da, db, n, dd, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, dist, dd, (size_t)n, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
+int obs_hamming_knn2(obs_matcher* m, const uint8_t* descriptors, int n_keyframes, int n_desc, const int32_t* pairs, int n_pairs,
+                     int th_low, float nnratio, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!descriptors || !pairs || !best_idx) return fail(OBS_ERR_INVALID, "null argument");
+    if (n_keyframes < 1 || n_desc < 1 || n_desc > 65535 || n_pairs < 1) return fail(OBS_ERR_INVALID, "sizes out of range (1 <= n_desc <= 65535)");
+    const uint8_t* dd = nullptr; const int* dp = nullptr;
+    if ((rc = dev_in(m, 0, descriptors, (size_t)n_keyframes * n_desc * 32, &dd))) return rc;
+    if ((uintptr_t)dd & 15) return fail(OBS_ERR_INVALID, "device descriptors must be 16-byte aligned");
+    if ((rc = dev_in(m, 1, pairs, (size_t)n_pairs * 2, &dp))) return rc;
+    if (!is_device(pairs))
+        for (int i = 0; i < 2 * n_pairs; i++)
+            if (pairs[i] < 0 || pairs[i] >= n_keyframes) return fail(OBS_ERR_INVALID, "pair %d names keyframe %d of %d", i / 2, pairs[i], n_keyframes);
+    const size_t cnt = (size_t)n_pairs * n_desc;
+    Knn2Args a;
+    a.desc = reinterpret_cast<const uint4*>(dd);
+    a.n = n_desc; a.pairs = reinterpret_cast<const int2*>(dp); a.nPairs = n_pairs;
+    a.thLow = th_low; a.nnratio = nnratio;
+    if ((rc = dev_out(m, 2, best_idx, cnt, &a.bestIdx))) return rc;
+    if ((rc = dev_out(m, 3, best_dist, best_dist ? cnt : 0, &a.bestDist))) return rc;
+    if ((rc = dev_out(m, 4, second_dist, second_dist ? cnt : 0, &a.secondDist))) return rc;
+    CU(launch_knn2(a, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, best_idx, a.bestIdx, cnt, &queued))) return rc;
+    if ((rc = host_back(m, best_dist, a.bestDist, cnt, &queued))) return rc;
+    if ((rc = host_back(m, second_dist, a.secondDist, cnt, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+"""Host-side mirror of the reference's ``ORB_SLAM2::ORBmatcher`` (include/ORBmatcher.h:37-102) over the
+C ABI, for the searches Tracking runs on every frame.  The reference walks Frame / MapPoint objects;
+here the same quantities are flat arrays named after the members they come from.  Every array
+argument may be a numpy array (host memory) or an ``int`` device address (e.g. ``tensor.data_ptr()``);
+the work runs in the CUDA kernels of ``csrc/matcher.cu`` -- there is no CPU implementation behind this.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._capi import (KEYPOINT_DTYPE, FrameParams, FrameView, LastFrameView, MapPointView, addr, check, lib, ptr)
+
+FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48       # include/Frame.h:41-42
+
+
+def _f32(a):
+    return a if isinstance(a, int) or a is None else np.ascontiguousarray(a, np.float32)
+
+
+def _i32(a):
+    return a if isinstance(a, int) or a is None else np.ascontiguousarray(a, np.int32)
+
+
+def _u8(a):
+    return a if isinstance(a, int) or a is None else np.ascontiguousarray(a, np.uint8)
+
+
+class FrameSet:
+    """A batch of frames as the matchers see them (mvKeysUn, mDescriptors, mvuRight, image bounds, camera,
+    the 64x48 grid built on the device).  ``bounds`` = (mnMinX, mnMaxX, mnMinY, mnMaxY); ``camera`` =
+    (fx, fy, cx, cy, mbf, mb)."""
+
+    def __init__(self, matcher, scale_factors, bounds, camera=(1, 1, 0, 0, 0, 0), max_frames=1, max_keypoints=2048):
+        self.matcher = matcher
+        prm = FrameParams()
+        prm.min_x, prm.max_x, prm.min_y, prm.max_y = (float(b) for b in bounds)
+        prm.fx, prm.fy, prm.cx, prm.cy, prm.mbf, prm.mb = (float(c) for c in camera)
+        sf = np.asarray(scale_factors, np.float32)
+        prm.nlevels = len(sf)
+        for i, v in enumerate(sf):
+            prm.scale_factors[i] = float(v)
+        self.scale_factors = sf
+        self._h = C.c_void_p()
+        check(lib().obs_frame_set_create(matcher._h, C.byref(prm), int(max_frames), int(max_keypoints), C.byref(self._h)))
+        self.max_frames = int(max_frames)
+        self.cap = (int(max_keypoints) + 31) & ~31
+        self.counts = []
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().obs_frame_set_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def upload(self, frames):
+        """frames: list of (keys_un, descriptors, u_right or None) host arrays."""
+        views = (FrameView * len(frames))()
+        keep = []
+        for v, (k, d, ur) in zip(views, frames):
+            k = np.ascontiguousarray(k, KEYPOINT_DTYPE)
+            d = _u8(d)
+            ur = _f32(ur)
+            keep.append((k, d, ur))
+            v.n = len(k)
+            v.keys_un, v.descriptors, v.u_right = addr(k), addr(d), addr(ur)
+        check(lib().obs_frame_set_upload(self._h, views, len(frames)))
+        self.counts = [len(k) for k, _, _ in keep]
+        return self
+
+    def from_extractor(self, extractor, d_u_right=None):
+        check(lib().obs_frame_set_from_extractor(self._h, extractor._h, ptr(d_u_right)))
+        self.counts = None
+        return self
+
+    def __len__(self):
+        return lib().obs_frame_set_count(self._h)
+
+    def grid(self, frame=0):
+        start = np.empty(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, np.int32)
+        idx = np.empty(self.cap, np.int32)
+        check(lib().obs_frame_set_grid(self._h, frame, ptr(start), ptr(idx), self.cap))
+        return start, idx[:start[-1]].copy()
+
+
+class ORBmatcher:
+    """``ORBmatcher(nnratio=0.6, checkOri=True)`` -- ORBmatcher.h:41."""
+
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30      # ORBmatcher.cc:37-39
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        self._h = C.c_void_p()
+        check(lib().obs_matcher_create(int(device), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().obs_matcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    @property
+    def stream(self):
+        return lib().obs_matcher_stream(self._h)
+
+    def sync(self):
+        check(lib().obs_matcher_sync(self._h))
+
+    def last_rounds(self):
+        out = np.zeros(4096, np.int32)
+        n = lib().obs_matcher_last_rounds(self._h, ptr(out), len(out))
+        return out[:max(n, 0)].copy()
+
+    def frame_set(self, *args, **kw):
+        return FrameSet(self, *args, **kw)
+
+    # ---- ORBmatcher.cc:1647-1663
+    def DescriptorDistance(self, a, b):
+        a = _u8(a).reshape(-1, 32)
+        b = _u8(b).reshape(-1, 32)
+        out = np.empty(len(a), np.int32)
+        check(lib().obs_descriptor_distance(self._h, ptr(a), ptr(b), len(a), ptr(out)))
+        return out
+
+    # ---- ORBmatcher.cc:1601-1642
+    def ComputeThreeMaxima(self, bin_sizes):
+        h = _i32(bin_sizes)
+        h2 = h.reshape(-1, h.shape[-1])
+        ind = np.empty((len(h2), 3), np.int32)
+        check(lib().obs_compute_three_maxima(self._h, ptr(h2), len(h2), h2.shape[1], ptr(ind)))
+        return ind if h.ndim > 1 else tuple(int(i) for i in ind[0])
+
+    def _outs(self, frames, kp_match, n_matches):
+        B = len(frames)
+        if kp_match is None:
+            kp_match = np.empty((B, frames.cap), np.int32)
+        if n_matches is None:
+            n_matches = np.empty(B, np.int32)
+        return kp_match, n_matches
+
+    # ---- ORBmatcher.cc:45-129
+    def SearchByProjection(self, frames, in_view, proj_x, proj_y, proj_xr, scale_level, view_cos, descriptors,
+                           observations, th=1.0, n_points=None, per_frame=False, kp_observations=None,
+                           kp_match=None, n_matches=None):
+        """SearchByProjection(Frame&, const vector<MapPoint*>&, th) for every frame of ``frames``.  Returns
+        (n_matches[B], kp_match[B, cap]): kp_match[b, k] = index of the map point assigned to keypoint k
+        (-1 = none)."""
+        v = MapPointView()
+        arrs = [_u8(in_view), _f32(proj_x), _f32(proj_y), _f32(proj_xr), _i32(scale_level), _f32(view_cos),
+                _u8(descriptors), _i32(observations)]
+        if n_points is None:
+            n_points = arrs[0].shape[-1] if not isinstance(arrs[0], int) else None
+        v.n, v.per_frame = int(n_points), int(bool(per_frame))
+        (v.in_view, v.proj_x, v.proj_y, v.proj_xr, v.scale_level, v.view_cos, v.descriptors, v.observations) = (addr(a) for a in arrs)
+        kp_match, n_matches = self._outs(frames, kp_match, n_matches)
+        check(lib().obs_search_by_projection(self._h, frames._h, C.byref(v), float(th), self.mfNNratio,
+                                             ptr(_i32(kp_observations)), ptr(kp_match), ptr(n_matches)))
+        return n_matches, kp_match
+
+    # ---- ORBmatcher.cc:1328-1470
+    def SearchByProjectionLast(self, current, has_point, world_pos, octave, angle, descriptors, observations,
+                               tcw_last, tcw_current, th, mono, n_points=None, per_frame=False,
+                               kp_observations=None, kp_match=None, n_matches=None):
+        """SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono).  kp_match: -1 untouched,
+        -2 reset to NULL by the rotation check, else the last-frame keypoint whose map point was assigned."""
+        v = LastFrameView()
+        arrs = [_u8(has_point), _f32(world_pos), _i32(octave), _f32(angle), _u8(descriptors), _i32(observations),
+                _f32(tcw_last), _f32(tcw_current)]
+        if n_points is None:
+            n_points = arrs[0].shape[-1]
+        v.n, v.per_frame = int(n_points), int(bool(per_frame))
+        (v.has_point, v.world_pos, v.octave, v.angle, v.descriptors, v.observations, v.tcw_last, v.tcw_current) = (addr(a) for a in arrs)
+        kp_match, n_matches = self._outs(current, kp_match, n_matches)
+        check(lib().obs_search_by_projection_last(self._h, current._h, C.byref(v), float(th), int(bool(mono)),
+                                                  int(self.mbCheckOrientation), ptr(_i32(kp_observations)),
+                                                  ptr(kp_match), ptr(n_matches)))
+        return n_matches, kp_match
+
+    # ---- ORBmatcher.cc:405-520
+    def SearchForInitialization(self, f1, f2, prev_matched, window_size=10, matches12=None, n_matches=None):
+        """Returns (n_matches[B], vnMatches12[B, cap1]); ``prev_matched`` ([B, cap1, 2] float32) is updated in place."""
+        B = len(f1)
+        if matches12 is None:
+            matches12 = np.empty((B, f1.cap), np.int32)
+        if n_matches is None:
+            n_matches = np.empty(B, np.int32)
+        if not isinstance(prev_matched, int):
+            assert prev_matched.dtype == np.float32 and prev_matched.flags.c_contiguous
+        check(lib().obs_search_for_initialization(self._h, f1._h, f2._h, ptr(prev_matched), ptr(matches12), int(window_size),
+                                                  self.mfNNratio, int(self.mbCheckOrientation), ptr(n_matches)))
+        return n_matches, matches12
+
+    # ---- brute force best / second best + ratio (candidate loop of SearchByBoW, ORBmatcher.cc:200-229)
+    def knn2(self, descriptors, pairs, n_keyframes=None, n_desc=None, th_low=None, best_idx=None, best_dist=None,
+             second_dist=None, want_dists=True):
+        d = _u8(descriptors)
+        if n_keyframes is None:
+            n_keyframes, n_desc = d.shape[0], d.shape[1]
+        pr = _i32(pairs)
+        n_pairs = len(pr) if not isinstance(pr, int) else None
+        if best_idx is None:
+            best_idx = np.empty((n_pairs, n_desc), np.int32)
+            if want_dists:
+                best_dist = np.empty((n_pairs, n_desc), np.int32)
+                second_dist = np.empty((n_pairs, n_desc), np.int32)
+        elif n_pairs is None:
+            raise ValueError("device pair lists need explicit outputs")
+        check(lib().obs_hamming_knn2(self._h, ptr(d), int(n_keyframes), int(n_desc), ptr(pr), int(n_pairs),
+                                     int(self.TH_LOW if th_low is None else th_low), self.mfNNratio,
+                                     ptr(best_idx), ptr(best_dist), ptr(second_dist)))
+        return best_idx, best_dist, second_dist

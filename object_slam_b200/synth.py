@@ -96,3 +96,163 @@ def flip_bits(desc, nflip, rng):
             pos = rng.choice(256, size=k, replace=False)
             np.bitwise_xor.at(out[i], pos >> 3, (1 << (pos & 7)).astype(np.uint8))
     return out
+
+
+# ----------------------------------------------------------------------------- matcher inputs
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")])
+
+
+def scale_factors(nlevels=8, scale_factor=1.2):
+    """mvScaleFactor as the ORBextractor constructor builds it (float * double -> float, ORBextractor.cc:415-420)."""
+    s = np.ones(nlevels, np.float32)
+    for i in range(1, nlevels):
+        s[i] = np.float32(np.float64(s[i - 1]) * np.float64(np.float32(scale_factor)))
+    return s
+
+
+def synthetic_frame(shape, n, seed, nlevels=8, stereo_fraction=0.7, bf=TUM_BF):
+    """A frame as the matchers see it without running the extractor: level-major keypoints with the
+    extractor's per-level share, random descriptors, mvuRight from a synthetic depth (Frame.cc:898-902)
+    for `stereo_fraction` of the keypoints (-1 elsewhere).  Returns (keys, descriptors, u_right)."""
+    h, w = shape
+    rng = np.random.default_rng(seed)
+    sf = scale_factors(nlevels)
+    share = (1 / 1.2) ** np.arange(nlevels)
+    per = np.floor(n * share / share.sum()).astype(int)
+    per[-1] += n - per.sum()
+    keys = np.zeros(n, KEYPOINT_DTYPE)
+    pos = 0
+    for l, c in enumerate(per):
+        lw, lh = w / sf[l], h / sf[l]
+        x = rng.integers(19, max(20, int(lw) - 19), c).astype(np.float32)
+        y = rng.integers(19, max(20, int(lh) - 19), c).astype(np.float32)
+        keys["x"][pos:pos + c] = x * sf[l] if l else x
+        keys["y"][pos:pos + c] = y * sf[l] if l else y
+        keys["octave"][pos:pos + c] = l
+        keys["size"][pos:pos + c] = np.float32(int(31 * sf[l]))
+        pos += c
+    keys["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    keys["response"] = rng.integers(7, 120, n).astype(np.float32)
+    keys["class_id"] = -1
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    z = rng.uniform(0.5, 8.0, n).astype(np.float32)
+    ur = (keys["x"] - np.float32(bf) / z).astype(np.float32)
+    ur[rng.random(n) >= stereo_fraction] = -1.0
+    return keys, desc, ur
+
+
+def map_points_for_frame(keys, desc, shape, n_points, seed, nlevels=8, bf=TUM_BF, anchored=0.5):
+    """cfg3-style local map projected into a frame (the fields Frame::isInFrustum leaves on each MapPoint).
+    A fraction `anchored` of the points sits near the keypoint its descriptor was derived from (sigma 2 px,
+    predicted level = octave or octave+1); the rest is uniform over the image with a uniform level.
+    Descriptors: a frame descriptor with k ~ U{0..60} flipped bits.  Returns a dict of arrays."""
+    h, w = shape
+    rng = np.random.default_rng(seed)
+    n = len(keys)
+    src = rng.integers(0, max(n, 1), n_points)
+    anch = rng.random(n_points) < anchored
+    u = rng.uniform(0, w, n_points).astype(np.float32)
+    v = rng.uniform(0, h, n_points).astype(np.float32)
+    level = rng.integers(0, nlevels, n_points).astype(np.int32)
+    if n:
+        u[anch] = (keys["x"][src[anch]] + rng.normal(0, 2, anch.sum())).astype(np.float32)
+        v[anch] = (keys["y"][src[anch]] + rng.normal(0, 2, anch.sum())).astype(np.float32)
+        level[anch] = np.minimum(keys["octave"][src[anch]] + rng.integers(0, 2, anch.sum()), nlevels - 1)
+        d = flip_bits(desc[src], rng.integers(0, 61, n_points), rng)
+    else:
+        d = rng.integers(0, 256, (n_points, 32), dtype=np.uint8)
+    z = rng.uniform(0.5, 8.0, n_points).astype(np.float32)
+    return dict(in_view=(rng.random(n_points) < 0.95).astype(np.uint8), proj_x=u, proj_y=v,
+                proj_xr=(u - np.float32(bf) / z).astype(np.float32), scale_level=level,
+                view_cos=rng.uniform(0.5, 1.0, n_points).astype(np.float32), descriptors=d,
+                observations=rng.integers(0, 4, n_points).astype(np.int32))
+
+
+def camera_for(shape, bf=TUM_BF):
+    """(fx, fy, cx, cy, mbf, mb) of a pinhole camera filling `shape` (TUM1.yaml-like for 640x480)."""
+    h, w = shape
+    fx = np.float32(0.82 * w)
+    return (float(fx), float(fx), w / 2 - 0.5, h / 2 - 0.5, float(bf), float(np.float32(bf) / fx))
+
+
+def _rot(rx, ry, rz):
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    return (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @
+            np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+
+
+def motion_pair(shape, n, seed, nlevels=8, bf=TUM_BF, forward=0.0):
+    """A last frame with map points and the current frame that re-observes them after a small motion
+    (`forward` metres along the optical axis on top of a random few-centimetre motion).  Returns
+    (last, current): last = dict(has_point, world_pos, octave, angle, descriptors, observations, tcw_last,
+    tcw_current); current = (keys, descriptors, u_right)."""
+    h, w = shape
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, mbf, mb = camera_for(shape, bf)
+    keysL, descL, _ = synthetic_frame(shape, n, seed + 17, nlevels, bf=bf)
+    z = rng.uniform(1.0, 10.0, n)
+    Pc = np.stack([(keysL["x"] - cx) / fx * z, (keysL["y"] - cy) / fy * z, z], 1)
+    Rl = _rot(*rng.normal(0, 0.02, 3)); tl = rng.normal(0, 0.05, 3)
+    Pw = (Pc - tl) @ Rl                     # world = Rl^T (Pc - tl)
+    Rc = _rot(*rng.normal(0, 0.01, 3)) @ Rl
+    tc = tl + rng.normal(0, 0.03, 3) + np.array([0, 0, -forward])
+    Tl = np.hstack([Rl, tl[:, None]]).astype(np.float32)
+    Tc = np.hstack([Rc, tc[:, None]]).astype(np.float32)
+    Pcur = Pw @ Rc.T + tc
+    keysC = keysL.copy()
+    keysC["x"] = (fx * Pcur[:, 0] / Pcur[:, 2] + cx + rng.normal(0, 0.7, n)).astype(np.float32)
+    keysC["y"] = (fy * Pcur[:, 1] / Pcur[:, 2] + cy + rng.normal(0, 0.7, n)).astype(np.float32)
+    rot_noise = rng.normal(0, 4, n)
+    wild = rng.random(n) < 0.1
+    rot_noise[wild] = rng.uniform(0, 360, wild.sum())
+    keysC["angle"] = np.mod(keysL["angle"] + rot_noise, 360).astype(np.float32)
+    descC = flip_bits(descL, rng.integers(0, 50, n), rng)
+    urC = (keysC["x"] - np.float32(mbf) / Pcur[:, 2]).astype(np.float32)
+    urC[rng.random(n) < 0.3] = -1.0
+    perm = rng.permutation(n)               # the current frame lists its keypoints in another order
+    # keep it level-major like a real frame
+    perm = perm[np.argsort(keysC["octave"][perm], kind="stable")]
+    last = dict(has_point=(rng.random(n) < 0.8).astype(np.uint8), world_pos=Pw.astype(np.float32),
+                octave=keysL["octave"].astype(np.int32), angle=keysL["angle"].copy(),
+                descriptors=flip_bits(descL, rng.integers(0, 10, n), rng), observations=rng.integers(0, 3, n).astype(np.int32),
+                tcw_last=Tl, tcw_current=Tc)
+    return last, (keysC[perm], descC[perm], urC[perm])
+
+
+def init_pair(shape, n, seed, nlevels=8):
+    """Two monocular frames for SearchForInitialization: the second re-observes the first after a small
+    image-plane flow.  Returns ((keys1, desc1, None), (keys2, desc2, None), prev_matched[n, 2])."""
+    rng = np.random.default_rng(seed)
+    k1, d1, _ = synthetic_frame(shape, n, seed + 31, nlevels)
+    k2 = k1.copy()
+    flow = rng.normal(0, 6, (n, 2))
+    k2["x"] = (k1["x"] + flow[:, 0]).astype(np.float32)
+    k2["y"] = (k1["y"] + flow[:, 1]).astype(np.float32)
+    rot_noise = rng.normal(0, 4, n)
+    wild = rng.random(n) < 0.1
+    rot_noise[wild] = rng.uniform(0, 360, wild.sum())
+    k2["angle"] = np.mod(k1["angle"] + rot_noise, 360).astype(np.float32)
+    d2 = flip_bits(d1, rng.integers(0, 70, n), rng)
+    # duplicate some descriptors so that several frame-1 keypoints compete for one frame-2 keypoint
+    dup = rng.integers(0, n, n // 10)
+    d1 = d1.copy()
+    d1[dup] = flip_bits(d1[(dup + 1) % n], rng.integers(0, 8, len(dup)), rng)
+    perm = rng.permutation(n)
+    perm = perm[np.argsort(k2["octave"][perm], kind="stable")]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    return (k1, d1, None), (k2[perm], d2[perm], None), prev
+
+
+def keyframe_descriptors(n_keyframes, n_desc, seed, planted=0.3):
+    """cfg5: uniform random descriptors; a fraction `planted` of keyframe i+1's descriptors are noisy copies
+    (0..40 flipped bits) of keyframe i's."""
+    rng = np.random.default_rng(seed)
+    d = rng.integers(0, 256, (n_keyframes, n_desc, 32), dtype=np.uint8)
+    m = int(n_desc * planted)
+    for k in range(1, n_keyframes):
+        src = rng.choice(n_desc, m, replace=False)
+        dst = rng.choice(n_desc, m, replace=False)
+        d[k, dst] = flip_bits(d[k - 1, src], rng.integers(0, 41, m), rng)
+    return d

@@ -87,6 +87,18 @@ def _bind_match(L):
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_frame_create.restype = C.c_void_p
+    L.orc_frame_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 4
+    L.orc_frame_destroy.argtypes = [C.c_void_p]
+    L.orc_frame_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_features_in_area.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.orc_compute_three_maxima.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_search_by_projection_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.orc_search_by_projection_last.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_search_for_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
+    L.orc_hamming_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_project_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_minus_rt_t.argtypes = [C.c_void_p, C.c_void_p]
 
 
 def _ptr(a):
@@ -274,3 +286,117 @@ def stereo_match(kpsL, descL, kpsR, descR, pyrL, pyrR, scale, inv_scale, mbf, mi
                            arrL, arrR, _ptr(lw), _ptr(lh), n, _ptr(scale), _ptr(inv_scale),
                            float(mbf), float(minD), float(maxD), _ptr(ur), _ptr(dp), _ptr(sad))
     return ur[:nL], dp[:nL], sad[:nL]
+
+
+class OracleFrame:
+    """Flat view of a Frame for the matchers: mvKeysUn, mDescriptors, mvuRight, image bounds and the
+    64x48 grid (Frame.cc:455-470, :567-632), restated in match_oracle.cpp."""
+
+    def __init__(self, keys_un, desc, u_right=None, bounds=None):
+        self.keys = np.ascontiguousarray(keys_un, KEYPOINT_DTYPE)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.n = len(self.keys)
+        assert len(self.desc) == self.n
+        self.u_right = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        self.bounds = tuple(float(b) for b in bounds)          # (minX, maxX, minY, maxY)
+        self._h = lib().orc_frame_create(_ptr(self.keys), _ptr(self.desc),
+                                         None if self.u_right is None else _ptr(self.u_right), self.n, *self.bounds)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_frame_destroy(self._h)
+            self._h = None
+
+    def grid(self):
+        start = np.empty(64 * 48 + 1, np.int32)
+        idx = np.empty(max(self.n, 1), np.int32)
+        lib().orc_frame_grid(self._h, _ptr(start), _ptr(idx))
+        return start, idx[:start[-1]]
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.empty(max(self.n, 1), np.int32)
+        n = lib().orc_features_in_area(self._h, x, y, r, min_level, max_level, _ptr(out), len(out))
+        return out[:n].copy()
+
+
+def compute_three_maxima(sizes):
+    sizes = np.ascontiguousarray(sizes, np.int32)
+    ind = np.empty(3, np.int32)
+    lib().orc_compute_three_maxima(_ptr(sizes), len(sizes), _ptr(ind))
+    return tuple(int(i) for i in ind)
+
+
+def _state(frame, kp_obs):
+    obs = np.zeros(max(frame.n, 1), np.int32)
+    if kp_obs is not None:
+        obs[:frame.n] = kp_obs
+    return obs, np.full(max(frame.n, 1), -1, np.int32)
+
+
+def search_by_projection_map(frame, scale, in_view, proj_x, proj_y, proj_xr, level, view_cos, mp_desc, mp_obs,
+                             th, nnratio, kp_obs=None):
+    """ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>, th).  Returns (nmatches, kp_match, kp_obs_out)."""
+    scale = np.ascontiguousarray(scale, np.float32)
+    in_view = np.ascontiguousarray(in_view, np.uint8)
+    f = [np.ascontiguousarray(a, np.float32) for a in (proj_x, proj_y, proj_xr)]
+    level = np.ascontiguousarray(level, np.int32)
+    view_cos = np.ascontiguousarray(view_cos, np.float32)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    mp_obs = np.ascontiguousarray(mp_obs, np.int32)
+    obs, match = _state(frame, kp_obs)
+    n = lib().orc_search_by_projection_map(frame._h, _ptr(scale), len(in_view), _ptr(in_view), _ptr(f[0]), _ptr(f[1]), _ptr(f[2]),
+                                           _ptr(level), _ptr(view_cos), _ptr(mp_desc), _ptr(mp_obs), th, nnratio,
+                                           _ptr(obs), _ptr(match))
+    return n, match[:frame.n], obs[:frame.n]
+
+
+def search_by_projection_last(frame, scale, cam, tcw_cur, tcw_last, last_has_point, last_pos, last_octave, last_angle,
+                              mp_desc, mp_obs, th, mono, check_ori=True, kp_obs=None):
+    """ORBmatcher::SearchByProjection(Frame& Current, const Frame& Last, th, bMono).  cam = (fx, fy, cx, cy, mbf, mb);
+    tcw_* = 3x4 row-major [R|t]."""
+    scale = np.ascontiguousarray(scale, np.float32)
+    cam = np.ascontiguousarray(cam, np.float32)
+    tc = np.ascontiguousarray(tcw_cur, np.float32).reshape(12)
+    tl = np.ascontiguousarray(tcw_last, np.float32).reshape(12)
+    has = np.ascontiguousarray(last_has_point, np.uint8)
+    pos = np.ascontiguousarray(last_pos, np.float32).reshape(-1, 3)
+    octv = np.ascontiguousarray(last_octave, np.int32)
+    ang = np.ascontiguousarray(last_angle, np.float32)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    mp_obs = np.ascontiguousarray(mp_obs, np.int32)
+    obs, match = _state(frame, kp_obs)
+    n = lib().orc_search_by_projection_last(frame._h, _ptr(scale), _ptr(cam), _ptr(tc), _ptr(tl), len(has), _ptr(has), _ptr(pos),
+                                            _ptr(octv), _ptr(ang), _ptr(mp_desc), _ptr(mp_obs), th, int(mono), int(check_ori),
+                                            _ptr(obs), _ptr(match))
+    return n, match[:frame.n], obs[:frame.n]
+
+
+def search_for_initialization(f1, f2, prev_matched, window, nnratio, check_ori=True):
+    """ORBmatcher::SearchForInitialization.  Returns (nmatches, matches12, prev_matched_out)."""
+    pm = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    m12 = np.empty(max(f1.n, 1), np.int32)
+    n = lib().orc_search_for_initialization(f1._h, f2._h, _ptr(pm), _ptr(m12), int(window), nnratio, int(check_ori))
+    return n, m12[:f1.n], pm
+
+
+def hamming_knn2(q, db, th_low=50, nnratio=0.6):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    db = np.ascontiguousarray(db, np.uint8).reshape(-1, 32)
+    bi = np.empty(max(len(q), 1), np.int32); bd = np.empty_like(bi); sd = np.empty_like(bi)
+    lib().orc_hamming_knn2(_ptr(q), len(q), _ptr(db), len(db), th_low, nnratio, _ptr(bi), _ptr(bd), _ptr(sd))
+    return bi[:len(q)], bd[:len(q)], sd[:len(q)]
+
+
+def project_points(tcw, pos):
+    tcw = np.ascontiguousarray(tcw, np.float32).reshape(12)
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+    out = np.empty_like(pos)
+    lib().orc_project_points(_ptr(tcw), _ptr(pos), len(pos), _ptr(out))
+    return out
+
+
+def minus_rt_t(tcw):
+    tcw = np.ascontiguousarray(tcw, np.float32).reshape(12)
+    out = np.empty(3, np.float32)
+    lib().orc_minus_rt_t(_ptr(tcw), _ptr(out))
+    return out

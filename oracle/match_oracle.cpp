@@ -159,10 +159,382 @@ static void stereo_match(const KeyPt* kL, const uint8_t* dL, int nL, const KeyPt
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Flat view of what the matchers read of a Frame (include/Frame.h): undistorted keypoints, descriptors,
+// mvuRight, the image bounds and the 64x48 keypoint grid.
+// ------------------------------------------------------------------------------------------------
+static const int GRID_COLS = 64, GRID_ROWS = 48;      // include/Frame.h:41-42
+
+struct FrameV {
+    int n = 0;
+    std::vector<KeyPt> k;          // mvKeysUn
+    std::vector<uint8_t> d;        // mDescriptors, n x 32
+    std::vector<float> uR;         // mvuRight (-1 = monocular point)
+    float minX = 0, maxX = 0, minY = 0, maxY = 0;
+    float invW = 0, invH = 0;      // mfGridElementWidthInv / HeightInv, Frame.cc:101-102
+    std::vector<std::vector<size_t>> grid;   // mGrid[ix][iy] -> index ix*GRID_ROWS+iy
+
+    // Frame.cc:622-632
+    bool pos_in_grid(const KeyPt& kp, int& posX, int& posY) const {
+        posX = (int)roundf((kp.x - minX) * invW);
+        posY = (int)roundf((kp.y - minY) * invH);
+        if (posX < 0 || posX >= GRID_COLS || posY < 0 || posY >= GRID_ROWS) return false;
+        return true;
+    }
+    // Frame.cc:455-470
+    void assign_features_to_grid() {
+        grid.assign((size_t)GRID_COLS * GRID_ROWS, std::vector<size_t>());
+        for (int i = 0; i < n; i++) {
+            int gx, gy;
+            if (pos_in_grid(k[i], gx, gy)) grid[(size_t)gx * GRID_ROWS + gy].push_back(i);
+        }
+    }
+    // Frame.cc:567-620
+    std::vector<size_t> features_in_area(float x, float y, float r, int minLevel = -1, int maxLevel = -1) const {
+        std::vector<size_t> vIndices;
+        const int nMinCellX = std::max(0, (int)floorf((x - minX - r) * invW));
+        if (nMinCellX >= GRID_COLS) return vIndices;
+        const int nMaxCellX = std::min(GRID_COLS - 1, (int)ceilf((x - minX + r) * invW));
+        if (nMaxCellX < 0) return vIndices;
+        const int nMinCellY = std::max(0, (int)floorf((y - minY - r) * invH));
+        if (nMinCellY >= GRID_ROWS) return vIndices;
+        const int nMaxCellY = std::min(GRID_ROWS - 1, (int)ceilf((y - minY + r) * invH));
+        if (nMaxCellY < 0) return vIndices;
+        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+            for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+                const std::vector<size_t>& vCell = grid[(size_t)ix * GRID_ROWS + iy];
+                for (size_t j = 0; j < vCell.size(); j++) {
+                    const KeyPt& kpUn = k[vCell[j]];
+                    if (bCheckLevels) {
+                        if (kpUn.octave < minLevel) continue;
+                        if (maxLevel >= 0)
+                            if (kpUn.octave > maxLevel) continue;
+                    }
+                    const float distx = kpUn.x - x;
+                    const float disty = kpUn.y - y;
+                    if (fabsf(distx) < r && fabsf(disty) < r) vIndices.push_back(vCell[j]);
+                }
+            }
+        return vIndices;
+    }
+};
+
+// ORBmatcher.cc:1601-1642 over bin sizes.
+static void compute_three_maxima(const int* histoSize, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = histoSize[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// rotation-histogram bin of a match, ORBmatcher.cc:1425-1433 (same text at :472-480, :1556-1564)
+static inline int rot_bin(float angle1, float angle2) {
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = angle1 - angle2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// The pointer state F.mvpMapPoints[idx] is modelled by two arrays over the keypoints:
+//   kpObs[idx]   = Observations() of the map point the keypoint currently holds (0 when it holds none
+//                  or a point without observations) -- the only thing the matchers ask of it;
+//   kpMatch[idx] = -1 untouched by this call, >= 0 index (into this call's point list) of the point
+//                  assigned last, -2 reset to NULL by the rotation check.
+
+// ORBmatcher.cc:131-137
+static inline float radius_by_viewing_cos(float viewCos) { return viewCos > 0.998 ? 2.5f : 4.0f; }
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), ORBmatcher.cc:45-129.
+// Per map point: inView = mbTrackInView && !isBad(); projX/projY/projXR = mTrackProjX/Y/XR;
+// level = mnTrackScaleLevel; viewCos = mTrackViewCos; mpObs = Observations().
+static int search_by_projection_map(const FrameV& F, const float* scale, int nMP, const uint8_t* inView,
+                                    const float* projX, const float* projY, const float* projXR, const int* level,
+                                    const float* viewCos, const uint8_t* mpDesc, const int* mpObs, float th, float nnratio,
+                                    int* kpObs, int* kpMatch) {
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    for (int iMP = 0; iMP < nMP; iMP++) {
+        if (!inView[iMP]) continue;
+        const int nPredictedLevel = level[iMP];
+        float r = radius_by_viewing_cos(viewCos[iMP]);
+        if (bFactor) r *= th;
+        const std::vector<size_t> vIndices =
+            F.features_in_area(projX[iMP], projY[iMP], r * scale[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel);
+        if (vIndices.empty()) continue;
+        const uint8_t* MPdescriptor = mpDesc + (size_t)iMP * 32;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (size_t vi = 0; vi < vIndices.size(); vi++) {
+            const size_t idx = vIndices[vi];
+            if (kpObs[idx] > 0) continue;
+            if (F.uR[idx] > 0) {
+                const float er = fabsf(projXR[iMP] - F.uR[idx]);
+                if (er > r * scale[nPredictedLevel]) continue;
+            }
+            const int dist = descriptor_distance(MPdescriptor, &F.d[idx * 32]);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = F.k[idx].octave;
+                bestIdx = (int)idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = F.k[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            kpMatch[bestIdx] = iMP;
+            kpObs[bestIdx] = mpObs[iMP];
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+// cv::Mat float arithmetic of the pose expressions, pinned to cv2 4.13 (tests/test_oracle_matchers.py):
+// A(3x3)*x(3x1)+c runs gemm's small-matrix branch -- binary32 products and sums left to right, then
+// (float)((double)t*alpha + (double)c*beta); -A.t()*x runs the generic branch with binary64 accumulation.
+static inline void mat_rx_plus_t(const float* T, const float* x, float* out) {   // T = 3x4 row-major [R|t]
+    for (int r = 0; r < 3; r++) {
+        const float t0 = T[4 * r + 0] * x[0] + T[4 * r + 1] * x[1] + T[4 * r + 2] * x[2];
+        out[r] = (float)((double)t0 * 1.0 + (double)T[4 * r + 3] * 1.0);
+    }
+}
+static inline void mat_minus_rt_t(const float* T, float* out) {                  // -R^T * t
+    for (int r = 0; r < 3; r++) {
+        double s = 0;
+        for (int kk = 0; kk < 3; kk++) s += (double)T[4 * kk + r] * (double)T[4 * kk + 3];
+        out[r] = (float)(s * -1.0);
+    }
+}
+
+struct Camera { float fx, fy, cx, cy, mbf, mb; };
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono), ORBmatcher.cc:1328-1470.
+// Per last-frame keypoint i: lastHasPoint = mvpMapPoints[i] && !mvbOutlier[i]; lastPos = GetWorldPos();
+// lastOctave = mvKeys[i].octave; lastAngle = mvKeysUn[i].angle; mpDesc = GetDescriptor(); mpObs = Observations().
+static int search_by_projection_last(const FrameV& Cur, const float* scale, const Camera& cam, const float* TcwCur,
+                                     const float* TcwLast, int nLast, const uint8_t* lastHasPoint, const float* lastPos,
+                                     const int* lastOctave, const float* lastAngle, const uint8_t* mpDesc, const int* mpObs,
+                                     float th, bool bMono, bool checkOri, int* kpObs, int* kpMatch) {
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    float twc[3], tlc[3];
+    mat_minus_rt_t(TcwCur, twc);
+    mat_rx_plus_t(TcwLast, twc, tlc);
+    const bool bForward = tlc[2] > cam.mb && !bMono;
+    const bool bBackward = -tlc[2] > cam.mb && !bMono;
+    for (int i = 0; i < nLast; i++) {
+        if (!lastHasPoint[i]) continue;
+        float x3Dc[3];
+        mat_rx_plus_t(TcwCur, lastPos + 3 * i, x3Dc);
+        const float xc = x3Dc[0], yc = x3Dc[1];
+        const float invzc = 1.0 / x3Dc[2];
+        if (invzc < 0) continue;
+        float u = cam.fx * xc * invzc + cam.cx;
+        float v = cam.fy * yc * invzc + cam.cy;
+        if (u < Cur.minX || u > Cur.maxX) continue;
+        if (v < Cur.minY || v > Cur.maxY) continue;
+        const int nLastOctave = lastOctave[i];
+        const float radius = th * scale[nLastOctave];
+        std::vector<size_t> vIndices2;
+        if (bForward) vIndices2 = Cur.features_in_area(u, v, radius, nLastOctave);
+        else if (bBackward) vIndices2 = Cur.features_in_area(u, v, radius, 0, nLastOctave);
+        else vIndices2 = Cur.features_in_area(u, v, radius, nLastOctave - 1, nLastOctave + 1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = mpDesc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (size_t vi = 0; vi < vIndices2.size(); vi++) {
+            const size_t i2 = vIndices2[vi];
+            if (kpObs[i2] > 0) continue;
+            if (Cur.uR[i2] > 0) {
+                const float ur = u - cam.mbf * invzc;
+                const float er = fabsf(ur - Cur.uR[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = descriptor_distance(dMP, &Cur.d[i2 * 32]);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = (int)i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            kpMatch[bestIdx2] = i;
+            kpObs[bestIdx2] = mpObs[i];
+            nmatches++;
+            if (checkOri) rotHist[rot_bin(lastAngle[i], Cur.k[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, sizes[HISTO_LENGTH];
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    kpMatch[rotHist[i][j]] = -2;
+                    kpObs[rotHist[i][j]] = 0;
+                    nmatches--;
+                }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchForInitialization, ORBmatcher.cc:405-520.  prevMatched: n1 x (x,y), in/out.
+static int search_for_initialization(const FrameV& F1, const FrameV& F2, float* prevMatched, int* vnMatches12,
+                                     int windowSize, float nnratio, bool checkOri) {
+    int nmatches = 0;
+    for (int i = 0; i < F1.n; i++) vnMatches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> vMatchedDistance(F2.n, INT_MAX);
+    std::vector<int> vnMatches21(F2.n, -1);
+    for (int i1 = 0; i1 < F1.n; i1++) {
+        const KeyPt kp1 = F1.k[i1];
+        const int level1 = kp1.octave;
+        if (level1 > 0) continue;
+        std::vector<size_t> vIndices2 = F2.features_in_area(prevMatched[2 * i1], prevMatched[2 * i1 + 1], (float)windowSize, level1, level1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* d1 = &F1.d[(size_t)i1 * 32];
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (size_t vi = 0; vi < vIndices2.size(); vi++) {
+            const size_t i2 = vIndices2[vi];
+            const int dist = descriptor_distance(d1, &F2.d[i2 * 32]);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = (int)i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) {
+                    vnMatches12[vnMatches21[bestIdx2]] = -1;
+                    nmatches--;
+                }
+                vnMatches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (checkOri) rotHist[rot_bin(F1.k[i1].angle, F2.k[bestIdx2].angle)].push_back(i1);
+            }
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, sizes[HISTO_LENGTH];
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) {
+                const int idx1 = rotHist[i][j];
+                if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+            }
+        }
+    }
+    for (int i1 = 0; i1 < F1.n; i1++)
+        if (vnMatches12[i1] >= 0) {
+            prevMatched[2 * i1] = F2.k[vnMatches12[i1]].x;
+            prevMatched[2 * i1 + 1] = F2.k[vnMatches12[i1]].y;
+        }
+    return nmatches;
+}
+
+// Brute-force best / second-best Hamming search with the ratio test: the inner loop of
+// ORBmatcher::SearchByBoW (ORBmatcher.cc:200-229) over one list of candidates, without the
+// "already matched" bookkeeping (every query is independent).  bestIdx = -1 when rejected.
+static void hamming_knn2(const uint8_t* q, int nq, const uint8_t* db, int nd, int thLow, float nnratio,
+                         int* bestIdx, int* bestDist, int* secondDist) {
+    for (int i = 0; i < nq; i++) {
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int j = 0; j < nd; j++) {
+            const int dist = descriptor_distance(q + (size_t)i * 32, db + (size_t)j * 32);
+            if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = j; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        bestDist[i] = bestDist1;
+        secondDist[i] = bestDist2;
+        bestIdx[i] = -1;
+        if (bestDist1 <= thLow)
+            if ((float)bestDist1 < nnratio * (float)bestDist2) bestIdx[i] = bestIdxF;
+    }
+}
+
 }  // namespace orc
 
 using namespace orc;
 extern "C" {
+
+void* orc_frame_create(const void* keysUn, const uint8_t* desc, const float* uRight, int n,
+                       float minX, float maxX, float minY, float maxY) {
+    FrameV* F = new FrameV;
+    F->n = n;
+    F->k.assign((const KeyPt*)keysUn, (const KeyPt*)keysUn + n);
+    F->d.assign(desc, desc + (size_t)n * 32);
+    if (uRight) F->uR.assign(uRight, uRight + n); else F->uR.assign(n, -1.0f);
+    F->minX = minX; F->maxX = maxX; F->minY = minY; F->maxY = maxY;
+    F->invW = (float)GRID_COLS / (maxX - minX);
+    F->invH = (float)GRID_ROWS / (maxY - minY);
+    F->assign_features_to_grid();
+    return F;
+}
+void orc_frame_destroy(void* f) { delete (FrameV*)f; }
+
+// CSR of the grid in mGrid[ix][iy] order: cellStart has 64*48+1 entries.
+void orc_frame_grid(const void* f, int* cellStart, int* cellIdx) {
+    const FrameV* F = (const FrameV*)f;
+    int pos = 0;
+    for (int c = 0; c < GRID_COLS * GRID_ROWS; c++) {
+        cellStart[c] = pos;
+        for (size_t j = 0; j < F->grid[c].size(); j++) cellIdx[pos++] = (int)F->grid[c][j];
+    }
+    cellStart[GRID_COLS * GRID_ROWS] = pos;
+}
+
+int orc_features_in_area(const void* f, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap) {
+    std::vector<size_t> v = ((const FrameV*)f)->features_in_area(x, y, r, minLevel, maxLevel);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = (int)v[i];
+    return (int)v.size();
+}
+
+void orc_compute_three_maxima(const int* histoSize, int L, int* ind) {
+    ind[0] = ind[1] = ind[2] = -1;
+    compute_three_maxima(histoSize, L, ind[0], ind[1], ind[2]);
+}
+
+int orc_search_by_projection_map(const void* f, const float* scale, int nMP, const uint8_t* inView, const float* projX,
+                                 const float* projY, const float* projXR, const int* level, const float* viewCos,
+                                 const uint8_t* mpDesc, const int* mpObs, float th, float nnratio, int* kpObs, int* kpMatch) {
+    return search_by_projection_map(*(const FrameV*)f, scale, nMP, inView, projX, projY, projXR, level, viewCos, mpDesc, mpObs,
+                                    th, nnratio, kpObs, kpMatch);
+}
+
+int orc_search_by_projection_last(const void* f, const float* scale, const float* cam6, const float* TcwCur,
+                                  const float* TcwLast, int nLast, const uint8_t* lastHasPoint, const float* lastPos,
+                                  const int* lastOctave, const float* lastAngle, const uint8_t* mpDesc, const int* mpObs,
+                                  float th, int bMono, int checkOri, int* kpObs, int* kpMatch) {
+    Camera cam{cam6[0], cam6[1], cam6[2], cam6[3], cam6[4], cam6[5]};
+    return search_by_projection_last(*(const FrameV*)f, scale, cam, TcwCur, TcwLast, nLast, lastHasPoint, lastPos, lastOctave,
+                                     lastAngle, mpDesc, mpObs, th, bMono != 0, checkOri != 0, kpObs, kpMatch);
+}
+
+int orc_search_for_initialization(const void* f1, const void* f2, float* prevMatched, int* vnMatches12, int windowSize,
+                                  float nnratio, int checkOri) {
+    return search_for_initialization(*(const FrameV*)f1, *(const FrameV*)f2, prevMatched, vnMatches12, windowSize, nnratio,
+                                     checkOri != 0);
+}
+
+void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* db, int nd, int thLow, float nnratio, int* bestIdx,
+                      int* bestDist, int* secondDist) {
+    hamming_knn2(q, nq, db, nd, thLow, nnratio, bestIdx, bestDist, secondDist);
+}
+
+void orc_project_points(const float* Tcw, const float* pos, int n, float* out) {
+    for (int i = 0; i < n; i++) mat_rx_plus_t(Tcw, pos + 3 * i, out + 3 * i);
+}
+void orc_minus_rt_t(const float* Tcw, float* out) { mat_minus_rt_t(Tcw, out); }
 
 int orc_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
 

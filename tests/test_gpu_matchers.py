@@ -1,0 +1,278 @@
+"""Parity of the CUDA matchers (csrc/matcher.cu, through the C ABI) with the oracle: bit-exact match
+indices, counts and updated state, on the same seeded inputs."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from object_slam_b200 import synth
+
+from matcher_cases import MP_KEYS, LAST_KEYS, bounds, map_case, oracle_frame, oracle_init, oracle_last, oracle_map
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TUM, KITTI = synth.TUM_SHAPE, synth.KITTI_SHAPE
+
+
+@pytest.fixture(scope="module")
+def M(gpu):
+    from object_slam_b200.matcher import ORBmatcher
+    m = ORBmatcher(0.8, True)
+    yield m
+    m.close()
+
+
+def frame_set(M, shape, frames, cap=None):
+    cap = cap or max(len(f[0]) for f in frames)
+    fs = M.frame_set(synth.scale_factors(), bounds(shape), synth.camera_for(shape), max_frames=len(frames), max_keypoints=max(cap, 1))
+    return fs.upload(frames)
+
+
+def test_descriptor_distance_and_three_maxima(M):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
+    b[:100] = a[:100]
+    got = M.DescriptorDistance(a, b)
+    want = np.unpackbits(a ^ b, axis=1).sum(1)
+    assert np.array_equal(got, want)
+    h = rng.integers(0, 40, (500, 30)).astype(np.int32)
+    h[:50] = 0
+    h[50:100] = (rng.random((50, 30)) < 0.1) * rng.integers(0, 100, (50, 30))
+    got = M.ComputeThreeMaxima(h)
+    for i in range(len(h)):
+        assert tuple(got[i]) == oracle.compute_three_maxima(h[i])
+
+
+@pytest.mark.parametrize("shape,n", [(TUM, 1000), (KITTI, 2000), (TUM, 37), (TUM, 0)])
+def test_grid_matches_assign_features_to_grid(M, shape, n):
+    frames = [synth.synthetic_frame(shape, n, s) for s in (1, 2, 3)]
+    if n:       # keypoints on and beyond the borders exercise the round()/drop rule of PosInGrid
+        frames[0][0]["x"][:5] = [0.0, shape[1] - 0.4, shape[1] - 5.0, -3.0, shape[1] + 2.0]
+        frames[0][0]["y"][5:9] = [0.0, shape[0] - 0.4, shape[0] - 5.1, -1.0]
+    fs = frame_set(M, shape, frames, cap=max(n, 1))
+    for b, f in enumerate(frames):
+        start, idx = fs.grid(b)
+        ostart, oidx = oracle_frame(f, shape).grid()
+        assert np.array_equal(start, ostart) and np.array_equal(idx, oidx)
+
+
+def run_map(M, shape, cases, th, nnratio, per_frame=True):
+    M.mfNNratio = nnratio
+    frames = [c[0] for c in cases]
+    fs = frame_set(M, shape, frames)
+    if per_frame:
+        arrs = [np.stack([c[1][k] for c in cases]) for k in MP_KEYS]
+    else:
+        arrs = [cases[0][1][k] for k in MP_KEYS]
+    kp_obs = None
+    if any(c[2] is not None for c in cases):
+        kp_obs = np.zeros((len(cases), fs.cap), np.int32)
+        for b, c in enumerate(cases):
+            if c[2] is not None:
+                kp_obs[b, :len(c[2])] = c[2]
+    n, match = M.SearchByProjection(fs, *arrs, th=th, per_frame=per_frame, kp_observations=kp_obs)
+    return n, match, fs
+
+
+@pytest.mark.parametrize("n_kp,n_mp,locked,th,anchored", [
+    (1000, 20000, 0.0, 3.0, 0.5),      # cfg3: RGB-D tracking, th = 3 (Tracking.cc:1451)
+    (1000, 3000, 0.25, 1.0, 0.7),      # th == 1: no factor (ORBmatcher.cc:49)
+    (2000, 5000, 0.1, 5.0, 0.9),       # wide windows (th = 5 after relocalisation, Tracking.cc:1454): > 8 candidates per point
+    (50, 400, 0.0, 3.0, 0.5),
+])
+def test_search_by_projection_matches_oracle(M, n_kp, n_mp, locked, th, anchored):
+    shape = TUM
+    cases = [map_case(shape, n_kp, n_mp, s, locked, anchored) for s in (0, 1, 2)]
+    n, match, fs = run_map(M, shape, cases, th, 0.8)
+    total = 0
+    for b, (frame, mp, kp_obs) in enumerate(cases):
+        on, omatch = oracle_map(frame, shape, mp, th, 0.8, kp_obs)
+        assert n[b] == on
+        assert np.array_equal(match[b, :n_kp], omatch)
+        assert np.all(match[b, n_kp:] == -1)
+        total += on
+    assert total > 0
+
+
+def test_search_by_projection_shared_points_and_edges(M):
+    shape = TUM
+    frame, mp, _ = map_case(shape, 800, 4000, 5)
+    other = synth.synthetic_frame(shape, 640, 6)
+    empty = synth.synthetic_frame(shape, 0, 7)
+    cases = [(frame, mp, None), (other, mp, None), (empty, mp, None)]
+    n, match, fs = run_map(M, shape, cases, 3.0, 0.8, per_frame=False)
+    for b, (f, _, _) in enumerate(cases):
+        on, omatch = oracle_map(f, shape, mp, 3.0, 0.8)
+        assert n[b] == on and np.array_equal(match[b, :len(f[0])], omatch)
+    assert n[2] == 0
+    # nothing in view / every keypoint already taken / no points at all
+    mp0 = dict(mp); mp0["in_view"] = np.zeros_like(mp["in_view"])
+    n, match, _ = run_map(M, shape, [(frame, mp0, None)], 3.0, 0.8)
+    assert n[0] == 0 and np.all(match == -1)
+    n, match, _ = run_map(M, shape, [(frame, mp, np.ones(800, np.int32))], 3.0, 0.8)
+    assert n[0] == 0 and np.all(match == -1)
+    mpe = {k: v[:0] for k, v in mp.items()}
+    n, match, _ = run_map(M, shape, [(frame, mpe, None)], 3.0, 0.8)
+    assert n[0] == 0 and np.all(match == -1)
+    # points without observations never lock: later points overwrite (n counts every assignment)
+    mpz = dict(mp); mpz["observations"] = np.zeros_like(mp["observations"])
+    n, match, _ = run_map(M, shape, [(frame, mpz, None)], 3.0, 0.8)
+    on, omatch = oracle_map(frame, shape, mpz, 3.0, 0.8)
+    assert n[0] == on and np.array_equal(match[0, :800], omatch) and on > (omatch >= 0).sum()
+    assert M.last_rounds()[0] == 1
+
+
+def test_search_by_projection_adversarial_chain(M):
+    """Every point wants the same few keypoints: long dependency chains for the lock resolution."""
+    shape = TUM
+    frame = synth.synthetic_frame(shape, 64, 9)
+    keys, desc, ur = frame
+    keys["x"] = 300 + (np.arange(64) % 8) * 3.0
+    keys["y"] = 200 + (np.arange(64) // 8) * 3.0
+    keys["octave"] = 0
+    ur[:] = -1
+    rng = np.random.default_rng(10)
+    n_mp = 3000
+    mp = dict(in_view=np.ones(n_mp, np.uint8), proj_x=np.full(n_mp, 310, np.float32), proj_y=np.full(n_mp, 210, np.float32),
+              proj_xr=np.zeros(n_mp, np.float32), scale_level=np.zeros(n_mp, np.int32), view_cos=np.full(n_mp, 0.9, np.float32),
+              descriptors=synth.flip_bits(desc[rng.integers(0, 64, n_mp)], rng.integers(0, 90, n_mp), rng),
+              observations=rng.integers(0, 2, n_mp).astype(np.int32))
+    n, match, _ = run_map(M, shape, [(frame, mp, None)], 3.0, 0.95)
+    on, omatch = oracle_map(frame, shape, mp, 3.0, 0.95)
+    assert n[0] == on and np.array_equal(match[0, :64], omatch)
+    assert M.last_rounds()[0] >= 3
+
+
+@pytest.mark.parametrize("mono,forward,th", [(False, 0.0, 7.0), (False, 0.6, 7.0), (False, -0.6, 14.0), (True, 0.6, 15.0)])
+def test_search_by_projection_last_matches_oracle(M, mono, forward, th):
+    shape = TUM
+    pairs = [synth.motion_pair(shape, 1000, s, forward=forward) for s in (20, 21, 22)]
+    fs = frame_set(M, shape, [p[1] for p in pairs])
+    arrs = [np.stack([p[0][k] for p in pairs]) for k in LAST_KEYS]
+    tl = np.stack([p[0]["tcw_last"] for p in pairs]); tc = np.stack([p[0]["tcw_current"] for p in pairs])
+    for check_ori in (True, False):
+        M.mbCheckOrientation = check_ori
+        n, match = M.SearchByProjectionLast(fs, *arrs, tl, tc, th, mono, per_frame=True)
+        for b, (last, cur) in enumerate(pairs):
+            on, omatch = oracle_last(cur, shape, last, th, mono, check_ori)
+            assert n[b] == on and np.array_equal(match[b, :1000], omatch)
+            assert on > 200
+    M.mbCheckOrientation = True
+
+
+@pytest.mark.parametrize("shape,n,window,ratio", [(KITTI, 2000, 100, 0.9), (TUM, 1000, 100, 0.9), (TUM, 1000, 30, 0.6), (TUM, 5, 100, 0.9)])
+def test_search_for_initialization_matches_oracle(M, shape, n, window, ratio):
+    M.mfNNratio = ratio
+    cases = [synth.init_pair(shape, n, s) for s in (40, 41)]
+    f1 = frame_set(M, shape, [c[0] for c in cases])
+    f2 = frame_set(M, shape, [c[1] for c in cases])
+    prev = np.zeros((2, f1.cap, 2), np.float32)
+    for b, c in enumerate(cases):
+        prev[b, :n] = c[2]
+    for check_ori in (True, False):
+        M.mbCheckOrientation = check_ori
+        pv = prev.copy()
+        nm, m12 = M.SearchForInitialization(f1, f2, pv, window)
+        for b, (a, bb, p) in enumerate(cases):
+            on, om12, opm = oracle_init(a, bb, shape, p, window, ratio, check_ori)
+            assert nm[b] == on and np.array_equal(m12[b, :n], om12) and np.array_equal(pv[b, :n], opm)
+    # second round, as Tracking calls it again with the updated vbPrevMatched
+    nm2, m12b = M.SearchForInitialization(f1, f2, pv, window)
+    on, om12, opm = oracle_init(cases[0][0], cases[0][1], shape, oracle_init(cases[0][0], cases[0][1], shape, cases[0][2], window, ratio, False)[2], window, ratio, False)
+    assert nm2[0] == on and np.array_equal(m12b[0, :n], om12)
+    M.mbCheckOrientation = True
+    M.mfNNratio = 0.8
+
+
+def test_knn2_matches_oracle(M):
+    M.mfNNratio = 0.6
+    D = synth.keyframe_descriptors(5, 2000, 3)
+    pairs = np.array([(i, j) for i in range(5) for j in range(5) if i != j], np.int32)
+    bi, bd, sd = M.knn2(D, pairs)
+    for p, (a, b) in enumerate(pairs):
+        obi, obd, osd = oracle.hamming_knn2(D[a], D[b], 50, 0.6)
+        assert np.array_equal(bi[p], obi) and np.array_equal(bd[p], obd) and np.array_equal(sd[p], osd)
+    assert (bi >= 0).sum() > 1000
+    # ragged size (not a multiple of the tile), self match, duplicate database rows: lowest index wins ties
+    D2 = synth.keyframe_descriptors(2, 333, 4)
+    D2[1, 100] = D2[1, 7]
+    D2[0, 5] = D2[1, 7]
+    bi, bd, sd = M.knn2(D2, np.array([(0, 1), (1, 1)], np.int32))
+    for p, (a, b) in enumerate([(0, 1), (1, 1)]):
+        obi, obd, osd = oracle.hamming_knn2(D2[a], D2[b], 50, 0.6)
+        assert np.array_equal(bi[p], obi) and np.array_equal(bd[p], obd) and np.array_equal(sd[p], osd)
+    assert bd[0, 5] == 0 and sd[0, 5] == 0 and bi[0, 5] == -1
+    M.mfNNratio = 0.8
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "match_*.npz"))), ids=os.path.basename)
+def test_golden_fixtures(M, path):
+    g = np.load(path)
+    kind, seed = str(g["kind"]), int(g["seed"])
+    shape = TUM
+    if kind == "map":
+        case = map_case(shape, 1000, 20000 if seed == 0 else 3000, seed, 0.0 if seed == 0 else 0.25)
+        n, match, _ = run_map(M, shape, [case], 3.0, 0.8)
+        assert n[0] == g["n_matches"] and np.array_equal(match[0, :1000], g["kp_match"])
+    elif kind in ("last", "last_forward"):
+        last, cur = synth.motion_pair(shape, 1000, seed, forward=0.6 if kind == "last_forward" else 0.0)
+        fs = frame_set(M, shape, [cur])
+        n, match = M.SearchByProjectionLast(fs, *[last[k] for k in LAST_KEYS], last["tcw_last"], last["tcw_current"], 7.0, False)
+        assert n[0] == g["n_matches"] and np.array_equal(match[0, :1000], g["kp_match"])
+    elif kind == "init":
+        M.mfNNratio = 0.9
+        f1, f2, prev = synth.init_pair(KITTI, 2000, seed)
+        s1, s2 = frame_set(M, KITTI, [f1]), frame_set(M, KITTI, [f2])
+        pv = np.zeros((1, s1.cap, 2), np.float32); pv[0, :2000] = prev
+        n, m12 = M.SearchForInitialization(s1, s2, pv, 100)
+        M.mfNNratio = 0.8
+        assert n[0] == g["n_matches"] and np.array_equal(m12[0, :2000], g["matches12"]) and np.array_equal(pv[0, :2000], g["prev_matched"])
+    elif kind == "knn2":
+        M.mfNNratio = 0.6
+        D = synth.keyframe_descriptors(3, 2000, seed)
+        bi, bd, sd = M.knn2(D, np.array([(1, 0)], np.int32))
+        M.mfNNratio = 0.8
+        assert np.array_equal(bi[0], g["best_idx"]) and np.array_equal(bd[0], g["best_dist"]) and np.array_equal(sd[0], g["second_dist"])
+
+
+def test_device_pointers_and_extractor_frames(M):
+    """Device-resident inputs/outputs (torch tensors) and frames taken straight from an extraction."""
+    import torch
+    from object_slam_b200.extractor import ORBextractor
+    shape = TUM
+    imgs = [synth.blocky_image(shape, s) for s in (50, 51)]
+    ex = ORBextractor(1000, 1.2, 8, 20, 7, max_size=(640, 480), max_batch=2)
+    res = ex.extract_batch(imgs)
+    fs = M.frame_set(ex.GetScaleFactors(), bounds(shape), synth.camera_for(shape), max_frames=2, max_keypoints=ex.capacity)
+    fs.from_extractor(ex)
+    mps = [synth.map_points_for_frame(k, d, shape, 6000, 60 + b) for b, (k, d) in enumerate(res)]
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.stack([m[k] for m in mps])).to(dev) for k in MP_KEYS]
+    kp_match = torch.full((2, fs.cap), -7, dtype=torch.int32, device=dev)
+    n_matches = torch.zeros(2, dtype=torch.int32, device=dev)
+    M.mfNNratio = 0.8
+    torch.cuda.synchronize()
+    M.SearchByProjection(fs, *[x.data_ptr() for x in t], th=3.0, n_points=6000, per_frame=True,
+                         kp_match=kp_match.data_ptr(), n_matches=n_matches.data_ptr())
+    M.sync()
+    for b, (k, d) in enumerate(res):
+        start, idx = fs.grid(b)
+        ostart, oidx = oracle_frame((k, d, None), shape).grid()
+        assert np.array_equal(start, ostart) and np.array_equal(idx, oidx)
+        on, omatch = oracle_map((k, d, None), shape, mps[b], 3.0, 0.8)
+        assert int(n_matches[b]) == on and np.array_equal(kp_match[b, :len(k)].cpu().numpy(), omatch)
+        assert on > 100
+
+
+def test_errors(M):
+    from object_slam_b200._capi import ObsError
+    with pytest.raises(ObsError):
+        M.frame_set(synth.scale_factors(), (0, 0, 0, 480), max_frames=1, max_keypoints=10)
+    fs = M.frame_set(synth.scale_factors(), bounds(TUM), max_frames=1, max_keypoints=32)
+    with pytest.raises(ObsError):
+        fs.upload([synth.synthetic_frame(TUM, 100, 0)])          # more keypoints than the set holds
+    with pytest.raises(ObsError):
+        M.SearchByProjection(fs, *[np.zeros(1, np.uint8)] * 8)   # empty frame set
