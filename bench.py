@@ -158,6 +158,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=256, help="stereo frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="stereo", choices=["stereo", "knn2", "projection"],
+                    help="stereo = configs[1] (the headline); knn2 = configs[4] keyframe-vs-keyframe Hamming matching; "
+                         "projection = configs[2] TUM-shape extraction + SearchByProjection against a 20k-point map")
+    ap.add_argument("--keyframes", type=int, default=4096, help="knn2: keyframes in total (sharded over the GPUs)")
+    ap.add_argument("--window", type=int, default=8, help="knn2: every keyframe is matched against the +-window neighbours")
+    ap.add_argument("--map-points", type=int, default=20000, help="projection: map points per frame")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -165,6 +171,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.workload != "stereo":
+        import bench_match
+        return bench_match.run(args, rank, local_rank, world, ClockSampler)
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return

@@ -279,6 +279,33 @@ int obs_hamming_knn2(obs_matcher* m, const uint8_t* descriptors, int n_keyframes
                      const int32_t* pairs, int n_pairs, int th_low, float nnratio,
                      int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
 
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU exchange step of batched keyframe-vs-keyframe matching: every rank (one process per GPU)
+ * owns a contiguous shard of the keyframes as queries and needs all descriptor sets as database.
+ * The all-gather runs over NCCL (bound at run time with dlopen, so the host process's own NCCL is
+ * shared) on the communicator's stream, in n_chunks pieces of each rank's shard, each signalled by
+ * an event: obs_hamming_knn2 calls on pairs whose database keyframes are already present overlap the
+ * rest of the transfer.  Extraction, stereo and projection search shard by frame with no collective.
+ * --------------------------------------------------------------------------------------- */
+typedef struct obs_comm obs_comm;
+int obs_comm_nccl_version(void);                                /* e.g. 22809, or -1 when NCCL cannot be loaded */
+int obs_comm_unique_id(uint8_t* id128);                         /* ncclGetUniqueId; 128 bytes, to be broadcast by the host */
+int obs_comm_create(const uint8_t* id128, int rank, int n_ranks, int device, obs_comm** out);
+int obs_comm_destroy(obs_comm* c);
+/* d_all (n_ranks x local_bytes, device) receives rank r's d_local (local_bytes, device, the same on every
+ * rank, a multiple of 32) at offset r*local_bytes.  producer_stream: the cudaStream_t that wrote d_local.
+ * Chunk k covers descriptors [n*k/n_chunks, n*(k+1)/n_chunks) of every shard. */
+int obs_comm_allgather(obs_comm* c, const uint8_t* d_local, size_t local_bytes, uint8_t* d_all, int n_chunks,
+                       void* producer_stream);
+/* Make consumer_stream (e.g. obs_matcher_stream) wait until chunk `chunk` of the last all-gather has arrived. */
+int obs_comm_wait(obs_comm* c, int chunk, void* consumer_stream);
+
+/* Roofline denominator of the matchers, measured on `device`: register-resident 256-bit Hamming
+ * distances per second (in 1e9/s).  mode 0: 8 xor + 8 popc + adds per distance (the instruction mix of
+ * ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1647-1663, with hardware popc); mode 1: the same
+ * through three carry-save adders (5 popc); mode 3: four carry-save adders (4 popc); mode 2: popc only. */
+int obs_microbench_popc(int device, int mode, double* gdist_per_s);
+
 #ifdef __cplusplus
 }
 #endif

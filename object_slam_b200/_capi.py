@@ -96,6 +96,13 @@ _PROTOS = {
     "obs_search_for_initialization": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int, _vp]),
     "obs_compute_three_maxima": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "obs_descriptor_distance": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    "obs_comm_nccl_version": (C.c_int, []),
+    "obs_comm_unique_id": (C.c_int, [_vp]),
+    "obs_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "obs_comm_destroy": (C.c_int, [_vp]),
+    "obs_comm_allgather": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int, _vp]),
+    "obs_comm_wait": (C.c_int, [_vp, C.c_int, _vp]),
+    "obs_microbench_popc": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "obs_hamming_knn2": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp]),
 }
 

@@ -7,17 +7,19 @@
 //                       order, ascending keypoint index inside a cell (AssignFeaturesToGrid :455-470).
 //   k_proj_candidates   one thread per projected point: GetFeaturesInArea (Frame.cc:567-620) in the
 //                       reference's cell order, the static filters of SearchByProjection, 256-bit
-//                       Hamming distances (__popc), up to 8 candidates cached as dist|level|index.
+//                       Hamming distances (__popc); the candidates (dist|level|index) go to a list of
+//                       8-slot chunks: 7 inline per point, further chunks from a per-frame pool.
 //   k_proj_resolve      one CTA per frame: the reference assigns map points to keypoints first come,
 //                       first served (a keypoint that received a point with Observations()>0 is
 //                       skipped by every later point, ORBmatcher.cc:87-89 / :1391-1393).  Point i
 //                       therefore sees keypoint k iff no earlier point locked it: T[k] = index of the
-//                       first locking point.  T is found by fixed-point iteration: every round all
-//                       points re-evaluate their candidates against the previous T in parallel and
-//                       the new T is the atomicMin of the locking claims.  By induction on the point
-//                       index the fixed point is unique and equals the sequential result (point i is
-//                       final once points 0..i-1 are).  Then: match counts, rotation histogram,
-//                       ComputeThreeMaxima (:1601-1642), reset of the inconsistent bins.
+//                       first locking point.  T is found by fixed-point iteration over blocks of 1024
+//                       consecutive points: all points of a block re-evaluate their candidates against
+//                       the previous claims in parallel and the new claims are the atomicMin of the
+//                       locking ones.  By induction on the point index the fixed point is unique and
+//                       equals the sequential result (point i is final once points 0..i-1 are); a
+//                       converged block's locks are final for all later blocks.  Then: match counts,
+//                       rotation histogram, ComputeThreeMaxima (:1601-1642), reset of the inconsistent bins.
 //   k_init_search       SearchForInitialization (:405-520): candidate lists in parallel, then one warp
 //                       replays the frame-1 keypoints in order (vMatchedDistance / vnMatches21 state in
 //                       shared memory; candidates of one keypoint spread over the lanes).
@@ -26,11 +28,14 @@
 // Float expressions use individually rounded binary32 operations (__fmul_rn & co), as the oracle.
 #include "matcher.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
 constexpr int TH_HIGH = 100, TH_LOW = 50;
 constexpr uint32_t CAND_EMPTY = 0xffffffffu;
+constexpr uint32_t CAND_LINK = 0x80000000u;      // slot 7 of a chunk: index of the next chunk in the frame's pool
+constexpr uint32_t CAND_TRUNC = 0x40000000u;     // on the first entry: the pool ran out, the list is incomplete
 constexpr int T_FREE = 0x7fffffff;
 
 __device__ __forceinline__ int hamming8(const uint32_t* a, const uint4 b0, const uint4 b1) {
@@ -294,43 +299,61 @@ __global__ void __launch_bounds__(128) k_proj_candidates(const __grid_constant__
     }
     const int M = num_points<V>(A);
     if (i >= M) return;
-    uint32_t* out = A.cand + ((size_t)b * M + i) * OBS_CAND_SLOTS;
+    uint32_t* chunk = A.cand + ((size_t)b * M + i) * OBS_CAND_SLOTS;
     const Query q = make_query<V>(A, b, i, V == 1 ? sDir : 0);
-    if (!q.valid) { out[0] = CAND_EMPTY; return; }
+    if (!q.valid) { chunk[0] = CAND_EMPTY; return; }
     uint32_t d[8];
     load_desc(point_desc<V>(A, b, i), d);
     const uint4* fd = A.F.desc + (size_t)b * A.F.cap * 2;
-    int cnt = 0;
+    uint32_t* const head = chunk;
+    uint32_t* pool = A.pool + (size_t)b * A.poolChunks * OBS_CAND_SLOTS;
+    int pos = 0;                 // next slot in `chunk`; slot 7 is reserved for the link / terminator
+    bool truncated = false;
     uint32_t first = CAND_EMPTY;
     for_each_in_area(A.F, b, q.u, q.v, q.r, q.minLevel, q.maxLevel, [&](int idx, const float4& k) {
-        if (!static_ok(A, b, idx, k, q)) return;
+        if (truncated || !static_ok(A, b, idx, k, q)) return;
         const int dist = hamming8(d, __ldg(fd + 2 * idx), __ldg(fd + 2 * idx + 1));
         const uint32_t e = ((uint32_t)dist << 20) | ((uint32_t)(__float_as_int(k.w) & 15) << 16) | (uint32_t)idx;
-        if (cnt == 0) first = e;
-        else if (cnt < OBS_CAND_SLOTS) out[cnt] = e;
-        cnt++;
+        if (pos == OBS_CAND_SLOTS - 1) {         // chunk full: continue in a chunk of the frame's pool
+            const int c = atomicAdd(A.poolCursor + b, 1);
+            if (c >= A.poolChunks) { truncated = true; return; }
+            chunk[OBS_CAND_SLOTS - 1] = CAND_LINK | (uint32_t)c;
+            chunk = pool + (size_t)c * OBS_CAND_SLOTS;
+            pos = 0;
+        }
+        if (chunk == head && pos == 0) first = e; else chunk[pos] = e;
+        pos++;
     });
-    if (cnt > OBS_CAND_SLOTS) first |= 0x80000000u;          // incomplete list: traverse again on demand
-    out[0] = first;
-    if (cnt > 0 && cnt < OBS_CAND_SLOTS) out[cnt] = CAND_EMPTY;
+    if (truncated) first |= CAND_TRUNC;          // pool exhausted: this point traverses the grid again on demand
+    else chunk[pos] = CAND_EMPTY;                // pos <= 7
+    if (chunk == head && pos == 0) { head[0] = CAND_EMPTY; return; }
+    head[0] = first;
 }
 
-// Best candidate of point i given the lock times T (shared memory); returns the keypoint index or -1.
+// Best candidate of point i; returns the keypoint index or -1.  A keypoint is hidden from point i when an
+// earlier block of points locked it (T, final) or an earlier point of the current block claims it (Tc).
 template <int V>
-__device__ __forceinline__ int evaluate(const ProjSearchArgs& A, int b, int i, int M, const int* T, int dir) {
+__device__ __forceinline__ int evaluate(const ProjSearchArgs& A, int b, int i, int M, const int* T, const int* Tc, int dir) {
     const uint4* c4 = reinterpret_cast<const uint4*>(A.cand + ((size_t)b * M + i) * OBS_CAND_SLOTS);
-    const uint4 lo = c4[0];
+    uint4 lo = c4[0];
     if (lo.x == CAND_EMPTY) return -1;
     Best B;
-    if (!(lo.x >> 31)) {
-        const uint4 hi = c4[1];
-        const uint32_t e[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    if (!(lo.x & CAND_TRUNC)) {
+        const uint4* pool = reinterpret_cast<const uint4*>(A.pool + (size_t)b * A.poolChunks * OBS_CAND_SLOTS);
+        for (;;) {
+            const uint4 hi = c4[1];
+            const uint32_t e[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            bool done = false;
 #pragma unroll
-        for (int s = 0; s < OBS_CAND_SLOTS; s++) {
-            if (e[s] == CAND_EMPTY) break;
-            const int k = (int)(e[s] & 0xffffu);
-            if (T[k] < i) continue;
-            B.upd((int)((e[s] >> 20) & 0x1ffu), (int)((e[s] >> 16) & 15u), k);
+            for (int s = 0; s < OBS_CAND_SLOTS - 1; s++) {
+                if (done || e[s] == CAND_EMPTY) { done = true; continue; }
+                const int k = (int)(e[s] & 0xffffu);
+                if (T[k] != T_FREE || Tc[k] < i) continue;
+                B.upd((int)((e[s] >> 20) & 0x1ffu), (int)((e[s] >> 16) & 15u), k);
+            }
+            if (done || e[7] == CAND_EMPTY) break;
+            c4 = pool + (size_t)(e[7] & 0x3fffffffu) * 2;
+            lo = c4[0];
         }
     } else {
         const Query q = make_query<V>(A, b, i, dir);
@@ -338,7 +361,7 @@ __device__ __forceinline__ int evaluate(const ProjSearchArgs& A, int b, int i, i
         load_desc(point_desc<V>(A, b, i), d);
         const uint4* fd = A.F.desc + (size_t)b * A.F.cap * 2;
         for_each_in_area(A.F, b, q.u, q.v, q.r, q.minLevel, q.maxLevel, [&](int idx, const float4& k) {
-            if (T[idx] < i) return;
+            if (T[idx] != T_FREE || Tc[idx] < i) return;
             if (!static_ok(A, b, idx, k, q)) return;
             B.upd(hamming8(d, __ldg(fd + 2 * idx), __ldg(fd + 2 * idx + 1)), __float_as_int(k.w) & 15, idx);
         });
@@ -357,56 +380,71 @@ __global__ void __launch_bounds__(1024) k_proj_resolve(const __grid_constant__ P
     __shared__ int sInd[3];
     __shared__ int sN, sDir;
     const int cap = A.F.cap, b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    int* T = sm;                // first locking point per keypoint
-    int* Tn = sm + cap;         // next round's T; afterwards: last non-locking point per keypoint
-    int* bad = sm + 2 * cap;    // keypoint named by a match of an inconsistent rotation bin
+    int* T = sm;                // first locking point per keypoint, final for the blocks already processed
+    int* Tc = sm + cap;         // claims of the current block (previous iteration)
+    int* Tn = sm + 2 * cap;     // claims of the current block (this iteration)
+    int* last = sm + 3 * cap;   // last non-locking point assigned per keypoint; afterwards: "reset by the rotation check"
     const int M = num_points<V>(A);
     const int n = A.F.n[b];
+    const bool ori = V == 1 && A.lf.checkOri;
     if (tid == 0) {
         sN = 0;
         sDir = V == 1 ? motion_direction(A.lf.tcwCur + (size_t)b * 12, A.lf.tcwLast + (size_t)b * 12, A.F.P.mb, A.lf.mono) : 0;
     }
     if (tid < OBS_HISTO_LENGTH) sHist[tid] = 0;
-    for (int k = tid; k < cap; k += nt) { T[k] = T_FREE; bad[k] = 0; }
+    for (int k = tid; k < cap; k += nt) { T[k] = T_FREE; Tc[k] = T_FREE; Tn[k] = T_FREE; last[k] = -1; }
     __syncthreads();
     const int dir = sDir;
-    int rounds = 0;
-    for (;;) {
-        for (int k = tid; k < cap; k += nt) Tn[k] = T_FREE;
-        __syncthreads();
-        for (int i = tid; i < M; i += nt) {
-            if (!point_locks<V>(A, b, i)) continue;
-            const int k = evaluate<V>(A, b, i, M, T, dir);
-            if (k >= 0) atomicMin(&Tn[k], i);
+    int iters = 0, mine = 0;
+    // Points are taken in blocks of blockDim consecutive indices.  Inside a block the claims are iterated to
+    // their fixed point (point i only depends on points < i, so the fixed point is the sequential result);
+    // then the block's locks become final and the next block starts.
+    for (int base = 0; base < M; base += nt) {
+        const int i = base + tid;
+        const bool active = i < M;
+        const bool locks = active && point_locks<V>(A, b, i);
+        int k = -1;
+        for (;;) {
+            k = active ? evaluate<V>(A, b, i, M, T, Tc, dir) : -1;
+            if (locks && k >= 0) atomicMin(&Tn[k], i);
+            iters++;
+            __syncthreads();
+            int changed = 0;
+            for (int kk = tid; kk < cap; kk += nt) {
+                const int v = Tn[kk];
+                changed |= (v != Tc[kk]);
+                Tc[kk] = v;
+                Tn[kk] = T_FREE;
+            }
+            if (!__syncthreads_or(changed)) break;
         }
-        __syncthreads();
-        int changed = 0;
-        for (int k = tid; k < cap; k += nt) { changed |= (Tn[k] != T[k]); }
-        changed = __syncthreads_or(changed);
-        for (int k = tid; k < cap; k += nt) T[k] = Tn[k];
-        rounds++;
-        __syncthreads();
-        if (!changed) break;
-    }
-    // final pass with the converged lock times
-    for (int k = tid; k < cap; k += nt) Tn[k] = -1;
-    __syncthreads();
-    const bool ori = V == 1 && A.lf.checkOri;
-    int mine = 0;
-    for (int i = tid; i < M; i += nt) {
-        int k = evaluate<V>(A, b, i, M, T, dir);
+        // the block has converged: k is final
         if (k >= 0) {
             mine++;
-            if (!point_locks<V>(A, b, i)) atomicMax(&Tn[k], i);
+            if (!locks) atomicMax(&last[k], i);
             if (ori) {
                 const int bin = rot_bin(A.lf.angle[(size_t)b * A.lf.stride + i], A.F.angle[(size_t)b * cap + k]);
                 atomicAdd(&sHist[bin], 1);
                 k |= bin << 16;
             }
         }
-        A.choice[(size_t)b * M + i] = k;
+        if (active) A.choice[(size_t)b * M + i] = k;
+        __syncthreads();
+        for (int kk = tid; kk < cap; kk += nt) {
+            if (Tc[kk] != T_FREE) { T[kk] = Tc[kk]; Tc[kk] = T_FREE; }       // a keypoint is claimed in one block only
+        }
+        __syncthreads();
     }
     if (mine) atomicAdd(&sN, mine);
+    __syncthreads();
+    // final owner per keypoint: the locking point if there is one (nothing is assigned after it), else the last
+    // non-locking point
+    for (int k = tid; k < cap; k += nt) {
+        int out = -1;
+        if (k < n) out = T[k] != T_FREE ? T[k] : last[k];
+        Tn[k] = out;
+        last[k] = 0;
+    }
     __syncthreads();
     if (ori) {
         if (tid == 0) three_maxima(sHist, OBS_HISTO_LENGTH, sInd[0], sInd[1], sInd[2]);
@@ -416,21 +454,13 @@ __global__ void __launch_bounds__(1024) k_proj_resolve(const __grid_constant__ P
             const int c = A.choice[(size_t)b * M + i];
             if (c < 0) continue;
             const int bin = c >> 16;
-            if (bin != sInd[0] && bin != sInd[1] && bin != sInd[2]) { bad[c & 0xffff] = 1; drop++; }
+            if (bin != sInd[0] && bin != sInd[1] && bin != sInd[2]) { last[c & 0xffff] = 1; drop++; }
         }
         if (drop) atomicSub(&sN, drop);
         __syncthreads();
     }
-    for (int k = tid; k < cap; k += nt) {
-        int out = -1;
-        if (k < n) {
-            if (bad[k]) out = -2;
-            else if (T[k] != T_FREE) out = T[k];
-            else out = Tn[k];
-        }
-        A.kpMatch[(size_t)b * cap + k] = out;
-    }
-    if (tid == 0) { A.nMatches[b] = sN; if (A.rounds) A.rounds[b] = rounds; }
+    for (int k = tid; k < cap; k += nt) A.kpMatch[(size_t)b * cap + k] = last[k] ? -2 : Tn[k];
+    if (tid == 0) { A.nMatches[b] = sN; if (A.rounds) A.rounds[b] = iters; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -558,11 +588,35 @@ __global__ void k_descriptor_distance(const uint8_t* a, const uint8_t* b, int n,
 constexpr int KNN_THREADS = 256;
 constexpr int KNN_TILE = 256;          // database descriptors staged per step (8 KB)
 
+// The POPC pipe issues 16 lanes/clk/SM against 64 for LOP3: carry-save adders (2 LOP3 each) fold the eight xor
+// words into fewer population counts.  sum(x0..x6) = s3 + 2*(c1+c2+c3) = s3 + 2*(s4 + 2*c4).
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& s, uint32_t& cy) {
+    s = a ^ b ^ c;
+    cy = (a & b) | (c & (a ^ b));
+}
+template <int MODE>
+__device__ __forceinline__ int hamming_knn(const uint32_t* q, const uint4 b0, const uint4 b1) {
+    if (MODE == 0) return hamming8(q, b0, b1);
+    const uint32_t x0 = q[0] ^ b0.x, x1 = q[1] ^ b0.y, x2 = q[2] ^ b0.z, x3 = q[3] ^ b0.w;
+    const uint32_t x4 = q[4] ^ b1.x, x5 = q[5] ^ b1.y, x6 = q[6] ^ b1.z, x7 = q[7] ^ b1.w;
+    uint32_t s1, c1, s2, c2, s3, c3;
+    csa(x0, x1, x2, s1, c1);
+    csa(x3, x4, x5, s2, c2);
+    csa(s1, s2, x6, s3, c3);
+    if (MODE == 1) return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+    uint32_t s4, c4;
+    csa(c1, c2, c3, s4, c4);
+    return __popc(s3) + __popc(x7) + 2 * __popc(s4) + 4 * __popc(c4);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(KNN_THREADS) k_knn2(const __grid_constant__ Knn2Args A) {
     __shared__ uint4 sDb[KNN_TILE * 2];
     const int tid = threadIdx.x;
-    const int2 pr = A.pairs[blockIdx.y];
-    const int qi = blockIdx.x * KNN_THREADS + tid;
+    const int qTiles = (A.n + KNN_THREADS - 1) / KNN_THREADS;
+    const int pair = blockIdx.x / qTiles;
+    const int2 pr = A.pairs[pair];
+    const int qi = (blockIdx.x - pair * qTiles) * KNN_THREADS + tid;
     const uint4* Q = A.desc + (size_t)pr.x * A.n * 2;
     const uint4* D = A.desc + (size_t)pr.y * A.n * 2;
     uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -577,7 +631,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn2(const __grid_constant__ Kn
         __syncthreads();
 #pragma unroll 4
         for (int j = 0; j < m; j++) {
-            const uint32_t key = ((uint32_t)hamming8(q, sDb[2 * j], sDb[2 * j + 1]) << 16) | (uint32_t)(base + j);
+            const uint32_t key = ((uint32_t)hamming_knn<MODE>(q, sDb[2 * j], sDb[2 * j + 1]) << 16) | (uint32_t)(base + j);
             const uint32_t hi = max(key, best);
             best = min(key, best);
             second = min(second, hi);
@@ -585,7 +639,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn2(const __grid_constant__ Kn
     }
     if (qi < A.n) {
         const int bd = (int)(best >> 16), sd = (int)(second >> 16);
-        const size_t o = (size_t)blockIdx.y * A.n + qi;
+        const size_t o = (size_t)pair * A.n + qi;
         int idx = -1;
         if (bd <= A.thLow && (float)bd < __fmul_rn(A.nnratio, (float)sd)) idx = (int)(best & 0xffffu);
         A.bestIdx[o] = idx;
@@ -605,8 +659,10 @@ cudaError_t launch_proj_search(const ProjSearchArgs& a, int variant, int nFrames
     const int M = variant == 0 ? a.mp.n : a.lf.n;
     if (nFrames <= 0) return cudaSuccess;
     const dim3 grid((std::max(M, 1) + 127) / 128, nFrames);
-    const size_t smem = (size_t)a.F.cap * 3 * sizeof(int);
+    const size_t smem = (size_t)a.F.cap * 4 * sizeof(int);
     cudaError_t e;
+    e = cudaMemsetAsync(a.poolCursor, 0, (size_t)nFrames * sizeof(int), st);
+    if (e != cudaSuccess) return e;
     if (variant == 0) {
         e = cudaFuncSetAttribute(k_proj_resolve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -641,7 +697,11 @@ cudaError_t launch_descriptor_distance(const uint8_t* a, const uint8_t* b, int n
 
 cudaError_t launch_knn2(const Knn2Args& a, cudaStream_t st) {
     if (a.nPairs <= 0 || a.n <= 0) return cudaSuccess;
-    const dim3 grid((a.n + KNN_THREADS - 1) / KNN_THREADS, a.nPairs);
-    k_knn2<<<grid, KNN_THREADS, 0, st>>>(a);
+    const long long blocks = (long long)((a.n + KNN_THREADS - 1) / KNN_THREADS) * a.nPairs;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    static const int mode = getenv("OBS_KNN2_MODE") ? atoi(getenv("OBS_KNN2_MODE")) : 1;
+    if (mode == 0) k_knn2<0><<<(unsigned)blocks, KNN_THREADS, 0, st>>>(a);
+    else if (mode == 1) k_knn2<1><<<(unsigned)blocks, KNN_THREADS, 0, st>>>(a);
+    else k_knn2<3><<<(unsigned)blocks, KNN_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }

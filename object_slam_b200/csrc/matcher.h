@@ -6,7 +6,7 @@
 #define OBS_GRID_ROWS 48          // FRAME_GRID_ROWS, include/Frame.h:42
 #define OBS_GRID_CELLS (OBS_GRID_COLS * OBS_GRID_ROWS)
 #define OBS_HISTO_LENGTH 30       // src/ORBmatcher.cc:39
-#define OBS_CAND_SLOTS 8          // cached candidates per projected point (more -> traversal on demand)
+#define OBS_CAND_SLOTS 8          // slots of one candidate chunk: 7 entries + link / terminator
 
 struct FrameParamsDev {
     float minX, maxX, minY, maxY, invW, invH;
@@ -55,7 +55,10 @@ struct ProjSearchArgs {
     LastFrameDev lf;
     float th, nnratio;
     const int* kpObs;         // [B][cap] or null
-    uint32_t* cand;           // [B][M][OBS_CAND_SLOTS]
+    uint32_t* cand;           // [B][M][OBS_CAND_SLOTS] first chunk of every point's candidate list
+    uint32_t* pool;           // [B][poolChunks][OBS_CAND_SLOTS] overflow chunks
+    int* poolCursor;          // [B]
+    int poolChunks;
     int* choice;              // [B][M]
     int* kpMatch;             // [B][cap]
     int* nMatches;            // [B]

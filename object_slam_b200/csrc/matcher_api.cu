@@ -16,7 +16,8 @@ struct obs_matcher {
     // staging slots for host inputs / device copies of host outputs
     static constexpr int SLOTS = 24;
     DevBuf<uint8_t> slot[SLOTS];
-    DevBuf<uint32_t> cand;
+    DevBuf<uint32_t> cand, pool;
+    DevBuf<int> poolCursor;
     DevBuf<int> choice, rounds;
     DevBuf<uint32_t> initList;
     DevBuf<int> initCount;
@@ -143,7 +144,7 @@ int obs_matcher_destroy(obs_matcher* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (auto& s : m->slot) s.release();
-    m->cand.release(); m->choice.release(); m->rounds.release(); m->initList.release(); m->initCount.release();
+    m->cand.release(); m->pool.release(); m->poolCursor.release(); m->choice.release(); m->rounds.release(); m->initList.release(); m->initCount.release();
     if (m->ev) cudaEventDestroy(m->ev);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -270,10 +271,13 @@ static int run_proj(obs_matcher* m, obs_frame_set* fs, ProjSearchArgs& a, int va
     if ((rc = dev_out(m, 21, kp_match, kc, &dMatch))) return rc;
     if ((rc = dev_out(m, 22, n_matches, (size_t)B, &dN))) return rc;
     CU(m->cand.ensure((size_t)B * std::max(M, 1) * OBS_CAND_SLOTS));
+    a.poolChunks = std::max(M, 64) * 2;
+    CU(m->pool.ensure((size_t)B * a.poolChunks * OBS_CAND_SLOTS));
+    CU(m->poolCursor.ensure((size_t)B));
     CU(m->choice.ensure((size_t)B * std::max(M, 1)));
     CU(m->rounds.ensure((size_t)B));
     a.F = fs->d;
-    a.cand = m->cand.p; a.choice = m->choice.p; a.kpMatch = dMatch; a.nMatches = dN; a.rounds = m->rounds.p;
+    a.cand = m->cand.p; a.pool = m->pool.p; a.poolCursor = m->poolCursor.p; a.choice = m->choice.p; a.kpMatch = dMatch; a.nMatches = dN; a.rounds = m->rounds.p;
     CU(launch_proj_search(a, variant, B, m->stream));
     bool queued = false;
     if ((rc = host_back(m, kp_match, dMatch, kc, &queued))) return rc;

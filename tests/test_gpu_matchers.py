@@ -122,7 +122,7 @@ def test_search_by_projection_shared_points_and_edges(M):
     n, match, _ = run_map(M, shape, [(frame, mpz, None)], 3.0, 0.8)
     on, omatch = oracle_map(frame, shape, mpz, 3.0, 0.8)
     assert n[0] == on and np.array_equal(match[0, :800], omatch) and on > (omatch >= 0).sum()
-    assert M.last_rounds()[0] == 1
+    assert M.last_rounds()[0] == (4000 + 1023) // 1024        # no locking point: one pass per block of 1024 points
 
 
 def test_search_by_projection_adversarial_chain(M):
