@@ -276,3 +276,17 @@ def test_errors(M):
         fs.upload([synth.synthetic_frame(TUM, 100, 0)])          # more keypoints than the set holds
     with pytest.raises(ObsError):
         M.SearchByProjection(fs, *[np.zeros(1, np.uint8)] * 8)   # empty frame set
+
+
+def test_two_gpu_allgather_and_sharded_matching(gpu):
+    """The NCCL exchange step (csrc/comm.cu) and sharded keyframe matching on 2 GPUs; skipped on a 1-GPU box."""
+    import subprocess
+    import sys
+    from object_slam_b200 import _capi
+    if _capi.lib().obs_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "check_allgather.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout
