@@ -123,11 +123,13 @@ int obs_extractor_get_level(obs_extractor* e, int image_index, int level, int wh
 int obs_extractor_get_candidates(obs_extractor* e, int image_index, int level, int32_t* xyr, int cap, int* n_out);
 int obs_extractor_get_selected(obs_extractor* e, int image_index, int level, int32_t* xyr, int cap, int* n_out);
 
-/* Per-stage device timing for benchmarks.  While profiling is on, every extraction on the handle
- * (and every stereo match whose left handle it is) is bracketed by CUDA events on its stream, up to
- * 128 calls.  obs_extractor_stage_ms synchronises the device and returns the SUM over the recorded
+/* Per-stage device timing for benchmarks.  While profiling is on, every stage of every extraction on the
+ * handle (and every stereo match whose left handle it is) is bracketed by CUDA events on the stream it runs on,
+ * up to 128 calls.  obs_extractor_stage_ms synchronises the device and returns the SUM over the recorded
  * calls of each stage's time in ms: stage_ms[OBS_NUM_STAGES] = {pyramid, FAST, quadtree, blur,
- * orientation+descriptors}; *stereo_ms = stereo match + outlier filter. */
+ * orientation+descriptors}; *stereo_ms = stereo match + outlier filter.  The blur runs on an auxiliary stream
+ * beside FAST + quadtree (both depend on the pyramid only), so the stage times of a call overlap and need not
+ * add up to its duration. */
 #define OBS_NUM_STAGES 5
 int obs_extractor_set_profiling(obs_extractor* e, int on);
 int obs_extractor_stage_ms(obs_extractor* e, float* stage_ms, float* stereo_ms, int* n_calls, int* n_stereo_calls);

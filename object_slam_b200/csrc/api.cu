@@ -6,7 +6,9 @@
 #include "host_util.h"
 #include "matcher_api.h"
 
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -57,7 +59,10 @@ struct obs_extractor {
     int device = 0;
     int maxW = 0, maxH = 0, maxBatch = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaStream_t aux = nullptr;    // the blur runs here, beside FAST + quadtree (both only need the pyramid)
+    cudaEvent_t done = nullptr, fork = nullptr, join = nullptr;
+    cudaStream_t cin = nullptr, cout = nullptr;       // host path: upload / download streams of the chunk pipeline
+    std::vector<cudaEvent_t> chunkIn, chunkDone;
 
     // tables of the constructor (src/ORBextractor.cc:410-470)
     std::vector<float> scale, invScale, sigma2, invSigma2;
@@ -90,7 +95,7 @@ struct obs_extractor {
 
     // optional per-stage CUDA-event timing (obs_extractor_set_profiling)
     bool prof = false;
-    std::vector<cudaEvent_t> pev;  // ring of PROF_SLOTS x (OBS_NUM_STAGES + 1) events
+    std::vector<cudaEvent_t> pev;  // ring of PROF_SLOTS x OBS_NUM_STAGES x (start, end) events
     int profCalls = 0;
     std::vector<cudaEvent_t> sev;  // stereo: ring of PROF_SLOTS x 2 events (owned by the left handle)
     int stereoCalls = 0;
@@ -273,23 +278,44 @@ int set_shape(obs_extractor* e, int w, int h, int nimg, cudaStream_t st) {
     return OBS_OK;
 }
 
-// Enqueue the whole extraction of `nimg` images on `st`.
-int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st) {
+// Enqueue the whole extraction of `nimg` images on `st`.  Dependencies: pyramid -> {FAST -> quadtree} and
+// pyramid -> blur, both -> describe; the blur is forked to the handle's auxiliary stream so that it fills the
+// SMs the latency-bound quadtree leaves idle.
+int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st, int img0 = 0, bool last = true, bool forkBlur = true) {
     const Geom& g = e->g;
+    const size_t o = (size_t)img0;
+    PyrPtrs P = e->ptrs;
+    P.l0 += o * P.l0ImgStride;
+    P.slab += o * P.slabStride;
+    uint8_t* blurP = e->blur.p + o * g.slabBytes;
+    uint32_t* candP = e->cand.p + o * g.slotTotal;
+    int* cellCountP = e->cellCount.p + o * g.nCellsTotal;
+    uint32_t* selP = e->sel.p + o * g.nlevels * g.selCap;
+    int* selCountP = e->selCount.p + o * g.nlevels;
     cudaEvent_t* ev = nullptr;
-    if (e->prof && e->profCalls < PROF_SLOTS) ev = e->pev.data() + (size_t)e->profCalls * (OBS_NUM_STAGES + 1);
+    if (e->prof && e->profCalls < PROF_SLOTS && img0 == 0 && last) ev = e->pev.data() + (size_t)e->profCalls * (2 * OBS_NUM_STAGES);
     if (ev) CU(cudaEventRecord(ev[0], st));
-    CU(launch_pyramid(g, e->ptrs, e->dXtab.p, e->dYtab.p, nimg, st));
+    CU(launch_pyramid(g, P, e->dXtab.p, e->dYtab.p, nimg, st));
     if (ev) CU(cudaEventRecord(ev[1], st));
-    CU(launch_fast(g, e->ptrs, e->dFastCtas.p, e->cand.p, e->cellCount.p, nimg, st));
+    cudaStream_t bs = forkBlur ? e->aux : st;
+    if (forkBlur) {
+        CU(cudaEventRecord(e->fork, st));
+        CU(cudaStreamWaitEvent(e->aux, e->fork, 0));
+    }
+    if (ev) CU(cudaEventRecord(ev[6], bs));
+    CU(launch_blur(g, P, blurP, g.slabBytes, nimg, bs));
+    if (ev) CU(cudaEventRecord(ev[7], bs));
+    if (forkBlur) CU(cudaEventRecord(e->join, e->aux));
     if (ev) CU(cudaEventRecord(ev[2], st));
-    CU(launch_quadtree(g, e->nodeCap, e->cand.p, e->cellCount.p, e->keyScratch.p, e->nodeScratch.p, e->sel.p, e->selCount.p, nimg, st));
-    if (ev) CU(cudaEventRecord(ev[3], st));
-    CU(launch_blur(g, e->ptrs, e->blur.p, g.slabBytes, nimg, st));
-    if (ev) CU(cudaEventRecord(ev[4], st));
-    CU(launch_describe(g, e->ptrs, e->blur.p, g.slabBytes, e->sel.p, e->selCount.p, e->records.p, e->recordBytes, nimg, st));
-    if (ev) { CU(cudaEventRecord(ev[5], st)); e->profCalls++; }
-    e->lastN = nimg;
+    CU(launch_fast(g, P, e->dFastCtas.p, candP, cellCountP, nimg, st));
+    if (ev) { CU(cudaEventRecord(ev[3], st)); CU(cudaEventRecord(ev[4], st)); }
+    CU(launch_quadtree(g, e->nodeCap, candP, cellCountP, e->keyScratch.p + o * g.slotTotal, e->nodeScratch.p + o * g.slotTotal, selP, selCountP, nimg, st));
+    if (ev) CU(cudaEventRecord(ev[5], st));
+    if (forkBlur) CU(cudaStreamWaitEvent(st, e->join, 0));
+    if (ev) CU(cudaEventRecord(ev[8], st));
+    CU(launch_describe(g, P, blurP, g.slabBytes, selP, selCountP, e->records.p + o * e->recordBytes, e->recordBytes, nimg, st));
+    if (ev) { CU(cudaEventRecord(ev[9], st)); e->profCalls++; }
+    e->lastN = img0 + nimg;
     e->lastStream = st;
     return OBS_OK;
 }
@@ -341,7 +367,12 @@ int obs_extractor_create(const obs_orb_params* params, int max_w, int max_h, int
     e->maxW = max_w; e->maxH = max_h; e->maxBatch = max_batch;
     build_tables(e);
     cudaError_t se = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking);
     if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->join, cudaEventDisableTiming);
+    if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&e->cin, cudaStreamNonBlocking);
+    if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&e->cout, cudaStreamNonBlocking);
     if (se != cudaSuccess) { delete e; return fail(OBS_ERR_CUDA, "stream/event creation: %s", cudaGetErrorString(se)); }
     int rc = set_shape(e, max_w, max_h, max_batch, e->stream);
     if (rc != OBS_OK) { obs_extractor_destroy(e); return rc; }
@@ -360,6 +391,13 @@ int obs_extractor_destroy(obs_extractor* e) {
     for (cudaEvent_t ev : e->pev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->sev) cudaEventDestroy(ev);
     if (e->done) cudaEventDestroy(e->done);
+    if (e->fork) cudaEventDestroy(e->fork);
+    if (e->join) cudaEventDestroy(e->join);
+    for (cudaEvent_t ev : e->chunkIn) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->chunkDone) cudaEventDestroy(ev);
+    if (e->cin) cudaStreamDestroy(e->cin);
+    if (e->cout) cudaStreamDestroy(e->cout);
+    if (e->aux) cudaStreamDestroy(e->aux);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return OBS_OK;
@@ -384,7 +422,7 @@ int obs_extractor_set_profiling(obs_extractor* e, int on) {
     int rc = check_handle(e);
     if (rc) return rc;
     if (on && e->pev.empty()) {
-        e->pev.resize((size_t)PROF_SLOTS * (OBS_NUM_STAGES + 1));
+        e->pev.resize((size_t)PROF_SLOTS * (2 * OBS_NUM_STAGES));
         for (cudaEvent_t& ev : e->pev) CU(cudaEventCreate(&ev));
         e->sev.resize((size_t)PROF_SLOTS * 2);
         for (cudaEvent_t& ev : e->sev) CU(cudaEventCreate(&ev));
@@ -403,8 +441,8 @@ int obs_extractor_stage_ms(obs_extractor* e, float* stage_ms, float* stereo_ms, 
         float sum = 0.f;
         for (int c = 0; c < e->profCalls; c++) {
             float ms = 0.f;
-            const cudaEvent_t* ev = e->pev.data() + (size_t)c * (OBS_NUM_STAGES + 1);
-            CU(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+            const cudaEvent_t* ev = e->pev.data() + (size_t)c * (2 * OBS_NUM_STAGES);
+            CU(cudaEventElapsedTime(&ms, ev[2 * s], ev[2 * s + 1]));
             sum += ms;
         }
         if (stage_ms) stage_ms[s] = sum;
@@ -466,6 +504,86 @@ int obs_extract_batch(obs_extractor* e, const uint8_t* const* images, int n_imag
     bool oneBlock = is_pinned(images[0]);
     const size_t imgBytes = stride * (size_t)h;
     for (int i = 1; oneBlock && i < n_images; i++) oneBlock = images[i] == images[i - 1] + imgBytes;
+    e->ptrs.l0 = e->pyr.p;
+    e->ptrs.l0ImgStride = g.slabBytes;
+    e->ptrs.l0Pitch = g.lv[0].pitch;
+    e->ptrs.slab = e->pyr.p;
+    e->ptrs.slabStride = g.slabBytes;
+    const bool pinnedOut = keypoints && descriptors && is_pinned(keypoints) && is_pinned(descriptors) && cap > 0;
+    if (oneBlock && pinnedOut && n_images >= 8) {
+        // Chunk pipeline: upload of chunk c+1 (copy-in stream), extraction of chunk c and download of chunk c-1
+        // (copy-out stream) overlap; page-locked memory on both sides, no staging.  Consecutive chunks alternate
+        // between the handle's two compute streams, so one chunk's latency-bound quadtree runs beside the next
+        // chunk's FAST / blur instead of serialising the pipeline.
+        const int nChunks = n_images >= 32 ? 4 : 2;
+        while ((int)e->chunkIn.size() < nChunks) {
+            cudaEvent_t a, b;
+            CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            e->chunkIn.push_back(a); e->chunkDone.push_back(b);
+        }
+        CU(e->rawIn.ensure((size_t)e->maxBatch * imgBytes + 16));
+        CU(e->stageOut.ensure((size_t)e->maxBatch * sizeof(int)));
+        int* cnts = reinterpret_cast<int*>(e->stageOut.p);
+        const int m = cap < g.kpCap ? cap : g.kpCap;
+        // the previous call's device work (a stereo match may still read the pyramids) precedes the first upload
+        CU(cudaEventRecord(e->done, st));
+        CU(cudaStreamWaitEvent(e->cin, e->done, 0));
+        CU(cudaStreamWaitEvent(e->aux, e->done, 0));
+        static const bool trace = getenv("OBS_TRACE") != nullptr;
+        cudaEvent_t tev[6 * 4];
+        if (trace) for (auto& t : tev) cudaEventCreate(&t);
+        const auto tHost0 = std::chrono::steady_clock::now();
+        for (int c = 0; c < nChunks; c++) {
+            const int c0 = (int)((long long)n_images * c / nChunks), c1 = (int)((long long)n_images * (c + 1) / nChunks);
+            if (c1 <= c0) continue;
+            if (trace) cudaEventRecord(tev[6 * c + 0], e->cin);
+            CU(cudaMemcpyAsync(e->rawIn.p + (size_t)c0 * imgBytes, images[c0], (size_t)(c1 - c0) * imgBytes, cudaMemcpyHostToDevice, e->cin));
+            if (trace) cudaEventRecord(tev[6 * c + 1], e->cin);
+            CU(cudaEventRecord(e->chunkIn[c], e->cin));
+            cudaStream_t cs = (c & 1) ? e->aux : st;
+            CU(cudaStreamWaitEvent(cs, e->chunkIn[c], 0));
+            if (trace) cudaEventRecord(tev[6 * c + 2], cs);
+            CU(launch_repack(e->rawIn.p + (size_t)c0 * imgBytes, imgBytes, stride, e->pyr.p + (size_t)c0 * g.slabBytes, g.slabBytes, (int)p0, w, h, c1 - c0, cs));
+            rc = run_pipeline(e, c1 - c0, cs, c0, false, false);
+            if (rc) return rc;
+            if (trace) cudaEventRecord(tev[6 * c + 3], cs);
+            CU(cudaEventRecord(e->chunkDone[c], cs));
+            CU(cudaStreamWaitEvent(e->cout, e->chunkDone[c], 0));
+            if (trace) cudaEventRecord(tev[6 * c + 4], e->cout);
+            const uint8_t* rec = e->records.p + (size_t)c0 * e->recordBytes;
+            CU(cudaMemcpy2DAsync(cnts + c0, sizeof(int), rec, e->recordBytes, sizeof(int), c1 - c0, cudaMemcpyDeviceToHost, e->cout));
+            CU(cudaMemcpy2DAsync(keypoints + (size_t)c0 * cap, (size_t)cap * 28, rec + OBS_HDR_INTS * 4, e->recordBytes, (size_t)m * 28, c1 - c0, cudaMemcpyDeviceToHost, e->cout));
+            CU(cudaMemcpy2DAsync(descriptors + (size_t)c0 * cap * 32, (size_t)cap * 32, rec + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28, e->recordBytes, (size_t)m * 32, c1 - c0, cudaMemcpyDeviceToHost, e->cout));
+            if (trace) cudaEventRecord(tev[6 * c + 5], e->cout);
+        }
+        // later consumers (stereo match, frame-set build) order themselves after the handle stream
+        CU(cudaEventRecord(e->join, e->aux));
+        CU(cudaStreamWaitEvent(st, e->join, 0));
+        e->lastN = n_images;
+        e->lastStream = st;
+        const auto tHost1 = std::chrono::steady_clock::now();
+        CU(cudaStreamSynchronize(e->cout));
+        if (trace) {
+            const auto tHost2 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[obs trace %p] enqueue %.3f ms, total %.3f ms;", (void*)e,
+                    std::chrono::duration<double, std::milli>(tHost1 - tHost0).count(), std::chrono::duration<double, std::milli>(tHost2 - tHost0).count());
+            for (int c = 0; c < nChunks; c++) {
+                float t[6];
+                for (int k = 0; k < 6; k++) cudaEventElapsedTime(&t[k], tev[0], tev[6 * c + k]);
+                fprintf(stderr, " c%d in %.3f-%.3f run %.3f-%.3f out %.3f-%.3f;", c, t[0], t[1], t[2], t[3], t[4], t[5]);
+            }
+            fprintf(stderr, "\n");
+            for (auto& t : tev) cudaEventDestroy(t);
+        }
+        int status = OBS_OK;
+        for (int i = 0; i < n_images; i++) {
+            n_out[i] = cnts[i];
+            if (cnts[i] > cap) status = OBS_ERR_CAPACITY;
+        }
+        if (status) return fail(status, "caller capacity %d smaller than the keypoint count", cap);
+        return OBS_OK;
+    }
     if (oneBlock) {
         CU(e->rawIn.ensure((size_t)e->maxBatch * imgBytes + 16));
         CU(cudaMemcpyAsync(e->rawIn.p, images[0], (size_t)n_images * imgBytes, cudaMemcpyHostToDevice, st));
@@ -666,7 +784,9 @@ int obs_stereo_match_device(obs_extractor* L, obs_extractor* R, float mbf, float
     // later work on either handle must not overwrite the inputs while the match runs
     CU(cudaEventRecord(L->done, st));
     if (R->stream != st) CU(cudaStreamWaitEvent(R->stream, L->done, 0));
+    if (R->lastStream != st && R->lastStream != R->stream) CU(cudaStreamWaitEvent(R->lastStream, L->done, 0));
     if (L->stream != st) CU(cudaStreamWaitEvent(L->stream, L->done, 0));
+    if (L->lastStream != st && L->lastStream != L->stream) CU(cudaStreamWaitEvent(L->lastStream, L->done, 0));
     L->lastStream = st;
     if (d_u_right) *d_u_right = L->uRight.p;
     if (d_depth) *d_depth = L->depth.p;
