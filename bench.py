@@ -208,12 +208,25 @@ def main():
     torch.cuda.set_stream(tstream)
     stream, stream2 = tstream.cuda_stream, tstream2.cuda_stream
 
+    # Device-resident pipelines: each owns an extractor pair and two streams; consecutive steps go to alternate
+    # pipelines, so the tail of one batch overlaps the head of the next (all kernels here are latency / issue
+    # bound, none fills the machine alone).
+    NPIPES = int(os.environ.get("OBS_BENCH_PIPES", "2"))
+    dpipes = [(exL, exR, tstream, tstream2)]
+    for _ in range(NPIPES - 1):
+        dpipes.append((ORBextractor(NFEAT, 1.2, 8, 20, 7, max_size=(W, H), max_batch=F, device=local_rank),
+                       ORBextractor(NFEAT, 1.2, 8, 20, 7, max_size=(W, H), max_batch=F, device=local_rank),
+                       torch.cuda.Stream(), torch.cuda.Stream()))
+    step_no = [0]
+
     def step_device():
         # the two eyes on two streams, like the reference's two extraction threads (Frame.cc:78-81); the stereo match
         # (left stream) waits for the right eye inside the library, and the right eye's next extraction waits for it
-        exL.extract_device(dL.data_ptr(), F, W, H, PITCH, H * PITCH, stream)
-        exR.extract_device(dR.data_ptr(), F, W, H, PITCH, H * PITCH, stream2)
-        stereo_match_device(exL, exR, synth.KITTI_BF, 0.0, synth.KITTI_FX, stream)
+        eL, eR, sA, sB = dpipes[step_no[0] % NPIPES]
+        step_no[0] += 1
+        eL.extract_device(dL.data_ptr(), F, W, H, PITCH, H * PITCH, sA.cuda_stream)
+        eR.extract_device(dR.data_ptr(), F, W, H, PITCH, H * PITCH, sB.cuda_stream)
+        stereo_match_device(eL, eR, synth.KITTI_BF, 0.0, synth.KITTI_FX, sA.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -222,21 +235,38 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, NPIPES)):
         step_device()
-    exL.set_profiling(True)
-    exR.set_profiling(True)
+    step_no[0] = 0
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    tstream2.wait_stream(tstream)          # nothing of the timed region starts before ev0
+    for _, _, sA, sB in dpipes:            # nothing of the timed region starts before ev0
+        for st_ in (sA, sB):
+            if st_ is not tstream:
+                st_.wait_stream(tstream)
     for _ in range(args.steps):
         step_device()
-    ev1.record()                           # left stream: the last stereo match has waited for the right eye
+    for _, _, sA, sB in dpipes:            # ev1 follows the last kernel of every pipeline
+        for st_ in (sA, sB):
+            if st_ is not tstream:
+                tstream.wait_stream(st_)
+    ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
+    # per-kernel durations: a profiling pass of the same run directly after the timed region, one eye at a time with
+    # the stages serialised (in the timed region four streams overlap, so per-kernel brackets there include waiting)
+    exL.set_profiling(True)
+    exR.set_profiling(True)
+    for _ in range(min(args.steps, 10)):
+        exL.extract_device(dL.data_ptr(), F, W, H, PITCH, H * PITCH, stream)
+        torch.cuda.synchronize()
+        exR.extract_device(dR.data_ptr(), F, W, H, PITCH, H * PITCH, stream2)
+        torch.cuda.synchronize()
+        stereo_match_device(exL, exR, synth.KITTI_BF, 0.0, synth.KITTI_FX, stream)
+        torch.cuda.synchronize()
     stL, ncL, nsL = exL.stage_ms()
     stR, ncR, _ = exR.stage_ms()
     exL.set_profiling(False)
@@ -327,7 +357,8 @@ def main():
     per_launch_ms = {k: (stL[k] + stR[k]) / max(ncL + ncR, 1) for k in ORBextractor.STAGES}
     per_launch_ms["stereo"] = stL["stereo"] / max(nsL, 1)
     step_ms = ms_total / args.steps
-    shares = {k: (2 * v if k != "stereo" else v) / step_ms for k, v in per_launch_ms.items()}
+    serial_ms = sum((2 * v if k != "stereo" else v) for k, v in per_launch_ms.items())
+    shares = {k: (2 * v if k != "stereo" else v) / serial_ms for k, v in per_launch_ms.items()}
     dominant = max(shares, key=shares.get)
     traffic = None
     try:
@@ -342,8 +373,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "per_launch_ms": per_launch_ms, "share_of_step": shares,
-                "note": "stage times are CUDA-event brackets inside the timed region; the two eyes run on two streams and the blur runs "
-                        "beside FAST + quadtree, so stages overlap and the shares add up to more than 1",
+                "serialised_step_ms": serial_ms,
+                "note": "per_launch_ms: CUDA-event brackets of a profiling pass run directly after the timed region with every kernel "
+                        "serialised (shares are of that serial sum); in the timed region the eyes, the blur and consecutive batches "
+                        "overlap on four streams, which is why ms_per_step is below serialised_step_ms",
                 "whole_step": {"algorithmic_bytes": F * 19.5e6, "achieved": F * 19.5e6 / (step_ms * 1e-3) / 1e9,
                                "frac": F * 19.5e6 / (step_ms * 1e-3) / 1e9 / peak}}
 

@@ -127,9 +127,9 @@ int obs_extractor_get_selected(obs_extractor* e, int image_index, int level, int
  * handle (and every stereo match whose left handle it is) is bracketed by CUDA events on the stream it runs on,
  * up to 128 calls.  obs_extractor_stage_ms synchronises the device and returns the SUM over the recorded
  * calls of each stage's time in ms: stage_ms[OBS_NUM_STAGES] = {pyramid, FAST, quadtree, blur,
- * orientation+descriptors}; *stereo_ms = stereo match + outlier filter.  The blur runs on an auxiliary stream
- * beside FAST + quadtree (both depend on the pyramid only), so the stage times of a call overlap and need not
- * add up to its duration. */
+ * orientation+descriptors}; *stereo_ms = stereo match + outlier filter.  Without profiling the blur runs on an
+ * auxiliary stream beside FAST + quadtree (both depend on the pyramid only); while profiling is on the stages
+ * of a call are serialised so that their brackets do not overlap. */
 #define OBS_NUM_STAGES 5
 int obs_extractor_set_profiling(obs_extractor* e, int on);
 int obs_extractor_stage_ms(obs_extractor* e, float* stage_ms, float* stereo_ms, int* n_calls, int* n_stereo_calls);

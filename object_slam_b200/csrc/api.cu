@@ -476,7 +476,7 @@ int obs_extract_batch_device(obs_extractor* e, const uint8_t* d_images, int n_im
     e->ptrs.l0Pitch = (int)stride;
     e->ptrs.slab = e->pyr.p;
     e->ptrs.slabStride = e->g.slabBytes;
-    return run_pipeline(e, n_images, st);
+    return run_pipeline(e, n_images, st, 0, true, !e->prof);      // profiling: stages serialised, so their brackets do not overlap
 }
 
 int obs_extract_batch(obs_extractor* e, const uint8_t* const* images, int n_images, int w, int h,
@@ -605,7 +605,7 @@ int obs_extract_batch(obs_extractor* e, const uint8_t* const* images, int n_imag
     e->ptrs.l0Pitch = g.lv[0].pitch;
     e->ptrs.slab = e->pyr.p;
     e->ptrs.slabStride = g.slabBytes;
-    rc = run_pipeline(e, n_images, st);
+    rc = run_pipeline(e, n_images, st, 0, true, !e->prof);
     if (rc) return rc;
     return obs_extractor_fetch(e, keypoints, descriptors, cap, n_out);
 }
