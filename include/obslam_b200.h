@@ -253,6 +253,36 @@ int obs_search_by_projection_last(obs_matcher* m, obs_frame_set* current, const 
                                   float th, int mono, int check_orientation, const int32_t* kp_observations,
                                   int32_t* kp_match, int32_t* n_matches);
 
+/* Fields of the map points read by the two keyframe searches below; n entries per frame (per_frame as above). */
+typedef struct obs_keyframe_points_view {
+    int32_t n;
+    int32_t per_frame;
+    const uint8_t* valid;                   /* pMP && !pMP->isBad() && not in the already-found set */
+    const float* world_pos;                 /* GetWorldPos(), n x 3 */
+    const float* min_distance;              /* GetMinDistanceInvariance() */
+    const float* max_distance;              /* GetMaxDistanceInvariance() */
+    const float* max_distance_raw;          /* mfMaxDistance, read by MapPoint::PredictScale (src/MapPoint.cc:488-519) */
+    const float* normal;                    /* GetNormal(), n x 3 (Sim3 variant only, else NULL) */
+    const float* angle;                     /* pKF->mvKeysUn[i].angle (keyframe variant only, else NULL) */
+    const uint8_t* descriptors;             /* GetDescriptor(), n x 32 */
+    const float* tcw;                       /* 12 floats per frame: rows 0..2 of CurrentFrame.mTcw, resp. [Rcw | tcw] of Scw */
+} obs_keyframe_points_view;
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist),
+ * src/ORBmatcher.cc:1472-1599 (relocalisation): projection, distance gate, MapPoint::PredictScale (glibc logf restated
+ * on the device), window search on levels [l-1, l+1], best distance <= orb_dist, rotation check.  kp_taken (in, may be
+ * NULL): != 0 where mvpMapPoints[k] is non-NULL (any point blocks).  kp_match as above (-2 = reset by the rotation check). */
+int obs_search_by_projection_keyframe(obs_matcher* m, obs_frame_set* current, const obs_keyframe_points_view* points,
+                                      float th, int orb_dist, int check_orientation, const int32_t* kp_taken,
+                                      int32_t* kp_match, int32_t* n_matches);
+
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>&
+ * vpMatched, th), src/ORBmatcher.cc:290-403 (loop closing), after the decomposition of Scw (:299-304, tcw = [Rcw | tcw]):
+ * the frames of `keyframes` are the keyframes' keypoints (KeyFrame::GetFeaturesInArea, src/KeyFrame.cc:569-608, is the
+ * Frame function without level filter).  kp_taken: != 0 where vpMatched[k] is non-NULL. */
+int obs_search_by_projection_sim3(obs_matcher* m, obs_frame_set* keyframes, const obs_keyframe_points_view* points,
+                                  int th, const int32_t* kp_taken, int32_t* kp_match, int32_t* n_matches);
+
 /* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:405-520: frame i of f1 against frame i of f2.
  * prev_matched: n_frames x max_keypoints(f1) x 2 floats, in/out (vbPrevMatched); matches12:
  * n_frames x max_keypoints(f1) (vnMatches12). */

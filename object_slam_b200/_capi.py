@@ -48,6 +48,12 @@ class LastFrameView(C.Structure):
                 ("tcw_last", C.c_void_p), ("tcw_current", C.c_void_p)]
 
 
+class KeyFramePointsView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("per_frame", C.c_int32), ("valid", C.c_void_p), ("world_pos", C.c_void_p),
+                ("min_distance", C.c_void_p), ("max_distance", C.c_void_p), ("max_distance_raw", C.c_void_p),
+                ("normal", C.c_void_p), ("angle", C.c_void_p), ("descriptors", C.c_void_p), ("tcw", C.c_void_p)]
+
+
 class ObsError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"obslam_b200 error {code}: {msg}")
@@ -93,6 +99,8 @@ _PROTOS = {
     "obs_frame_set_grid": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
     "obs_search_by_projection": (C.c_int, [_vp, _vp, C.POINTER(MapPointView), C.c_float, C.c_float, _vp, _vp, _vp]),
     "obs_search_by_projection_last": (C.c_int, [_vp, _vp, C.POINTER(LastFrameView), C.c_float, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "obs_search_by_projection_keyframe": (C.c_int, [_vp, _vp, C.POINTER(KeyFramePointsView), C.c_float, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "obs_search_by_projection_sim3": (C.c_int, [_vp, _vp, C.POINTER(KeyFramePointsView), C.c_int, _vp, _vp, _vp]),
     "obs_search_for_initialization": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int, _vp]),
     "obs_compute_three_maxima": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "obs_descriptor_distance": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),

@@ -189,7 +189,7 @@ __device__ __forceinline__ int rot_bin(float a1, float a2) {
 struct Query {
     float u, v, r, ur, rthr;
     int minLevel, maxLevel;
-    bool valid, locks;
+    bool valid, locks, stereo;
 };
 
 // cv::Mat A(3x3)*x+c on floats: binary32 products and sums left to right, the final addition in binary64
@@ -214,10 +214,66 @@ __device__ int motion_direction(const float* Tc, const float* Tl, float mb, int 
     return fwd | (bwd << 1);
 }
 
+// glibc >= 2.27 logf (ARM optimized-routines; table __logf_data of this image's libm): binary64 evaluation, result
+// rounded to binary32.  Equals libm's logf on all 2,130,706,432 positive normal floats (with and without FMA
+// contraction of the binary64 operations; tests/test_oracle_matchers.py checks a strided sweep).
+__device__ const double d_logf_tab[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2}, {0x1.49539f0f010b0p+0, -0x1.01eae7f513a67p-2},
+    {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3}, {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8ea0p+0, -0x1.1aa2bc79c8100p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4}, {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5},
+    {0x1p+0, 0x0p+0}, {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5}, {0x1.ca4b31f026aa0p-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3}, {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3}, {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},
+    {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+
+__device__ float logf_glibc(float x) {
+    uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix * 2 == 0) return -__int_as_float(0x7f800000);                  // log(0) = -inf
+        if (ix == 0x7f800000u) return x;                                       // log(inf) = inf
+        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return __int_as_float(0x7fc00000);   // log(negative), log(nan)
+        ix = __float_as_uint(__fmul_rn(x, 8388608.0f));                        // subnormal: normalise
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (tmp >> 19) & 15;
+    const int k = (int)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const double z = (double)__uint_as_float(iz);
+    const double r = __dsub_rn(__dmul_rn(z, d_logf_tab[i][0]), 1.0);
+    const double y0 = __dadd_rn(d_logf_tab[i][1], __dmul_rn((double)k, 0x1.62e42fefa39efp-1));
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(0x1.5575b0be00b6ap-2, r), -0x1.ffffef20a4123p-2);
+    y = __dadd_rn(__dmul_rn(-0x1.00ea348b88334p-2, r2), y);
+    y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+    return __double2float_rn(y);
+}
+
+// MapPoint::PredictScale, MapPoint.cc:488-519.  The float -> int conversion follows x86 (cvttss2si): values that do not
+// fit (incl. NaN and +-inf) become INT_MIN, which the clamp below turns into level 0.
+__device__ __forceinline__ int predict_scale(float maxDistRaw, float dist, float logScaleFactor, int nLevels) {
+    const float ratio = __fdiv_rn(maxDistRaw, dist);
+    const float q = ceilf(__fdiv_rn(logf_glibc(ratio), logScaleFactor));
+    int nScale = (q >= -2147483648.0f && q < 2147483648.0f) ? (int)q : (int)0x80000000;
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= nLevels) nScale = nLevels - 1;
+    return nScale;
+}
+
+// camera centre -Rcw^T * tcw (binary64 accumulation, the generic gemm branch)
+__device__ __forceinline__ void camera_centre(const float* Tc, float* Ow) {
+    for (int r = 0; r < 3; r++) {
+        double s = __dmul_rn((double)Tc[r], (double)Tc[3]);
+        s = __dadd_rn(s, __dmul_rn((double)Tc[4 + r], (double)Tc[7]));
+        s = __dadd_rn(s, __dmul_rn((double)Tc[8 + r], (double)Tc[11]));
+        Ow[r] = __double2float_rn(-s);
+    }
+}
+
 template <int V>
 __device__ __forceinline__ Query make_query(const ProjSearchArgs& A, int b, int i, int dir) {
     Query q;
-    q.valid = false; q.locks = false; q.u = q.v = q.r = q.ur = q.rthr = 0.f; q.minLevel = q.maxLevel = -1;
+    q.valid = false; q.locks = false; q.stereo = V < 2; q.u = q.v = q.r = q.ur = q.rthr = 0.f; q.minLevel = q.maxLevel = -1;
     const FrameParamsDev& P = A.F.P;
     if (V == 0) {
         const size_t o = (size_t)b * A.mp.stride + i;
@@ -231,6 +287,48 @@ __device__ __forceinline__ Query make_query(const ProjSearchArgs& A, int b, int 
         q.u = A.mp.projX[o]; q.v = A.mp.projY[o]; q.ur = A.mp.projXR[o];
         q.minLevel = lvl - 1; q.maxLevel = lvl;
         q.locks = A.mp.obs[o] > 0;
+        q.valid = true;
+    } else if (V >= 2) {
+        const size_t o = (size_t)b * A.kf.stride + i;
+        if (!A.kf.valid[o]) return q;
+        const float* Tc = A.kf.tcw + (size_t)b * 12;
+        const float* p = A.kf.pos + o * 3;
+        const float x0 = p[0], x1 = p[1], x2 = p[2];
+        const float xc = row_rx_plus_t(Tc, 0, x0, x1, x2);
+        const float yc = row_rx_plus_t(Tc, 1, x0, x1, x2);
+        const float zc = row_rx_plus_t(Tc, 2, x0, x1, x2);
+        float u, v;
+        if (V == 2) {                                                   // :1500-1510 (no depth-sign test here)
+            const float invzc = __double2float_rn(__ddiv_rn(1.0, (double)zc));
+            u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, xc), invzc), P.cx);
+            v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, yc), invzc), P.cy);
+            if (u < P.minX || u > P.maxX) return q;
+            if (v < P.minY || v > P.maxY) return q;
+        } else {                                                        // :320-335
+            if (zc < 0.0f) return q;
+            const float invz = __fdiv_rn(1.0f, zc);
+            u = __fadd_rn(__fmul_rn(P.fx, __fmul_rn(xc, invz)), P.cx);
+            v = __fadd_rn(__fmul_rn(P.fy, __fmul_rn(yc, invz)), P.cy);
+            if (!(u >= P.minX && u < P.maxX && v >= P.minY && v < P.maxY)) return q;
+        }
+        float Ow[3];
+        camera_centre(Tc, Ow);
+        const float po0 = __fsub_rn(x0, Ow[0]), po1 = __fsub_rn(x1, Ow[1]), po2 = __fsub_rn(x2, Ow[2]);
+        const double ss = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)po0), __dmul_rn((double)po1, (double)po1)),
+                                    __dmul_rn((double)po2, (double)po2));
+        const float dist = __double2float_rn(__dsqrt_rn(ss));            // cv::norm
+        if (dist < A.kf.minDist[o] || dist > A.kf.maxDist[o]) return q;
+        if (V == 3) {                                                   // viewing angle below 60 degrees, :347-350
+            const float* nrm = A.kf.normal + o * 3;
+            const double dt = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)nrm[0]), __dmul_rn((double)po1, (double)nrm[1])),
+                                        __dmul_rn((double)po2, (double)nrm[2]));
+            if (dt < __dmul_rn(0.5, (double)dist)) return q;
+        }
+        const int lvl = predict_scale(A.kf.maxDistRaw[o], dist, A.kf.logScaleFactor, P.nlevels);
+        q.r = __fmul_rn(A.th, P.scale[lvl]);
+        q.u = u; q.v = v;
+        q.minLevel = lvl - 1; q.maxLevel = V == 2 ? lvl + 1 : lvl;
+        q.locks = true;                                                 // any assigned point blocks the keypoint (:1536, :367)
         q.valid = true;
     } else {
         const size_t o = (size_t)b * A.lf.stride + i;
@@ -262,18 +360,22 @@ __device__ __forceinline__ Query make_query(const ProjSearchArgs& A, int b, int 
     return q;
 }
 
-template <int V> __device__ __forceinline__ int num_points(const ProjSearchArgs& A) { return V == 0 ? A.mp.n : A.lf.n; }
+template <int V> __device__ __forceinline__ int num_points(const ProjSearchArgs& A) { return V == 0 ? A.mp.n : V == 1 ? A.lf.n : A.kf.n; }
 template <int V> __device__ __forceinline__ const uint4* point_desc(const ProjSearchArgs& A, int b, int i) {
-    return V == 0 ? A.mp.desc + ((size_t)b * A.mp.stride + i) * 2 : A.lf.desc + ((size_t)b * A.lf.stride + i) * 2;
+    return V == 0 ? A.mp.desc + ((size_t)b * A.mp.stride + i) * 2
+         : V == 1 ? A.lf.desc + ((size_t)b * A.lf.stride + i) * 2 : A.kf.desc + ((size_t)b * A.kf.stride + i) * 2;
 }
 template <int V> __device__ __forceinline__ bool point_locks(const ProjSearchArgs& A, int b, int i) {
-    return V == 0 ? A.mp.obs[(size_t)b * A.mp.stride + i] > 0 : A.lf.obs[(size_t)b * A.lf.stride + i] > 0;
+    return V == 0 ? A.mp.obs[(size_t)b * A.mp.stride + i] > 0 : V == 1 ? A.lf.obs[(size_t)b * A.lf.stride + i] > 0 : true;
+}
+template <int V> __device__ __forceinline__ float point_angle(const ProjSearchArgs& A, int b, int i) {
+    return V == 1 ? A.lf.angle[(size_t)b * A.lf.stride + i] : A.kf.angle[(size_t)b * A.kf.stride + i];
 }
 
 // the keypoint-side filters that do not change during the call (ORBmatcher.cc:87-96 / :1391-1402)
 __device__ __forceinline__ bool static_ok(const ProjSearchArgs& A, int b, int idx, const float4& k, const Query& q) {
     if (A.kpObs && A.kpObs[(size_t)b * A.F.cap + idx] > 0) return false;
-    if (k.z > 0) {
+    if (q.stereo && k.z > 0) {
         const float er = fabsf(__fsub_rn(q.ur, k.z));
         if (er > q.rthr) return false;
     }
@@ -366,7 +468,7 @@ __device__ __forceinline__ int evaluate(const ProjSearchArgs& A, int b, int i, i
             B.upd(hamming8(d, __ldg(fd + 2 * idx), __ldg(fd + 2 * idx + 1)), __float_as_int(k.w) & 15, idx);
         });
     }
-    if (B.d1 > TH_HIGH) return -1;
+    if (B.d1 > (V >= 2 ? A.kf.distTh : TH_HIGH)) return -1;
     if (V == 0) {
         if (B.l1 == B.l2 && (float)B.d1 > __fmul_rn(A.nnratio, (float)B.d2)) return -1;     // :118-121
     }
@@ -386,7 +488,7 @@ __global__ void __launch_bounds__(1024) k_proj_resolve(const __grid_constant__ P
     int* last = sm + 3 * cap;   // last non-locking point assigned per keypoint; afterwards: "reset by the rotation check"
     const int M = num_points<V>(A);
     const int n = A.F.n[b];
-    const bool ori = V == 1 && A.lf.checkOri;
+    const bool ori = (V == 1 && A.lf.checkOri) || (V == 2 && A.kf.checkOri);
     if (tid == 0) {
         sN = 0;
         sDir = V == 1 ? motion_direction(A.lf.tcwCur + (size_t)b * 12, A.lf.tcwLast + (size_t)b * 12, A.F.P.mb, A.lf.mono) : 0;
@@ -423,7 +525,7 @@ __global__ void __launch_bounds__(1024) k_proj_resolve(const __grid_constant__ P
             mine++;
             if (!locks) atomicMax(&last[k], i);
             if (ori) {
-                const int bin = rot_bin(A.lf.angle[(size_t)b * A.lf.stride + i], A.F.angle[(size_t)b * cap + k]);
+                const int bin = rot_bin(point_angle<V>(A, b, i), A.F.angle[(size_t)b * cap + k]);
                 atomicAdd(&sHist[bin], 1);
                 k |= bin << 16;
             }
@@ -656,24 +758,28 @@ cudaError_t launch_frame_build(const FrameBuildArgs& a, int nFrames, cudaStream_
 }
 
 cudaError_t launch_proj_search(const ProjSearchArgs& a, int variant, int nFrames, cudaStream_t st) {
-    const int M = variant == 0 ? a.mp.n : a.lf.n;
+    const int M = variant == 0 ? a.mp.n : variant == 1 ? a.lf.n : a.kf.n;
     if (nFrames <= 0) return cudaSuccess;
     const dim3 grid((std::max(M, 1) + 127) / 128, nFrames);
     const size_t smem = (size_t)a.F.cap * 4 * sizeof(int);
     cudaError_t e;
     e = cudaMemsetAsync(a.poolCursor, 0, (size_t)nFrames * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    if (variant == 0) {
-        e = cudaFuncSetAttribute(k_proj_resolve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_proj_candidates<0><<<grid, 128, 0, st>>>(a);
-        k_proj_resolve<0><<<nFrames, 1024, smem, st>>>(a);
-    } else {
-        e = cudaFuncSetAttribute(k_proj_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_proj_candidates<1><<<grid, 128, 0, st>>>(a);
-        k_proj_resolve<1><<<nFrames, 1024, smem, st>>>(a);
+#define OBS_PROJ_CASE(VV)                                                                                                   \
+    case VV:                                                                                                                \
+        e = cudaFuncSetAttribute(k_proj_resolve<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+        if (e != cudaSuccess) return e;                                                                                     \
+        k_proj_candidates<VV><<<grid, 128, 0, st>>>(a);                                                                     \
+        k_proj_resolve<VV><<<nFrames, 1024, smem, st>>>(a);                                                                 \
+        break;
+    switch (variant) {
+        OBS_PROJ_CASE(0)
+        OBS_PROJ_CASE(1)
+        OBS_PROJ_CASE(2)
+        OBS_PROJ_CASE(3)
+        default: return cudaErrorInvalidValue;
     }
+#undef OBS_PROJ_CASE
     return cudaGetLastError();
 }
 

@@ -49,10 +49,22 @@ struct LastFrameDev {         // SearchByProjection(Frame& Current, const Frame&
     const float* tcwLast; const float* tcwCur;      // [B][12]
     int mono, checkOri;
 };
+struct KeyFramePtsDev {       // SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist) and (KeyFrame*, Scw, points, matched, th)
+    int n; size_t stride;
+    const uint8_t* valid; const float* pos; const float* minDist; const float* maxDist; const float* maxDistRaw;
+    const float* normal;      // Scw variant
+    const float* angle;       // KeyFrame variant
+    const uint4* desc;
+    const float* tcw;         // [B][12]
+    float logScaleFactor;     // mfLogScaleFactor = logf(mfScaleFactor)
+    int distTh;               // ORBdist / TH_LOW
+    int checkOri;
+};
 struct ProjSearchArgs {
     FrameSetDev F;
     MapPointDev mp;
     LastFrameDev lf;
+    KeyFramePtsDev kf;
     float th, nnratio;
     const int* kpObs;         // [B][cap] or null
     uint32_t* cand;           // [B][M][OBS_CAND_SLOTS] first chunk of every point's candidate list
@@ -64,7 +76,7 @@ struct ProjSearchArgs {
     int* nMatches;            // [B]
     int* rounds;              // [B] resolution rounds (diagnostics)
 };
-// variant 0: map points (ORBmatcher.cc:45-129); 1: last frame (:1328-1470)
+// variant 0: map points (ORBmatcher.cc:45-129); 1: last frame (:1328-1470); 2: keyframe (:1472-1599); 3: Sim3 keyframe (:290-403)
 cudaError_t launch_proj_search(const ProjSearchArgs& a, int variant, int nFrames, cudaStream_t st);
 
 struct InitSearchArgs {       // SearchForInitialization (:405-520)

@@ -5,6 +5,7 @@
 #include "matcher_api.h"
 #include "host_util.h"
 
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -351,6 +352,51 @@ int obs_search_by_projection_last(obs_matcher* m, obs_frame_set* cur, const obs_
     a.lf.mono = mono != 0; a.lf.checkOri = check_orientation != 0;
     a.th = th; a.nnratio = 0.f;
     return run_proj(m, cur, a, 1, M, kp_observations, kp_match, n_matches);
+}
+
+static int run_keyframe_search(obs_matcher* m, obs_frame_set* fs, const obs_keyframe_points_view* pts, int variant, float th, int distTh,
+                               int checkOri, const int32_t* kp_taken, int32_t* kp_match, int32_t* n_matches) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!fs || !pts || !kp_match || !n_matches) return fail(OBS_ERR_INVALID, "null argument");
+    if (fs->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if (fs->nFrames < 1) return fail(OBS_ERR_STATE, "frame set is empty");
+    if (pts->n < 0 || !pts->tcw) return fail(OBS_ERR_INVALID, "negative point count or null pose");
+    if (pts->n > 0 && (!pts->valid || !pts->world_pos || !pts->min_distance || !pts->max_distance || !pts->max_distance_raw ||
+                       !pts->descriptors || (variant == 3 && !pts->normal) || (variant == 2 && checkOri && !pts->angle)))
+        return fail(OBS_ERR_INVALID, "null map point array");
+    const int B = fs->nFrames, M = pts->n;
+    const size_t cnt = (size_t)M * (pts->per_frame ? B : 1);
+    ProjSearchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.kf.n = M; a.kf.stride = pts->per_frame ? (size_t)M : 0;
+    const uint8_t* dsc = nullptr;
+    if ((rc = dev_in(m, 0, pts->valid, cnt, &a.kf.valid))) return rc;
+    if ((rc = dev_in(m, 1, pts->world_pos, cnt * 3, &a.kf.pos))) return rc;
+    if ((rc = dev_in(m, 2, pts->min_distance, cnt, &a.kf.minDist))) return rc;
+    if ((rc = dev_in(m, 3, pts->max_distance, cnt, &a.kf.maxDist))) return rc;
+    if ((rc = dev_in(m, 4, pts->max_distance_raw, cnt, &a.kf.maxDistRaw))) return rc;
+    if ((rc = dev_in(m, 5, pts->normal, pts->normal ? cnt * 3 : 0, &a.kf.normal))) return rc;
+    if ((rc = dev_in(m, 6, pts->angle, pts->angle ? cnt : 0, &a.kf.angle))) return rc;
+    if ((rc = dev_in(m, 7, pts->descriptors, cnt * 32, &dsc))) return rc;
+    if ((rc = dev_in(m, 8, pts->tcw, (size_t)B * 12, &a.kf.tcw))) return rc;
+    if ((uintptr_t)dsc & 15) return fail(OBS_ERR_INVALID, "device descriptors must be 16-byte aligned");
+    a.kf.desc = reinterpret_cast<const uint4*>(dsc);
+    a.kf.logScaleFactor = logf(fs->prm.nlevels > 1 ? fs->prm.scale_factors[1] : 1.2f);      // Frame.cc:71: mfLogScaleFactor = log(mfScaleFactor)
+    a.kf.distTh = distTh;
+    a.kf.checkOri = checkOri != 0;
+    a.th = th; a.nnratio = 0.f;
+    return run_proj(m, fs, a, variant, M, kp_taken, kp_match, n_matches);
+}
+
+int obs_search_by_projection_keyframe(obs_matcher* m, obs_frame_set* current, const obs_keyframe_points_view* points, float th,
+                                      int orb_dist, int check_orientation, const int32_t* kp_taken, int32_t* kp_match, int32_t* n_matches) {
+    return run_keyframe_search(m, current, points, 2, th, orb_dist, check_orientation, kp_taken, kp_match, n_matches);
+}
+
+int obs_search_by_projection_sim3(obs_matcher* m, obs_frame_set* keyframes, const obs_keyframe_points_view* points, int th,
+                                  const int32_t* kp_taken, int32_t* kp_match, int32_t* n_matches) {
+    return run_keyframe_search(m, keyframes, points, 3, (float)th, 50 /* TH_LOW */, 0, kp_taken, kp_match, n_matches);
 }
 
 int obs_search_for_initialization(obs_matcher* m, obs_frame_set* f1, obs_frame_set* f2, float* prev_matched, int32_t* matches12,

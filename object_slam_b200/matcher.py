@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._capi import (KEYPOINT_DTYPE, FrameParams, FrameView, LastFrameView, MapPointView, addr, check, lib, ptr)
+from ._capi import (KEYPOINT_DTYPE, FrameParams, FrameView, KeyFramePointsView, LastFrameView, MapPointView, addr, check, lib, ptr)
 
 FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48       # include/Frame.h:41-42
 
@@ -176,6 +176,38 @@ class ORBmatcher:
         check(lib().obs_search_by_projection_last(self._h, current._h, C.byref(v), float(th), int(bool(mono)),
                                                   int(self.mbCheckOrientation), ptr(_i32(kp_observations)),
                                                   ptr(kp_match), ptr(n_matches)))
+        return n_matches, kp_match
+
+    def _kf_view(self, pts, tcw, n_points, per_frame):
+        v = KeyFramePointsView()
+        arrs = dict(valid=_u8(pts["valid"]), world_pos=_f32(pts["world_pos"]), min_distance=_f32(pts["min_distance"]),
+                    max_distance=_f32(pts["max_distance"]), max_distance_raw=_f32(pts["max_distance_raw"]),
+                    normal=_f32(pts.get("normal")), angle=_f32(pts.get("angle")), descriptors=_u8(pts["descriptors"]), tcw=_f32(tcw))
+        if n_points is None:
+            n_points = arrs["valid"].shape[-1]
+        v.n, v.per_frame = int(n_points), int(bool(per_frame))
+        for k, a in arrs.items():
+            setattr(v, k, addr(a))
+        return v, arrs
+
+    # ---- ORBmatcher.cc:1472-1599
+    def SearchByProjectionKeyFrame(self, current, pts, tcw, th, orb_dist, n_points=None, per_frame=False, kp_taken=None,
+                                   kp_match=None, n_matches=None):
+        """SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist).  pts: dict(valid, world_pos,
+        min_distance, max_distance, max_distance_raw, angle, descriptors)."""
+        v, keep = self._kf_view(pts, tcw, n_points, per_frame)
+        kp_match, n_matches = self._outs(current, kp_match, n_matches)
+        check(lib().obs_search_by_projection_keyframe(self._h, current._h, C.byref(v), float(th), int(orb_dist), int(self.mbCheckOrientation),
+                                                      ptr(_i32(kp_taken)), ptr(kp_match), ptr(n_matches)))
+        return n_matches, kp_match
+
+    # ---- ORBmatcher.cc:290-403
+    def SearchByProjectionSim3(self, keyframes, pts, tcw, th, n_points=None, per_frame=False, kp_taken=None, kp_match=None, n_matches=None):
+        """SearchByProjection(KeyFrame* pKF, Scw, vpPoints, vpMatched, th) after the decomposition of Scw; pts as above with
+        `normal` instead of `angle`."""
+        v, keep = self._kf_view(pts, tcw, n_points, per_frame)
+        kp_match, n_matches = self._outs(keyframes, kp_match, n_matches)
+        check(lib().obs_search_by_projection_sim3(self._h, keyframes._h, C.byref(v), int(th), ptr(_i32(kp_taken)), ptr(kp_match), ptr(n_matches)))
         return n_matches, kp_match
 
     # ---- ORBmatcher.cc:405-520

@@ -256,3 +256,25 @@ def keyframe_descriptors(n_keyframes, n_desc, seed, planted=0.3):
         dst = rng.choice(n_desc, m, replace=False)
         d[k, dst] = flip_bits(d[k - 1, src], rng.integers(0, 41, m), rng)
     return d
+
+
+def keyframe_points(last, seed, camera_centre=(0.0, 0.0, 0.0)):
+    """Map-point fields for the relocalisation / loop-closing searches, on top of a `motion_pair` last frame: scale
+    invariance distances around the true distance, normals (mean viewing directions) mostly along the ray, 10 % invalid points."""
+    rng = np.random.default_rng(seed)
+    pos = last["world_pos"]
+    n = len(pos)
+    d = np.linalg.norm(pos - np.asarray(camera_centre, np.float32), axis=1).astype(np.float32)
+    # mfMaxDistance such that MapPoint::PredictScale lands on the keypoint's octave (70 %) or next to it
+    delta = rng.choice([0, 0, 0, 0, 0, 0, 0, -1, 1, 2], n)
+    raw = (d * np.power(1.2, last["octave"] - 0.5 + delta)).astype(np.float32)
+    mind = (np.float32(0.8) * (raw / np.float32(1.2 ** 7))).astype(np.float32)
+    maxd = (np.float32(1.2) * raw).astype(np.float32)
+    far = rng.random(n) < 0.05
+    maxd[far] = (d[far] * 0.5).astype(np.float32)                         # outside the invariance region
+    nrm = pos / np.linalg.norm(pos, axis=1, keepdims=True) + rng.normal(0, 0.3, (n, 3))      # mean viewing direction (camera -> point)
+    flip = rng.random(n) < 0.1
+    nrm[flip] *= -1                                                        # seen from behind: fails the 60-degree test
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    return dict(valid=(rng.random(n) < 0.9).astype(np.uint8), world_pos=pos, min_distance=mind, max_distance=maxd,
+                max_distance_raw=raw, normal=nrm.astype(np.float32), angle=last["angle"], descriptors=last["descriptors"])

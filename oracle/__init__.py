@@ -97,6 +97,13 @@ def _bind_match(L):
     L.orc_search_by_projection_last.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_search_for_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
     L.orc_hamming_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_search_by_projection_keyframe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_search_by_projection_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_logf.restype = C.c_float
+    L.orc_logf.argtypes = [C.c_float]
+    L.orc_norm3.restype = C.c_float
+    L.orc_norm3.argtypes = [C.c_void_p]
+    L.orc_predict_scale.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
     L.orc_project_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.orc_minus_rt_t.argtypes = [C.c_void_p, C.c_void_p]
 
@@ -400,3 +407,43 @@ def minus_rt_t(tcw):
     out = np.empty(3, np.float32)
     lib().orc_minus_rt_t(_ptr(tcw), _ptr(out))
     return out
+
+
+def logf(x):
+    return float(lib().orc_logf(float(x)))
+
+
+def norm3(v):
+    v = np.ascontiguousarray(v, np.float32)
+    return float(lib().orc_norm3(_ptr(v)))
+
+
+def _kf_points(pts, key):
+    return [np.ascontiguousarray(pts[k], t) for k, t in (("valid", np.uint8), ("world_pos", np.float32), ("min_distance", np.float32),
+                                                          ("max_distance", np.float32), ("max_distance_raw", np.float32), (key, np.float32),
+                                                          ("descriptors", np.uint8))]
+
+
+def search_by_projection_keyframe(frame, scale, cam, tcw, pts, th, orb_dist, check_ori=True, kp_taken=None):
+    """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist).  pts: dict(valid, world_pos, min_distance,
+    max_distance, max_distance_raw, angle, descriptors).  Returns (nmatches, kp_match)."""
+    scale = np.ascontiguousarray(scale, np.float32)
+    cam = np.ascontiguousarray(cam, np.float32)
+    tcw = np.ascontiguousarray(tcw, np.float32).reshape(12)
+    a = _kf_points(pts, "angle")
+    taken, match = _state(frame, kp_taken)
+    n = lib().orc_search_by_projection_keyframe(frame._h, _ptr(scale), len(scale), logf(scale[1]), _ptr(cam), _ptr(tcw), len(a[0]),
+                                                *[_ptr(x) for x in a], th, int(orb_dist), int(check_ori), _ptr(taken), _ptr(match))
+    return n, match[:frame.n]
+
+
+def search_by_projection_sim3(frame, scale, cam, tcw, pts, th, kp_taken=None):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) after the decomposition of Scw."""
+    scale = np.ascontiguousarray(scale, np.float32)
+    cam = np.ascontiguousarray(cam, np.float32)
+    tcw = np.ascontiguousarray(tcw, np.float32).reshape(12)
+    a = _kf_points(pts, "normal")
+    taken, match = _state(frame, kp_taken)
+    n = lib().orc_search_by_projection_sim3(frame._h, _ptr(scale), len(scale), logf(scale[1]), _ptr(cam), _ptr(tcw), len(a[0]),
+                                            *[_ptr(x) for x in a], int(th), _ptr(taken), _ptr(match))
+    return n, match[:frame.n]

@@ -11,6 +11,8 @@
 //   Frame::GetFeaturesInArea                     src/Frame.cc:567-620
 //   ORBmatcher::SearchByProjection(F, MapPoints) src/ORBmatcher.cc:45-129, RadiusByViewingCos :131
 //   ORBmatcher::SearchByProjection(F, LastF)     src/ORBmatcher.cc:1328-1470
+//   ORBmatcher::SearchByProjection(F, KF, ...)   src/ORBmatcher.cc:1472-1599;  (KF, Scw, ...) :290-403
+//   MapPoint::PredictScale                       src/MapPoint.cc:488-519
 //   ORBmatcher::SearchForInitialization          src/ORBmatcher.cc:405-520
 //   ORBmatcher::ComputeThreeMaxima               src/ORBmatcher.cc:1601-1642
 // Parity status: "parity unpinned" by upstream (the reference ships no tests, fixtures or golden
@@ -442,6 +444,138 @@ static int search_for_initialization(const FrameV& F1, const FrameV& F2, float* 
     return nmatches;
 }
 
+// MapPoint::PredictScale, MapPoint.cc:488-519 (log and ceil resolve to the float overloads: the headers pull
+// `using namespace std` into the global namespace, include/ObjectTypes.h:14).
+static inline int predict_scale(float maxDistanceRaw, float currentDist, float logScaleFactor, int nLevels) {
+    const float ratio = maxDistanceRaw / currentDist;
+    int nScale = (int)ceilf(logf(ratio) / logScaleFactor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= nLevels) nScale = nLevels - 1;
+    return nScale;
+}
+
+// cv::norm(3x1 CV_32F) = sqrt of the binary64 sum of squares; Mat::dot of two 3x1 CV_32F = binary64 sum of products
+static inline float norm3(const float* v) {
+    double s = 0;
+    for (int i = 0; i < 3; i++) { const double d = v[i]; s += d * d; }
+    return (float)std::sqrt(s);
+}
+static inline double dot3(const float* a, const float* b) {
+    double s = 0;
+    for (int i = 0; i < 3; i++) s += (double)a[i] * (double)b[i];
+    return s;
+}
+
+// Per map point of the two searches below: valid = pMP && !isBad() && not in the already-found set;
+// pos = GetWorldPos(); minDist/maxDist = Get{Min,Max}DistanceInvariance(); maxDistRaw = mfMaxDistance (PredictScale);
+// normal = GetNormal(); angle = pKF->mvKeysUn[i].angle; desc = GetDescriptor().
+// kpTaken[idx] != 0 <=> mvpMapPoints[idx] / vpMatched[idx] is non-NULL (any point blocks, with or without observations).
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist),
+// ORBmatcher.cc:1472-1599.
+static int search_by_projection_keyframe(const FrameV& Cur, const float* scale, int nLevels, float logScaleFactor, const Camera& cam,
+                                         const float* Tcw, int nPts, const uint8_t* valid, const float* pos, const float* minDist,
+                                         const float* maxDist, const float* maxDistRaw, const float* angle, const uint8_t* desc,
+                                         float th, int ORBdist, bool checkOri, int* kpTaken, int* kpMatch) {
+    int nmatches = 0;
+    float Ow[3];
+    mat_minus_rt_t(Tcw, Ow);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < nPts; i++) {
+        if (!valid[i]) continue;
+        float x3Dc[3];
+        mat_rx_plus_t(Tcw, pos + 3 * i, x3Dc);
+        const float xc = x3Dc[0], yc = x3Dc[1];
+        const float invzc = 1.0 / x3Dc[2];
+        const float u = cam.fx * xc * invzc + cam.cx;
+        const float v = cam.fy * yc * invzc + cam.cy;
+        if (u < Cur.minX || u > Cur.maxX) continue;
+        if (v < Cur.minY || v > Cur.maxY) continue;
+        const float PO[3] = {pos[3 * i] - Ow[0], pos[3 * i + 1] - Ow[1], pos[3 * i + 2] - Ow[2]};
+        const float dist3D = norm3(PO);
+        if (dist3D < minDist[i] || dist3D > maxDist[i]) continue;
+        const int nPredictedLevel = predict_scale(maxDistRaw[i], dist3D, logScaleFactor, nLevels);
+        const float radius = th * scale[nPredictedLevel];
+        const std::vector<size_t> vIndices2 = Cur.features_in_area(u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (size_t vi = 0; vi < vIndices2.size(); vi++) {
+            const size_t i2 = vIndices2[vi];
+            if (kpTaken[i2]) continue;
+            const int dist = descriptor_distance(dMP, &Cur.d[i2 * 32]);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = (int)i2; }
+        }
+        if (bestDist <= ORBdist) {
+            kpMatch[bestIdx2] = i;
+            kpTaken[bestIdx2] = 1;
+            nmatches++;
+            if (checkOri) rotHist[rot_bin(angle[i], Cur.k[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, sizes[HISTO_LENGTH];
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    kpMatch[rotHist[i][j]] = -2;
+                    kpTaken[rotHist[i][j]] = 0;
+                    nmatches--;
+                }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, th),
+// ORBmatcher.cc:290-403, after the decomposition of Scw (:299-304): Tcw = [Rcw | tcw] with Rcw = sRcw/scw, tcw = Scw.col(3)/scw.
+static int search_by_projection_sim3(const FrameV& KF, const float* scale, int nLevels, float logScaleFactor, const Camera& cam,
+                                     const float* Tcw, int nPts, const uint8_t* valid, const float* pos, const float* minDist,
+                                     const float* maxDist, const float* maxDistRaw, const float* normal, const uint8_t* desc,
+                                     int th, int* kpTaken, int* kpMatch) {
+    int nmatches = 0;
+    float Ow[3];
+    mat_minus_rt_t(Tcw, Ow);
+    for (int iMP = 0; iMP < nPts; iMP++) {
+        if (!valid[iMP]) continue;
+        const float* p3Dw = pos + 3 * iMP;
+        float p3Dc[3];
+        mat_rx_plus_t(Tcw, p3Dw, p3Dc);
+        if (p3Dc[2] < 0.0) continue;
+        const float invz = 1 / p3Dc[2];
+        const float x = p3Dc[0] * invz;
+        const float y = p3Dc[1] * invz;
+        const float u = cam.fx * x + cam.cx;
+        const float v = cam.fy * y + cam.cy;
+        if (!(u >= KF.minX && u < KF.maxX && v >= KF.minY && v < KF.maxY)) continue;      // KeyFrame::IsInImage, KeyFrame.cc:610-613
+        const float PO[3] = {p3Dw[0] - Ow[0], p3Dw[1] - Ow[1], p3Dw[2] - Ow[2]};
+        const float dist = norm3(PO);
+        if (dist < minDist[iMP] || dist > maxDist[iMP]) continue;
+        if (dot3(PO, normal + 3 * iMP) < 0.5 * dist) continue;
+        const int nPredictedLevel = predict_scale(maxDistRaw[iMP], dist, logScaleFactor, nLevels);
+        const float radius = th * scale[nPredictedLevel];
+        const std::vector<size_t> vIndices = KF.features_in_area(u, v, radius);          // KeyFrame::GetFeaturesInArea, KeyFrame.cc:569-608
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = desc + (size_t)iMP * 32;
+        int bestDist = 256, bestIdx = -1;
+        for (size_t vi = 0; vi < vIndices.size(); vi++) {
+            const size_t idx = vIndices[vi];
+            if (kpTaken[idx]) continue;
+            const int kpLevel = KF.k[idx].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const int dist2 = descriptor_distance(dMP, &KF.d[idx * 32]);
+            if (dist2 < bestDist) { bestDist = dist2; bestIdx = (int)idx; }
+        }
+        if (bestDist <= TH_LOW) {
+            kpMatch[bestIdx] = iMP;
+            kpTaken[bestIdx] = 1;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
 // Brute-force best / second-best Hamming search with the ratio test: the inner loop of
 // ORBmatcher::SearchByBoW (ORBmatcher.cc:200-229) over one list of candidates, without the
 // "already matched" bookkeeping (every query is independent).  bestIdx = -1 when rejected.
@@ -530,6 +664,28 @@ void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* db, int nd, int t
                       int* bestDist, int* secondDist) {
     hamming_knn2(q, nq, db, nd, thLow, nnratio, bestIdx, bestDist, secondDist);
 }
+
+int orc_search_by_projection_keyframe(const void* f, const float* scale, int nLevels, float logScaleFactor, const float* cam6,
+                                      const float* Tcw, int nPts, const uint8_t* valid, const float* pos, const float* minDist,
+                                      const float* maxDist, const float* maxDistRaw, const float* angle, const uint8_t* desc,
+                                      float th, int ORBdist, int checkOri, int* kpTaken, int* kpMatch) {
+    Camera cam{cam6[0], cam6[1], cam6[2], cam6[3], cam6[4], cam6[5]};
+    return search_by_projection_keyframe(*(const FrameV*)f, scale, nLevels, logScaleFactor, cam, Tcw, nPts, valid, pos, minDist, maxDist,
+                                         maxDistRaw, angle, desc, th, ORBdist, checkOri != 0, kpTaken, kpMatch);
+}
+
+int orc_search_by_projection_sim3(const void* f, const float* scale, int nLevels, float logScaleFactor, const float* cam6,
+                                  const float* Tcw, int nPts, const uint8_t* valid, const float* pos, const float* minDist,
+                                  const float* maxDist, const float* maxDistRaw, const float* normal, const uint8_t* desc, int th,
+                                  int* kpTaken, int* kpMatch) {
+    Camera cam{cam6[0], cam6[1], cam6[2], cam6[3], cam6[4], cam6[5]};
+    return search_by_projection_sim3(*(const FrameV*)f, scale, nLevels, logScaleFactor, cam, Tcw, nPts, valid, pos, minDist, maxDist,
+                                     maxDistRaw, normal, desc, th, kpTaken, kpMatch);
+}
+
+float orc_logf(float x) { return logf(x); }
+float orc_norm3(const float* v) { return norm3(v); }
+int orc_predict_scale(float maxDistRaw, float dist, float logScaleFactor, int nLevels) { return predict_scale(maxDistRaw, dist, logScaleFactor, nLevels); }
 
 void orc_project_points(const float* Tcw, const float* pos, int n, float* out) {
     for (int i = 0; i < n; i++) mat_rx_plus_t(Tcw, pos + 3 * i, out + 3 * i);

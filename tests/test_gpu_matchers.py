@@ -222,6 +222,15 @@ def test_golden_fixtures(M, path):
         fs = frame_set(M, shape, [cur])
         n, match = M.SearchByProjectionLast(fs, *[last[k] for k in LAST_KEYS], last["tcw_last"], last["tcw_current"], 7.0, False)
         assert n[0] == g["n_matches"] and np.array_equal(match[0, :1000], g["kp_match"])
+    elif kind in ("keyframe", "sim3"):
+        last, cur = synth.motion_pair(shape, 1000, seed)
+        pts = synth.keyframe_points(last, seed + 100)
+        fs = frame_set(M, shape, [cur])
+        if kind == "keyframe":
+            n, match = M.SearchByProjectionKeyFrame(fs, pts, last["tcw_current"], 10.0, 100)
+        else:
+            n, match = M.SearchByProjectionSim3(fs, pts, last["tcw_current"], 10)
+        assert n[0] == g["n_matches"] and np.array_equal(match[0, :1000], g["kp_match"])
     elif kind == "init":
         M.mfNNratio = 0.9
         f1, f2, prev = synth.init_pair(KITTI, 2000, seed)
@@ -290,3 +299,44 @@ def test_two_gpu_allgather_and_sharded_matching(gpu):
                         "--master-port", "29533", os.path.join(root, "tools", "check_allgather.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout
+
+
+@pytest.mark.parametrize("th,orb_dist,forward", [(10.0, 100, 0.0), (3.0, 64, 0.0), (10.0, 100, 3.0)])
+def test_search_by_projection_keyframe_matches_oracle(M, th, orb_dist, forward):
+    """Relocalisation search (ORBmatcher.cc:1472-1599): projection, distance gate, PredictScale (device logf), rotation check."""
+    shape = TUM
+    pairs = [synth.motion_pair(shape, 1000, s, forward=forward) for s in (70, 71)]
+    pts = [synth.keyframe_points(p[0], 80 + i) for i, p in enumerate(pairs)]
+    fs = frame_set(M, shape, [p[1] for p in pairs])
+    stacked = {k: np.stack([q[k] for q in pts]) for k in pts[0]}
+    tcw = np.stack([p[0]["tcw_current"] for p in pairs])
+    rng = np.random.default_rng(5)
+    taken = (rng.random((2, fs.cap)) < 0.1).astype(np.int32)
+    for check_ori in (True, False):
+        M.mbCheckOrientation = check_ori
+        n, match = M.SearchByProjectionKeyFrame(fs, stacked, tcw, th, orb_dist, per_frame=True, kp_taken=taken)
+        for b, (last, cur) in enumerate(pairs):
+            on, om = oracle.search_by_projection_keyframe(oracle_frame(cur, shape), synth.scale_factors(), synth.camera_for(shape),
+                                                          last["tcw_current"], pts[b], th, orb_dist, check_ori, taken[b, :1000])
+            assert n[b] == on and np.array_equal(match[b, :1000], om)
+            assert on > 100 or forward > 0
+    M.mbCheckOrientation = True
+
+
+@pytest.mark.parametrize("th", [10, 4])
+def test_search_by_projection_sim3_matches_oracle(M, th):
+    """Loop-closing search (ORBmatcher.cc:290-403) after the decomposition of Scw."""
+    shape = TUM
+    pairs = [synth.motion_pair(shape, 1000, s) for s in (90, 91, 92)]
+    pts = [synth.keyframe_points(p[0], 95 + i) for i, p in enumerate(pairs)]
+    fs = frame_set(M, shape, [p[1] for p in pairs])
+    stacked = {k: np.stack([q[k] for q in pts]) for k in pts[0]}
+    tcw = np.stack([p[0]["tcw_current"] for p in pairs])
+    rng = np.random.default_rng(6)
+    taken = (rng.random((3, fs.cap)) < 0.2).astype(np.int32)
+    n, match = M.SearchByProjectionSim3(fs, stacked, tcw, th, per_frame=True, kp_taken=taken)
+    for b, (last, cur) in enumerate(pairs):
+        on, om = oracle.search_by_projection_sim3(oracle_frame(cur, shape), synth.scale_factors(), synth.camera_for(shape),
+                                                  last["tcw_current"], pts[b], th, taken[b, :1000])
+        assert n[b] == on and np.array_equal(match[b, :1000], om)
+        assert on > 100

@@ -14,7 +14,7 @@ import oracle  # noqa: E402
 from object_slam_b200 import synth  # noqa: E402
 import matcher_cases as mc  # noqa: E402
 
-CASES = [("map", 0), ("map", 1), ("last", 2), ("last_forward", 3), ("init", 4), ("knn2", 5)]
+CASES = [("map", 0), ("map", 1), ("last", 2), ("last_forward", 3), ("init", 4), ("knn2", 5), ("keyframe", 6), ("sim3", 7)]
 
 
 def compute(kind, seed):
@@ -31,6 +31,15 @@ def compute(kind, seed):
         f1, f2, prev = synth.init_pair(synth.KITTI_SHAPE, 2000, seed)
         n, m12, pm = mc.oracle_init(f1, f2, synth.KITTI_SHAPE, prev, 100, 0.9)
         return dict(n_matches=np.int32(n), matches12=m12, prev_matched=pm)
+    if kind in ("keyframe", "sim3"):
+        last, cur = synth.motion_pair(shape, 1000, seed)
+        pts = synth.keyframe_points(last, seed + 100)
+        F = mc.oracle_frame(cur, shape)
+        if kind == "keyframe":
+            n, match = oracle.search_by_projection_keyframe(F, synth.scale_factors(), synth.camera_for(shape), last["tcw_current"], pts, 10.0, 100)
+        else:
+            n, match = oracle.search_by_projection_sim3(F, synth.scale_factors(), synth.camera_for(shape), last["tcw_current"], pts, 10)
+        return dict(n_matches=np.int32(n), kp_match=match)
     if kind == "knn2":
         D = synth.keyframe_descriptors(3, 2000, seed)
         bi, bd, sd = oracle.hamming_knn2(D[1], D[0], 50, 0.6)
