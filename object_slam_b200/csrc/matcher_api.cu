@@ -23,6 +23,7 @@ struct obs_matcher {
     DevBuf<uint32_t> initList;
     DevBuf<int> initCount;
     std::vector<int> lastRounds;
+    std::vector<obs_frame_set*> sets;   // frame sets created on this matcher (orphaned, not freed, when it is destroyed first)
 };
 
 struct obs_frame_set {
@@ -144,6 +145,7 @@ int obs_matcher_destroy(obs_matcher* m) {
     if (!m) return OBS_OK;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    for (obs_frame_set* fs : m->sets) fs->m = nullptr;     // their buffers stay valid until obs_frame_set_destroy
     for (auto& s : m->slot) s.release();
     m->cand.release(); m->pool.release(); m->poolCursor.release(); m->choice.release(); m->rounds.release(); m->initList.release(); m->initCount.release();
     if (m->ev) cudaEventDestroy(m->ev);
@@ -194,13 +196,19 @@ int obs_frame_set_create(obs_matcher* m, const obs_frame_params* params, int max
     fs->d.n = fs->n.p; fs->d.kp = fs->kp.p; fs->d.angle = fs->angle.p; fs->d.desc = fs->desc.p;
     fs->d.cellStart = fs->cellStart.p; fs->d.cellIdx = fs->cellIdx.p;
     fs->d.P = to_dev(*params);
+    m->sets.push_back(fs);
     *out = fs;
     return OBS_OK;
 }
 
 int obs_frame_set_destroy(obs_frame_set* fs) {
     if (!fs) return OBS_OK;
-    if (fs->m) { cudaSetDevice(fs->m->device); cudaStreamSynchronize(fs->m->stream); }
+    if (fs->m) {
+        cudaSetDevice(fs->m->device);
+        cudaStreamSynchronize(fs->m->stream);
+        for (size_t i = 0; i < fs->m->sets.size(); i++)
+            if (fs->m->sets[i] == fs) { fs->m->sets.erase(fs->m->sets.begin() + i); break; }
+    }
     fs->n.release(); fs->kp.release(); fs->angle.release(); fs->desc.release(); fs->cellStart.release(); fs->cellIdx.release();
     fs->hStage.release(); fs->dStage.release();
     delete fs;
