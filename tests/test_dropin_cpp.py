@@ -68,3 +68,66 @@ def test_dropin_matches_oracle(gpu):
                                       t["scale"], t["inv_scale"], synth.KITTI_BF, 0.0, synth.KITTI_FX)
     assert k.tobytes() == kL.tobytes() and np.array_equal(desc, dL)
     assert np.array_equal(ur, our) and np.array_equal(dp, odp)
+
+
+# ----------------------------------------------------------------------------- the matcher mirror (host/ORBmatcher.h)
+def _build_matcher(out):
+    cmd = ["g++", "-std=gnu++11", "-O2", "-I" + os.path.join(ROOT, "oracle", "cvshim"), "-I" + os.path.join(ROOT, "include"),
+           "-I" + HOST, "-o", out, os.path.join(HOST, "matcher_check.cpp"),
+           "-L" + os.path.dirname(_capi.LIB_PATH), "-lobslam_b200", "-Wl,-rpath," + os.path.dirname(_capi.LIB_PATH)]
+    subprocess.check_call(cmd)
+
+
+def _frame_bytes(frame, shape):
+    k, d, ur = frame
+    cam = synth.camera_for(shape)
+    hdr = np.array([len(k), 0 if ur is None else 1], np.int32).tobytes()
+    fl = np.array([0, shape[1], 0, shape[0], *cam], np.float32).tobytes()
+    out = hdr + fl + synth.scale_factors().tobytes() + np.ascontiguousarray(k).tobytes() + np.ascontiguousarray(d).tobytes()
+    if ur is not None:
+        out += np.ascontiguousarray(ur, np.float32).tobytes()
+    return out
+
+
+def test_matcher_mirror_compiles_and_names_match_reference_header():
+    with tempfile.TemporaryDirectory() as d:
+        _build_matcher(os.path.join(d, "matcher_check"))
+    ref = "/root/reference/include/ORBmatcher.h"
+    if os.path.exists(ref):
+        theirs, mine = open(ref).read(), open(os.path.join(HOST, "ORBmatcher.h")).read()
+        for name in ("ORBmatcher(float nnratio=0.6, bool checkOri=true)", "static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b)",
+                     "int SearchByProjection(", "int SearchForInitialization(", "TH_LOW", "TH_HIGH", "HISTO_LENGTH", "ComputeThreeMaxima",
+                     "mfNNratio", "mbCheckOrientation"):
+            assert name in theirs and name in mine, name
+
+
+@pytest.mark.gpu
+def test_matcher_mirror_matches_oracle(gpu):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import matcher_cases as mc
+    shape = synth.TUM_SHAPE
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "matcher_check")
+        _build_matcher(exe)
+        # SearchByProjection(Frame&, const vector<MapPoint*>&, th)
+        frame, mp, _ = mc.map_case(shape, 1000, 5000, 11)
+        blob = _frame_bytes(frame, shape) + np.array([5000], np.int32).tobytes() + np.array([3.0, 0.8], np.float32).tobytes()
+        for key, dt in zip(mc.MP_KEYS, (np.uint8, np.float32, np.float32, np.float32, np.int32, np.float32, np.uint8, np.int32)):
+            blob += np.ascontiguousarray(mp[key], dt).tobytes()
+        open(os.path.join(d, "map.bin"), "wb").write(blob)
+        subprocess.check_call([exe, "map", os.path.join(d, "map.bin"), os.path.join(d, "map.out")])
+        res = np.fromfile(os.path.join(d, "map.out"), np.int32)
+        on, om = mc.oracle_map(frame, shape, mp, 3.0, 0.8)
+        assert res[0] == on and np.array_equal(res[1:], om)
+        # SearchForInitialization
+        f1, f2, prev = synth.init_pair(shape, 1000, 12)
+        blob = _frame_bytes(f1, shape) + _frame_bytes(f2, shape) + np.array([100], np.int32).tobytes() + np.array([0.9], np.float32).tobytes()
+        blob += np.ascontiguousarray(prev, np.float32).tobytes()
+        open(os.path.join(d, "init.bin"), "wb").write(blob)
+        subprocess.check_call([exe, "init", os.path.join(d, "init.bin"), os.path.join(d, "init.out")])
+        raw = open(os.path.join(d, "init.out"), "rb").read()
+        n = np.frombuffer(raw[:4], np.int32)[0]
+        m12 = np.frombuffer(raw[4:4 + 4000], np.int32)
+        pm = np.frombuffer(raw[4 + 4000:], np.float32).reshape(-1, 2)
+        on, om12, opm = mc.oracle_init(f1, f2, shape, prev, 100, 0.9)
+        assert n == on and np.array_equal(m12, om12) and np.array_equal(pm, opm)
