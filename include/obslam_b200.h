@@ -151,6 +151,24 @@ int obs_stereo_match_device(obs_extractor* left, obs_extractor* right, float mbf
 
 
 /* ---------------------------------------------------------------------------------------
+ * Front-end neighbours of the extractor inside Tracking::GrabImage* and the Frame constructors, so that an RGB-D or
+ * colour stereo frame only crosses PCIe once.  Device-resident images; `stream` NULL = the handle's stream.
+ * --------------------------------------------------------------------------------------- */
+/* cvtColor(im, im, CV_RGB2GRAY | CV_BGR2GRAY | CV_RGBA2GRAY | CV_BGRA2GRAY), src/Tracking.cc:202-227, :247-258, :290-301.
+ * channels: 3 or 4; rgb_order: 1 = first channel is red (mbRGB), 0 = blue.  Strides in bytes. */
+int obs_gray_from_color(obs_extractor* e, const uint8_t* d_src, int n_images, int w, int h, int channels, int rgb_order,
+                        size_t src_stride, size_t src_image_stride, uint8_t* d_gray, size_t gray_stride,
+                        size_t gray_image_stride, void* stream);
+/* imDepth.convertTo(imDepth, CV_32F, mDepthMapFactor), src/Tracking.cc:262-263, for 16-bit depth maps. */
+int obs_depth_to_float(obs_extractor* e, const uint16_t* d_src, int n_images, int w, int h, size_t src_stride,
+                       size_t src_image_stride, float factor, float* d_dst, size_t dst_stride, size_t dst_image_stride,
+                       void* stream);
+/* Frame::ComputeStereoFromRGBD, src/Frame.cc:883-904, on the keypoints of the last extraction (taken as undistorted):
+ * mvuRight / mvDepth as device arrays of n_images x obs_extractor_max_keypoints floats (-1 = no depth). */
+int obs_stereo_from_rgbd(obs_extractor* e, const float* d_depth, size_t depth_stride, size_t depth_image_stride, float mbf,
+                         void* stream, const float** d_u_right, const float** d_depth_out);
+
+/* ---------------------------------------------------------------------------------------
  * Matchers.  Replace the Hamming searches of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:37-102)
  * that Tracking runs on every frame.  The reference walks pointer graphs (Frame, MapPoint); the
  * entry points below take the same quantities as flat arrays, named after the members they are

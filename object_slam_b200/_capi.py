@@ -86,6 +86,9 @@ _PROTOS = {
     "obs_extractor_stage_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "obs_stereo_match": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_float, _vp, _vp, C.c_int]),
     "obs_stereo_match_device": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_float, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "obs_gray_from_color": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, _vp, C.c_size_t, C.c_size_t, _vp]),
+    "obs_depth_to_float": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_float, _vp, C.c_size_t, C.c_size_t, _vp]),
+    "obs_stereo_from_rgbd": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_float, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "obs_matcher_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "obs_matcher_destroy": (C.c_int, [_vp]),
     "obs_matcher_stream": (_vp, [_vp]),

@@ -832,6 +832,51 @@ int obs_frame_set_from_extractor(obs_frame_set* fs, obs_extractor* e, const floa
                                       e->recordBytes / 4, e->lastN, e->lastStream);
 }
 
+int obs_gray_from_color(obs_extractor* e, const uint8_t* d_src, int n_images, int w, int h, int channels, int rgb_order,
+                        size_t src_stride, size_t src_image_stride, uint8_t* d_gray, size_t gray_stride, size_t gray_image_stride, void* stream) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (!d_src || !d_gray || n_images < 1 || w < 1 || h < 1) return fail(OBS_ERR_INVALID, "bad argument");
+    if (channels != 3 && channels != 4) return fail(OBS_ERR_INVALID, "channels must be 3 or 4 (the reference converts 3- and 4-channel images, Tracking.cc:202-227)");
+    if (src_stride < (size_t)w * channels || gray_stride < (size_t)w) return fail(OBS_ERR_INVALID, "stride smaller than a row");
+    if (!is_device(d_src) || !is_device(d_gray)) return fail(OBS_ERR_INVALID, "both images must be device memory");
+    CU(launch_gray(d_src, src_stride, src_image_stride, d_gray, gray_stride, gray_image_stride, w, h, channels, rgb_order != 0, n_images,
+                   stream ? (cudaStream_t)stream : e->stream));
+    return OBS_OK;
+}
+
+int obs_depth_to_float(obs_extractor* e, const uint16_t* d_src, int n_images, int w, int h, size_t src_stride, size_t src_image_stride,
+                       float factor, float* d_dst, size_t dst_stride, size_t dst_image_stride, void* stream) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (!d_src || !d_dst || n_images < 1 || w < 1 || h < 1) return fail(OBS_ERR_INVALID, "bad argument");
+    if (src_stride < (size_t)w * 2 || dst_stride < (size_t)w * 4 || (src_stride & 1) || (dst_stride & 3)) return fail(OBS_ERR_INVALID, "bad stride");
+    if (!is_device(d_src) || !is_device(d_dst)) return fail(OBS_ERR_INVALID, "both images must be device memory");
+    CU(launch_depth_scale(reinterpret_cast<const uint8_t*>(d_src), src_stride, src_image_stride, reinterpret_cast<uint8_t*>(d_dst), dst_stride,
+                          dst_image_stride, w, h, factor, n_images, stream ? (cudaStream_t)stream : e->stream));
+    return OBS_OK;
+}
+
+int obs_stereo_from_rgbd(obs_extractor* e, const float* d_depth, size_t depth_stride, size_t depth_image_stride, float mbf, void* stream,
+                         const float** d_u_right, const float** d_depth_out) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (!d_depth || !is_device(d_depth)) return fail(OBS_ERR_INVALID, "the depth images must be device memory");
+    if (e->lastN < 1) return fail(OBS_ERR_STATE, "no extraction yet");
+    if (depth_stride < (size_t)e->g.w * 4 || (depth_stride & 3)) return fail(OBS_ERR_INVALID, "bad depth stride");
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    const size_t cnt = (size_t)e->lastN * e->g.kpCap;
+    CU(e->uRight.ensure(cnt));
+    CU(e->depth.ensure(cnt));
+    if (e->lastStream != st) { CU(cudaEventRecord(e->done, e->lastStream)); CU(cudaStreamWaitEvent(st, e->done, 0)); }
+    CU(launch_rgbd_stereo(e->records.p, e->recordBytes, e->g.kpCap, reinterpret_cast<const uint8_t*>(d_depth), depth_stride, depth_image_stride,
+                          e->g.w, e->g.h, mbf, e->uRight.p, e->depth.p, e->lastN, st));
+    e->lastStream = st;
+    if (d_u_right) *d_u_right = e->uRight.p;
+    if (d_depth_out) *d_depth_out = e->depth.p;
+    return OBS_OK;
+}
+
 int obs_host_alloc(size_t bytes, void** out) {
     if (!out) return fail(OBS_ERR_INVALID, "null argument");
     *out = nullptr;

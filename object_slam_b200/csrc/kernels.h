@@ -45,3 +45,11 @@ struct StereoArgs {
     float2* rightXO;                 // nimg x kpCap: (x, octave bits) of the right keypoints
 };
 cudaError_t launch_stereo(const StereoArgs& a, int nimg, cudaStream_t st);
+
+// frontend.cu -- colour -> grey, depth scaling, Frame::ComputeStereoFromRGBD (src/Tracking.cc:202-263, src/Frame.cc:883-904)
+cudaError_t launch_gray(const uint8_t* src, size_t srcStride, size_t srcImgStride, uint8_t* dst, size_t dstStride, size_t dstImgStride,
+                        int w, int h, int channels, int rgbOrder, int nimg, cudaStream_t st);
+cudaError_t launch_depth_scale(const uint8_t* src, size_t srcStride, size_t srcImgStride, uint8_t* dst, size_t dstStride, size_t dstImgStride,
+                               int w, int h, float factor, int nimg, cudaStream_t st);
+cudaError_t launch_rgbd_stereo(const uint8_t* records, size_t recordBytes, int kpCap, const uint8_t* depth, size_t depthStride,
+                               size_t depthImgStride, int w, int h, float mbf, float* uRight, float* depthOut, int nimg, cudaStream_t st);

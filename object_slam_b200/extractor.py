@@ -141,6 +141,25 @@ class ORBextractor:
         check(lib().obs_extractor_results_device(self._h, C.byref(p), C.byref(rb), C.byref(cap)))
         return p.value, rb.value, cap.value
 
+    # ---- front-end neighbours (device-resident): Tracking.cc:202-263, Frame.cc:883-904
+    def gray_from_color(self, d_src, n_images, w, h, channels, rgb_order, src_stride, src_image_stride, d_gray, gray_stride,
+                        gray_image_stride, stream=None):
+        check(lib().obs_gray_from_color(self._h, C.c_void_p(int(d_src)), int(n_images), int(w), int(h), int(channels), int(bool(rgb_order)),
+                                        int(src_stride), int(src_image_stride), C.c_void_p(int(d_gray)), int(gray_stride),
+                                        int(gray_image_stride), C.c_void_p(int(stream) if stream else 0)))
+
+    def depth_to_float(self, d_src, n_images, w, h, src_stride, src_image_stride, factor, d_dst, dst_stride, dst_image_stride, stream=None):
+        check(lib().obs_depth_to_float(self._h, C.c_void_p(int(d_src)), int(n_images), int(w), int(h), int(src_stride), int(src_image_stride),
+                                       float(factor), C.c_void_p(int(d_dst)), int(dst_stride), int(dst_image_stride),
+                                       C.c_void_p(int(stream) if stream else 0)))
+
+    def stereo_from_rgbd(self, d_depth, depth_stride, depth_image_stride, mbf, stream=None):
+        """Frame::ComputeStereoFromRGBD on the last extraction; returns the device addresses of mvuRight and mvDepth."""
+        pu, pd = C.c_void_p(), C.c_void_p()
+        check(lib().obs_stereo_from_rgbd(self._h, C.c_void_p(int(d_depth)), int(depth_stride), int(depth_image_stride), float(mbf),
+                                         C.c_void_p(int(stream) if stream else 0), C.byref(pu), C.byref(pd)))
+        return pu.value, pd.value
+
     STAGES = ("pyramid", "fast", "quadtree", "blur", "describe")
 
     def set_profiling(self, on):

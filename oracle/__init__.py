@@ -447,3 +447,31 @@ def search_by_projection_sim3(frame, scale, cam, tcw, pts, th, kp_taken=None):
     n = lib().orc_search_by_projection_sim3(frame._h, _ptr(scale), len(scale), logf(scale[1]), _ptr(cam), _ptr(tcw), len(a[0]),
                                             *[_ptr(x) for x in a], int(th), _ptr(taken), _ptr(match))
     return n, match[:frame.n]
+
+
+# ----------------------------------------------------------------------------- front-end neighbours (numpy restatements)
+def gray_from_color(img, rgb_order=True):
+    """cvtColor(..., CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY) of Tracking::GrabImage* (Tracking.cc:202-227),
+    OpenCV's 8-bit path: (R*9798 + G*19235 + B*3735 + 16384) >> 15 (pinned to cv2 4.13 on all 2^24 colours in the tests)."""
+    img = np.asarray(img, np.uint8)
+    r, g, b = (img[..., 0], img[..., 1], img[..., 2]) if rgb_order else (img[..., 2], img[..., 1], img[..., 0])
+    return ((r.astype(np.int64) * 9798 + g.astype(np.int64) * 19235 + b.astype(np.int64) * 3735 + 16384) >> 15).astype(np.uint8)
+
+
+def depth_to_float(depth_u16, factor):
+    """imDepth.convertTo(imDepth, CV_32F, mDepthMapFactor), Tracking.cc:262-263: binary32 product of the value and the factor."""
+    return (np.asarray(depth_u16).astype(np.float32) * np.float32(factor)).astype(np.float32)
+
+
+def stereo_from_rgbd(keys, depth_f32, mbf):
+    """Frame::ComputeStereoFromRGBD, Frame.cc:883-904 (mvKeysUn == mvKeys: no distortion)."""
+    n = len(keys)
+    ur = np.full(n, -1, np.float32)
+    dp = np.full(n, -1, np.float32)
+    for i in range(n):
+        u, v = keys["x"][i], keys["y"][i]
+        d = depth_f32[int(v), int(u)]                   # cv::Mat::at<float>(float, float): the indices truncate
+        if d > 0:
+            dp[i] = d
+            ur[i] = np.float32(u - np.float32(np.float32(mbf) / d))
+    return ur, dp
