@@ -31,7 +31,6 @@ constexpr int FT_ROWS = 66;            // hCell <= 60, + 6
 constexpr int FT_THREADS = 256;
 constexpr int FT_LIST = 8192;          // queue capacity == max interior pixels per CTA (host enforces)
 constexpr int FT_MAXCELLS = 8;
-constexpr int FT_SEG = FT_LIST / 8 + FT_PITCH;   // capacity of one warp's queue: its share of the rows, rounded up by one row
 
 __host__ __device__ inline int fast_cells_per_cta(int wCell, int hCell) {
     int cg = (FT_PITCH - 15 - 6) / wCell;
@@ -78,8 +77,131 @@ __device__ __forceinline__ int row_bits(const uint32_t* bm, int a, int b) {
     return n;
 }
 
-// per byte: 0x80 where the byte of y exceeds t (t < 128, K = (127 - t) * 0x01010101)
-__device__ __forceinline__ unsigned over_threshold(unsigned y, unsigned K) { return ((y & 0x7f7f7f7fu) + K) | y; }
+// Pretest of one word (4 pixels): 0x80 in every byte whose pixel can be a corner at threshold t
+// (t < 128, K = (127 - t) * 0x01010101) and whose column is enabled in ok.  Every 9-arc holds one of
+// the ring pixels {0,8} and one of {4,12}; "(|d0| | |d8|) > t" is implied by |d0| > t or |d8| > t.
+__device__ __forceinline__ unsigned pretest_word(unsigned C, unsigned up, unsigned dn, unsigned l3, unsigned r3, unsigned K, unsigned ok) {
+    const unsigned a = __vabsdiffu4(C, up), b = __vabsdiffu4(C, dn);
+    const unsigned c = __vabsdiffu4(C, l3), d = __vabsdiffu4(C, r3);
+    const unsigned y = ((((a | b) & 0x7f7f7f7fu) + K) | a | b);
+    const unsigned z = ((((c | d) & 0x7f7f7f7fu) + K) | c | d);
+    return y & z & ok;
+}
+
+struct FastShared {
+    uint32_t bitmap[FT_ROWS][8];               // emitted keypoints, one bit per tile pixel
+    uint16_t rowOfs[FT_MAXCELLS][FT_ROWS];     // per cell: keypoints in the rows above
+    uint8_t colCell[FT_PITCH];                 // tile column -> cell of the run
+    uint8_t colFlags[FT_PITCH];                // bit 0: has a left neighbour inside its cell, bit 1: a right one
+    uint8_t colOK[FT_PITCH];                   // 0x80: the column takes part in the current phase
+    int cellAny[FT_MAXCELLS];
+    int qCount;
+};
+
+// One detection phase at threshold t over the columns enabled in sh.colOK:
+//   pass 1  byte-SIMD pretest, 32 pixels per lane (two 16-pixel chunks, 128 columns apart so that a quarter
+//           warp's LDS.128 is conflict free), 4 rows per warp; flags gathered into one word per lane, expanded
+//           into the CTA's queue (one shared-memory atomic per warp and 1024 pixels);
+//   pass 2  exact score, one lane per queued pixel, every warp on its own slice of the queue, corners
+//           compacted in place;
+//   pass 3  strict 3x3 non-max suppression inside the cell over the corners; survivors set their bitmap bit.
+__device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, uint16_t* Q, FastShared& sh, int t,
+                                           int rHi, bool markCells) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned ltMask = (1u << lane) - 1;
+    {
+        const int l8 = lane & 7, sub = lane >> 3;
+        const uint4 okA = *reinterpret_cast<const uint4*>(sh.colOK + 16 * l8);
+        const uint4 okB = *reinterpret_cast<const uint4*>(sh.colOK + 128 + 16 * l8);
+        const bool cheap = t < 128;
+        const unsigned K = (unsigned)(127 - min(t, 127)) * 0x01010101u;
+        for (int rb = 3 + 4 * warp; rb < rHi; rb += 4 * (FT_THREADS / 32)) {
+            const int r = rb + sub;
+            unsigned acc = 0;
+            if (r < rHi) {
+                if (cheap) {
+                    const uint8_t* rowp = tile + r * FT_PITCH + 16 * l8;
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const uint8_t* cp = rowp + 128 * q;
+                        const uint4 C = *reinterpret_cast<const uint4*>(cp);
+                        const uint4 U = *reinterpret_cast<const uint4*>(cp + 3 * FT_PITCH);
+                        const uint4 D = *reinterpret_cast<const uint4*>(cp - 3 * FT_PITCH);
+                        const unsigned L = *reinterpret_cast<const unsigned*>(cp - 4);
+                        const unsigned R = *reinterpret_cast<const unsigned*>(cp + 16);
+                        const uint4 ok = q ? okB : okA;
+                        const unsigned f0 = pretest_word(C.x, U.x, D.x, __byte_perm(L, C.x, 0x4321), __byte_perm(C.x, C.y, 0x6543), K, ok.x);
+                        const unsigned f1 = pretest_word(C.y, U.y, D.y, __byte_perm(C.x, C.y, 0x4321), __byte_perm(C.y, C.z, 0x6543), K, ok.y);
+                        const unsigned f2 = pretest_word(C.z, U.z, D.z, __byte_perm(C.y, C.z, 0x4321), __byte_perm(C.z, C.w, 0x6543), K, ok.z);
+                        const unsigned f3 = pretest_word(C.w, U.w, D.w, __byte_perm(C.z, C.w, 0x4321), __byte_perm(C.w, R, 0x6543), K, ok.w);
+                        // flag of (chunk q, word i, byte j) -> bit 8 j + 4 q + i
+                        acc |= ((f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4)) << (4 * q);
+                    }
+                } else {                                   // thresholds >= 128: no cheap rejection, score everything enabled
+                    acc = (okA.x >> 7) | (okA.y >> 6) | (okA.z >> 5) | (okA.w >> 4) | (okB.x >> 3) | (okB.y >> 2) | (okB.z >> 1) | okB.w;
+                }
+            }
+            const int n = __popc(acc);
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            int base = 0;
+            if (lane == 31 && incl > 0) base = atomicAdd(&sh.qCount, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint16_t* out = Q + base + incl - n;
+            const unsigned e0 = (unsigned)(r << 8) | (unsigned)(l8 << 5);
+            while (acc) {
+                const int b = 31 - __clz(acc);
+                acc ^= 1u << b;
+                *out++ = (uint16_t)(e0 + b);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 2
+    const int total = sh.qCount;
+    const int per = ((total + FT_THREADS - 1) / FT_THREADS) * 32;
+    const int start = warp * per, end = min(start + per, total);
+    int nC = 0;
+    for (int i0 = start; i0 < end; i0 += 32) {
+        const int i = i0 + lane;
+        int pos = 0, s = 0;
+        if (i < end) {
+            const unsigned e = Q[i];
+            // entry: row << 8 | l8 << 5 | j << 3 | q << 2 | i  ->  column = q << 7 | l8 << 4 | i << 2 | j
+            const unsigned c = ((e & 4u) << 5) | ((e >> 1) & 0x70u) | ((e & 3u) << 2) | ((e >> 3) & 3u);
+            pos = (int)((e & 0xff00u) | c);
+            const int contrast = fast_contrast(tile + pos);
+            if (contrast > t && contrast > 1) s = contrast - 1;            // OpenCV: score = corner contrast - 1
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, s > 0);
+        if (s > 0) {
+            score[pos] = (uint8_t)s;
+            Q[start + nC + __popc(bal & ltMask)] = (uint16_t)pos;
+        }
+        nC += __popc(bal);
+    }
+    __syncthreads();
+
+    // ---- pass 3
+    for (int i = lane; i < nC; i += 32) {
+        const int pos = Q[start + i];
+        const int c = pos & 255;
+        const uint8_t* sc = score + pos;
+        const int fl = sh.colFlags[c];
+        int m = max(sc[-FT_PITCH], sc[FT_PITCH]);
+        const int mL = max(max(sc[-FT_PITCH - 1], sc[-1]), sc[FT_PITCH - 1]);
+        const int mR = max(max(sc[-FT_PITCH + 1], sc[1]), sc[FT_PITCH + 1]);
+        if (fl & 1) m = max(m, mL);
+        if (fl & 2) m = max(m, mR);
+        if (sc[0] > m) {
+            atomicOr(&sh.bitmap[pos >> 8][c >> 5], 1u << (c & 31));
+            if (markCells) sh.cellAny[sh.colCell[c]] = 1;
+        }
+    }
+    __syncthreads();
+}
 
 __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant__ Geom g, const PyrPtrs p,
                                                            const FastCta* __restrict__ ctaTab, int tileRows,
@@ -87,14 +209,10 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
     extern __shared__ __align__(16) uint8_t sm[];
     uint8_t* tile = sm;                                   // tileRows x FT_PITCH pixels
     uint8_t* score = sm + tileRows * FT_PITCH;            // same geometry, 0 = not a corner
-    uint16_t* list = reinterpret_cast<uint16_t*>(sm + 2 * tileRows * FT_PITCH);    // 8 warp-private pixel queues: row << 8 | col
-    __shared__ uint32_t bitmap[FT_ROWS][8];               // emitted keypoints, one bit per tile pixel
-    __shared__ uint16_t rowOfs[FT_MAXCELLS][FT_ROWS];     // per cell: keypoints in the rows above
-    __shared__ uint8_t colCell[FT_PITCH], colIn[FT_PITCH];   // tile column -> cell of the run, column inside the cell
-    __shared__ int sCellAny[FT_MAXCELLS];
+    uint16_t* Q = reinterpret_cast<uint16_t*>(sm + 2 * tileRows * FT_PITCH);    // pixel queue of the CTA
+    __shared__ __align__(16) FastShared sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned ltMask = (1u << lane) - 1;
     const int img = blockIdx.y;
     const FastCta cta = ctaTab[blockIdx.x];
     const int level = cta.level, ci = cta.ci, j0 = cta.j0, nCellsHere = cta.n;
@@ -106,190 +224,96 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
     const int wCell = lg.wCell, hCell = lg.hCell;
     const int X0 = OBS_BORDER + j0 * wCell, Y0 = OBS_BORDER + ci * hCell;
     const int X1 = min(X0 + nCellsHere * wCell + 6, maxBX), Y1 = min(Y0 + hCell + 6, maxBY);
-    const int sw = X1 - X0, sh = Y1 - Y0;
-    if (sw < 7 || sh < 7) {                               // no interior pixel: every cell of the run is empty
+    const int sw = X1 - X0, shh = Y1 - Y0;
+    if (sw < 7 || shh < 7) {                              // no interior pixel: every cell of the run is empty
         if (tid < nCellsHere) countOut[tid] = 0;
         return;
     }
     const int xa = X0 & ~15;                              // tile column 0 <-> level column xa
     const int cLo = X0 + 3 - xa, cHi = X1 - 3 - xa;       // interior columns in tile coordinates
-    const int rLo = 3, rHi = sh - 3;                      // interior rows
+    const int rLo = 3, rHi = shh - 3;                     // interior rows
 
-    // ---- stage the window (128-bit loads), clear the maps, build the column tables
+    // ---- stage the window (128-bit loads, 16 lanes per row), clear the maps, build the column tables
     {
         int pitch;
         const uint8_t* base = level_ptr(p, g, img, level, pitch);
         const int nVec = (X1 - xa + 15) >> 4;             // <= 16
-        for (int i = tid; i < sh * 16; i += FT_THREADS) {
-            const int r = i >> 4, v = i & 15;
-            if (v < nVec) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(Y0 + r) * pitch + xa) + v);
-                *reinterpret_cast<uint4*>(tile + r * FT_PITCH + 16 * v) = q;
-            }
+        const int v = tid & 15;
+        const uint8_t* src = base + (size_t)(Y0 + (tid >> 4)) * pitch + xa + 16 * v;
+        const size_t srcStep = (size_t)pitch * (FT_THREADS / 16);
+        const bool ld = v < nVec;
+        for (int r = tid >> 4; r < shh; r += FT_THREADS / 16, src += srcStep) {
+            if (ld) *reinterpret_cast<uint4*>(tile + r * FT_PITCH + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src));
             *reinterpret_cast<uint4*>(score + r * FT_PITCH + 16 * v) = make_uint4(0, 0, 0, 0);
         }
-        for (int i = tid; i < FT_ROWS * 8; i += FT_THREADS) (&bitmap[0][0])[i] = 0;
+        for (int i = tid; i < FT_ROWS * 8; i += FT_THREADS) (&sh.bitmap[0][0])[i] = 0;
+        const int lastCol = maxBX - 4 - xa;               // tile column of the level's last interior column
         const int xr = max(tid + xa - OBS_EDGE, 0);       // column relative to the level's first interior column
         const int cc = xr / wCell;
-        colCell[tid] = (uint8_t)min(max(cc - j0, 0), FT_MAXCELLS - 1);
-        colIn[tid] = (uint8_t)(xr - cc * wCell);
-        if (tid < FT_MAXCELLS) sCellAny[tid] = 0;
+        const int inCell = xr - cc * wCell;
+        sh.colCell[tid] = (uint8_t)min(max(cc - j0, 0), FT_MAXCELLS - 1);
+        sh.colFlags[tid] = (uint8_t)((inCell > 0 ? 1 : 0) | ((inCell < wCell - 1 && tid < lastCol) ? 2 : 0));
+        sh.colOK[tid] = (tid >= cLo && tid < cHi) ? 0x80 : 0;
+        if (tid < FT_MAXCELLS) sh.cellAny[tid] = 0;
+        if (tid == 0) sh.qCount = 0;
     }
     __syncthreads();
 
-    // Each warp owns the interior rows rLo + warp, + 8, ... and a private queue: no atomics, and
-    // every later filtering step compacts the queue in place.
-    uint16_t* seg = list + warp * FT_SEG;
+    // ---- phase A: cv::FAST(cell, iniThFAST) for every cell of the run (:809).  A corner at iniTh only
+    // competes with neighbours that are corners at iniTh as well, so nothing below iniTh is scored here.
+    fast_phase(tile, score, Q, sh, g.iniTh, rHi, true);
 
-    // ---- pass 1: compass-point rejection, 8 pixels per lane, one row per iteration, survivors queued.
-    // Every 9-arc holds one of ring pixels {0,8} and one of {4,12}; (|d0| | |d8|) > t is implied by
-    // |d0| > t or |d8| > t, so "(|d0| | |d8|) > t and (|d4| | |d12|) > t" is a necessary condition.
-    const int tLow = min(g.iniTh, g.minTh);
-    int nQ = 0;
-    {
-        const int w0 = (cLo >> 2) & ~1, w1 = (cHi + 3) >> 2;     // even-aligned word range covering the interior columns
-        const unsigned K = (unsigned)(127 - min(tLow, 127)) * 0x01010101u;
-        const int wA = w0 + 2 * lane;
-        const int c0 = wA * 4;
-        unsigned edgeMask = wA < w1 ? 0xffu : 0u;
-        if (c0 < cLo) edgeMask &= 0xffu << (cLo - c0);
-        if (c0 + 8 > cHi && c0 < cHi) edgeMask &= 0xffu >> (c0 + 8 - cHi);
-        for (int r = rLo + warp; r < rHi; r += FT_THREADS / 32) {
-            unsigned m8 = 0;
-            if (edgeMask) {
-                const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + r * FT_PITCH);
-                const uint2 C = *reinterpret_cast<const uint2*>(row + wA);
-                const uint2 up = *reinterpret_cast<const uint2*>(row + wA + 3 * (FT_PITCH / 4));
-                const uint2 dn = *reinterpret_cast<const uint2*>(row + wA - 3 * (FT_PITCH / 4));
-                const unsigned L = row[wA - 1], R = row[wA + 2];
-                unsigned f0, f1;
-                if (tLow < 128) {
-                    const unsigned y0 = __vabsdiffu4(C.x, up.x) | __vabsdiffu4(C.x, dn.x);
-                    const unsigned z0 = __vabsdiffu4(C.x, __byte_perm(L, C.x, 0x4321)) | __vabsdiffu4(C.x, __byte_perm(C.x, C.y, 0x6543));
-                    const unsigned y1 = __vabsdiffu4(C.y, up.y) | __vabsdiffu4(C.y, dn.y);
-                    const unsigned z1 = __vabsdiffu4(C.y, __byte_perm(C.x, C.y, 0x4321)) | __vabsdiffu4(C.y, __byte_perm(C.y, R, 0x6543));
-                    f0 = over_threshold(y0, K) & over_threshold(z0, K) & 0x80808080u;
-                    f1 = over_threshold(y1, K) & over_threshold(z1, K) & 0x80808080u;
-                } else {
-                    f0 = f1 = 0x80808080u;                 // thresholds >= 128: no cheap rejection, score everything
-                }
-                // gather the 8 flag bits (bit 7 of each byte)
-                m8 = ((((f0 >> 7) * 0x00204081u) >> 21 & 0xfu) | (((f1 >> 7) * 0x00204081u) >> 17 & 0xf0u)) & edgeMask;
-            }
-            const int n = __popc(m8);
-            int incl = n;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            uint16_t* out = seg + nQ + incl - n;
-            const int e0 = (r << 8) | c0;
-            while (m8) {
-                const int b = __ffs(m8) - 1;
-                m8 &= m8 - 1;
-                *out++ = (uint16_t)(e0 + b);
-            }
-            nQ += __shfl_sync(0xffffffffu, incl, 31);
+    // ---- phase B: cells whose suppressed result is empty are redone at minThFAST (:811-816)
+    if (g.minTh < g.iniTh) {
+        bool redo = false;
+        for (int cl = 0; cl < nCellsHere; cl++) redo |= sh.cellAny[cl] == 0;
+        if (redo) {                                       // CTA-uniform
+            __syncthreads();
+            sh.colOK[tid] = (tid >= cLo && tid < cHi && sh.cellAny[sh.colCell[tid]] == 0) ? 0x80 : 0;
+            if (tid == 0) sh.qCount = 0;
+            __syncthreads();
+            fast_phase(tile, score, Q, sh, g.minTh, rHi, false);
         }
     }
-    __syncwarp();
 
-    // ---- pass 2: exact score of the queued pixels, one lane each; corners stay queued
-    int nC = 0;
-    for (int i0 = 0; i0 < nQ; i0 += 32) {
-        const int i = i0 + lane;
-        int e = 0, s = 0;
-        if (i < nQ) {
-            e = seg[i];
-            const int contrast = fast_contrast(tile + (e >> 8) * FT_PITCH + (e & 255));
-            if (contrast > tLow && contrast > 1) s = contrast - 1;            // OpenCV: score = corner contrast - 1
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, s > 0);
-        if (s > 0) {
-            score[(e >> 8) * FT_PITCH + (e & 255)] = (uint8_t)s;
-            seg[nC + __popc(bal & ltMask)] = (uint16_t)e;
-        }
-        nC += __popc(bal);
-    }
-    __syncthreads();
-
-    // ---- pass 3: strict 3x3 non-max suppression inside each cell, over the corners only; survivors stay queued
-    const int lastCol = maxBX - 4 - xa;                    // tile column of the level's last interior column
-    int nS = 0;
-    for (int i0 = 0; i0 < nC; i0 += 32) {
-        const int i = i0 + lane;
-        bool keep = false;
-        int e = 0;
-        if (i < nC) {
-            e = seg[i];
-            const int c = e & 255;
-            const uint8_t* sc = score + (e >> 8) * FT_PITCH + c;
-            const int s = sc[0];
-            const int inCell = colIn[c];
-            const bool hasL = inCell > 0, hasR = inCell < wCell - 1 && c < lastCol;
-            int m = max(sc[-FT_PITCH], sc[FT_PITCH]);
-            if (hasL) m = max(m, max(max(sc[-FT_PITCH - 1], sc[-1]), sc[FT_PITCH - 1]));
-            if (hasR) m = max(m, max(max(sc[-FT_PITCH + 1], sc[1]), sc[FT_PITCH + 1]));
-            keep = s > m;
-            if (keep && s >= g.iniTh) sCellAny[colCell[c]] = 1;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) seg[nS + __popc(bal & ltMask)] = (uint16_t)e;
-        nS += __popc(bal);
-    }
-    __syncthreads();
-
-    // ---- pass 4: threshold fallback per cell (:809-816); mark what is emitted
-    int nE = 0;
-    for (int i0 = 0; i0 < nS; i0 += 32) {
-        const int i = i0 + lane;
-        bool keep = false;
-        int e = 0;
-        if (i < nS) {
-            e = seg[i];
-            const int r = e >> 8, c = e & 255;
-            const int T = sCellAny[colCell[c]] ? g.iniTh : g.minTh;
-            keep = score[r * FT_PITCH + c] >= T;
-            if (keep) atomicOr(&bitmap[r][c >> 5], 1u << (c & 31));
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) seg[nE + __popc(bal & ltMask)] = (uint16_t)e;
-        nE += __popc(bal);
-    }
-    __syncthreads();
-
-    // ---- pass 5: per cell, keypoints per row -> exclusive prefix over the rows (one warp per cell)
+    // ---- per cell, keypoints per row -> exclusive prefix over the rows (one warp per cell)
     for (int cl = warp; cl < nCellsHere; cl += FT_THREADS / 32) {
         const int cx0 = OBS_EDGE + (j0 + cl) * wCell - xa; // first interior tile column of the cell
         const int cx1 = min(cx0 + wCell, cHi);
         int carry = 0;
         for (int rb = rLo; rb < rHi; rb += 32) {
             const int r = rb + lane;
-            const int n = (r < rHi && cx1 > cx0) ? row_bits(bitmap[r], cx0, cx1) : 0;
+            const int n = (r < rHi && cx1 > cx0) ? row_bits(sh.bitmap[r], cx0, cx1) : 0;
             int incl = n;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (r < rHi) rowOfs[cl][r] = (uint16_t)(carry + incl - n);
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (r < rHi) sh.rowOfs[cl][r] = (uint16_t)(carry + incl - n);
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
         if (lane == 0) countOut[cl] = carry;
     }
     __syncthreads();
 
-    // ---- pass 6: write the keypoints in row-major order inside each cell (cv::FAST's order)
-    for (int i = lane; i < nE; i += 32) {
-        const int e = seg[i];
-        const int r = e >> 8, c = e & 255;
-        const int cl = colCell[c];
-        const int cx0 = OBS_EDGE + (j0 + cl) * wCell - xa;
-        const int pos = rowOfs[cl][r] + (c > cx0 ? row_bits(bitmap[r], cx0, c) : 0);
-        uint32_t* slot = cand + (size_t)img * g.slotTotal + lg.slotBase + (size_t)(ci * lg.nCols + j0 + cl) * lg.cellCap;
-        // coordinates relative to the 16-px border origin, :820-825
-        slot[pos] = pack_key(xa + c - OBS_BORDER, Y0 + r - OBS_BORDER, score[r * FT_PITCH + c]);
+    // ---- write the keypoints in row-major order inside each cell (cv::FAST's order)
+    for (int i = tid; i < shh * 8; i += FT_THREADS) {
+        const int r = i >> 3;
+        uint32_t word = sh.bitmap[r][i & 7];
+        while (word) {
+            const int c = ((i & 7) << 5) + __ffs(word) - 1;
+            word &= word - 1;
+            const int cl = sh.colCell[c];
+            const int cx0 = OBS_EDGE + (j0 + cl) * wCell - xa;
+            const int pos = sh.rowOfs[cl][r] + (c > cx0 ? row_bits(sh.bitmap[r], cx0, c) : 0);
+            uint32_t* slot = cand + (size_t)img * g.slotTotal + lg.slotBase + (size_t)(ci * lg.nCols + j0 + cl) * lg.cellCap;
+            // coordinates relative to the 16-px border origin, :820-825
+            slot[pos] = pack_key(xa + c - OBS_BORDER, Y0 + r - OBS_BORDER, score[r * FT_PITCH + c]);
+        }
     }
 }
 
 }  // namespace
 
-size_t fast_smem_bytes(int tileRows) { return (size_t)2 * tileRows * FT_PITCH + (size_t)8 * FT_SEG * 2; }
+size_t fast_smem_bytes(int tileRows) { return (size_t)2 * tileRows * FT_PITCH + (size_t)FT_LIST * 2 + 16; }
 
 cudaError_t fast_prepare(int tileRows) {
     return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(tileRows));
