@@ -90,7 +90,7 @@ __device__ __forceinline__ unsigned pretest_word(unsigned C, unsigned up, unsign
 
 struct FastShared {
     uint32_t bitmap[FT_ROWS][8];               // emitted keypoints, one bit per tile pixel
-    uint16_t rowOfs[FT_MAXCELLS][FT_ROWS];     // per cell: keypoints in the rows above
+    int rowOfs[FT_MAXCELLS][FT_ROWS];          // per cell: keypoints per row, then keypoints in the rows above
     uint8_t colCell[FT_PITCH];                 // tile column -> cell of the run
     uint8_t colFlags[FT_PITCH];                // bit 0: has a left neighbour inside its cell, bit 1: a right one
     uint8_t colOK[FT_PITCH];                   // 0x80: the column takes part in the current phase
@@ -197,7 +197,9 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
         if (fl & 2) m = max(m, mR);
         if (sc[0] > m) {
             atomicOr(&sh.bitmap[pos >> 8][c >> 5], 1u << (c & 31));
-            if (markCells) sh.cellAny[sh.colCell[c]] = 1;
+            const int cl = sh.colCell[c];
+            atomicAdd(&sh.rowOfs[cl][pos >> 8], 1);
+            if (markCells) sh.cellAny[cl] = 1;
         }
     }
     __syncthreads();
@@ -246,16 +248,19 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
             if (ld) *reinterpret_cast<uint4*>(tile + r * FT_PITCH + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src));
             *reinterpret_cast<uint4*>(score + r * FT_PITCH + 16 * v) = make_uint4(0, 0, 0, 0);
         }
-        for (int i = tid; i < FT_ROWS * 8; i += FT_THREADS) (&sh.bitmap[0][0])[i] = 0;
+        for (int i = tid; i < shh * 8; i += FT_THREADS) (&sh.bitmap[0][0])[i] = 0;
         const int lastCol = maxBX - 4 - xa;               // tile column of the level's last interior column
-        const int xr = max(tid + xa - OBS_EDGE, 0);       // column relative to the level's first interior column
-        const int cc = xr / wCell;
-        const int inCell = xr - cc * wCell;
-        sh.colCell[tid] = (uint8_t)min(max(cc - j0, 0), FT_MAXCELLS - 1);
+        int inCell = max(tid - (X0 + 3 - xa), 0);         // column relative to the first interior column of the run
+        int cc = 0;                                       // cell of the run (< 8): three compare-subtract steps
+        if (inCell >= 4 * wCell) { inCell -= 4 * wCell; cc += 4; }
+        if (inCell >= 2 * wCell) { inCell -= 2 * wCell; cc += 2; }
+        if (inCell >= wCell) { inCell -= wCell; cc += 1; }
+        sh.colCell[tid] = (uint8_t)cc;
         sh.colFlags[tid] = (uint8_t)((inCell > 0 ? 1 : 0) | ((inCell < wCell - 1 && tid < lastCol) ? 2 : 0));
         sh.colOK[tid] = (tid >= cLo && tid < cHi) ? 0x80 : 0;
         if (tid < FT_MAXCELLS) sh.cellAny[tid] = 0;
         if (tid == 0) sh.qCount = 0;
+        for (int i = tid; i < FT_MAXCELLS * FT_ROWS; i += FT_THREADS) (&sh.rowOfs[0][0])[i] = 0;
     }
     __syncthreads();
 
@@ -265,10 +270,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
 
     // ---- phase B: cells whose suppressed result is empty are redone at minThFAST (:811-816)
     if (g.minTh < g.iniTh) {
-        bool redo = false;
-        for (int cl = 0; cl < nCellsHere; cl++) redo |= sh.cellAny[cl] == 0;
-        if (redo) {                                       // CTA-uniform
-            __syncthreads();
+        if (__syncthreads_or(tid < nCellsHere && sh.cellAny[tid] == 0)) {
             sh.colOK[tid] = (tid >= cLo && tid < cHi && sh.cellAny[sh.colCell[tid]] == 0) ? 0x80 : 0;
             if (tid == 0) sh.qCount = 0;
             __syncthreads();
@@ -278,16 +280,14 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
 
     // ---- per cell, keypoints per row -> exclusive prefix over the rows (one warp per cell)
     for (int cl = warp; cl < nCellsHere; cl += FT_THREADS / 32) {
-        const int cx0 = OBS_EDGE + (j0 + cl) * wCell - xa; // first interior tile column of the cell
-        const int cx1 = min(cx0 + wCell, cHi);
         int carry = 0;
         for (int rb = rLo; rb < rHi; rb += 32) {
             const int r = rb + lane;
-            const int n = (r < rHi && cx1 > cx0) ? row_bits(sh.bitmap[r], cx0, cx1) : 0;
+            const int n = r < rHi ? sh.rowOfs[cl][r] : 0;
             int incl = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            if (r < rHi) sh.rowOfs[cl][r] = (uint16_t)(carry + incl - n);
+            if (r < rHi) sh.rowOfs[cl][r] = carry + incl - n;
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
         if (lane == 0) countOut[cl] = carry;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant
 
 }  // namespace
 
-size_t fast_smem_bytes(int tileRows) { return (size_t)2 * tileRows * FT_PITCH + (size_t)FT_LIST * 2 + 16; }
+size_t fast_smem_bytes(int tileRows) { return (size_t)2 * tileRows * FT_PITCH + (size_t)FT_LIST * 2; }
 
 cudaError_t fast_prepare(int tileRows) {
     return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(tileRows));
