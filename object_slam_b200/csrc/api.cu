@@ -160,6 +160,30 @@ void resize_taps(int ssize, int dsize, bool isX, ResizeTap* out) {
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// Source footprint of the tiled resize kernel (pyramid.cu): every group of four output columns must read
+// within 7 source bytes, and the staged source tile of a 128 x 64 output tile must fit shared memory.
+void resize_tile_geometry(const LevelGeom& S, LevelGeom& D, const ResizeTap* xt, const ResizeTap* yt) {
+    D.rsPitch = D.rsRows = 0;
+    int maxBytes = 0, maxRows = 0;
+    for (int x = 0; x < D.w; x += 4) {
+        const int last = std::min(x + 3, D.w - 1);
+        for (int i = x; i <= last; i++) if (xt[i].ofs - xt[x].ofs < 0 || xt[i].ofs - xt[x].ofs > 6) return;
+    }
+    for (int x = 0; x < D.w; x += RESIZE_TILE_W) {
+        const int last = std::min(x + RESIZE_TILE_W, D.w) - 1;
+        maxBytes = std::max(maxBytes, xt[last].ofs + 1 - (xt[x].ofs & ~15) + 1);
+    }
+    for (int y = 0; y < D.h; y += RESIZE_TILE_H) {
+        const int last = std::min(y + RESIZE_TILE_H, D.h) - 1;
+        const int y0 = std::min(std::max(yt[y].ofs, 0), S.h - 1), y1 = std::min(std::max(yt[last].ofs + 1, 0), S.h - 1);
+        if (y1 < y0) return;
+        maxRows = std::max(maxRows, y1 - y0 + 1);
+    }
+    const int pitch = round_up(maxBytes, 16) + 16;
+    if ((size_t)pitch * maxRows > 96 * 1024) return;
+    D.rsPitch = pitch; D.rsRows = maxRows;
+}
+
 // Level sizes, FAST cell grid, slot layout for an image shape.
 void build_geometry(obs_extractor* e, int w, int h) {
     Geom& g = e->g;
@@ -236,6 +260,7 @@ void build_geometry(obs_extractor* e, int w, int h) {
     for (int l = 1; l < nl; l++) {
         resize_taps(g.lv[l - 1].w, g.lv[l].w, true, e->hXtab.data() + g.lv[l].xtab);
         resize_taps(g.lv[l - 1].h, g.lv[l].h, false, e->hYtab.data() + g.lv[l].ytab);
+        resize_tile_geometry(g.lv[l - 1], g.lv[l], e->hXtab.data() + g.lv[l].xtab, e->hYtab.data() + g.lv[l].ytab);
     }
 }
 
@@ -251,6 +276,7 @@ int set_shape(obs_extractor* e, int w, int h, int nimg, cudaStream_t st) {
                 return fail(OBS_ERR_INVALID, "image %dx%d exceeds the 12-bit key coordinate range", w, h);
         CU(quadtree_prepare(e->nodeCap));
         CU(fast_prepare(e->g.fastTileRows));
+        CU(pyramid_prepare(e->g));
         CU(e->dXtab.ensure(e->hXtab.size()));
         CU(e->dYtab.ensure(e->hYtab.size()));
         CU(e->dFastCtas.ensure(std::max<size_t>(e->hFastCtas.size(), 1)));

@@ -28,6 +28,8 @@ struct LevelGeom {
     int blurTileBase;    // first CTA of this level in the blur grid
     int blurTilesX;      // tiles per row of the blur grid
     int blurEdgeBase;    // first border-strip work item of this level
+    int rsPitch;         // resize of this level from the previous one: shared-memory row pitch of the staged source
+    int rsRows;          //   tile (0 = taps too far apart for the tiled kernel) and its row capacity
     float scale;         // mvScaleFactor[level]
     float invScale;      // mvInvScaleFactor[level]
     float patchSize;     // (float)(int)(31 * scale), :838

@@ -4,6 +4,9 @@
 #include "common.cuh"
 
 // K1  pyramid.cu   -- ComputePyramid (src/ORBextractor.cc:1107-1132), levels 1..n-1
+#define RESIZE_TILE_W 128          // output tile of the tiled resize kernel
+#define RESIZE_TILE_H 64
+cudaError_t pyramid_prepare(const Geom& g);
 cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, const ResizeTap* ytab, int nimg, cudaStream_t st);
 
 cudaError_t launch_repack(const uint8_t* src, size_t srcImgStride, size_t srcPitch, uint8_t* dst, size_t dstImgStride,

@@ -11,6 +11,7 @@
 // (a0*S[x] + a1*S[x+1]) and reuses the lower source row of one output row as the upper row of the
 // next when the vertical taps allow; the vertical blend is two IMAD.HI per pixel.
 #include "kernels.h"
+#include <algorithm>
 
 namespace {
 
@@ -127,6 +128,107 @@ __global__ void __launch_bounds__(32 * RS_BANDS) k_resize(const __grid_constant_
     }
 }
 
+// Tiled variant for the usual scale factors (every group of four output columns reads within 7 source bytes,
+// LevelGeom::rsPitch > 0).  A CTA stages the source footprint of a 128 x 64 output tile in shared memory with
+// 128-bit loads; a thread owns four output columns of a 16-row band.  No clamping is left in the loop: rows
+// are rebased in a shared copy of the y taps, columns by the staged pitch.
+// (b * h) >> 16 == umulhi(b << 16, h); the result cannot exceed 255 because a pair of weights sums to at most 2049.
+constexpr int RT_ROWS = 16;          // output rows per thread
+constexpr int RT_BANDS = RESIZE_TILE_H / RT_ROWS;
+
+struct __align__(16) YTap { int off0, off1; unsigned b0, b1; };   // byte offsets of the two source rows inside the staged tile, weights << 16
+
+__device__ __forceinline__ void hrow_tile(const uint8_t* row, int shift, const unsigned (&w)[4], const unsigned (&sel)[4], unsigned (&hs)[4]) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(row);
+    const unsigned w0 = q[0], w1 = q[1], w2 = q[2];
+    const unsigned U0 = __funnelshift_r(w0, w1, shift), U1 = __funnelshift_r(w1, w2, shift);
+#pragma unroll
+    for (int i = 0; i < 4; i++) hs[i] = __dp2a_lo(w[i], __byte_perm(U0, U1, sel[i]), 0u) >> 4;
+}
+
+__global__ void __launch_bounds__(32 * RT_BANDS) k_resize_tile(const __grid_constant__ Geom g, const PyrPtrs p,
+                                                               const ResizeTap* __restrict__ xtab,
+                                                               const ResizeTap* __restrict__ ytab, int level) {
+    extern __shared__ __align__(16) uint8_t tile[];
+    __shared__ YTap sY[RESIZE_TILE_H];
+    const LevelGeom& D = g.lv[level];
+    const LevelGeom& S = g.lv[level - 1];
+    const int img = blockIdx.z, tid = threadIdx.y * 32 + threadIdx.x;
+    const int tx0 = blockIdx.x * RESIZE_TILE_W, ty0 = blockIdx.y * RESIZE_TILE_H;
+    const int tw = min(RESIZE_TILE_W, D.w - tx0), th = min(RESIZE_TILE_H, D.h - ty0);
+    const ResizeTap* xt = xtab + D.xtab;
+    const ResizeTap* yt = ytab + D.ytab;
+    int spitch, dpitch;
+    const uint8_t* src = level_ptr(p, g, img, level - 1, spitch);
+    uint8_t* dst = const_cast<uint8_t*>(level_ptr(p, g, img, level, dpitch));
+    const int xs0 = xt[tx0].ofs & ~15, xs1 = xt[tx0 + tw - 1].ofs + 1;
+    const int ys0 = min(max(yt[ty0].ofs, 0), S.h - 1), ys1 = min(max(yt[ty0 + th - 1].ofs + 1, 0), S.h - 1);
+    const int pitch = D.rsPitch;
+    {
+        // rows of the source are padded to a multiple of 16 bytes (slab pitch 128; level 0: 16-byte aligned stride)
+        const int nVec = min((xs1 - xs0) / 16 + 1, (spitch - xs0) >> 4), nRows = ys1 - ys0 + 1;
+        constexpr int RSTEP = 32 * RT_BANDS / 16;
+        for (int v = tid & 15; v < nVec; v += 16) {
+            const uint4* gp = reinterpret_cast<const uint4*>(src + (size_t)(ys0 + (tid >> 4)) * spitch + xs0) + v;
+            uint8_t* tp = tile + (tid >> 4) * pitch + 16 * v;
+            const size_t gstep = (size_t)spitch * RSTEP / 16;
+            int r = tid >> 4;
+            for (; r + 3 * RSTEP < nRows; r += 4 * RSTEP, gp += 4 * gstep, tp += 4 * RSTEP * pitch) {
+                const uint4 a = __ldg(gp), b = __ldg(gp + gstep), c = __ldg(gp + 2 * gstep), d = __ldg(gp + 3 * gstep);
+                *reinterpret_cast<uint4*>(tp) = a;
+                *reinterpret_cast<uint4*>(tp + RSTEP * pitch) = b;
+                *reinterpret_cast<uint4*>(tp + 2 * RSTEP * pitch) = c;
+                *reinterpret_cast<uint4*>(tp + 3 * RSTEP * pitch) = d;
+            }
+            for (; r < nRows; r += RSTEP, gp += gstep, tp += RSTEP * pitch) *reinterpret_cast<uint4*>(tp) = __ldg(gp);
+        }
+        if (tid < th) {
+            const ResizeTap t = yt[ty0 + tid];
+            YTap y;
+            y.off0 = (min(max(t.ofs, 0), S.h - 1) - ys0) * pitch;
+            y.off1 = (min(max(t.ofs + 1, 0), S.h - 1) - ys0) * pitch;
+            y.b0 = (unsigned)t.a0 << 16; y.b1 = (unsigned)t.a1 << 16;
+            sY[tid] = y;
+        }
+    }
+    __syncthreads();
+    const int dx0 = tx0 + 4 * threadIdx.x, r0 = threadIdx.y * RT_ROWS;
+    if (dx0 >= D.w || r0 >= th) return;
+    const int nOut = min(RT_ROWS, th - r0);
+
+    unsigned w[4], sel[4];
+    int ofs0;
+    {
+        const ResizeTap t0 = xt[dx0];
+        ofs0 = t0.ofs;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const ResizeTap tx = i ? xt[min(dx0 + i, D.w - 1)] : t0;
+            const int o = tx.ofs - ofs0;                    // 0..6 (host-checked)
+            w[i] = (unsigned)(unsigned short)tx.a0 | ((unsigned)(unsigned short)tx.a1 << 16);
+            sel[i] = (unsigned)o | ((unsigned)(o + 1) << 4);
+        }
+    }
+    const int rel = ofs0 - xs0;
+    const uint8_t* col = tile + (rel & ~3);
+    const int shift = 8 * (rel & 3);
+    uint8_t* out = dst + (size_t)(ty0 + r0) * dpitch + dx0;
+
+    // Every output row filters its two source rows afresh: at scale 1.2 that is 2 row filters per output row
+    // instead of 1.2, but the loop carries no state, no branches and no register shuffling.
+#pragma unroll 4
+    for (int r = 0; r < nOut; r++, out += dpitch) {
+        const YTap y = sY[r0 + r];
+        unsigned hA[4], hB[4];
+        hrow_tile(col + y.off0, shift, w, sel, hA);
+        hrow_tile(col + y.off1, shift, w, sel, hB);
+        unsigned o = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) o += ((__umulhi(y.b0, hA[i]) + __umulhi(y.b1, hB[i]) + 2u) >> 2) << (8 * i);
+        *reinterpret_cast<uint32_t*>(out) = o;          // rows are padded to the pitch
+    }
+}
+
 // Host uploads arrive as one contiguous block (rows of w bytes); level 0 lives in the slab with a
 // 128-byte row pitch so that every later stage can use aligned vector loads.
 __global__ void __launch_bounds__(256) k_repack(const uint8_t* __restrict__ src, size_t srcImgStride, size_t srcPitch,
@@ -164,8 +266,21 @@ cudaError_t launch_repack(const uint8_t* src, size_t srcImgStride, size_t srcPit
     return cudaGetLastError();
 }
 
+cudaError_t pyramid_prepare(const Geom& g) {
+    size_t need = 0;
+    for (int l = 1; l < g.nlevels; l++) need = std::max(need, (size_t)g.lv[l].rsPitch * g.lv[l].rsRows);
+    if (need <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(k_resize_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+}
+
 cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, const ResizeTap* ytab, int nimg, cudaStream_t st) {
     for (int l = 1; l < g.nlevels; l++) {
+        if (g.lv[l].rsPitch > 0) {
+            dim3 block(32, RT_BANDS);
+            dim3 grid((g.lv[l].w + RESIZE_TILE_W - 1) / RESIZE_TILE_W, (g.lv[l].h + RESIZE_TILE_H - 1) / RESIZE_TILE_H, nimg);
+            k_resize_tile<<<grid, block, (size_t)g.lv[l].rsPitch * g.lv[l].rsRows, st>>>(g, p, xtab, ytab, l);
+            continue;
+        }
         dim3 block(32, RS_BANDS);
         dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + RS_ROWS * RS_BANDS - 1) / (RS_ROWS * RS_BANDS), nimg);
         k_resize<<<grid, block, 0, st>>>(g, p, xtab, ytab, l);
