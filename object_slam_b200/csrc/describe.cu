@@ -74,98 +74,142 @@ __device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp)
     if (n & 1) { *sinp = cv; *cosp = sv; } else { *sinp = sv; *cosp = cv; }
 }
 
+constexpr int DESC_PER_WARP = 8;     // keypoints per warp: tables and the level offsets are set up once per 64 keypoints
+constexpr int PR = 18, PP = 40;      // rBRIEF window radius (pattern radius <= 18.39), staged row pitch (10 words)
+
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Geom g, const PyrPtrs p,
                                                               const uint8_t* __restrict__ blurSlab, size_t blurStride,
                                                               const uint32_t* __restrict__ sel, const int* __restrict__ selCount,
                                                               uint8_t* __restrict__ records, size_t recordBytes) {
     __shared__ float4 pat[256];                 // (x0, y0, x1, y1) of point pair 8*lane + k at [k * 32 + lane] (conflict-free)
+    // rowMask[|v|][i]: 0xff in the bytes of patch word i (columns u = -15 + 4 i + k) that lie inside the circular patch
+    // (row OBS_HALF_PATCH + 1 is empty: the 32nd row slot of the warp's sweep)
+    __shared__ uint32_t rowMask[OBS_HALF_PATCH + 2][8];
+    __shared__ int levelEnd[OBS_MAX_LEVELS + 1];  // keypoints up to and including level l (level-major output order)
+    __shared__ __align__(16) uint8_t patch[DESC_WARPS][(2 * PR + 1) * PP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int img = blockIdx.y;
+    uint8_t* rec = records + (size_t)img * recordBytes;
     for (int i = tid; i < 256; i += DESC_WARPS * 32) {
         const int pr = (i & 31) * 8 + (i >> 5);
         pat[i] = make_float4((float)d_pattern[4 * pr], (float)d_pattern[4 * pr + 1], (float)d_pattern[4 * pr + 2], (float)d_pattern[4 * pr + 3]);
     }
+    if (tid < (OBS_HALF_PATCH + 2) * 8) {
+        const int av = tid >> 3, wi = tid & 7;
+        uint32_t m = 0;
+        if (av <= OBS_HALF_PATCH)
+            for (int k = 0; k < 4; k++) if (abs(-OBS_HALF_PATCH + 4 * wi + k) <= g.umax[av]) m |= 0xffu << (8 * k);
+        rowMask[av][wi] = m;
+    }
+    if (warp == DESC_WARPS - 1) {
+        // lanes 0..nlevels-1 hold the per-level counts, a warp scan gives the offsets
+        const int myCnt = lane < g.nlevels ? selCount[(size_t)img * g.nlevels + lane] : 0;
+        int incl = myCnt;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane <= OBS_MAX_LEVELS) levelEnd[lane] = incl;
+        if (blockIdx.x == 0 && lane < g.nlevels) {      // header: n, per-level counts
+            reinterpret_cast<int32_t*>(rec)[1 + lane] = myCnt;
+            if (lane == g.nlevels - 1) reinterpret_cast<int32_t*>(rec)[0] = incl;
+        }
+    }
     __syncthreads();
-
-    const int img = blockIdx.y;
-    const int j = blockIdx.x * DESC_WARPS + warp;              // output index of this warp's keypoint (level-major)
-    // level of keypoint j: lanes 0..nlevels-1 hold the per-level counts, a warp scan gives the offsets
-    const int* cnt = selCount + (size_t)img * g.nlevels;
-    const int myCnt = lane < g.nlevels ? cnt[lane] : 0;
-    int incl = myCnt;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const int total = __shfl_sync(0xffffffffu, incl, OBS_MAX_LEVELS - 1);
-    const unsigned owner = __ballot_sync(0xffffffffu, lane < g.nlevels && j >= incl - myCnt && j < incl);
-    uint8_t* rec = records + (size_t)img * recordBytes;
-    const int prevCnt = __shfl_up_sync(0xffffffffu, myCnt, 1);
-    if (j == 0 && lane <= g.nlevels) reinterpret_cast<int32_t*>(rec)[lane] = lane == 0 ? total : prevCnt;   // header: n, per-level counts
-    if (owner == 0) return;
-    const int level = __ffs(owner) - 1;
-    const int local = j - (__shfl_sync(0xffffffffu, incl, level) - __shfl_sync(0xffffffffu, myCnt, level));
-
-    const LevelGeom& lg = g.lv[level];
-    const uint32_t key = sel[((size_t)img * g.nlevels + level) * g.selCap + local];
-    const int cx = key_x(key) + OBS_BORDER, cy = key_y(key) + OBS_BORDER;       // :837-838
-
-    // ---- IC_Angle on the unblurred level (:77-104): integer moments over the circular patch.
-    // Lane = column u of the patch; the patch is symmetric, so column u spans rows |v| <= umax[|u|].
-    int pitch;
-    const uint8_t* im = level_ptr(p, g, img, level, pitch);
-    const uint8_t* c = im + (size_t)cy * pitch + cx;
-    const int u = lane - OBS_HALF_PATCH;
-    const int vm = lane < 31 ? g.umax[abs(u)] : -1;
-    int colSum = 0, m01 = 0;
-#pragma unroll
-    for (int v = -OBS_HALF_PATCH; v <= OBS_HALF_PATCH; v++) {
-        const int a = v < 0 ? -v : v;
-        int val = 0;
-        if (a <= vm) val = c[v * pitch + u];
-        colSum += val;
-        m01 += v * val;
-    }
-    const int m10 = __reduce_add_sync(0xffffffffu, u * colSum);
-    m01 = __reduce_add_sync(0xffffffffu, m01);
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // ---- rBRIEF on the blurred level (:108-147): lane i produces descriptor byte i
-    const float factorPI = (float)(3.14159265358979323846 / 180.f);
-    float a, b;
-    sincosf_glibc(__fmul_rn(angle, factorPI), &b, &a);
-    const uint8_t* cb = blurSlab + (size_t)img * blurStride + lg.off + (size_t)cy * lg.pitch + cx;
-    const int bp = lg.pitch;
-    int t0[8], t1[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const float4 q = pat[k * 32 + lane];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)));
-        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, b), __fmul_rn(q.w, a)));
-        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(q.z, a), __fmul_rn(q.w, b)));
-        t0[k] = cb[r0 * bp + q0];
-        t1[k] = cb[r1 * bp + q1];
-    }
-    int val = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) val |= (t0[k] < t1[k]) << k;
+    const int total = levelEnd[g.nlevels - 1];
     uint8_t* kpOut = rec + OBS_HDR_INTS * 4;
     uint8_t* descOut = kpOut + (size_t)g.kpCap * 28;
-    descOut[(size_t)j * 32 + lane] = (uint8_t)val;
+    uint8_t* mp = patch[warp];
 
-    // ---- keypoint record (cv::KeyPoint layout); pt scaled to level-0 coordinates (:1094-1101)
-    if (lane < 7) {
-        float fx = (float)cx, fy = (float)cy;
-        if (level != 0) { fx = __fmul_rn(fx, lg.scale); fy = __fmul_rn(fy, lg.scale); }
-        uint32_t w;
-        switch (lane) {
-            case 0: w = __float_as_uint(fx); break;
-            case 1: w = __float_as_uint(fy); break;
-            case 2: w = __float_as_uint(lg.patchSize); break;
-            case 3: w = __float_as_uint(angle); break;
-            case 4: w = __float_as_uint((float)key_r(key)); break;
-            case 5: w = (uint32_t)level; break;
-            default: w = 0xffffffffu; break;     // class_id = -1
+    for (int it = 0; it < DESC_PER_WARP; it++) {
+        const int j = (blockIdx.x * DESC_PER_WARP + it) * DESC_WARPS + warp;     // output index of the keypoint (level-major)
+        if (j >= total) break;
+        const int level = __popc(__ballot_sync(0xffffffffu, lane < g.nlevels - 1 && j >= levelEnd[min(lane, OBS_MAX_LEVELS)]));
+        const int local = j - (level ? levelEnd[level - 1] : 0);
+        const LevelGeom& lg = g.lv[level];
+        const uint32_t key = sel[((size_t)img * g.nlevels + level) * g.selCap + local];
+        const int cx = key_x(key) + OBS_BORDER, cy = key_y(key) + OBS_BORDER;       // :837-838
+
+        // ---- stage the 37 x 37 window of the blurred level around the keypoint (the rotated pattern stays within
+        // 18 px): 10 aligned words per row, three rows per warp-wide load; the 16 gathers of a lane then hit
+        // shared memory instead of 16 x 32 scattered sectors.  Issued first so that it overlaps the moments.
+        const uint8_t* win = blurSlab + (size_t)img * blurStride + lg.off + (size_t)(cy - PR) * lg.pitch + (cx - PR);
+        const int bmis = (int)(reinterpret_cast<uintptr_t>(win) & 3);
+        {
+            const int r3 = lane / 10, wi = lane - 10 * r3;                     // lanes 30, 31 idle
+            const unsigned bpitch = (unsigned)lg.pitch;
+            const uint8_t* gp = win - bmis + (size_t)(r3 * bpitch) + 4 * wi;
+            uint32_t* sp = reinterpret_cast<uint32_t*>(mp) + r3 * (PP / 4) + wi;
+            if (r3 < 3) {
+#pragma unroll
+                for (int r = 0; r < 2 * PR + 1; r += 3)
+                    if (r + 2 < 2 * PR + 1 || r + r3 < 2 * PR + 1)
+                        sp[r * (PP / 4)] = __ldg(reinterpret_cast<const uint32_t*>(gp + (size_t)bpitch * (unsigned)r));
+            }
         }
-        reinterpret_cast<uint32_t*>(kpOut + (size_t)j * 28)[lane] = w;
+
+        // ---- IC_Angle on the unblurred level (:77-104): integer moments over the circular patch.
+        // A quarter warp owns a patch row per step (4 rows per step, 8 steps); a lane fetches two neighbouring aligned
+        // words of its row, shifts its four patch bytes u = -15 + 4 wi .. +3 into place, masks them to the row's extent
+        // |u| <= umax[|v|] and sums I and (u + 15) I by integer dot products.  Rows are word aligned (pitch % 4 == 0),
+        // so the shift is the same for all lanes; a warp-wide load touches four 36-byte row segments.
+        int pitch;
+        const uint8_t* im = level_ptr(p, g, img, level, pitch);
+        int m10 = 0, m01 = 0;
+        {
+            const int wi = lane & 7, r4 = lane >> 3;
+            const uint8_t* rowp = im + (size_t)(cy - OBS_HALF_PATCH + r4) * pitch + (cx - OBS_HALF_PATCH);
+            const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(rowp) & 3);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp - mis) + wi;
+            const unsigned uw = 0x03020100u + 0x04040404u * wi;
+            int s0 = 0, s1 = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const int v = 4 * t + r4 - OBS_HALF_PATCH;
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(wp) + (size_t)(unsigned)pitch * (unsigned)(4 * t));
+                const unsigned W = __funnelshift_r(__ldg(q), __ldg(q + 1), 8 * mis) & rowMask[abs(v)][wi];
+                const int rs = (int)__dp4a(W, 0x01010101u, 0u);
+                s0 += rs;
+                s1 = (int)__dp4a(W, uw, (unsigned)s1);
+                m01 += v * rs;
+            }
+            m10 = s1 - OBS_HALF_PATCH * s0;
+        }
+        m10 = __reduce_add_sync(0xffffffffu, m10);
+        m01 = __reduce_add_sync(0xffffffffu, m01);
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+        // ---- rBRIEF on the blurred level (:108-147): lane i produces descriptor byte i
+        const float factorPI = (float)(3.14159265358979323846 / 180.f);
+        float a, b;
+        sincosf_glibc(__fmul_rn(angle, factorPI), &b, &a);
+        __syncwarp();
+        const uint8_t* cb = mp + PR * PP + PR + bmis;
+        unsigned val = 0;
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            const float4 q = pat[k * 32 + lane];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)));
+            const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, b), __fmul_rn(q.w, a)));
+            const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(q.z, a), __fmul_rn(q.w, b)));
+            const int d = (int)cb[r0 * PP + q0] - (int)cb[r1 * PP + q1];        // t0 < t1  <=>  d < 0
+            val = __funnelshift_l((unsigned)d, val, 1);                           // shift the sign bit in; bit k last for k = 0
+        }
+        descOut[(size_t)j * 32 + lane] = (uint8_t)val;
+        __syncwarp();                                    // the window is restaged by the next keypoint
+
+        // ---- keypoint record (cv::KeyPoint layout); pt scaled to level-0 coordinates (:1094-1101)
+        if (lane < 7) {
+            float fx = (float)cx, fy = (float)cy;
+            if (level != 0) { fx = __fmul_rn(fx, lg.scale); fy = __fmul_rn(fy, lg.scale); }
+            uint32_t w = 0xffffffffu;                    // class_id = -1
+            w = lane == 5 ? (uint32_t)level : w;
+            w = lane == 4 ? __float_as_uint((float)key_r(key)) : w;
+            w = lane == 3 ? __float_as_uint(angle) : w;
+            w = lane == 2 ? __float_as_uint(lg.patchSize) : w;
+            w = lane == 1 ? __float_as_uint(fy) : w;
+            w = lane == 0 ? __float_as_uint(fx) : w;
+            reinterpret_cast<uint32_t*>(kpOut + (size_t)j * 28)[lane] = w;
+        }
     }
 }
 
@@ -174,7 +218,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
 cudaError_t launch_describe(const Geom& g, PyrPtrs p, const uint8_t* blurSlab, size_t blurStride,
                             const uint32_t* sel, const int* selCount, uint8_t* records, size_t recordBytes,
                             int nimg, cudaStream_t st) {
-    dim3 grid((g.kpCap + DESC_WARPS - 1) / DESC_WARPS, nimg);
+    dim3 grid((g.kpCap + DESC_WARPS * DESC_PER_WARP - 1) / (DESC_WARPS * DESC_PER_WARP), nimg);
     k_describe<<<grid, DESC_WARPS * 32, 0, st>>>(g, p, blurSlab, blurStride, sel, selCount, records, recordBytes);
     return cudaGetLastError();
 }
