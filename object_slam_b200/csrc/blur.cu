@@ -5,10 +5,10 @@
 // The blurred level is only read by the descriptor stage.
 //
 // The stage is instruction-issue bound before it is HBM bound, so it is built around integer dot
-// products: a thread owns a 4-pixel column strip and walks down the rows.  Per row it loads three
-// aligned words straight from global/L1 (no shared memory, no barriers), forms the four horizontal
-// sums with IDP.4A (two dot products of 4 bytes each), keeps them packed as u16 pairs of vertically
-// adjacent rows, and produces each output pixel with four IDP.2A over an 8-row register window.
+// products: a thread owns a 4-pixel column strip and walks down the rows of a tile staged in shared
+// memory, forms the four horizontal sums with IDP.4A (two dot products of 4 bytes each), keeps them
+// packed as u16 pairs of vertically adjacent rows, and produces each output pixel with four IDP.2A
+// over an 8-row register window.
 #include "kernels.h"
 
 namespace {
@@ -23,28 +23,66 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-// 12 source bytes x-4 .. x+7 of one row as three words; columns outside the level are reflected.
-__device__ __forceinline__ void load_window(const uint8_t* __restrict__ row, int x, int W, bool interior,
-                                            unsigned& A, unsigned& B, unsigned& C) {
-    if (interior) {
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(row + x);
-        A = __ldg(q - 1); B = __ldg(q); C = __ldg(q + 1);
-    } else {
-        unsigned w[3] = {0, 0, 0};
-#pragma unroll
-        for (int b = 1; b < 12; b++) {                       // bytes x-3 .. x+7 (x-4 is never used)
-            const int xx = x - 4 + b;
-            const int sx = xx < W + 3 ? reflect101(xx, W) : 0;
-            w[b >> 2] |= (unsigned)row[sx] << (8 * (b & 3));
-        }
-        A = w[0]; B = w[1]; C = w[2];
-    }
-}
+// Tiled kernel: a CTA stages the 128 x 128 tile plus its 3-pixel apron in shared memory (aligned 128-bit loads; rows
+// and columns outside the level are reflected while staging, so the filter loop has no border case), then a
+// thread owns a 4-pixel column strip of a 32-row band and walks down the rows: 3 LDS, 8 IDP.4A for the four
+// horizontal sums, rows paired as u16x2, 4 IDP.2A per output pixel over an 8-row register window.
+constexpr int BT_PITCH = BL_TW + 32;        // staged columns tx0 - 16 .. tx0 + 143
+constexpr int BT_ROWS = BL_TH + 6;
 
-// One strip (4 columns at x, output rows y0 .. y0+nOut-1) of one level.
-template <bool INTERIOR>
-__device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int pitch, uint8_t* __restrict__ dst, int dpitch,
-                                           int x, int y0, int W, int H) {
+__global__ void __launch_bounds__(32 * BL_BANDS) k_blur_tile(const __grid_constant__ Geom g, const PyrPtrs p,
+                                                              uint8_t* __restrict__ blurSlab, size_t blurStride) {
+    extern __shared__ __align__(16) uint8_t tile[];
+    const int img = blockIdx.y, tid = threadIdx.y * 32 + threadIdx.x;
+    int t = (int)blockIdx.x, level = 0;
+#pragma unroll 1
+    for (int l = 1; l < g.nlevels; l++) if (t >= g.lv[l].blurTileBase) level = l;
+    const LevelGeom& lg = g.lv[level];
+    t -= lg.blurTileBase;
+    const int ty = t / lg.blurTilesX, tx = t - ty * lg.blurTilesX;
+    const int W = lg.w, H = lg.h;
+    const int tx0 = tx * BL_TW, ty0 = ty * BL_TH;
+    int pitch;
+    const uint8_t* src = level_ptr(p, g, img, level, pitch);
+    const int nRows = min(BT_ROWS, H + 3 - (ty0 - 3));             // staged rows: level rows ty0 - 3 .. min(ty0 + 130, H + 2)
+    {
+        // 10 vectors per row; vectors that start outside [0, pitch) are skipped (their bytes are either unused or
+        // written by the reflection pass below)
+        const int v = tid % 10, r0 = tid / 10;                      // 12 rows per sweep, threads 120..127 idle
+        const int gx = tx0 - 16 + 16 * v;
+        if (r0 < 12 && gx >= 0 && gx + 16 <= pitch) {
+            uint8_t* tp = tile + r0 * BT_PITCH + 16 * v;
+            if (ty0 >= 3 && ty0 - 3 + nRows <= H) {                // no row reflection in this tile
+                const uint8_t* sp = src + (size_t)(ty0 - 3 + r0) * pitch + gx;
+                const size_t step = (size_t)pitch * 12;
+                for (int r = r0; r < nRows; r += 12, sp += step, tp += 12 * BT_PITCH)
+                    *reinterpret_cast<uint4*>(tp) = __ldg(reinterpret_cast<const uint4*>(sp));
+            } else {
+                for (int r = r0; r < nRows; r += 12, tp += 12 * BT_PITCH)
+                    *reinterpret_cast<uint4*>(tp) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(ty0 - 3 + r, H) * pitch + gx));
+            }
+        }
+    }
+    const bool border = tx0 == 0 || tx0 + BL_TW + 8 > W;          // CTA-uniform
+    if (border) {
+        __syncthreads();
+        // columns -3..-1 and W.. of the tile, byte-wise from the level
+        for (int r = tid; r < nRows; r += 32 * BL_BANDS) {
+            const uint8_t* row = src + (size_t)reflect101(ty0 - 3 + r, H) * pitch;
+            uint8_t* trow = tile + r * BT_PITCH + 16 - tx0;
+            if (tx0 == 0) for (int c = -3; c < 0; c++) trow[c] = row[reflect101(c, W)];
+            for (int c = max(W, tx0); c < min(W + 7, tx0 + BL_TW + 8); c++) trow[c] = c < W + 3 ? row[reflect101(c, W)] : 0;
+        }
+    }
+    __syncthreads();
+
+    const int x = tx0 + 4 * threadIdx.x, y0 = ty0 + threadIdx.y * BL_ROWS;
+    if (x >= W || y0 >= H) return;
+    const int nOut = min(BL_ROWS, H - y0);
+    const uint32_t* col = reinterpret_cast<const uint32_t*>(tile + threadIdx.y * BL_ROWS * BT_PITCH + 16 + 4 * threadIdx.x);
+    const size_t dpitch = (size_t)lg.pitch;
+    uint8_t* dst = blurSlab + (size_t)img * blurStride + lg.off + (size_t)y0 * dpitch + x - 6 * dpitch;   // row j - 6 of the band
+
     const unsigned WA = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // taps 0..3
     const unsigned WB = 48u | (34u << 8) | (18u << 16);                    // taps 4..6
     unsigned Q[8][4];           // Q[j & 7][k] = (H_j[k], H_{j-1}[k]) as u16 pairs, k = column in the strip
@@ -53,38 +91,28 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
     for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int k = 0; k < 4; k++) Q[i][k] = 0;
-
-    const int nOut = min(BL_ROWS, H - y0);
-    const bool yInside = y0 >= 3 && y0 + nOut + 3 <= H;          // no row reflection needed
 #pragma unroll 1
     for (int jb = 0; jb < BL_ROWS + 8; jb += 8) {
         if (jb >= nOut + 6) break;
-        // issue the loads of all 8 rows of the block first: 24 independent words in flight per thread
-        unsigned Aw[8], Bw[8], Cw[8];
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
-            int sy = y0 - 3 + jb + jj;
-            if (!yInside) sy = reflect101(sy, H);
-            load_window(src + (size_t)sy * pitch, x, W, INTERIOR, Aw[jj], Bw[jj], Cw[jj]);
-        }
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-            const int j = jb + jj;                             // staged row j <-> level row y0 - 3 + j
-            const unsigned A = Aw[jj], B = Bw[jj], C = Cw[jj];
+            const int j = jb + jj;                             // staged row j of the band <-> level row y0 - 3 + j
+            const uint32_t* q0 = col + j * (BT_PITCH / 4);
+            const unsigned A = q0[-1], B = q0[0], C = q0[1];
             // horizontal pass: output k needs bytes k+1 .. k+7 of the 12-byte window
             unsigned hs[4];
             hs[0] = __dp4a(__byte_perm(B, C, 0x4321), WB, __dp4a(__byte_perm(A, B, 0x4321), WA, 0u));
             hs[1] = __dp4a(__byte_perm(B, C, 0x5432), WB, __dp4a(__byte_perm(A, B, 0x5432), WA, 0u));
             hs[2] = __dp4a(__byte_perm(B, C, 0x6543), WB, __dp4a(__byte_perm(A, B, 0x6543), WA, 0u));
             hs[3] = __dp4a(C, WB, __dp4a(B, WA, 0u));
-            const unsigned curLo = hs[0] | (hs[1] << 16), curHi = hs[2] | (hs[3] << 16);
+            const unsigned curLo = __byte_perm(hs[0], hs[1], 0x5410), curHi = __byte_perm(hs[2], hs[3], 0x5410);
             unsigned* q = Q[jj];
             q[0] = __byte_perm(curLo, prevLo, 0x5410);
             q[1] = __byte_perm(curLo, prevLo, 0x7632);
             q[2] = __byte_perm(curHi, prevHi, 0x5410);
             q[3] = __byte_perm(curHi, prevHi, 0x7632);
             prevLo = curLo; prevHi = curHi;
-            // vertical pass for output row yo = y0 + j - 6 (rows yo-3 .. yo+3 are staged rows j-6 .. j)
+            // vertical pass for output row yo = j - 6 of the band (rows yo-3 .. yo+3 are staged rows j-6 .. j)
             const int yo = j - 6;
             if (yo >= 0 && yo < nOut) {
                 const unsigned* q3 = Q[jj];                    // (H_{y+3}, H_{y+2})
@@ -101,62 +129,19 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
                     acc[k] = a;                                // < 2^24: the output byte is byte 2
                 }
                 const unsigned o = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
-                *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + yo) * dpitch) = o;
+                *reinterpret_cast<uint32_t*>(dst + dpitch * (unsigned)jj) = o;
             }
         }
-    }
-}
-
-// Grid: blurEdgeCtas CTAs first, then blurTilesTotal CTAs of interior strips (128 x 128 pixel tiles).  The edge CTAs are those
-// whose threads each take one border strip (the first strip of a row band and the strips that touch
-// the right border) -- the reflecting loads are kept out of the interior warps.
-__global__ void __launch_bounds__(32 * BL_BANDS) k_blur(const __grid_constant__ Geom g, const PyrPtrs p,
-                                                         uint8_t* __restrict__ blurSlab, size_t blurStride) {
-    const int img = blockIdx.y;
-    int t = (int)blockIdx.x - g.blurEdgeCtas;          // the (slower) border CTAs are scheduled first
-    if (t >= 0) {
-        int level = 0;
-#pragma unroll 1
-        for (int l = 1; l < g.nlevels; l++) if (t >= g.lv[l].blurTileBase) level = l;
-        const LevelGeom& lg = g.lv[level];
-        t -= lg.blurTileBase;
-        const int ty = t / lg.blurTilesX, tx = t - ty * lg.blurTilesX;
-        const int W = lg.w, H = lg.h;
-        const int x = tx * BL_TW + threadIdx.x * 4;               // first column of this thread's strip
-        const int y0 = ty * BL_TH + threadIdx.y * BL_ROWS;        // first output row
-        if (x < 4 || x + 8 > W || y0 >= H) return;                // border strips belong to the edge CTAs
-        int pitch;
-        const uint8_t* src = level_ptr(p, g, img, level, pitch);
-        blur_strip<true>(src, pitch, blurSlab + (size_t)img * blurStride + lg.off + x, lg.pitch, x, y0, W, H);
-    } else {
-        int e = (int)blockIdx.x * (32 * BL_BANDS) + threadIdx.y * 32 + threadIdx.x;
-        int level = -1;
-#pragma unroll 1
-        for (int l = 0; l < g.nlevels; l++) if (e >= g.lv[l].blurEdgeBase) level = l;
-        if (level < 0) return;
-        const LevelGeom& lg = g.lv[level];
-        e -= lg.blurEdgeBase;
-        const int W = lg.w, H = lg.h;
-        // border strips of a level: strip 0 and every strip with x + 8 > W (at most 2 of them)
-        const int nStrips = (W + 3) >> 2;
-        const int firstRight = max(1, (W - 8 + 4) >> 2);           // first strip index s >= 1 with 4 s + 8 > W
-        const int perBand = 1 + max(0, nStrips - firstRight);
-        const int band = e / perBand, k = e - band * perBand;
-        const int y0 = band * BL_ROWS;
-        if (y0 >= H) return;
-        const int strip = k == 0 ? 0 : firstRight + k - 1;
-        const int x = strip * 4;
-        int pitch;
-        const uint8_t* src = level_ptr(p, g, img, level, pitch);
-        blur_strip<false>(src, pitch, blurSlab + (size_t)img * blurStride + lg.off + x, lg.pitch, x, y0, W, H);
+        dst += 8 * dpitch;
     }
 }
 
 }  // namespace
 
 cudaError_t launch_blur(const Geom& g, PyrPtrs p, uint8_t* blurSlab, size_t blurStride, int nimg, cudaStream_t st) {
-    dim3 grid(g.blurTilesTotal + g.blurEdgeCtas, nimg);
+    if (g.blurTilesTotal == 0) return cudaSuccess;
+    dim3 grid(g.blurTilesTotal, nimg);
     dim3 block(32, BL_BANDS);
-    k_blur<<<grid, block, 0, st>>>(g, p, blurSlab, blurStride);
+    k_blur_tile<<<grid, block, BT_PITCH * (BT_ROWS + 2), st>>>   /* the 8-row blocks of the loop touch two rows past the apron */(g, p, blurSlab, blurStride);
     return cudaGetLastError();
 }
