@@ -329,6 +329,51 @@ int obs_hamming_knn2(obs_matcher* m, const uint8_t* descriptors, int n_keyframes
                      const int32_t* pairs, int n_pairs, int th_low, float nnratio,
                      int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
 
+/* One side of a DBoW2-gated search for a batch of n_pairs keyframes / frames with `cap` keypoint slots and
+ * `node_cap` feature-vector slots each.  DBoW2 is an un-vendored third-party dependency of the reference
+ * (Thirdparty/DBoW2); its FeatureVector (std::map<NodeId, std::vector<unsigned> >, KeyFrame::mFeatVec /
+ * Frame::mFeatVec) is passed as a CSR: node_id ascending (the map's iteration order), node_start, node_idx
+ * (the vectors' contents, in order).  Host or device arrays. */
+typedef struct obs_bow_side {
+    int32_t cap, node_cap;
+    const int32_t* n;                       /* [n_pairs] keypoints */
+    const uint8_t* descriptors;             /* [n_pairs][cap][32] mDescriptors */
+    const obs_keypoint* keys_un;            /* [n_pairs][cap] mvKeysUn (pt, angle, octave are read) */
+    const uint8_t* valid;                   /* [n_pairs][cap] see the calls; NULL = all */
+    const float* u_right;                   /* [n_pairs][cap] mvuRight (triangulation only); NULL = monocular */
+    const int32_t* n_nodes;                 /* [n_pairs] mFeatVec.size() */
+    const uint32_t* node_id;                /* [n_pairs][node_cap] */
+    const int32_t* node_start;              /* [n_pairs][node_cap + 1] */
+    const int32_t* node_idx;                /* [n_pairs][cap] */
+} obs_bow_side;
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:159-288: side1 = the keyframe with
+ * valid = "vpMapPointsKF[i] && !isBad()", side2 = the frame (valid NULL), strict_low = 0 (bestDist1 <= th_low); the
+ * reference's vpMapPointMatches[iF] is the map point of keyframe keypoint match21[iF].
+ * ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&), :522-655: valid on both sides, strict_low = 1
+ * (bestDist1 < th_low); vpMatches12[i1] is the map point of keypoint match12[i1] of the second keyframe.
+ * match12: [n_pairs][side1.cap], match21: [n_pairs][side2.cap] (-1 = none), n_matches: [n_pairs] the return values.
+ * Includes the rotation-histogram check (ComputeThreeMaxima) when check_orientation != 0. */
+int obs_search_by_bow(obs_matcher* m, const obs_bow_side* side1, const obs_bow_side* side2, int n_pairs, int th_low,
+                      int strict_low, float nnratio, int check_orientation, int32_t* match12, int32_t* match21,
+                      int32_t* n_matches);
+
+/* ORBmatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, cv::Mat F12, vector<pair<size_t,size_t>>&, bOnlyStereo),
+ * src/ORBmatcher.cc:657-823 with CheckDistEpipolarLine (:139-156).  valid = "GetMapPoint(i) == NULL" on both sides;
+ * f12: [n_pairs][9] row-major; epipole: [n_pairs][2] = (ex, ey) of :663-671 (computed by the caller with the
+ * reference's cv::Mat expressions); level_sigma2 / scale_factors: pKF2->mvLevelSigma2 / mvScaleFactors (nlevels floats).
+ * match12[i1] = i2 or -1 (vMatchedPairs lists the pairs in ascending i1). */
+int obs_search_for_triangulation(obs_matcher* m, const obs_bow_side* side1, const obs_bow_side* side2, int n_pairs,
+                                 const float* f12, const float* epipole, const float* level_sigma2,
+                                 const float* scale_factors, int nlevels, int only_stereo, int check_orientation,
+                                 int32_t* match12, int32_t* n_matches);
+
+/* MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:345-410, batched over n_points map points: the descriptors of
+ * point p's good observations are descriptors[start[p] .. start[p+1]) (32 bytes each); best[p] = index inside that list of
+ * the descriptor with the least median Hamming distance to the others (first wins), -1 for an empty list. */
+int obs_distinctive_descriptors(obs_matcher* m, const uint8_t* descriptors, const int32_t* start, int n_points,
+                                int32_t* best);
+
 /* ---------------------------------------------------------------------------------------
  * Multi-GPU exchange step of batched keyframe-vs-keyframe matching: every rank (one process per GPU)
  * owns a contiguous shard of the keyframes as queries and needs all descriptor sets as database.

@@ -54,6 +54,12 @@ class KeyFramePointsView(C.Structure):
                 ("normal", C.c_void_p), ("angle", C.c_void_p), ("descriptors", C.c_void_p), ("tcw", C.c_void_p)]
 
 
+class BowSide(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("node_cap", C.c_int32), ("n", C.c_void_p), ("descriptors", C.c_void_p), ("keys_un", C.c_void_p),
+                ("valid", C.c_void_p), ("u_right", C.c_void_p), ("n_nodes", C.c_void_p), ("node_id", C.c_void_p),
+                ("node_start", C.c_void_p), ("node_idx", C.c_void_p)]
+
+
 class ObsError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"obslam_b200 error {code}: {msg}")
@@ -114,6 +120,9 @@ _PROTOS = {
     "obs_comm_allgather": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int, _vp]),
     "obs_comm_wait": (C.c_int, [_vp, C.c_int, _vp]),
     "obs_microbench_popc": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "obs_search_by_bow": (C.c_int, [_vp, C.POINTER(BowSide), C.POINTER(BowSide), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
+    "obs_search_for_triangulation": (C.c_int, [_vp, C.POINTER(BowSide), C.POINTER(BowSide), C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "obs_distinctive_descriptors": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "obs_hamming_knn2": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp]),
 }
 

@@ -205,7 +205,7 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(FT_THREADS) k_fast_cells(const __grid_constant__ Geom g, const PyrPtrs p,
+__global__ void __launch_bounds__(FT_THREADS, 5) k_fast_cells(const __grid_constant__ Geom g, const PyrPtrs p,
                                                            const FastCta* __restrict__ ctaTab, int tileRows,
                                                            uint32_t* __restrict__ cand, int* __restrict__ cellCount) {
     extern __shared__ __align__(16) uint8_t sm[];

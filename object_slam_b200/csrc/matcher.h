@@ -102,3 +102,38 @@ struct Knn2Args {
     int* bestIdx; int* bestDist; int* secondDist;   // [P][n]; the last two may be null
 };
 cudaError_t launch_knn2(const Knn2Args& a, cudaStream_t st);
+
+// ---- DBoW2-gated matchers (bow.cu).  One side = B keyframes/frames, `cap` keypoint slots and `nodeCap`
+// feature-vector slots each; the DBoW2::FeatureVector is a CSR (node ids ascending like the std::map).
+struct BowSideDev {
+    int cap, nodeCap;
+    const int* n;             // [B]
+    const uint4* desc;        // [B][cap][2]
+    const float* keys;        // [B][cap][7]  cv::KeyPoint words (x, y, size, angle, response, octave, class_id)
+    const uint8_t* valid;     // [B][cap] or null
+    const float* uRight;      // [B][cap] or null
+    const int* nNodes;        // [B]
+    const uint32_t* nodeId;   // [B][nodeCap]
+    const int* nodeStart;     // [B][nodeCap + 1]
+    const int* nodeIdx;       // [B][cap]
+};
+struct BowSearchArgs {        // SearchByBoW (ORBmatcher.cc:159-288, :522-655)
+    BowSideDev A, B;
+    int thLow, strictLow; float nnratio; int checkOri;
+    int* match12;             // [B][A.cap]
+    int* match21;             // [B][B.cap]
+    int* nMatches;            // [B]
+};
+cudaError_t launch_bow_search(const BowSearchArgs& a, int nPairs, cudaStream_t st);
+struct TriSearchArgs {        // SearchForTriangulation (ORBmatcher.cc:657-823)
+    BowSideDev A, B;
+    const float* f12;         // [B][9]
+    const float* epipole;     // [B][2]
+    float sigma2[OBS_MAX_LEVELS], scale[OBS_MAX_LEVELS];
+    int onlyStereo, checkOri;
+    int* match12;             // [B][A.cap]
+    int* nMatches;            // [B]
+};
+cudaError_t launch_tri_search(const TriSearchArgs& a, int nPairs, cudaStream_t st);
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:345-410) over a CSR of descriptor lists
+cudaError_t launch_distinctive(const uint4* desc, const int* start, int nPoints, int* best, cudaStream_t st);

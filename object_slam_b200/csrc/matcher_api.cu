@@ -498,4 +498,102 @@ int obs_hamming_knn2(obs_matcher* m, const uint8_t* descriptors, int n_keyframes
     return OBS_OK;
 }
 
+static int bow_side_dev(obs_matcher* m, int slot0, const obs_bow_side* s, int B, bool needUr, BowSideDev* d) {
+    if (!s || !s->n || !s->descriptors || !s->keys_un || !s->n_nodes || !s->node_id || !s->node_start || !s->node_idx)
+        return fail(OBS_ERR_INVALID, "null field in obs_bow_side");
+    if (s->cap < 1 || s->cap > 65535 || s->node_cap < 1) return fail(OBS_ERR_INVALID, "obs_bow_side: 1 <= cap <= 65535, node_cap >= 1");
+    int rc;
+    const size_t kc = (size_t)B * s->cap;
+    const uint8_t* dsc = nullptr; const obs_keypoint* keys = nullptr;
+    d->cap = s->cap; d->nodeCap = s->node_cap;
+    if ((rc = dev_in(m, slot0 + 0, s->n, (size_t)B, &d->n))) return rc;
+    if ((rc = dev_in(m, slot0 + 1, s->descriptors, kc * 32, &dsc))) return rc;
+    if ((uintptr_t)dsc & 15) return fail(OBS_ERR_INVALID, "device descriptors must be 16-byte aligned");
+    d->desc = reinterpret_cast<const uint4*>(dsc);
+    if ((rc = dev_in(m, slot0 + 2, s->keys_un, kc, &keys))) return rc;
+    d->keys = reinterpret_cast<const float*>(keys);
+    if ((rc = dev_in(m, slot0 + 3, s->valid, s->valid ? kc : 0, &d->valid))) return rc;
+    d->uRight = nullptr;
+    if (needUr && (rc = dev_in(m, slot0 + 4, s->u_right, s->u_right ? kc : 0, &d->uRight))) return rc;
+    if ((rc = dev_in(m, slot0 + 5, s->n_nodes, (size_t)B, &d->nNodes))) return rc;
+    if ((rc = dev_in(m, slot0 + 6, s->node_id, (size_t)B * s->node_cap, &d->nodeId))) return rc;
+    if ((rc = dev_in(m, slot0 + 7, s->node_start, (size_t)B * (s->node_cap + 1), &d->nodeStart))) return rc;
+    if ((rc = dev_in(m, slot0 + 8, s->node_idx, kc, &d->nodeIdx))) return rc;
+    return OBS_OK;
+}
+
+int obs_search_by_bow(obs_matcher* m, const obs_bow_side* side1, const obs_bow_side* side2, int n_pairs, int th_low,
+                      int strict_low, float nnratio, int check_orientation, int32_t* match12, int32_t* match21, int32_t* n_matches) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!match12 || !match21 || !n_matches) return fail(OBS_ERR_INVALID, "null argument");
+    if (n_pairs < 1) return fail(OBS_ERR_INVALID, "n_pairs < 1");
+    BowSearchArgs a;
+    if ((rc = bow_side_dev(m, 0, side1, n_pairs, false, &a.A))) return rc;
+    if ((rc = bow_side_dev(m, 9, side2, n_pairs, false, &a.B))) return rc;
+    a.thLow = th_low; a.strictLow = strict_low != 0; a.nnratio = nnratio; a.checkOri = check_orientation != 0;
+    const size_t c1 = (size_t)n_pairs * side1->cap, c2 = (size_t)n_pairs * side2->cap;
+    if ((rc = dev_out(m, 20, match12, c1, &a.match12))) return rc;
+    if ((rc = dev_out(m, 21, match21, c2, &a.match21))) return rc;
+    if ((rc = dev_out(m, 22, n_matches, (size_t)n_pairs, &a.nMatches))) return rc;
+    CU(launch_bow_search(a, n_pairs, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, match12, a.match12, c1, &queued))) return rc;
+    if ((rc = host_back(m, match21, a.match21, c2, &queued))) return rc;
+    if ((rc = host_back(m, n_matches, a.nMatches, (size_t)n_pairs, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
+int obs_search_for_triangulation(obs_matcher* m, const obs_bow_side* side1, const obs_bow_side* side2, int n_pairs,
+                                 const float* f12, const float* epipole, const float* level_sigma2, const float* scale_factors,
+                                 int nlevels, int only_stereo, int check_orientation, int32_t* match12, int32_t* n_matches) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!f12 || !epipole || !level_sigma2 || !scale_factors || !match12 || !n_matches) return fail(OBS_ERR_INVALID, "null argument");
+    if (n_pairs < 1 || nlevels < 1 || nlevels > OBS_MAX_LEVELS) return fail(OBS_ERR_INVALID, "n_pairs / nlevels out of range");
+    if (is_device(level_sigma2) || is_device(scale_factors)) return fail(OBS_ERR_INVALID, "level tables are host arrays");
+    TriSearchArgs a;
+    memset(&a, 0, sizeof(a));
+    if ((rc = bow_side_dev(m, 0, side1, n_pairs, true, &a.A))) return rc;
+    if ((rc = bow_side_dev(m, 9, side2, n_pairs, true, &a.B))) return rc;
+    if ((rc = dev_in(m, 18, f12, (size_t)n_pairs * 9, &a.f12))) return rc;
+    if ((rc = dev_in(m, 19, epipole, (size_t)n_pairs * 2, &a.epipole))) return rc;
+    for (int l = 0; l < nlevels; l++) { a.sigma2[l] = level_sigma2[l]; a.scale[l] = scale_factors[l]; }
+    a.onlyStereo = only_stereo != 0; a.checkOri = check_orientation != 0;
+    const size_t c1 = (size_t)n_pairs * side1->cap;
+    if ((rc = dev_out(m, 20, match12, c1, &a.match12))) return rc;
+    if ((rc = dev_out(m, 22, n_matches, (size_t)n_pairs, &a.nMatches))) return rc;
+    CU(launch_tri_search(a, n_pairs, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, match12, a.match12, c1, &queued))) return rc;
+    if ((rc = host_back(m, n_matches, a.nMatches, (size_t)n_pairs, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
+int obs_distinctive_descriptors(obs_matcher* m, const uint8_t* descriptors, const int32_t* start, int n_points, int32_t* best) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!start || !best || n_points < 1) return fail(OBS_ERR_INVALID, "null argument or n_points < 1");
+    if (is_device(start) && !is_device(descriptors)) return fail(OBS_ERR_INVALID, "start on the device needs descriptors on the device");
+    const uint8_t* dd = nullptr; const int* ds = nullptr; int* db = nullptr;
+    size_t total = 0;
+    if (!is_device(start)) {
+        for (int p = 0; p < n_points; p++) if (start[p + 1] < start[p]) return fail(OBS_ERR_INVALID, "start must not decrease");
+        total = (size_t)start[n_points];
+        if (total && !descriptors) return fail(OBS_ERR_INVALID, "null descriptors");
+    }
+    if ((rc = dev_in(m, 0, descriptors, total * 32, &dd))) return rc;
+    if (is_device(descriptors)) dd = descriptors;
+    if ((uintptr_t)dd & 15) return fail(OBS_ERR_INVALID, "device descriptors must be 16-byte aligned");
+    if ((rc = dev_in(m, 1, start, (size_t)n_points + 1, &ds))) return rc;
+    if ((rc = dev_out(m, 2, best, (size_t)n_points, &db))) return rc;
+    CU(launch_distinctive(reinterpret_cast<const uint4*>(dd), ds, n_points, db, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, best, db, (size_t)n_points, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
 }  // extern "C"

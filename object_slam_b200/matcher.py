@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._capi import (KEYPOINT_DTYPE, FrameParams, FrameView, KeyFramePointsView, LastFrameView, MapPointView, addr, check, lib, ptr)
+from ._capi import (KEYPOINT_DTYPE, BowSide, FrameParams, FrameView, KeyFramePointsView, LastFrameView, MapPointView, addr, check, lib, ptr)
 
 FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48       # include/Frame.h:41-42
 
@@ -243,3 +243,70 @@ class ORBmatcher:
                                      int(self.TH_LOW if th_low is None else th_low), self.mfNNratio,
                                      ptr(best_idx), ptr(best_dist), ptr(second_dist)))
         return best_idx, best_dist, second_dist
+
+    # ---- DBoW2-gated searches.  A "side" is a list of dicts, one per keyframe / frame, with the keys n, descriptors,
+    # keys_un, valid (or None), u_right (or None), node_id, node_start, node_idx (the DBoW2::FeatureVector as a CSR,
+    # node ids ascending); pairs are side1[i] x side2[i].
+    @staticmethod
+    def _pack_side(frames, use_valid=True):
+        B = len(frames)
+        cap = max(max(int(f["n"]) for f in frames), 1)
+        node_cap = max(max(len(f["node_id"]) for f in frames), 1)
+        pk = dict(n=np.zeros(B, np.int32), descriptors=np.zeros((B, cap, 32), np.uint8), keys_un=np.zeros((B, cap), KEYPOINT_DTYPE),
+                  n_nodes=np.zeros(B, np.int32), node_id=np.zeros((B, node_cap), np.uint32),
+                  node_start=np.zeros((B, node_cap + 1), np.int32), node_idx=np.zeros((B, cap), np.int32))
+        has_valid = use_valid and any(f.get("valid") is not None for f in frames)
+        has_ur = any(f.get("u_right") is not None for f in frames)
+        pk["valid"] = np.ones((B, cap), np.uint8) if has_valid else None
+        pk["u_right"] = np.full((B, cap), -1.0, np.float32) if has_ur else None
+        for b, f in enumerate(frames):
+            n, k = int(f["n"]), len(f["node_id"])
+            pk["n"][b] = n; pk["n_nodes"][b] = k
+            pk["descriptors"][b, :n] = f["descriptors"][:n]
+            pk["keys_un"][b, :n] = f["keys_un"][:n]
+            pk["node_id"][b, :k] = f["node_id"]
+            pk["node_start"][b, :k + 1] = f["node_start"]
+            pk["node_start"][b, k + 1:] = f["node_start"][-1] if k else 0
+            pk["node_idx"][b, :n] = f["node_idx"][:n]
+            if has_valid and f.get("valid") is not None:
+                pk["valid"][b, :n] = f["valid"][:n]
+            if has_ur and f.get("u_right") is not None:
+                pk["u_right"][b, :n] = f["u_right"][:n]
+        side = BowSide(cap, node_cap, *[ptr(pk[k]) for k in ("n", "descriptors", "keys_un", "valid", "u_right", "n_nodes",
+                                                               "node_id", "node_start", "node_idx")])
+        return side, pk
+
+    def SearchByBoW(self, side1, side2, keyframe_pair=False, th_low=None):
+        """ORBmatcher::SearchByBoW: keyframe_pair=False -> (KeyFrame*, Frame&) src/ORBmatcher.cc:159-288 (side2's valid
+        is ignored, read match21: frame keypoint -> keyframe keypoint); keyframe_pair=True -> (KeyFrame*, KeyFrame*)
+        :522-655 (read match12).  Returns (n_matches [B], match12 [B, cap1], match21 [B, cap2])."""
+        s1, k1 = self._pack_side(side1)
+        s2, k2 = self._pack_side(side2, use_valid=keyframe_pair)
+        B = len(side1)
+        m12 = np.empty((B, s1.cap), np.int32); m21 = np.empty((B, s2.cap), np.int32); nm = np.empty(B, np.int32)
+        check(lib().obs_search_by_bow(self._h, C.byref(s1), C.byref(s2), B, int(self.TH_LOW if th_low is None else th_low),
+                                      int(keyframe_pair), self.mfNNratio, int(self.mbCheckOrientation), ptr(m12), ptr(m21), ptr(nm)))
+        return nm, m12, m21
+
+    def SearchForTriangulation(self, side1, side2, f12, epipole, level_sigma2, scale_factors, bOnlyStereo=False):
+        """ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:657-823.  valid = keypoint has no map point yet.
+        Returns (n_matches [B], match12 [B, cap1]); vMatchedPairs of pair b = [(i, match12[b, i]) for ascending i with a match]."""
+        s1, k1 = self._pack_side(side1)
+        s2, k2 = self._pack_side(side2)
+        B = len(side1)
+        f = np.ascontiguousarray(f12, np.float32).reshape(B, 9)
+        ep = np.ascontiguousarray(epipole, np.float32).reshape(B, 2)
+        s2l = np.ascontiguousarray(level_sigma2, np.float32); sfl = np.ascontiguousarray(scale_factors, np.float32)
+        m12 = np.empty((B, s1.cap), np.int32); nm = np.empty(B, np.int32)
+        check(lib().obs_search_for_triangulation(self._h, C.byref(s1), C.byref(s2), B, ptr(f), ptr(ep), ptr(s2l), ptr(sfl), len(sfl),
+                                                 int(bOnlyStereo), int(self.mbCheckOrientation), ptr(m12), ptr(nm)))
+        return nm, m12
+
+    def ComputeDistinctiveDescriptors(self, descriptors, start):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:345-410) for a batch of map points: descriptors of point p
+        are rows start[p]..start[p+1]; returns the index (inside the point's list) of the chosen descriptor, -1 if empty."""
+        d = _u8(descriptors); st = _i32(start)
+        n_points = len(st) - 1
+        best = np.empty(max(n_points, 1), np.int32)
+        check(lib().obs_distinctive_descriptors(self._h, ptr(d), ptr(st), n_points, ptr(best)))
+        return best[:n_points]

@@ -278,3 +278,68 @@ def keyframe_points(last, seed, camera_centre=(0.0, 0.0, 0.0)):
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
     return dict(valid=(rng.random(n) < 0.9).astype(np.uint8), world_pos=pos, min_distance=mind, max_distance=maxd,
                 max_distance_raw=raw, normal=nrm.astype(np.float32), angle=last["angle"], descriptors=last["descriptors"])
+
+
+def feature_vector(node_of_keypoint):
+    """DBoW2::FeatureVector of a frame as a CSR: (node_id ascending, node_start, node_idx); inside a node the keypoint
+    indices ascend (DBoW2 appends features in index order)."""
+    node_of_keypoint = np.asarray(node_of_keypoint, np.int64)
+    order = np.argsort(node_of_keypoint, kind="stable")
+    ids, counts = np.unique(node_of_keypoint, return_counts=True)
+    start = np.zeros(len(ids) + 1, np.int32)
+    start[1:] = np.cumsum(counts)
+    return ids.astype(np.uint32), start, order.astype(np.int32)
+
+
+def bow_pair(shape, n, seed, n_nodes=100, nlevels=8, copies=0.6):
+    """Two keyframes as the DBoW2-gated matchers read them (SearchByBoW, SearchForTriangulation): keyframe 2 holds
+    noisy copies of `copies` of keyframe 1's keypoints (descriptor with 0..45 flipped bits, same row up to a few px
+    -- the epipolar geometry of a pure x translation, F12 = [0 0 0; 0 0 -1; 0 1 0] --, common in-plane rotation with
+    outliers, mostly the same vocabulary node).  Returns (side1, side2, extra); a side is a dict with n, descriptors,
+    keys_un, valid, u_right, node_id, node_start, node_idx."""
+    rng = np.random.default_rng(seed)
+    k1, d1, ur1 = synthetic_frame(shape, n, seed)
+    k2, d2, ur2 = synthetic_frame(shape, n, seed + 7919)
+    node1 = rng.integers(0, n_nodes, n) * 37 + 11
+    node2 = rng.integers(0, n_nodes, n) * 37 + 11
+    m = int(copies * n)
+    src = rng.choice(n, m, replace=False)
+    dst = rng.choice(n, m, replace=False)
+    d2[dst] = flip_bits(d1[src], rng.integers(0, 46, m), rng)
+    k2["x"][dst] = np.clip(k1["x"][src] - rng.uniform(2, 60, m).astype(np.float32), 1, shape[1] - 2)
+    k2["y"][dst] = k1["y"][src] + rng.choice([0, 0, 0.5, -1, 1.5, -3, 6, -12], m).astype(np.float32) * scale_factors(nlevels)[k1["octave"][src]]
+    k2["octave"][dst] = np.clip(k1["octave"][src] + rng.choice([0, 0, 0, 1, -1], m), 0, nlevels - 1)
+    rot = np.where(rng.random(m) < 0.85, 12.0 + rng.normal(0, 3, m), rng.uniform(0, 360, m))
+    k2["angle"][dst] = np.mod(k1["angle"][src] - rot, 360).astype(np.float32)
+    same = rng.random(m) < 0.9
+    node2[dst[same]] = node1[src[same]]
+    sides = []
+    for k, d, ur, node in ((k1, d1, ur1, node1), (k2, d2, ur2, node2)):
+        ids, start, idx = feature_vector(node)
+        sides.append(dict(n=n, descriptors=d, keys_un=k, valid=(rng.random(n) < 0.7).astype(np.uint8), u_right=ur,
+                          node_id=ids, node_start=start, node_idx=idx))
+    sf = scale_factors(nlevels)
+    extra = dict(f12=np.array([0, 0, 0, 0, 0, -1, 0, 1, 0], np.float32), epipole=(np.float32(shape[1] * 0.7), np.float32(shape[0] * 0.4)),
+                 scale_factors=sf, level_sigma2=(sf * sf).astype(np.float32))
+    return sides[0], sides[1], extra
+
+
+def observation_descriptors(n_points, seed, max_obs=24):
+    """Descriptor lists of n_points map points for MapPoint::ComputeDistinctiveDescriptors: 1..max_obs observations each,
+    noisy copies of one prototype with a few outliers.  Returns (descriptors [total, 32], start [n_points + 1])."""
+    rng = np.random.default_rng(seed)
+    cnt = rng.integers(1, max_obs + 1, n_points)
+    cnt[rng.random(n_points) < 0.05] = 0
+    start = np.zeros(n_points + 1, np.int32)
+    start[1:] = np.cumsum(cnt)
+    desc = np.zeros((int(start[-1]), 32), np.uint8)
+    for p in range(n_points):
+        c = int(cnt[p])
+        if c == 0:
+            continue
+        proto = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+        block = flip_bits(np.repeat(proto, c, 0), rng.integers(0, 60, c), rng)
+        out = rng.random(c) < 0.1
+        block[out] = rng.integers(0, 256, (int(out.sum()), 32), dtype=np.uint8)
+        desc[start[p]:start[p + 1]] = block
+    return desc, start

@@ -99,6 +99,9 @@ def _bind_match(L):
     L.orc_hamming_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_search_by_projection_keyframe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_search_by_projection_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_search_by_bow.argtypes = [C.c_void_p] * 14 + [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_search_for_triangulation.argtypes = [C.c_void_p] * 17 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.orc_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.orc_logf.restype = C.c_float
     L.orc_logf.argtypes = [C.c_float]
     L.orc_norm3.restype = C.c_float
@@ -475,3 +478,45 @@ def stereo_from_rgbd(keys, depth_f32, mbf):
             dp[i] = d
             ur[i] = np.float32(u - np.float32(np.float32(mbf) / d))
     return ur, dp
+
+
+def _bow_args(side, with_ur):
+    """ctypes arguments of one BowSide (keeps the converted arrays alive in the returned list)."""
+    hdr = np.array([side["n"], len(side["node_id"])], np.int32)
+    arrs = [hdr, np.ascontiguousarray(side["descriptors"], np.uint8), np.ascontiguousarray(side["keys_un"]),
+            None if side.get("valid") is None else np.ascontiguousarray(side["valid"], np.uint8)]
+    if with_ur:
+        arrs.append(None if side.get("u_right") is None else np.ascontiguousarray(side["u_right"], np.float32))
+    arrs += [np.ascontiguousarray(side["node_id"], np.uint32), np.ascontiguousarray(side["node_start"], np.int32),
+             np.ascontiguousarray(side["node_idx"], np.int32)]
+    return arrs, [None if a is None else _ptr(a) for a in arrs]
+
+
+def search_by_bow(side1, side2, th_low=50, strict=False, nnratio=0.7, check_ori=True):
+    """ORBmatcher::SearchByBoW, src/ORBmatcher.cc:159-288 (strict=False, read match21) and :522-655 (strict=True, read match12)."""
+    k1, a1 = _bow_args(side1, False)
+    k2, a2 = _bow_args(side2, False)
+    m12 = np.empty(max(side1["n"], 1), np.int32); m21 = np.empty(max(side2["n"], 1), np.int32)
+    n = lib().orc_search_by_bow(*a1, *a2, int(th_low), int(strict), nnratio, int(check_ori), _ptr(m12), _ptr(m21))
+    return n, m12[:side1["n"]], m21[:side2["n"]]
+
+
+def search_for_triangulation(side1, side2, f12, epipole, level_sigma2, scale_factors, only_stereo=False, check_ori=True):
+    """ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:657-823; valid = keypoint has no map point yet."""
+    k1, a1 = _bow_args(side1, True)
+    k2, a2 = _bow_args(side2, True)
+    f = np.ascontiguousarray(f12, np.float32).reshape(9)
+    s2 = np.ascontiguousarray(level_sigma2, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    m12 = np.empty(max(side1["n"], 1), np.int32)
+    n = lib().orc_search_for_triangulation(*a1, *a2, _ptr(f), float(epipole[0]), float(epipole[1]), _ptr(s2), _ptr(sf),
+                                           int(only_stereo), int(check_ori), _ptr(m12))
+    return n, m12[:side1["n"]]
+
+
+def distinctive_descriptors(desc, start):
+    """MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:345-410, for a CSR of descriptor lists."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    start = np.ascontiguousarray(start, np.int32)
+    best = np.empty(max(len(start) - 1, 1), np.int32)
+    lib().orc_distinctive_descriptors(_ptr(desc), _ptr(start), len(start) - 1, _ptr(best))
+    return best[:len(start) - 1]

@@ -596,6 +596,164 @@ static void hamming_knn2(const uint8_t* q, int nq, const uint8_t* db, int nd, in
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// DBoW2-gated matchers.  A DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>, un-vendored
+// Thirdparty/DBoW2) is passed as a CSR: nodeId[] ascending (the map's iteration order), nodeStart[], nodeIdx[].
+// ------------------------------------------------------------------------------------------------
+struct BowSide {
+    int n;                       // keypoints
+    const uint8_t* desc;         // n x 32
+    const KeyPt* keys;           // mvKeysUn
+    const uint8_t* valid;        // per keypoint, meaning depends on the caller (may be null = all)
+    const float* uRight;         // mvuRight (triangulation only; may be null = all -1)
+    int nNodes; const uint32_t* nodeId; const int* nodeStart; const int* nodeIdx;
+};
+
+// std::map::lower_bound over the ascending node ids
+static int bow_lower_bound(const BowSide& S, uint32_t id) {
+    return (int)(std::lower_bound(S.nodeId, S.nodeId + S.nNodes, id) - S.nodeId);
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), ORBmatcher.cc:159-288 (strictLow = 0: bestDist1 <= TH_LOW,
+// set 1 = the keyframe with valid = "has a good map point", set 2 = the frame, result read through match21) and
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&), :522-655 (strictLow = 1: bestDist1 < TH_LOW, valid on
+// both sides, result read through match12).  match12[i1] = i2 / match21[i2] = i1, -1 where there is no match.
+static int search_by_bow(const BowSide& A, const BowSide& B, int thLow, int strictLow, float nnratio, int checkOri,
+                         int* match12, int* match21) {
+    for (int i = 0; i < A.n; i++) match12[i] = -1;
+    for (int i = 0; i < B.n; i++) match21[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0;
+    int ia = 0, ib = 0;
+    while (ia < A.nNodes && ib < B.nNodes) {
+        if (A.nodeId[ia] == B.nodeId[ib]) {
+            for (int p1 = A.nodeStart[ia]; p1 < A.nodeStart[ia + 1]; p1++) {
+                const int idx1 = A.nodeIdx[p1];
+                if (A.valid && !A.valid[idx1]) continue;
+                const uint8_t* d1 = A.desc + (size_t)idx1 * 32;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int p2 = B.nodeStart[ib]; p2 < B.nodeStart[ib + 1]; p2++) {
+                    const int idx2 = B.nodeIdx[p2];
+                    if (match21[idx2] >= 0) continue;                         // vpMapPointMatches[realIdxF] / vbMatched2[idx2]
+                    if (B.valid && !B.valid[idx2]) continue;
+                    const int dist = descriptor_distance(d1, B.desc + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (strictLow ? bestDist1 < thLow : bestDist1 <= thLow) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        match12[idx1] = bestIdx2;
+                        match21[bestIdx2] = idx1;
+                        if (checkOri) rotHist[rot_bin(A.keys[idx1].angle, B.keys[bestIdx2].angle)].push_back(idx1);
+                        nmatches++;
+                    }
+                }
+            }
+            ia++; ib++;
+        } else if (A.nodeId[ia] < B.nodeId[ib]) ia = bow_lower_bound(A, B.nodeId[ib]);
+        else ib = bow_lower_bound(B, A.nodeId[ia]);
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, sizes[HISTO_LENGTH];
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) {
+                const int idx1 = rotHist[i][j];
+                match21[match12[idx1]] = -1;
+                match12[idx1] = -1;
+                nmatches--;
+            }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::CheckDistEpipolarLine, ORBmatcher.cc:139-156
+static bool check_dist_epipolar_line(const KeyPt& kp1, const KeyPt& kp2, const float* F12, const float* levelSigma2) {
+    const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+    const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+    const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+    const float num = a * kp2.x + b * kp2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * levelSigma2[kp2.octave];
+}
+
+// ORBmatcher::SearchForTriangulation, ORBmatcher.cc:657-823.  valid = "keypoint has no map point yet" (GetMapPoint == NULL)
+// on both sides.  (ex, ey): the epipole as :663-671 computes it.  The reference never sets vbMatched2 (:677 is only read),
+// so every keypoint of set 1 is matched on its own; ties on the distance go to the LAST candidate (dist > bestDist rejects).
+static int search_for_triangulation(const BowSide& A, const BowSide& B, const float* F12, float ex, float ey,
+                                    const float* levelSigma2, const float* scaleFactors, int onlyStereo, int checkOri,
+                                    int* match12) {
+    for (int i = 0; i < A.n; i++) match12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0;
+    int ia = 0, ib = 0;
+    while (ia < A.nNodes && ib < B.nNodes) {
+        if (A.nodeId[ia] == B.nodeId[ib]) {
+            for (int p1 = A.nodeStart[ia]; p1 < A.nodeStart[ia + 1]; p1++) {
+                const int idx1 = A.nodeIdx[p1];
+                if (A.valid && !A.valid[idx1]) continue;                      // already a map point
+                const bool bStereo1 = A.uRight && A.uRight[idx1] >= 0;
+                if (onlyStereo && !bStereo1) continue;
+                const KeyPt& kp1 = A.keys[idx1];
+                const uint8_t* d1 = A.desc + (size_t)idx1 * 32;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int p2 = B.nodeStart[ib]; p2 < B.nodeStart[ib + 1]; p2++) {
+                    const int idx2 = B.nodeIdx[p2];
+                    if (B.valid && !B.valid[idx2]) continue;
+                    const bool bStereo2 = B.uRight && B.uRight[idx2] >= 0;
+                    if (onlyStereo && !bStereo2) continue;
+                    const int dist = descriptor_distance(d1, B.desc + (size_t)idx2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const KeyPt& kp2 = B.keys[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2.x, distey = ey - kp2.y;
+                        if (distex * distex + distey * distey < 100 * scaleFactors[kp2.octave]) continue;
+                    }
+                    if (check_dist_epipolar_line(kp1, kp2, F12, levelSigma2)) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (checkOri) rotHist[rot_bin(kp1.angle, B.keys[bestIdx2].angle)].push_back(idx1);
+                }
+            }
+            ia++; ib++;
+        } else if (A.nodeId[ia] < B.nodeId[ib]) ia = bow_lower_bound(A, B.nodeId[ib]);
+        else ib = bow_lower_bound(B, A.nodeId[ia]);
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, sizes[HISTO_LENGTH];
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) { match12[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:345-410, over the descriptors of one map point's good
+// observations (n >= 1): index of the descriptor with the least median distance to the rest (first wins).
+static int distinctive_descriptor(const uint8_t* desc, int n) {
+    std::vector<int> D((size_t)n * n, 0);
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) D[(size_t)i * n + j] = D[(size_t)j * n + i] = descriptor_distance(desc + (size_t)i * 32, desc + (size_t)j * 32);
+    int bestMedian = INT_MAX, bestIdx = 0;
+    for (int i = 0; i < n; i++) {
+        std::vector<int> v(D.begin() + (size_t)i * n, D.begin() + (size_t)(i + 1) * n);
+        std::sort(v.begin(), v.end());
+        const int median = v[(size_t)(0.5 * (n - 1))];
+        if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+    }
+    return bestIdx;
+}
+
 }  // namespace orc
 
 using namespace orc;
@@ -701,6 +859,42 @@ int orc_stereo_match(const void* kL, const uint8_t* dL, int nL, const void* kR, 
     stereo_match((const KeyPt*)kL, dL, nL, (const KeyPt*)kR, dR, nR, pyrL, pyrR, lw, lh, nlevels, scale, invScale,
                  mbf, minD, maxD, uRight, depth, sadOut);
     return 0;
+}
+
+static BowSide bow_side(const int* hdr, const uint8_t* desc, const void* keys, const uint8_t* valid, const float* uRight,
+                        const uint32_t* nodeId, const int* nodeStart, const int* nodeIdx) {
+    BowSide S;
+    S.n = hdr[0]; S.nNodes = hdr[1];
+    S.desc = desc; S.keys = (const KeyPt*)keys; S.valid = valid; S.uRight = uRight;
+    S.nodeId = nodeId; S.nodeStart = nodeStart; S.nodeIdx = nodeIdx;
+    return S;
+}
+// hdr = {n, nNodes}
+int orc_search_by_bow(const int* hdrA, const uint8_t* descA, const void* keysA, const uint8_t* validA,
+                      const uint32_t* nodeIdA, const int* nodeStartA, const int* nodeIdxA,
+                      const int* hdrB, const uint8_t* descB, const void* keysB, const uint8_t* validB,
+                      const uint32_t* nodeIdB, const int* nodeStartB, const int* nodeIdxB,
+                      int thLow, int strictLow, float nnratio, int checkOri, int* match12, int* match21) {
+    return search_by_bow(bow_side(hdrA, descA, keysA, validA, nullptr, nodeIdA, nodeStartA, nodeIdxA),
+                         bow_side(hdrB, descB, keysB, validB, nullptr, nodeIdB, nodeStartB, nodeIdxB),
+                         thLow, strictLow, nnratio, checkOri, match12, match21);
+}
+int orc_search_for_triangulation(const int* hdrA, const uint8_t* descA, const void* keysA, const uint8_t* validA, const float* uRightA,
+                                 const uint32_t* nodeIdA, const int* nodeStartA, const int* nodeIdxA,
+                                 const int* hdrB, const uint8_t* descB, const void* keysB, const uint8_t* validB, const float* uRightB,
+                                 const uint32_t* nodeIdB, const int* nodeStartB, const int* nodeIdxB,
+                                 const float* F12, float ex, float ey, const float* levelSigma2, const float* scaleFactors,
+                                 int onlyStereo, int checkOri, int* match12) {
+    return search_for_triangulation(bow_side(hdrA, descA, keysA, validA, uRightA, nodeIdA, nodeStartA, nodeIdxA),
+                                    bow_side(hdrB, descB, keysB, validB, uRightB, nodeIdB, nodeStartB, nodeIdxB),
+                                    F12, ex, ey, levelSigma2, scaleFactors, onlyStereo, checkOri, match12);
+}
+// start: nPoints + 1 offsets into desc (descriptors of point p: [start[p], start[p+1])); best[p] = -1 for an empty list
+void orc_distinctive_descriptors(const uint8_t* desc, const int* start, int nPoints, int* best) {
+    for (int p = 0; p < nPoints; p++) {
+        const int n = start[p + 1] - start[p];
+        best[p] = n > 0 ? distinctive_descriptor(desc + (size_t)start[p] * 32, n) : -1;
+    }
 }
 
 }  // extern "C"

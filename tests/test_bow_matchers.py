@@ -1,0 +1,283 @@
+"""DBoW2-gated matchers (SearchByBoW x2, SearchForTriangulation) and ComputeDistinctiveDescriptors.
+
+CPU: the C++ oracle restatement (oracle/match_oracle.cpp) against an independent pure-Python restatement that
+walks std::map-like dicts the way the reference does, and against the committed fixtures.  GPU: the CUDA kernels
+(csrc/bow.cu) through the C ABI against the oracle, bit-exact (integer indices and counts)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from object_slam_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "bow_cases.npz")
+F32 = np.float32
+
+
+def _popcount(a, b):
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def _rot_bin(a1, a2):
+    rot = F32(a1) - F32(a2)
+    if rot < 0.0:
+        rot = F32(rot + F32(360.0))
+    v = float(F32(rot * F32(1.0 / 30)))
+    b = int(np.floor(v + 0.5)) if v >= 0 else int(np.ceil(v - 0.5))      # C round(): half away from zero
+    return 0 if b == 30 else b
+
+
+def _three_maxima(sizes):
+    max1 = max2 = max3 = 0
+    i1 = i2 = i3 = -1
+    for i, s in enumerate(sizes):
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            i3, i2, i1 = i2, i1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            i3, i2 = i2, i
+        elif s > max3:
+            max3, i3 = s, i
+    if max2 < F32(0.1) * F32(max1):
+        i2 = i3 = -1
+    elif max3 < F32(0.1) * F32(max1):
+        i3 = -1
+    return i1, i2, i3
+
+
+def _featvec(side):
+    """std::map<NodeId, vector<unsigned>>"""
+    return {int(side["node_id"][k]): [int(i) for i in side["node_idx"][side["node_start"][k]:side["node_start"][k + 1]]]
+            for k in range(len(side["node_id"]))}
+
+
+def _walk(fv1, fv2):
+    """the reference's two-iterator walk with lower_bound jumps: yields the vectors of the common nodes, ascending"""
+    k1, k2 = sorted(fv1), sorted(fv2)
+    a = b = 0
+    while a < len(k1) and b < len(k2):
+        if k1[a] == k2[b]:
+            yield fv1[k1[a]], fv2[k2[b]]
+            a += 1; b += 1
+        elif k1[a] < k2[b]:
+            a = int(np.searchsorted(k1, k2[b], "left"))
+        else:
+            b = int(np.searchsorted(k2, k1[a], "left"))
+
+
+def py_search_by_bow(s1, s2, th_low, strict, nnratio, check_ori):
+    m12 = -np.ones(s1["n"], np.int32); m21 = -np.ones(s2["n"], np.int32)
+    hist = [[] for _ in range(30)]
+    n = 0
+    for v1, v2 in _walk(_featvec(s1), _featvec(s2)):
+        for i1 in v1:
+            if s1.get("valid") is not None and not s1["valid"][i1]:
+                continue
+            b1, bi, b2 = 256, -1, 256
+            for i2 in v2:
+                if m21[i2] >= 0 or (s2.get("valid") is not None and not s2["valid"][i2]):
+                    continue
+                d = _popcount(s1["descriptors"][i1], s2["descriptors"][i2])
+                if d < b1:
+                    b2, b1, bi = b1, d, i2
+                elif d < b2:
+                    b2 = d
+            if (b1 < th_low if strict else b1 <= th_low) and F32(b1) < F32(nnratio) * F32(b2):
+                m12[i1] = bi; m21[bi] = i1; n += 1
+                if check_ori:
+                    hist[_rot_bin(s1["keys_un"]["angle"][i1], s2["keys_un"]["angle"][bi])].append(i1)
+    if check_ori:
+        keep = _three_maxima([len(h) for h in hist])
+        for b, h in enumerate(hist):
+            if b in keep:
+                continue
+            for i1 in h:
+                m21[m12[i1]] = -1; m12[i1] = -1; n -= 1
+    return n, m12, m21
+
+
+def py_search_for_triangulation(s1, s2, f12, epi, sigma2, sf, only_stereo, check_ori):
+    F = np.asarray(f12, F32).reshape(3, 3)
+    ex, ey = F32(epi[0]), F32(epi[1])
+    m12 = -np.ones(s1["n"], np.int32)
+    hist = [[] for _ in range(30)]
+    n = 0
+    k1, k2 = s1["keys_un"], s2["keys_un"]
+    for v1, v2 in _walk(_featvec(s1), _featvec(s2)):
+        for i1 in v1:
+            if not s1["valid"][i1]:
+                continue
+            st1 = s1["u_right"][i1] >= 0
+            if only_stereo and not st1:
+                continue
+            x1, y1 = k1["x"][i1], k1["y"][i1]
+            best, bi = 50, -1
+            for i2 in v2:
+                if not s2["valid"][i2]:
+                    continue
+                st2 = s2["u_right"][i2] >= 0
+                if only_stereo and not st2:
+                    continue
+                d = _popcount(s1["descriptors"][i1], s2["descriptors"][i2])
+                if d > 50 or d > best:
+                    continue
+                x2, y2, o2 = k2["x"][i2], k2["y"][i2], k2["octave"][i2]
+                if not st1 and not st2:
+                    dx, dy = F32(ex - x2), F32(ey - y2)
+                    if F32(F32(dx * dx) + F32(dy * dy)) < F32(F32(100) * sf[o2]):
+                        continue
+                a = F32(F32(F32(x1 * F[0, 0]) + F32(y1 * F[1, 0])) + F[2, 0])
+                b = F32(F32(F32(x1 * F[0, 1]) + F32(y1 * F[1, 1])) + F[2, 1])
+                c = F32(F32(F32(x1 * F[0, 2]) + F32(y1 * F[1, 2])) + F[2, 2])
+                num = F32(F32(F32(a * x2) + F32(b * y2)) + c)
+                den = F32(F32(a * a) + F32(b * b))
+                if den == 0:
+                    continue
+                dsqr = F32(F32(num * num) / den)
+                if float(dsqr) < 3.84 * float(sigma2[o2]):
+                    bi, best = i2, d
+            if bi >= 0:
+                m12[i1] = bi; n += 1
+                if check_ori:
+                    hist[_rot_bin(k1["angle"][i1], k2["angle"][bi])].append(i1)
+    if check_ori:
+        keep = _three_maxima([len(h) for h in hist])
+        for b, h in enumerate(hist):
+            if b not in keep:
+                for i1 in h:
+                    m12[i1] = -1; n -= 1
+    return n, m12
+
+
+def py_distinctive(desc, start):
+    out = []
+    for p in range(len(start) - 1):
+        d = desc[start[p]:start[p + 1]]
+        N = len(d)
+        if N == 0:
+            out.append(-1); continue
+        D = np.array([[_popcount(d[i], d[j]) for j in range(N)] for i in range(N)])
+        med = [sorted(D[i])[int(0.5 * (N - 1))] for i in range(N)]
+        out.append(int(np.argmin(med)))          # first minimum
+    return np.array(out, np.int32)
+
+
+CASES = [(120, 3, 12), (300, 4, 40), (300, 5, 7)]        # keypoints, seed, vocabulary nodes
+
+
+@pytest.mark.parametrize("n,seed,nodes", CASES)
+def test_oracle_vs_python_bow(n, seed, nodes):
+    a, b, x = synth.bow_pair(synth.TUM_SHAPE, n, seed, n_nodes=nodes)
+    for strict, ratio, ori in ((False, 0.7, True), (True, 0.8, True), (True, 0.6, False)):
+        b2 = b if strict else dict(b, valid=None)
+        got = oracle.search_by_bow(a, b2, 50, strict, ratio, ori)
+        want = py_search_by_bow(a, b2, 50, strict, ratio, ori)
+        assert got[0] == want[0] and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+        assert got[0] > 0
+
+
+@pytest.mark.parametrize("n,seed,nodes", CASES)
+def test_oracle_vs_python_triangulation(n, seed, nodes):
+    a, b, x = synth.bow_pair(synth.TUM_SHAPE, n, seed, n_nodes=nodes)
+    for only_stereo, ori in ((False, True), (True, True), (False, False)):
+        got = oracle.search_for_triangulation(a, b, x["f12"], x["epipole"], x["level_sigma2"], x["scale_factors"], only_stereo, ori)
+        want = py_search_for_triangulation(a, b, x["f12"], x["epipole"], x["level_sigma2"], x["scale_factors"], only_stereo, ori)
+        assert got[0] == want[0] and np.array_equal(got[1], want[1])
+    assert got[0] > 0
+
+
+def test_oracle_vs_python_distinctive():
+    d, s = synth.observation_descriptors(60, 9, max_obs=12)
+    assert np.array_equal(oracle.distinctive_descriptors(d, s), py_distinctive(d, s))
+
+
+def golden_cases():
+    out = {}
+    for n, seed, nodes in [(500, 11, 60), (1000, 12, 100)]:
+        a, b, x = synth.bow_pair(synth.TUM_SHAPE, n, seed, n_nodes=nodes)
+        k = f"{n}_{seed}"
+        r = oracle.search_by_bow(a, dict(b, valid=None), 50, False, 0.7, True)
+        out[f"bowA_n_{k}"] = np.int32(r[0]); out[f"bowA_m21_{k}"] = r[2]
+        r = oracle.search_by_bow(a, b, 50, True, 0.8, True)
+        out[f"bowB_n_{k}"] = np.int32(r[0]); out[f"bowB_m12_{k}"] = r[1]
+        r = oracle.search_for_triangulation(a, b, x["f12"], x["epipole"], x["level_sigma2"], x["scale_factors"], False, True)
+        out[f"tri_n_{k}"] = np.int32(r[0]); out[f"tri_m12_{k}"] = r[1]
+    d, s = synth.observation_descriptors(500, 13)
+    out["distinctive"] = oracle.distinctive_descriptors(d, s)
+    return out
+
+
+def test_oracle_matches_golden():
+    """fixtures written by tools/make_golden_bow.py from this oracle at the commit that introduced it"""
+    want = np.load(GOLDEN)
+    got = golden_cases()
+    assert sorted(want.files) == sorted(got)
+    for k in want.files:
+        assert np.array_equal(want[k], got[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.fixture(scope="module")
+def matcher():
+    from object_slam_b200.matcher import ORBmatcher
+    m = ORBmatcher(0.7, True)
+    yield m
+    m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nodes,B", [(300, 25, 3), (1000, 100, 4), (2000, 100, 2), (64, 1, 2)])
+def test_gpu_search_by_bow(matcher, n, nodes, B):
+    pairs = [synth.bow_pair(synth.TUM_SHAPE, n, 100 + i, n_nodes=nodes) for i in range(B)]
+    for kf_pair, ratio, ori in ((False, 0.7, True), (True, 0.8, True), (False, 0.9, False)):
+        matcher.mfNNratio, matcher.mbCheckOrientation = ratio, ori
+        nm, m12, m21 = matcher.SearchByBoW([p[0] for p in pairs], [p[1] for p in pairs], keyframe_pair=kf_pair)
+        for i, (a, b, _) in enumerate(pairs):
+            on, o12, o21 = oracle.search_by_bow(a, b if kf_pair else dict(b, valid=None), 50, kf_pair, ratio, ori)
+            assert nm[i] == on
+            assert np.array_equal(m12[i, :n], o12) and np.array_equal(m21[i, :n], o21)
+    matcher.mfNNratio, matcher.mbCheckOrientation = 0.7, True
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nodes,B", [(300, 25, 3), (1000, 100, 4), (2000, 100, 2)])
+def test_gpu_search_for_triangulation(matcher, n, nodes, B):
+    pairs = [synth.bow_pair(synth.TUM_SHAPE, n, 200 + i, n_nodes=nodes) for i in range(B)]
+    x = pairs[0][2]
+    f12 = np.stack([p[2]["f12"] for p in pairs]); ep = np.stack([np.array(p[2]["epipole"], np.float32) for p in pairs])
+    for only_stereo, ori in ((False, True), (True, True), (False, False)):
+        matcher.mbCheckOrientation = ori
+        nm, m12 = matcher.SearchForTriangulation([p[0] for p in pairs], [p[1] for p in pairs], f12, ep, x["level_sigma2"],
+                                                 x["scale_factors"], bOnlyStereo=only_stereo)
+        for i, (a, b, e) in enumerate(pairs):
+            on, o12 = oracle.search_for_triangulation(a, b, e["f12"], e["epipole"], e["level_sigma2"], e["scale_factors"], only_stereo, ori)
+            assert nm[i] == on and np.array_equal(m12[i, :n], o12)
+    matcher.mbCheckOrientation = True
+
+
+@pytest.mark.gpu
+def test_gpu_distinctive_descriptors(matcher):
+    for n_points, seed, mx in ((500, 1, 24), (3000, 2, 40), (10, 3, 70)):
+        d, s = synth.observation_descriptors(n_points, seed, max_obs=mx)
+        assert np.array_equal(matcher.ComputeDistinctiveDescriptors(d, s), oracle.distinctive_descriptors(d, s))
+
+
+@pytest.mark.gpu
+def test_gpu_bow_matches_golden(matcher):
+    want = np.load(GOLDEN)
+    for n, seed, nodes in [(500, 11, 60), (1000, 12, 100)]:
+        a, b, x = synth.bow_pair(synth.TUM_SHAPE, n, seed, n_nodes=nodes)
+        k = f"{n}_{seed}"
+        matcher.mfNNratio = 0.7
+        nm, m12, m21 = matcher.SearchByBoW([a], [b], keyframe_pair=False)
+        assert nm[0] == want[f"bowA_n_{k}"] and np.array_equal(m21[0, :n], want[f"bowA_m21_{k}"])
+        matcher.mfNNratio = 0.8
+        nm, m12, m21 = matcher.SearchByBoW([a], [b], keyframe_pair=True)
+        assert nm[0] == want[f"bowB_n_{k}"] and np.array_equal(m12[0, :n], want[f"bowB_m12_{k}"])
+        nm, m12 = matcher.SearchForTriangulation([a], [b], x["f12"], x["epipole"], x["level_sigma2"], x["scale_factors"])
+        assert nm[0] == want[f"tri_n_{k}"] and np.array_equal(m12[0, :n], want[f"tri_m12_{k}"])
+    matcher.mfNNratio = 0.7
+    d, s = synth.observation_descriptors(500, 13)
+    assert np.array_equal(matcher.ComputeDistinctiveDescriptors(d, s), want["distinctive"])
