@@ -52,16 +52,15 @@ __device__ __forceinline__ int fast_contrast(const uint8_t* c) {
     RING(0, 0, 3); RING(1, 1, 3); RING(2, 2, 2); RING(3, 3, 1); RING(4, 3, 0); RING(5, 3, -1); RING(6, 2, -2); RING(7, 1, -3);
     RING(8, 0, -3); RING(9, -1, -3); RING(10, -2, -2); RING(11, -3, -1); RING(12, -3, 0); RING(13, -3, 1); RING(14, -2, 2); RING(15, -1, 3);
 #undef RING
-    unsigned m2[16], m4[16];
+    // min over every run of 3, then of 9 (three runs of 3), then the max over the 16 arcs: 40 three-input ops
+    unsigned m3[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) m2[i] = __vminu2(P[i], P[(i + 1) & 15]);
-#pragma unroll
-    for (int i = 0; i < 16; i++) m4[i] = __vminu2(m2[i], m2[(i + 2) & 15]);
+    for (int i = 0; i < 16; i++) m3[i] = __vimin3_u16x2(P[i], P[(i + 1) & 15], P[(i + 2) & 15]);
     unsigned best = 0;
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
-        const unsigned a = __vimin3_u16x2(m4[i], m4[(i + 4) & 15], P[(i + 8) & 15]);
-        const unsigned b = __vimin3_u16x2(m4[i + 1], m4[(i + 5) & 15], P[(i + 9) & 15]);
+        const unsigned a = __vimin3_u16x2(m3[i], m3[(i + 3) & 15], m3[(i + 6) & 15]);
+        const unsigned b = __vimin3_u16x2(m3[i + 1], m3[(i + 4) & 15], m3[(i + 7) & 15]);
         best = __vimax3_u16x2(best, a, b);
     }
     return (int)max(best & 0xffffu, best >> 16) - 255;
