@@ -301,6 +301,17 @@ int obs_search_by_projection_keyframe(obs_matcher* m, obs_frame_set* current, co
 int obs_search_by_projection_sim3(obs_matcher* m, obs_frame_set* keyframes, const obs_keyframe_points_view* points,
                                   int th, const int32_t* kp_taken, int32_t* kp_match, int32_t* n_matches);
 
+/* Search half of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th), src/ORBmatcher.cc:825-966 (sim3 = 0; points->tcw =
+ * [GetRotation() | GetTranslation()], camera_centre = GetCameraCenter(), n_frames x 3) and of
+ * ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint), :974-1100 (sim3 = 1; points->tcw = the decomposed Scw as in
+ * obs_search_by_projection_sim3, camera_centre ignored).  points->valid = "pMP && !isBad() && !IsInKeyFrame(pKF)" (resp. not in
+ * spAlreadyFound); points->normal is required.  Per (keyframe, point): best_idx = keypoint with the smallest descriptor distance in
+ * the predicted window (-1 = none), best_dist (256 = none); both n_frames x points->n.  The caller accepts best_dist <= TH_LOW and does
+ * the Replace / AddObservation bookkeeping (:935-962, :1077-1094) -- the search reads none of that state, so its results are those of
+ * the reference's sequential loop. */
+int obs_fuse_search(obs_matcher* m, obs_frame_set* keyframes, const obs_keyframe_points_view* points, const float* camera_centre,
+                    float th, int sim3, int32_t* best_idx, int32_t* best_dist);
+
 /* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:405-520: frame i of f1 against frame i of f2.
  * prev_matched: n_frames x max_keypoints(f1) x 2 floats, in/out (vbPrevMatched); matches12:
  * n_frames x max_keypoints(f1) (vnMatches12). */

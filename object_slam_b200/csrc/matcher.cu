@@ -665,6 +665,71 @@ __global__ void __launch_bounds__(512) k_init_search(const __grid_constant__ Ini
     (void)n2;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fuse: projection of every map point into a keyframe and the best keypoint in the window.  One thread per
+// (keyframe, map point); unlike the projection searches nothing is locked during the search (the reference
+// mutates the map after each point, but the search itself never reads that state), so the points are independent.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fuse_search(const __grid_constant__ FuseSearchArgs A) {
+    const int b = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= A.kf.n) return;
+    const FrameParamsDev& P = A.F.P;
+    const size_t o = (size_t)b * A.kf.stride + i;
+    const size_t out = (size_t)b * A.kf.n + i;
+    int bestDist = 256, bestIdx = -1;
+    do {
+        if (!A.kf.valid[o]) break;
+        const float* Tc = A.kf.tcw + (size_t)b * 12;
+        const float* p = A.kf.pos + o * 3;
+        const float x0 = p[0], x1 = p[1], x2 = p[2];
+        const float xc = row_rx_plus_t(Tc, 0, x0, x1, x2);
+        const float yc = row_rx_plus_t(Tc, 1, x0, x1, x2);
+        const float zc = row_rx_plus_t(Tc, 2, x0, x1, x2);
+        if (zc < 0.0f) break;                                            // :857, :1012
+        const float invz = A.sim3 ? __double2float_rn(__ddiv_rn(1.0, (double)zc)) : __fdiv_rn(1.0f, zc);      // :1016 vs :860
+        const float u = __fadd_rn(__fmul_rn(P.fx, __fmul_rn(xc, invz)), P.cx);
+        const float v = __fadd_rn(__fmul_rn(P.fy, __fmul_rn(yc, invz)), P.cy);
+        if (!(u >= P.minX && u < P.maxX && v >= P.minY && v < P.maxY)) break;
+        const float ur = __fsub_rn(u, __fmul_rn(P.mbf, invz));
+        float Ow[3];
+        if (A.ow) { Ow[0] = A.ow[b * 3]; Ow[1] = A.ow[b * 3 + 1]; Ow[2] = A.ow[b * 3 + 2]; }
+        else camera_centre(Tc, Ow);
+        const float po0 = __fsub_rn(x0, Ow[0]), po1 = __fsub_rn(x1, Ow[1]), po2 = __fsub_rn(x2, Ow[2]);
+        const double ss = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)po0), __dmul_rn((double)po1, (double)po1)),
+                                    __dmul_rn((double)po2, (double)po2));
+        const float dist3D = __double2float_rn(__dsqrt_rn(ss));          // cv::norm
+        if (dist3D < A.kf.minDist[o] || dist3D > A.kf.maxDist[o]) break;
+        const float* nrm = A.kf.normal + o * 3;
+        const double dt = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)nrm[0]), __dmul_rn((double)po1, (double)nrm[1])),
+                                    __dmul_rn((double)po2, (double)nrm[2]));
+        if (dt < __dmul_rn(0.5, (double)dist3D)) break;                  // viewing angle below 60 degrees
+        const int lvl = predict_scale(A.kf.maxDistRaw[o], dist3D, A.kf.logScaleFactor, P.nlevels);
+        const float radius = __fmul_rn(A.th, P.scale[lvl]);
+        uint32_t q[8];
+        load_desc(A.kf.desc + o * 2, q);
+        const uint4* fd = A.F.desc + (size_t)b * A.F.cap * 2;
+        const bool sim3 = A.sim3 != 0;
+        for_each_in_area(A.F, b, u, v, radius, lvl - 1, lvl, [&](int idx, const float4& k) {
+            if (!sim3) {
+                const int oct = __float_as_int(k.w);
+                const float ex = __fsub_rn(u, k.x), ey = __fsub_rn(v, k.y);
+                if (k.z >= 0.0f) {                                        // reprojection error in stereo, :909-921
+                    const float er = __fsub_rn(ur, k.z);
+                    const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+                    if ((double)__fmul_rn(e2, A.invSigma2[oct]) > 7.8) return;
+                } else {
+                    const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                    if ((double)__fmul_rn(e2, A.invSigma2[oct]) > 5.99) return;
+                }
+            }
+            const int dist = hamming8(q, fd[idx * 2], fd[idx * 2 + 1]);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        });
+    } while (false);
+    A.bestIdx[out] = bestIdx;
+    A.bestDist[out] = bestDist;
+}
+
 __global__ void k_three_maxima(const int* binSizes, int nHist, int length, int* ind) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= nHist) return;
@@ -780,6 +845,12 @@ cudaError_t launch_proj_search(const ProjSearchArgs& a, int variant, int nFrames
         default: return cudaErrorInvalidValue;
     }
 #undef OBS_PROJ_CASE
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fuse_search(const FuseSearchArgs& a, int nFrames, cudaStream_t st) {
+    if (nFrames <= 0 || a.kf.n <= 0) return cudaSuccess;
+    k_fuse_search<<<dim3((a.kf.n + 127) / 128, nFrames), 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 

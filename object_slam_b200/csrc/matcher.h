@@ -91,6 +91,16 @@ struct InitSearchArgs {       // SearchForInitialization (:405-520)
 };
 cudaError_t launch_init_search(const InitSearchArgs& a, int nFrames, cudaStream_t st);
 
+struct FuseSearchArgs {       // search half of ORBmatcher::Fuse (ORBmatcher.cc:825-966 and :974-1100)
+    FrameSetDev F;
+    KeyFramePtsDev kf;        // valid, pos, minDist, maxDist, maxDistRaw, normal, desc, tcw, logScaleFactor
+    const float* ow;          // [B][3] GetCameraCenter(); null in the Sim3 variant (Ow = -Rcw.t()*tcw)
+    float invSigma2[OBS_MAX_LEVELS];
+    float th; int sim3;
+    int* bestIdx; int* bestDist;   // [B][n]
+};
+cudaError_t launch_fuse_search(const FuseSearchArgs& a, int nFrames, cudaStream_t st);
+
 cudaError_t launch_three_maxima(const int* binSizes, int nHist, int length, int* ind, cudaStream_t st);
 cudaError_t launch_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int* dist, cudaStream_t st);
 

@@ -407,6 +407,52 @@ int obs_search_by_projection_sim3(obs_matcher* m, obs_frame_set* keyframes, cons
     return run_keyframe_search(m, keyframes, points, 3, (float)th, 50 /* TH_LOW */, 0, kp_taken, kp_match, n_matches);
 }
 
+int obs_fuse_search(obs_matcher* m, obs_frame_set* fs, const obs_keyframe_points_view* pts, const float* camera_centre, float th,
+                    int sim3, int32_t* best_idx, int32_t* best_dist) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!fs || !pts || !best_idx || !best_dist) return fail(OBS_ERR_INVALID, "null argument");
+    if (fs->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if (fs->nFrames < 1) return fail(OBS_ERR_STATE, "frame set is empty");
+    if (pts->n < 1 || !pts->tcw) return fail(OBS_ERR_INVALID, "point count < 1 or null pose");
+    if (!pts->valid || !pts->world_pos || !pts->min_distance || !pts->max_distance || !pts->max_distance_raw || !pts->descriptors || !pts->normal)
+        return fail(OBS_ERR_INVALID, "null map point array");
+    if (!sim3 && !camera_centre) return fail(OBS_ERR_INVALID, "the keyframe variant needs GetCameraCenter()");
+    const int B = fs->nFrames, M = pts->n;
+    const size_t cnt = (size_t)M * (pts->per_frame ? B : 1);
+    FuseSearchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.F = fs->d;
+    a.kf.n = M; a.kf.stride = pts->per_frame ? (size_t)M : 0;
+    const uint8_t* dsc = nullptr;
+    if ((rc = dev_in(m, 0, pts->valid, cnt, &a.kf.valid))) return rc;
+    if ((rc = dev_in(m, 1, pts->world_pos, cnt * 3, &a.kf.pos))) return rc;
+    if ((rc = dev_in(m, 2, pts->min_distance, cnt, &a.kf.minDist))) return rc;
+    if ((rc = dev_in(m, 3, pts->max_distance, cnt, &a.kf.maxDist))) return rc;
+    if ((rc = dev_in(m, 4, pts->max_distance_raw, cnt, &a.kf.maxDistRaw))) return rc;
+    if ((rc = dev_in(m, 5, pts->normal, cnt * 3, &a.kf.normal))) return rc;
+    if ((rc = dev_in(m, 7, pts->descriptors, cnt * 32, &dsc))) return rc;
+    if ((rc = dev_in(m, 8, pts->tcw, (size_t)B * 12, &a.kf.tcw))) return rc;
+    if ((rc = dev_in(m, 9, sim3 ? nullptr : camera_centre, sim3 ? 0 : (size_t)B * 3, &a.ow))) return rc;
+    if ((uintptr_t)dsc & 15) return fail(OBS_ERR_INVALID, "device descriptors must be 16-byte aligned");
+    a.kf.desc = reinterpret_cast<const uint4*>(dsc);
+    a.kf.logScaleFactor = logf(fs->prm.nlevels > 1 ? fs->prm.scale_factors[1] : 1.2f);
+    for (int l = 0; l < fs->prm.nlevels && l < OBS_MAX_LEVELS; l++) {
+        const float sf = fs->prm.scale_factors[l];
+        a.invSigma2[l] = 1.0f / (sf * sf);                  // mvInvLevelSigma2, src/ORBextractor.cc:422-431
+    }
+    a.th = th; a.sim3 = sim3 != 0;
+    const size_t oc = (size_t)B * M;
+    if ((rc = dev_out(m, 20, best_idx, oc, &a.bestIdx))) return rc;
+    if ((rc = dev_out(m, 21, best_dist, oc, &a.bestDist))) return rc;
+    CU(launch_fuse_search(a, B, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, best_idx, a.bestIdx, oc, &queued))) return rc;
+    if ((rc = host_back(m, best_dist, a.bestDist, oc, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
 int obs_search_for_initialization(obs_matcher* m, obs_frame_set* f1, obs_frame_set* f2, float* prev_matched, int32_t* matches12,
                                   int window_size, float nnratio, int check_orientation, int32_t* n_matches) {
     int rc = check_matcher(m);

@@ -210,6 +210,18 @@ class ORBmatcher:
         check(lib().obs_search_by_projection_sim3(self._h, keyframes._h, C.byref(v), int(th), ptr(_i32(kp_taken)), ptr(kp_match), ptr(n_matches)))
         return n_matches, kp_match
 
+    # ---- ORBmatcher.cc:825-966 / :974-1100 (search half)
+    def FuseSearch(self, keyframes, pts, tcw, th, camera_centre=None, sim3=False, n_points=None, per_frame=False):
+        """Projection + best-keypoint search of ORBmatcher::Fuse for every keyframe of the set; pts as for SearchByProjectionSim3
+        (valid = pMP && !isBad() && !IsInKeyFrame(pKF)).  camera_centre: [B, 3] GetCameraCenter() (keyframe variant).  Returns
+        (best_idx, best_dist), each [B, n_points]; the caller accepts best_dist <= TH_LOW and applies Replace / AddObservation."""
+        v, keep = self._kf_view(pts, tcw, n_points, per_frame)
+        B = len(keyframes)
+        best_idx = np.empty((B, v.n), np.int32); best_dist = np.empty((B, v.n), np.int32)
+        check(lib().obs_fuse_search(self._h, keyframes._h, C.byref(v), ptr(_f32(camera_centre)), float(th), int(bool(sim3)),
+                                    ptr(best_idx), ptr(best_dist)))
+        return best_idx, best_dist
+
     # ---- ORBmatcher.cc:405-520
     def SearchForInitialization(self, f1, f2, prev_matched, window_size=10, matches12=None, n_matches=None):
         """Returns (n_matches[B], vnMatches12[B, cap1]); ``prev_matched`` ([B, cap1, 2] float32) is updated in place."""

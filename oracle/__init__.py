@@ -102,6 +102,7 @@ def _bind_match(L):
     L.orc_search_by_bow.argtypes = [C.c_void_p] * 14 + [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_search_for_triangulation.argtypes = [C.c_void_p] * 17 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.orc_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_fuse_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p]
     L.orc_logf.restype = C.c_float
     L.orc_logf.argtypes = [C.c_float]
     L.orc_norm3.restype = C.c_float
@@ -520,3 +521,19 @@ def distinctive_descriptors(desc, start):
     best = np.empty(max(len(start) - 1, 1), np.int32)
     lib().orc_distinctive_descriptors(_ptr(desc), _ptr(start), len(start) - 1, _ptr(best))
     return best[:len(start) - 1]
+
+
+def fuse_search(frame, scale, cam, tcw, pts, th, camera_centre=None, sim3=False):
+    """Search half of ORBmatcher::Fuse (src/ORBmatcher.cc:825-966, sim3=False; :974-1100, sim3=True).  pts as for
+    search_by_projection_sim3 (valid = pMP && !isBad() && !IsInKeyFrame).  Returns (best_idx, best_dist) per point."""
+    scale = np.ascontiguousarray(scale, np.float32)
+    inv_sigma2 = (np.float32(1.0) / (scale * scale)).astype(np.float32)          # Frame.cc / KeyFrame: mvInvLevelSigma2
+    cam = np.ascontiguousarray(cam, np.float32)
+    tcw = np.ascontiguousarray(tcw, np.float32).reshape(12)
+    ow = minus_rt_t(tcw) if camera_centre is None else np.ascontiguousarray(camera_centre, np.float32)
+    a = _kf_points(pts, "normal")
+    n = len(a[0])
+    bi = np.empty(max(n, 1), np.int32); bd = np.empty(max(n, 1), np.int32)
+    lib().orc_fuse_search(frame._h, _ptr(scale), _ptr(inv_sigma2), len(scale), logf(scale[1]), _ptr(cam), _ptr(tcw), _ptr(ow), int(sim3), n,
+                          *[_ptr(x) for x in a], float(th), _ptr(bi), _ptr(bd))
+    return bi[:n], bd[:n]

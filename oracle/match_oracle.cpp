@@ -576,6 +576,65 @@ static int search_by_projection_sim3(const FrameV& KF, const float* scale, int n
     return nmatches;
 }
 
+// The search half of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th), ORBmatcher.cc:825-966 (sim3 = 0: Tcw =
+// [GetRotation() | GetTranslation()], Ow = GetCameraCenter(), stereo / mono chi-square gates on the reprojection error) and of
+// ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint), :974-1100 (sim3 = 1: after the decomposition of Scw,
+// Ow = -Rcw.t()*tcw, invz = 1.0/z in binary64, no reprojection gate).  valid = "pMP && !isBad() && !IsInKeyFrame(pKF)".
+// Per map point: bestIdx (-1 = none) and bestDist; the replace / add-observation bookkeeping (map mutation) stays with the caller,
+// which accepts bestDist <= TH_LOW.  Nothing here depends on that bookkeeping, so the points are independent.
+static void fuse_search(const FrameV& KF, const float* scale, const float* invSigma2, int nLevels, float logScaleFactor, const Camera& cam,
+                        const float* Tcw, const float* OwIn, int sim3, int nPts, const uint8_t* valid, const float* pos,
+                        const float* minDist, const float* maxDist, const float* maxDistRaw, const float* normal, const uint8_t* desc,
+                        float th, int* bestIdxOut, int* bestDistOut) {
+    float Ow[3];
+    if (sim3) mat_minus_rt_t(Tcw, Ow); else memcpy(Ow, OwIn, sizeof(Ow));
+    for (int i = 0; i < nPts; i++) {
+        bestIdxOut[i] = -1; bestDistOut[i] = 256;
+        if (!valid[i]) continue;
+        const float* p3Dw = pos + 3 * i;
+        float p3Dc[3];
+        mat_rx_plus_t(Tcw, p3Dw, p3Dc);
+        if (p3Dc[2] < 0.0f) continue;
+        const float invz = sim3 ? (float)(1.0 / p3Dc[2]) : 1 / p3Dc[2];
+        const float x = p3Dc[0] * invz;
+        const float y = p3Dc[1] * invz;
+        const float u = cam.fx * x + cam.cx;
+        const float v = cam.fy * y + cam.cy;
+        if (!(u >= KF.minX && u < KF.maxX && v >= KF.minY && v < KF.maxY)) continue;      // KeyFrame::IsInImage
+        const float ur = u - cam.mbf * invz;
+        const float PO[3] = {p3Dw[0] - Ow[0], p3Dw[1] - Ow[1], p3Dw[2] - Ow[2]};
+        const float dist3D = norm3(PO);
+        if (dist3D < minDist[i] || dist3D > maxDist[i]) continue;
+        if (dot3(PO, normal + 3 * i) < 0.5 * dist3D) continue;
+        const int nPredictedLevel = predict_scale(maxDistRaw[i], dist3D, logScaleFactor, nLevels);
+        const float radius = th * scale[nPredictedLevel];
+        const std::vector<size_t> vIndices = KF.features_in_area(u, v, radius);
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx = -1;
+        for (size_t vi = 0; vi < vIndices.size(); vi++) {
+            const size_t idx = vIndices[vi];
+            const KeyPt& kp = KF.k[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            if (!sim3) {
+                if (KF.uR[idx] >= 0) {                                  // reprojection error in stereo, :909-921
+                    const float ex = u - kp.x, ey = v - kp.y, er = ur - KF.uR[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * invSigma2[kpLevel] > 7.8) continue;
+                } else {
+                    const float ex = u - kp.x, ey = v - kp.y;
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * invSigma2[kpLevel] > 5.99) continue;
+                }
+            }
+            const int dist = descriptor_distance(dMP, &KF.d[idx * 32]);
+            if (dist < bestDist) { bestDist = dist; bestIdx = (int)idx; }
+        }
+        bestIdxOut[i] = bestIdx; bestDistOut[i] = bestDist;
+    }
+}
+
 // Brute-force best / second-best Hamming search with the ratio test: the inner loop of
 // ORBmatcher::SearchByBoW (ORBmatcher.cc:200-229) over one list of candidates, without the
 // "already matched" bookkeeping (every query is independent).  bestIdx = -1 when rejected.
@@ -839,6 +898,15 @@ int orc_search_by_projection_sim3(const void* f, const float* scale, int nLevels
     Camera cam{cam6[0], cam6[1], cam6[2], cam6[3], cam6[4], cam6[5]};
     return search_by_projection_sim3(*(const FrameV*)f, scale, nLevels, logScaleFactor, cam, Tcw, nPts, valid, pos, minDist, maxDist,
                                      maxDistRaw, normal, desc, th, kpTaken, kpMatch);
+}
+
+void orc_fuse_search(const void* f, const float* scale, const float* invSigma2, int nLevels, float logScaleFactor, const float* cam6,
+                     const float* Tcw, const float* Ow, int sim3, int nPts, const uint8_t* valid, const float* pos, const float* minDist,
+                     const float* maxDist, const float* maxDistRaw, const float* normal, const uint8_t* desc, float th,
+                     int* bestIdx, int* bestDist) {
+    Camera cam{cam6[0], cam6[1], cam6[2], cam6[3], cam6[4], cam6[5]};
+    fuse_search(*(const FrameV*)f, scale, invSigma2, nLevels, logScaleFactor, cam, Tcw, Ow, sim3, nPts, valid, pos, minDist, maxDist,
+                maxDistRaw, normal, desc, th, bestIdx, bestDist);
 }
 
 float orc_logf(float x) { return logf(x); }

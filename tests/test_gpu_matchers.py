@@ -340,3 +340,23 @@ def test_search_by_projection_sim3_matches_oracle(M, th):
                                                   last["tcw_current"], pts[b], th, taken[b, :1000])
         assert n[b] == on and np.array_equal(match[b, :1000], om)
         assert on > 100
+
+
+@pytest.mark.parametrize("sim3,th", [(False, 3.0), (True, 4.0), (False, 2.5)])
+def test_fuse_search_matches_oracle(M, sim3, th):
+    """Search half of ORBmatcher::Fuse (ORBmatcher.cc:825-966 keyframe variant with the chi-square gates, :974-1100 Sim3 variant)."""
+    shape = TUM
+    pairs = [synth.motion_pair(shape, 1000, s) for s in (70, 71, 72)]
+    pts = [synth.keyframe_points(p[0], 75 + i) for i, p in enumerate(pairs)]
+    fs = frame_set(M, shape, [p[1] for p in pairs])
+    stacked = {k: np.stack([q[k] for q in pts]) for k in pts[0]}
+    tcw = np.stack([p[0]["tcw_current"] for p in pairs])
+    ow = np.stack([oracle.minus_rt_t(t) for t in tcw])
+    bi, bd = M.FuseSearch(fs, stacked, tcw, th, camera_centre=None if sim3 else ow, sim3=sim3, per_frame=True)
+    total = 0
+    for b, (last, cur) in enumerate(pairs):
+        oi, od = oracle.fuse_search(oracle_frame(cur, shape), synth.scale_factors(), synth.camera_for(shape), last["tcw_current"], pts[b], th,
+                                    camera_centre=ow[b], sim3=sim3)
+        assert np.array_equal(bi[b], oi) and np.array_equal(bd[b], od)
+        total += int(((od <= 50) & (oi >= 0)).sum())
+    assert total > 100
