@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=256, help="stereo frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-pipelines", type=int, default=3, help="host-buffer pipelines of the e2e leg (each: an extractor pair + pinned buffers)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (0 = min(steps, 12))")
     ap.add_argument("--workload", default="stereo", choices=["stereo", "knn2", "projection"],
                     help="stereo = configs[1] (the headline); knn2 = configs[4] keyframe-vs-keyframe Hamming matching; "
                          "projection = configs[2] TUM-shape extraction + SearchByProjection against a 20k-point map")
@@ -287,7 +289,7 @@ def main():
     # transfers overlap the other's kernels (double buffering across steps); throughput = frames / wall clock.
     from object_slam_b200._capi import pinned_empty, KEYPOINT_DTYPE
     cap = exL.capacity
-    WORKERS = 2
+    WORKERS = args.e2e_pipelines
 
     class Pipe:
         def __init__(self, eL, eR):
@@ -313,7 +315,7 @@ def main():
     for _ in range(WORKERS - 1):
         pipes.append(Pipe(ORBextractor(NFEAT, 1.2, 8, 20, 7, max_size=(W, H), max_batch=F, device=local_rank),
                           ORBextractor(NFEAT, 1.2, 8, 20, 7, max_size=(W, H), max_batch=F, device=local_rank)))
-    e2e_steps = max(4, min(args.steps, 10)) // WORKERS * WORKERS
+    e2e_steps = max(WORKERS, (args.e2e_steps or max(4, min(args.steps, 12))) // WORKERS * WORKERS)
 
     def run_pipes(nsteps):
         ths = [threading.Thread(target=lambda p=p: [p.step() for _ in range(nsteps // WORKERS)]) for p in pipes[1:]]
@@ -401,7 +403,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "obs_extract_batch x2 (two host threads) + obs_stereo_match, page-locked host buffers in and out; "
-                                            "2 pipelines take alternate steps (transfers of one overlap kernels of the other)"},
+                                            f"{WORKERS} pipelines take alternate steps (transfers of one overlap kernels of the other)"},
         "gpu_launches": 24 * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
