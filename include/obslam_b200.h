@@ -312,6 +312,16 @@ int obs_search_by_projection_sim3(obs_matcher* m, obs_frame_set* keyframes, cons
 int obs_fuse_search(obs_matcher* m, obs_frame_set* keyframes, const obs_keyframe_points_view* points, const float* camera_centre,
                     float th, int sim3, int32_t* best_idx, int32_t* best_dist);
 
+/* ORBmatcher::SearchBySim3(KeyFrame*, KeyFrame*, vector<MapPoint*>& vpMatches12, s12, R12, t12, th), src/ORBmatcher.cc:1102-1326, for
+ * n_frames keyframe pairs (frame i of kf1 with frame i of kf2).  points1 / points2: the map points of the keyframes' keypoints
+ * (n = number of keypoints; valid = "non-NULL, not bad, not already matched", :1131-1143, :1157-1162, :1232-1237; normal / angle unused);
+ * points1->tcw = [R1w | t1w], points2->tcw = [R2w | t2w]; t21 = [sR21 | t21] and t12 = [sR12 | t12] as :1119-1122 builds them
+ * (n_frames x 12 floats each).  match12[i1] = keypoint of kf2 where both directions agree (:1305-1319), else -1; n_found = the return
+ * value.  Both projections use the target frame set's camera (the reference uses pKF1's for both). */
+int obs_search_by_sim3(obs_matcher* m, obs_frame_set* kf1, obs_frame_set* kf2, const obs_keyframe_points_view* points1,
+                       const obs_keyframe_points_view* points2, const float* t21, const float* t12, float th,
+                       int32_t* match12, int32_t* n_found);
+
 /* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:405-520: frame i of f1 against frame i of f2.
  * prev_matched: n_frames x max_keypoints(f1) x 2 floats, in/out (vbPrevMatched); matches12:
  * n_frames x max_keypoints(f1) (vnMatches12). */

@@ -111,6 +111,7 @@ _PROTOS = {
     "obs_search_by_projection_keyframe": (C.c_int, [_vp, _vp, C.POINTER(KeyFramePointsView), C.c_float, C.c_int, C.c_int, _vp, _vp, _vp]),
     "obs_search_by_projection_sim3": (C.c_int, [_vp, _vp, C.POINTER(KeyFramePointsView), C.c_int, _vp, _vp, _vp]),
     "obs_fuse_search": (C.c_int, [_vp, _vp, C.POINTER(KeyFramePointsView), _vp, C.c_float, C.c_int, _vp, _vp]),
+    "obs_search_by_sim3": (C.c_int, [_vp, _vp, _vp, C.POINTER(KeyFramePointsView), C.POINTER(KeyFramePointsView), _vp, _vp, C.c_float, _vp, _vp]),
     "obs_search_for_initialization": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_int, _vp]),
     "obs_compute_three_maxima": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "obs_descriptor_distance": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),

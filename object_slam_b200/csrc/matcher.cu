@@ -682,33 +682,43 @@ __global__ void __launch_bounds__(128) k_fuse_search(const __grid_constant__ Fus
         const float* Tc = A.kf.tcw + (size_t)b * 12;
         const float* p = A.kf.pos + o * 3;
         const float x0 = p[0], x1 = p[1], x2 = p[2];
-        const float xc = row_rx_plus_t(Tc, 0, x0, x1, x2);
-        const float yc = row_rx_plus_t(Tc, 1, x0, x1, x2);
-        const float zc = row_rx_plus_t(Tc, 2, x0, x1, x2);
-        if (zc < 0.0f) break;                                            // :857, :1012
-        const float invz = A.sim3 ? __double2float_rn(__ddiv_rn(1.0, (double)zc)) : __fdiv_rn(1.0f, zc);      // :1016 vs :860
+        float xc = row_rx_plus_t(Tc, 0, x0, x1, x2);
+        float yc = row_rx_plus_t(Tc, 1, x0, x1, x2);
+        float zc = row_rx_plus_t(Tc, 2, x0, x1, x2);
+        if (A.sim3 == 2) {                                               // p3Dc2 = sR21*p3Dc1 + t21, :1169
+            const float* T2 = A.tcw2 + (size_t)b * 12;
+            const float a0 = xc, a1 = yc, a2 = zc;
+            xc = row_rx_plus_t(T2, 0, a0, a1, a2); yc = row_rx_plus_t(T2, 1, a0, a1, a2); zc = row_rx_plus_t(T2, 2, a0, a1, a2);
+        }
+        if (zc < 0.0f) break;                                            // :857, :1012, :1172
+        const float invz = A.sim3 ? __double2float_rn(__ddiv_rn(1.0, (double)zc)) : __fdiv_rn(1.0f, zc);      // :1016, :1175 vs :860
         const float u = __fadd_rn(__fmul_rn(P.fx, __fmul_rn(xc, invz)), P.cx);
         const float v = __fadd_rn(__fmul_rn(P.fy, __fmul_rn(yc, invz)), P.cy);
         if (!(u >= P.minX && u < P.maxX && v >= P.minY && v < P.maxY)) break;
         const float ur = __fsub_rn(u, __fmul_rn(P.mbf, invz));
-        float Ow[3];
-        if (A.ow) { Ow[0] = A.ow[b * 3]; Ow[1] = A.ow[b * 3 + 1]; Ow[2] = A.ow[b * 3 + 2]; }
-        else camera_centre(Tc, Ow);
-        const float po0 = __fsub_rn(x0, Ow[0]), po1 = __fsub_rn(x1, Ow[1]), po2 = __fsub_rn(x2, Ow[2]);
+        float po0 = xc, po1 = yc, po2 = zc;                              // SearchBySim3: dist3D = cv::norm(p3Dc2), :1188
+        if (A.sim3 != 2) {
+            float Ow[3];
+            if (A.ow) { Ow[0] = A.ow[b * 3]; Ow[1] = A.ow[b * 3 + 1]; Ow[2] = A.ow[b * 3 + 2]; }
+            else camera_centre(Tc, Ow);
+            po0 = __fsub_rn(x0, Ow[0]); po1 = __fsub_rn(x1, Ow[1]); po2 = __fsub_rn(x2, Ow[2]);
+        }
         const double ss = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)po0), __dmul_rn((double)po1, (double)po1)),
                                     __dmul_rn((double)po2, (double)po2));
         const float dist3D = __double2float_rn(__dsqrt_rn(ss));          // cv::norm
         if (dist3D < A.kf.minDist[o] || dist3D > A.kf.maxDist[o]) break;
-        const float* nrm = A.kf.normal + o * 3;
-        const double dt = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)nrm[0]), __dmul_rn((double)po1, (double)nrm[1])),
-                                    __dmul_rn((double)po2, (double)nrm[2]));
-        if (dt < __dmul_rn(0.5, (double)dist3D)) break;                  // viewing angle below 60 degrees
+        if (A.sim3 != 2) {
+            const float* nrm = A.kf.normal + o * 3;
+            const double dt = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)nrm[0]), __dmul_rn((double)po1, (double)nrm[1])),
+                                        __dmul_rn((double)po2, (double)nrm[2]));
+            if (dt < __dmul_rn(0.5, (double)dist3D)) break;              // viewing angle below 60 degrees
+        }
         const int lvl = predict_scale(A.kf.maxDistRaw[o], dist3D, A.kf.logScaleFactor, P.nlevels);
         const float radius = __fmul_rn(A.th, P.scale[lvl]);
         uint32_t q[8];
         load_desc(A.kf.desc + o * 2, q);
         const uint4* fd = A.F.desc + (size_t)b * A.F.cap * 2;
-        const bool sim3 = A.sim3 != 0;
+        const bool sim3 = A.sim3 != 0;                                  // no reprojection gate in the Scw / Sim3 variants
         for_each_in_area(A.F, b, u, v, radius, lvl - 1, lvl, [&](int idx, const float4& k) {
             if (!sim3) {
                 const int oct = __float_as_int(k.w);
@@ -728,6 +738,29 @@ __global__ void __launch_bounds__(128) k_fuse_search(const __grid_constant__ Fus
     } while (false);
     A.bestIdx[out] = bestIdx;
     A.bestDist[out] = bestDist;
+}
+
+// SearchBySim3 agreement, :1305-1319
+__global__ void __launch_bounds__(256) k_sim3_agree(const int* __restrict__ idx1, const int* __restrict__ dist1, int n1,
+                                                    const int* __restrict__ idx2, const int* __restrict__ dist2, int n2, int thHigh,
+                                                    int* __restrict__ match12, int* __restrict__ nFound) {
+    __shared__ int sCount;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) sCount = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i1 = threadIdx.x; i1 < n1; i1 += 256) {
+        int m = -1;
+        const int i2 = dist1[(size_t)b * n1 + i1] <= thHigh ? idx1[(size_t)b * n1 + i1] : -1;
+        if (i2 >= 0 && i2 < n2) {
+            const int back = dist2[(size_t)b * n2 + i2] <= thHigh ? idx2[(size_t)b * n2 + i2] : -1;
+            if (back == i1) { m = i2; mine++; }
+        }
+        match12[(size_t)b * n1 + i1] = m;
+    }
+    if (mine) atomicAdd(&sCount, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) nFound[b] = sCount;
 }
 
 __global__ void k_three_maxima(const int* binSizes, int nHist, int length, int* ind) {
@@ -851,6 +884,13 @@ cudaError_t launch_proj_search(const ProjSearchArgs& a, int variant, int nFrames
 cudaError_t launch_fuse_search(const FuseSearchArgs& a, int nFrames, cudaStream_t st) {
     if (nFrames <= 0 || a.kf.n <= 0) return cudaSuccess;
     k_fuse_search<<<dim3((a.kf.n + 127) / 128, nFrames), 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sim3_agree(const int* idx1, const int* dist1, int n1, const int* idx2, const int* dist2, int n2, int thHigh,
+                              int* match12, int* nFound, int nFrames, cudaStream_t st) {
+    if (nFrames <= 0) return cudaSuccess;
+    k_sim3_agree<<<nFrames, 256, 0, st>>>(idx1, dist1, n1, idx2, dist2, n2, thHigh, match12, nFound);
     return cudaGetLastError();
 }
 

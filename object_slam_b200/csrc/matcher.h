@@ -96,10 +96,14 @@ struct FuseSearchArgs {       // search half of ORBmatcher::Fuse (ORBmatcher.cc:
     KeyFramePtsDev kf;        // valid, pos, minDist, maxDist, maxDistRaw, normal, desc, tcw, logScaleFactor
     const float* ow;          // [B][3] GetCameraCenter(); null in the Sim3 variant (Ow = -Rcw.t()*tcw)
     float invSigma2[OBS_MAX_LEVELS];
-    float th; int sim3;
+    const float* tcw2;        // mode 2: second transform [B][12], p3Dc = T2 * (T1 * p3Dw)
+    float th; int sim3;       // 0: Fuse(KeyFrame*, points), 1: Fuse(KeyFrame*, Scw, ...), 2: one direction of SearchBySim3 (:1153-1226)
     int* bestIdx; int* bestDist;   // [B][n]
 };
 cudaError_t launch_fuse_search(const FuseSearchArgs& a, int nFrames, cudaStream_t st);
+// SearchBySim3 agreement (:1305-1319): vn1 [B][n1], vn2 [B][n2] = best indices with distance <= TH_HIGH applied here
+cudaError_t launch_sim3_agree(const int* idx1, const int* dist1, int n1, const int* idx2, const int* dist2, int n2, int thHigh,
+                              int* match12, int* nFound, int nFrames, cudaStream_t st);
 
 cudaError_t launch_three_maxima(const int* binSizes, int nHist, int length, int* ind, cudaStream_t st);
 cudaError_t launch_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int* dist, cudaStream_t st);

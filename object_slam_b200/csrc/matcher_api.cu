@@ -22,6 +22,7 @@ struct obs_matcher {
     DevBuf<int> choice, rounds;
     DevBuf<uint32_t> initList;
     DevBuf<int> initCount;
+    DevBuf<int> sim3Idx[2], sim3Dist[2];
     std::vector<int> lastRounds;
     std::vector<obs_frame_set*> sets;   // frame sets created on this matcher (orphaned, not freed, when it is destroyed first)
 };
@@ -449,6 +450,61 @@ int obs_fuse_search(obs_matcher* m, obs_frame_set* fs, const obs_keyframe_points
     bool queued = false;
     if ((rc = host_back(m, best_idx, a.bestIdx, oc, &queued))) return rc;
     if ((rc = host_back(m, best_dist, a.bestDist, oc, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
+static int sim3_side(obs_matcher* m, int slot0, obs_frame_set* target, const obs_keyframe_points_view* pts, const float* t2, float th,
+                     int B, FuseSearchArgs* a, DevBuf<int>& idx, DevBuf<int>& dist) {
+    int rc;
+    if (pts->n < 1 || !pts->tcw || !pts->valid || !pts->world_pos || !pts->min_distance || !pts->max_distance || !pts->max_distance_raw || !pts->descriptors)
+        return fail(OBS_ERR_INVALID, "null map point array or point count < 1");
+    const int M = pts->n;
+    const size_t cnt = (size_t)M * (pts->per_frame ? B : 1);
+    memset(a, 0, sizeof(*a));
+    a->F = target->d;
+    a->kf.n = M; a->kf.stride = pts->per_frame ? (size_t)M : 0;
+    const uint8_t* dsc = nullptr;
+    if ((rc = dev_in(m, slot0 + 0, pts->valid, cnt, &a->kf.valid))) return rc;
+    if ((rc = dev_in(m, slot0 + 1, pts->world_pos, cnt * 3, &a->kf.pos))) return rc;
+    if ((rc = dev_in(m, slot0 + 2, pts->min_distance, cnt, &a->kf.minDist))) return rc;
+    if ((rc = dev_in(m, slot0 + 3, pts->max_distance, cnt, &a->kf.maxDist))) return rc;
+    if ((rc = dev_in(m, slot0 + 4, pts->max_distance_raw, cnt, &a->kf.maxDistRaw))) return rc;
+    if ((rc = dev_in(m, slot0 + 5, pts->descriptors, cnt * 32, &dsc))) return rc;
+    if ((rc = dev_in(m, slot0 + 6, pts->tcw, (size_t)B * 12, &a->kf.tcw))) return rc;
+    if ((rc = dev_in(m, slot0 + 7, t2, (size_t)B * 12, &a->tcw2))) return rc;
+    if ((uintptr_t)dsc & 15) return fail(OBS_ERR_INVALID, "device descriptors must be 16-byte aligned");
+    a->kf.desc = reinterpret_cast<const uint4*>(dsc);
+    a->kf.logScaleFactor = logf(target->prm.nlevels > 1 ? target->prm.scale_factors[1] : 1.2f);
+    a->th = th; a->sim3 = 2;
+    CU(idx.ensure((size_t)B * M));
+    CU(dist.ensure((size_t)B * M));
+    a->bestIdx = idx.p; a->bestDist = dist.p;
+    return OBS_OK;
+}
+
+int obs_search_by_sim3(obs_matcher* m, obs_frame_set* kf1, obs_frame_set* kf2, const obs_keyframe_points_view* points1,
+                       const obs_keyframe_points_view* points2, const float* t21, const float* t12, float th,
+                       int32_t* match12, int32_t* n_found) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!kf1 || !kf2 || !points1 || !points2 || !t21 || !t12 || !match12 || !n_found) return fail(OBS_ERR_INVALID, "null argument");
+    if (kf1->m != m || kf2->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if (kf1->nFrames < 1 || kf1->nFrames != kf2->nFrames) return fail(OBS_ERR_STATE, "frame sets are empty or differ in size");
+    const int B = kf1->nFrames;
+    FuseSearchArgs a1, a2;
+    if ((rc = sim3_side(m, 0, kf2, points1, t21, th, B, &a1, m->sim3Idx[0], m->sim3Dist[0]))) return rc;      // KF1's points into KF2, :1153-1226
+    if ((rc = sim3_side(m, 8, kf1, points2, t12, th, B, &a2, m->sim3Idx[1], m->sim3Dist[1]))) return rc;      // KF2's points into KF1, :1228-1302
+    int *dMatch = nullptr, *dN = nullptr;
+    const size_t oc = (size_t)B * points1->n;
+    if ((rc = dev_out(m, 20, match12, oc, &dMatch))) return rc;
+    if ((rc = dev_out(m, 22, n_found, (size_t)B, &dN))) return rc;
+    CU(launch_fuse_search(a1, B, m->stream));
+    CU(launch_fuse_search(a2, B, m->stream));
+    CU(launch_sim3_agree(a1.bestIdx, a1.bestDist, points1->n, a2.bestIdx, a2.bestDist, points2->n, 100 /* TH_HIGH */, dMatch, dN, B, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, match12, dMatch, oc, &queued))) return rc;
+    if ((rc = host_back(m, n_found, dN, (size_t)B, &queued))) return rc;
     if (queued) CU(cudaStreamSynchronize(m->stream));
     return OBS_OK;
 }

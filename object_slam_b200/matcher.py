@@ -222,6 +222,19 @@ class ORBmatcher:
                                     ptr(best_idx), ptr(best_dist)))
         return best_idx, best_dist
 
+    # ---- ORBmatcher.cc:1102-1326
+    def SearchBySim3(self, kf1, kf2, pts1, pts2, t1w, t2w, t21, t12, th, per_frame=False):
+        """SearchBySim3 for every keyframe pair (kf1[i], kf2[i]); pts1 / pts2: dict(valid, world_pos, min_distance, max_distance,
+        max_distance_raw, descriptors) indexed by the keyframes' keypoints; t21 = [sR21 | t21], t12 = [sR12 | t12].
+        Returns (n_found [B], match12 [B, n1])."""
+        v1, keep1 = self._kf_view(pts1, t1w, None, per_frame)
+        v2, keep2 = self._kf_view(pts2, t2w, None, per_frame)
+        B = len(kf1)
+        a21, a12 = _f32(t21), _f32(t12)
+        m12 = np.empty((B, v1.n), np.int32); nf = np.empty(B, np.int32)
+        check(lib().obs_search_by_sim3(self._h, kf1._h, kf2._h, C.byref(v1), C.byref(v2), ptr(a21), ptr(a12), float(th), ptr(m12), ptr(nf)))
+        return nf, m12
+
     # ---- ORBmatcher.cc:405-520
     def SearchForInitialization(self, f1, f2, prev_matched, window_size=10, matches12=None, n_matches=None):
         """Returns (n_matches[B], vnMatches12[B, cap1]); ``prev_matched`` ([B, cap1, 2] float32) is updated in place."""

@@ -343,3 +343,53 @@ def observation_descriptors(n_points, seed, max_obs=24):
         block[out] = rng.integers(0, 256, (int(out.sum()), 32), dtype=np.uint8)
         desc[start[p]:start[p + 1]] = block
     return desc, start
+
+
+def sim3_pair(shape, n, seed, nlevels=8, bf=TUM_BF):
+    """Two keyframes that see the same n physical points from nearby poses, every keypoint carrying its own map point, and the
+    similarity between the cameras, as ORBmatcher::SearchBySim3 reads them.  Returns (kf1, kf2, pts1, pts2, poses):
+    kf = (keys_un, descriptors, u_right); pts = dict(valid, world_pos, min_distance, max_distance, max_distance_raw, descriptors)
+    indexed by the keyframe's keypoints; poses = dict(t1w, t2w, t21, t12) with t21 = [sR21 | t21], t12 = [sR12 | t12]."""
+    h, w = shape
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, mbf, mb = camera_for(shape, bf)
+    keys1, desc1, ur1 = synthetic_frame(shape, n, seed + 31, nlevels, bf=bf)
+    z = rng.uniform(1.0, 10.0, n)
+    Pc1 = np.stack([(keys1["x"] - cx) / fx * z, (keys1["y"] - cy) / fy * z, z], 1)
+    R1 = _rot(*rng.normal(0, 0.02, 3)); t1 = rng.normal(0, 0.05, 3)
+    Pw = (Pc1 - t1) @ R1
+    R2 = _rot(*rng.normal(0, 0.015, 3)) @ R1
+    t2 = t1 + rng.normal(0, 0.04, 3)
+    Pc2 = Pw @ R2.T + t2
+    keys2 = keys1.copy()
+    keys2["x"] = (fx * Pc2[:, 0] / Pc2[:, 2] + cx + rng.normal(0, 0.8, n)).astype(np.float32)
+    keys2["y"] = (fy * Pc2[:, 1] / Pc2[:, 2] + cy + rng.normal(0, 0.8, n)).astype(np.float32)
+    desc2 = flip_bits(desc1, rng.integers(0, 60, n), rng)
+    ur2 = (keys2["x"] - np.float32(mbf) / Pc2[:, 2]).astype(np.float32)
+    perm = rng.permutation(n)
+    perm = perm[np.argsort(keys2["octave"][perm], kind="stable")]
+    keys2, desc2, ur2, Pw2 = keys2[perm], desc2[perm], ur2[perm], Pw[perm] + rng.normal(0, 0.01, (n, 3))
+    s12 = 1.0 + rng.normal(0, 0.01)
+    R12 = R1 @ R2.T
+    t12 = t1 - R12 @ t2 + rng.normal(0, 0.005, 3)
+    sR12 = s12 * R12
+    sR21 = (1.0 / s12) * R12.T
+    t21 = -sR21 @ t12
+    f32 = lambda R, t: np.hstack([R, np.asarray(t)[:, None]]).astype(np.float32)
+
+    def points(P, octave, desc, Rt, tt, sd):
+        r = np.random.default_rng(sd)
+        d = np.linalg.norm(P @ Rt.T + tt, axis=1).astype(np.float32)          # distance from the camera it is projected into
+        delta = r.choice([0, 0, 0, 0, 0, 0, 0, -1, 1, 2], len(P))
+        raw = (d * np.power(1.2, octave - 0.5 + delta)).astype(np.float32)
+        mind = (np.float32(0.8) * (raw / np.float32(1.2 ** (nlevels - 1)))).astype(np.float32)
+        maxd = (np.float32(1.2) * raw).astype(np.float32)
+        far = r.random(len(P)) < 0.05
+        maxd[far] = (d[far] * 0.5).astype(np.float32)
+        return dict(valid=(r.random(len(P)) < 0.85).astype(np.uint8), world_pos=P.astype(np.float32), min_distance=mind, max_distance=maxd,
+                    max_distance_raw=raw, descriptors=flip_bits(desc, r.integers(0, 12, len(P)), r))
+
+    pts1 = points(Pw, keys1["octave"], desc1, R2, t2, seed + 1)
+    pts2 = points(Pw2, keys2["octave"], desc2, R1, t1, seed + 2)
+    poses = dict(t1w=f32(R1, t1), t2w=f32(R2, t2), t21=f32(sR21, t21), t12=f32(sR12, t12))
+    return (keys1, desc1, ur1), (keys2, desc2, ur2), pts1, pts2, poses

@@ -103,6 +103,7 @@ def _bind_match(L):
     L.orc_search_for_triangulation.argtypes = [C.c_void_p] * 17 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.orc_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.orc_fuse_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p]
+    L.orc_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 5 + ([C.c_int] + [C.c_void_p] * 6) * 2 + [C.c_float, C.c_void_p]
     L.orc_logf.restype = C.c_float
     L.orc_logf.argtypes = [C.c_float]
     L.orc_norm3.restype = C.c_float
@@ -537,3 +538,19 @@ def fuse_search(frame, scale, cam, tcw, pts, th, camera_centre=None, sim3=False)
     lib().orc_fuse_search(frame._h, _ptr(scale), _ptr(inv_sigma2), len(scale), logf(scale[1]), _ptr(cam), _ptr(tcw), _ptr(ow), int(sim3), n,
                           *[_ptr(x) for x in a], float(th), _ptr(bi), _ptr(bd))
     return bi[:n], bd[:n]
+
+
+def search_by_sim3(frame1, frame2, scale, cam, t1w, t2w, t21, t12, pts1, pts2, th):
+    """ORBmatcher::SearchBySim3, src/ORBmatcher.cc:1102-1326.  pts1 / pts2: map points of the keyframes' keypoints (valid = present,
+    not bad, not already matched); t21 = [sR21 | t21], t12 = [sR12 | t12] (12 floats each).  Returns (nFound, match12)."""
+    scale = np.ascontiguousarray(scale, np.float32)
+    cam = np.ascontiguousarray(cam, np.float32)
+    T = [np.ascontiguousarray(t, np.float32).reshape(12) for t in (t1w, t2w, t21, t12)]
+    def side(p):
+        return [np.ascontiguousarray(p[k], t) for k, t in (("valid", np.uint8), ("world_pos", np.float32), ("min_distance", np.float32),
+                                                           ("max_distance", np.float32), ("max_distance_raw", np.float32), ("descriptors", np.uint8))]
+    a, b = side(pts1), side(pts2)
+    m12 = np.empty(max(len(a[0]), 1), np.int32)
+    n = lib().orc_search_by_sim3(frame1._h, frame2._h, _ptr(scale), len(scale), logf(scale[1]), _ptr(cam), *[_ptr(t) for t in T],
+                                 len(a[0]), *[_ptr(x) for x in a], len(b[0]), *[_ptr(x) for x in b], float(th), _ptr(m12))
+    return n, m12[:len(a[0])]

@@ -635,6 +635,42 @@ static void fuse_search(const FrameV& KF, const float* scale, const float* invSi
     }
 }
 
+// One direction of ORBmatcher::SearchBySim3 (ORBmatcher.cc:1153-1226 resp. :1228-1302): map points of the source keyframe
+// (indexed by its keypoints) are taken to the target camera by p3Dc = T2 * (T1 * p3Dw) with T1 = [R1w | t1w] and
+// T2 = [sR21 | t21], projected, gated by the scale-invariance distances on cv::norm(p3Dc), and matched to the closest
+// descriptor in the predicted window; vnMatch[i] = bestIdx if bestDist <= TH_HIGH else -1.
+static void sim3_direction(const FrameV& Target, const float* scale, int nLevels, float logScaleFactor, const Camera& cam, const float* T1,
+                           const float* T2, int nPts, const uint8_t* valid, const float* pos, const float* minDist, const float* maxDist,
+                           const float* maxDistRaw, const uint8_t* desc, float th, int* vnMatch) {
+    for (int i = 0; i < nPts; i++) {
+        vnMatch[i] = -1;
+        if (!valid[i]) continue;
+        float pa[3], pc[3];
+        mat_rx_plus_t(T1, pos + 3 * i, pa);
+        mat_rx_plus_t(T2, pa, pc);
+        if (pc[2] < 0.0) continue;
+        const float invz = (float)(1.0 / pc[2]);
+        const float x = pc[0] * invz, y = pc[1] * invz;
+        const float u = cam.fx * x + cam.cx, v = cam.fy * y + cam.cy;
+        if (!(u >= Target.minX && u < Target.maxX && v >= Target.minY && v < Target.maxY)) continue;
+        const float dist3D = norm3(pc);
+        if (dist3D < minDist[i] || dist3D > maxDist[i]) continue;
+        const int nPredictedLevel = predict_scale(maxDistRaw[i], dist3D, logScaleFactor, nLevels);
+        const float radius = th * scale[nPredictedLevel];
+        const std::vector<size_t> vIndices = Target.features_in_area(u, v, radius);
+        if (vIndices.empty()) continue;
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (size_t vi = 0; vi < vIndices.size(); vi++) {
+            const size_t idx = vIndices[vi];
+            const int oct = Target.k[idx].octave;
+            if (oct < nPredictedLevel - 1 || oct > nPredictedLevel) continue;
+            const int dist = descriptor_distance(desc + (size_t)i * 32, &Target.d[idx * 32]);
+            if (dist < bestDist) { bestDist = dist; bestIdx = (int)idx; }
+        }
+        if (bestDist <= TH_HIGH) vnMatch[i] = bestIdx;
+    }
+}
+
 // Brute-force best / second-best Hamming search with the ratio test: the inner loop of
 // ORBmatcher::SearchByBoW (ORBmatcher.cc:200-229) over one list of candidates, without the
 // "already matched" bookkeeping (every query is independent).  bestIdx = -1 when rejected.
@@ -907,6 +943,27 @@ void orc_fuse_search(const void* f, const float* scale, const float* invSigma2, 
     Camera cam{cam6[0], cam6[1], cam6[2], cam6[3], cam6[4], cam6[5]};
     fuse_search(*(const FrameV*)f, scale, invSigma2, nLevels, logScaleFactor, cam, Tcw, Ow, sim3, nPts, valid, pos, minDist, maxDist,
                 maxDistRaw, normal, desc, th, bestIdx, bestDist);
+}
+
+// ORBmatcher::SearchBySim3, ORBmatcher.cc:1102-1326.  valid1 / valid2 = "map point non-NULL, not bad, not already matched"
+// (:1157-1162, :1232-1237 with vbAlreadyMatched of :1131-1143); T1w, T2w = [R | t] of the keyframes; T21 = [sR21 | t21],
+// T12 = [sR12 | t12] as :1119-1122 builds them.  match12[i1] = idx2 where both directions agree (:1305-1319), else -1.
+int orc_search_by_sim3(const void* f1, const void* f2, const float* scale, int nLevels, float logScaleFactor, const float* cam6,
+                       const float* T1w, const float* T2w, const float* T21, const float* T12,
+                       int n1, const uint8_t* valid1, const float* pos1, const float* minD1, const float* maxD1, const float* raw1, const uint8_t* desc1,
+                       int n2, const uint8_t* valid2, const float* pos2, const float* minD2, const float* maxD2, const float* raw2, const uint8_t* desc2,
+                       float th, int* match12) {
+    Camera cam{cam6[0], cam6[1], cam6[2], cam6[3], cam6[4], cam6[5]};
+    std::vector<int> vn1(std::max(n1, 1)), vn2(std::max(n2, 1));
+    sim3_direction(*(const FrameV*)f2, scale, nLevels, logScaleFactor, cam, T1w, T21, n1, valid1, pos1, minD1, maxD1, raw1, desc1, th, vn1.data());
+    sim3_direction(*(const FrameV*)f1, scale, nLevels, logScaleFactor, cam, T2w, T12, n2, valid2, pos2, minD2, maxD2, raw2, desc2, th, vn2.data());
+    int nFound = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        match12[i1] = -1;
+        const int idx2 = vn1[i1];
+        if (idx2 >= 0 && idx2 < n2 && vn2[idx2] == i1) { match12[i1] = idx2; nFound++; }
+    }
+    return nFound;
 }
 
 float orc_logf(float x) { return logf(x); }

@@ -360,3 +360,19 @@ def test_fuse_search_matches_oracle(M, sim3, th):
         assert np.array_equal(bi[b], oi) and np.array_equal(bd[b], od)
         total += int(((od <= 50) & (oi >= 0)).sum())
     assert total > 100
+
+
+@pytest.mark.parametrize("th", [7.5, 3.0])
+def test_search_by_sim3_matches_oracle(M, th):
+    """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1102-1326): both projection directions and the agreement check."""
+    shape = TUM
+    cases = [synth.sim3_pair(shape, 1000, s) for s in (40, 41, 42)]
+    s1 = frame_set(M, shape, [c[0] for c in cases]); s2 = frame_set(M, shape, [c[1] for c in cases])
+    st = lambda i: {k: np.stack([c[i][k] for c in cases]) for k in cases[0][i]}
+    T = {k: np.stack([c[4][k] for c in cases]) for k in cases[0][4]}
+    nf, m12 = M.SearchBySim3(s1, s2, st(2), st(3), T["t1w"], T["t2w"], T["t21"], T["t12"], th, per_frame=True)
+    for b, (k1, k2, p1, p2, P) in enumerate(cases):
+        on, om = oracle.search_by_sim3(oracle_frame(k1, shape), oracle_frame(k2, shape), synth.scale_factors(), synth.camera_for(shape),
+                                       P["t1w"], P["t2w"], P["t21"], P["t12"], p1, p2, th)
+        assert nf[b] == on and np.array_equal(m12[b], om)
+        assert on > 100
