@@ -154,13 +154,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=64, help="stereo frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=128, help="stereo frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=256, help="stereo frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-pipelines", type=int, default=3, help="host-buffer pipelines of the e2e leg (each: an extractor pair + pinned buffers)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (0 = min(steps, 12))")
-    ap.add_argument("--workload", default="stereo", choices=["stereo", "knn2", "projection"],
+    ap.add_argument("--workload", default="stereo", choices=["stereo", "knn2", "projection", "bow"],
                     help="stereo = configs[1] (the headline); knn2 = configs[4] keyframe-vs-keyframe Hamming matching; "
                          "projection = configs[2] TUM-shape extraction + SearchByProjection against a 20k-point map")
     ap.add_argument("--keyframes", type=int, default=4096, help="knn2: keyframes in total (sharded over the GPUs)")

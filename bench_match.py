@@ -412,7 +412,156 @@ def _hbm_peak():
         return 6650.0
 
 
+# ------------------------------------------------------------------------------------------------ bow
+def cpu_bow(pairs, cores, ratio):
+    import oracle
+    def one(p):
+        return oracle.search_by_bow(p[0], p[1], TH_LOW, True, ratio, True)[0]
+    with ThreadPoolExecutor(cores) as pool:
+        list(pool.map(one, pairs[:cores]))
+        t0 = time.perf_counter()
+        list(pool.map(one, pairs))
+        return time.perf_counter() - t0
+
+
+def run_bow(args, rank, local_rank, world, ClockSampler):
+    """SearchByBoW(KeyFrame*, KeyFrame*) (ORBmatcher.cc:522-655) over batches of synthetic keyframe pairs: 2000 keypoints, 100
+    vocabulary nodes, ratio 0.8; pairs sharded over the ranks, no collective (weak scaling)."""
+    NKP, NODES, RAT = 2000, 100, 0.8
+    Bp = args.frames                                           # keyframe pairs per step per GPU
+    metric = "keyframe pairs/s, ORBmatcher::SearchByBoW(KF, KF), 2000 keypoints per keyframe, 100 vocabulary nodes"
+    uniq = [synth.bow_pair(synth.KITTI_SHAPE, NKP, 500 + i, n_nodes=NODES)[:2] for i in range(8)]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        sp = [uniq[i % 8] for i in range(max(512 * cores, 2048))]
+        total = 0.0
+        for _ in range(args.warmup):
+            cpu_bow(sp[:cores], cores, RAT)
+        for _ in range(args.steps):
+            total += cpu_bow(sp, cores, RAT)
+        v = len(sp) * args.steps / total
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u32 popcount", "data": "synthetic",
+                          "config": {"workload": "SearchByBoW keyframe pairs", "pairs_per_step": len(sp)},
+                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                           "sample": f"{len(sp)} keyframe pairs per step, restated SearchByBoW (oracle/match_oracle.cpp)"},
+                          "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    from object_slam_b200._capi import BowSide, check, lib
+    from object_slam_b200.matcher import ORBmatcher
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    M = ORBmatcher(RAT, True, device=local_rank)
+    s1, k1 = M._pack_side([uniq[(rank * Bp + i) % 8][0] for i in range(Bp)])
+    s2, k2 = M._pack_side([uniq[(rank * Bp + i) % 8][1] for i in range(Bp)])
+
+    def to_dev(side, pk):
+        keep = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.uint8).reshape(-1)).to(dev) for k, v in pk.items() if v is not None}
+        d = BowSide(side.cap, side.node_cap, *[keep[k].data_ptr() if k in keep else None
+                                               for k in ("n", "descriptors", "keys_un", "valid", "u_right", "n_nodes", "node_id", "node_start", "node_idx")])
+        return d, keep
+    d1, keep1 = to_dev(s1, k1)
+    d2, keep2 = to_dev(s2, k2)
+    m12 = torch.empty((Bp, s1.cap), dtype=torch.int32, device=dev); m21 = torch.empty((Bp, s2.cap), dtype=torch.int32, device=dev)
+    nm = torch.empty(Bp, dtype=torch.int32, device=dev)
+    h12 = np.empty((Bp, s1.cap), np.int32); h21 = np.empty((Bp, s2.cap), np.int32); hn = np.empty(Bp, np.int32)
+
+    def step():
+        check(lib().obs_search_by_bow(M._h, C.byref(d1), C.byref(d2), Bp, TH_LOW, 1, RAT, 1, C.c_void_p(m12.data_ptr()),
+                                      C.c_void_p(m21.data_ptr()), C.c_void_p(nm.data_ptr())))
+
+    def step_host():
+        check(lib().obs_search_by_bow(M._h, C.byref(s1), C.byref(s2), Bp, TH_LOW, 1, RAT, 1, h12.ctypes.data_as(C.c_void_p),
+                                      h21.ctypes.data_as(C.c_void_p), hn.ctypes.data_as(C.c_void_p)))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ms_stream = torch.cuda.ExternalStream(M.stream)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ms_stream):
+        e0.record()
+    for _ in range(args.steps):
+        step()
+    with torch.cuda.stream(ms_stream):
+        e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t[0])
+    value = world * Bp * args.steps / (ms_total * 1e-3)
+    step_host()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * Bp * e2e_steps / float(t.item())
+    if rank == 0:
+        # distance evaluations of one step: per common node, valid keypoints of side 1 x keypoints of side 2 (an upper bound on what the
+        # kernel evaluates: matched keypoints of side 2 are skipped)
+        cand = 0
+        for a, b in uniq:
+            na = {int(a["node_id"][k]): (int(a["node_start"][k]), int(a["node_start"][k + 1])) for k in range(len(a["node_id"]))}
+            for k in range(len(b["node_id"])):
+                r = na.get(int(b["node_id"][k]))
+                if r:
+                    cand += int(a["valid"][a["node_idx"][r[0]:r[1]]].sum()) * int(b["valid"][b["node_idx"][b["node_start"][k]:b["node_start"][k + 1]]].sum())
+        cand_per_pair = cand / len(uniq)
+        popc_only = _popc_peak(2)
+        ach = 8.0 * cand_per_pair * Bp / (ms_total / args.steps * 1e-3)
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            sp = [uniq[i % 8] for i in range(max(1024 * cores, 4096))]
+            dt = cpu_bow(sp, cores, RAT)
+            cpu = {"value": len(sp) / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                   "sample": f"{len(sp)} keyframe pairs on {cores} host threads, {dt:.2f} s; restated SearchByBoW (oracle/match_oracle.cpp)"}
+        print(json.dumps({
+            "metric": metric, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 popcount",
+            "data": "synthetic",
+            "config": {"workload": f"SearchByBoW(KF, KF): {Bp} keyframe pairs per step per GPU, {NKP} keypoints, {NODES} nodes, ratio {RAT}, TH_LOW 50, "
+                                   "orientation check", "parallelism": f"pairs sharded over {world} GPU(s), no collective",
+                       "candidate_distances_per_pair": cand_per_pair, "accepted_matches_first_pair": int(nm[0].item())},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(sum(v.nbytes for v in list(k1.values()) + list(k2.values()) if v is not None)),
+                    "d2h_bytes_per_step": int(h12.nbytes + h21.nbytes + hn.nbytes), "steps": e2e_steps,
+                    "api": "obs_search_by_bow with host arrays in and out (pageable numpy buffers)"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "int-popc", "kernel": "k_bow_search", "achieved": ach / 1e12, "peak": popc_only * 8e9 / 1e12, "unit": "Tpopc/s",
+                         "frac": ach / (popc_only * 8e9), "traffic": None,
+                         "peak_source": "obs_microbench_popc mode 2 measured in this run; the kernel is latency bound (one warp per vocabulary "
+                                        "node, sequential over the node's keypoints as the reference's order demands), not popc bound"},
+            "cpu_baseline": cpu}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run(args, rank, local_rank, world, ClockSampler):
+    if args.workload == "bow":
+        return run_bow(args, rank, local_rank, world, ClockSampler)
     if args.workload == "knn2":
         return run_knn2(args, rank, local_rank, world, ClockSampler)
     return run_projection(args, rank, local_rank, world, ClockSampler)
