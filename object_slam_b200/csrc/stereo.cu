@@ -160,34 +160,57 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
                 const uint8_t* cL = imL + (size_t)cy * pl + cxL;
                 const uint8_t* cR = imR + (size_t)cy * pr + cxR;
                 const int centreL = cL[0];
-                int lv[4], offR[4];
+                // Lane's (up to 4) patch pixels e = lane + 32 t; for each it needs the 11 right-image bytes under the 11 shifts,
+                // fetched as four aligned words and shifted into place (three words A0..A2 = shifts -5..-2, -1..2, 3..5).
+                int lv[4];
+                unsigned A0[4], A1[4], A2[4];
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     const int e = lane + 32 * t;
                     const int py = e / 11, px = e - py * 11;
                     const bool on = e < 121;
                     lv[t] = on ? (int)cL[(py - w) * pl + (px - w)] - centreL : 0;
-                    offR[t] = on ? (py - w) * pr + (px - w) : 0x7fffffff;
+                    A0[t] = A1[t] = A2[t] = 0;
+                    if (on) {
+                        const uint8_t* rp = cR + (py - w) * pr + (px - w) - Ls;         // byte under shift -5
+                        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(rp) & 3);
+                        const uint32_t* q = reinterpret_cast<const uint32_t*>(rp - mis);
+                        const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = mis >= 2 ? __ldg(q + 3) : 0u;   // 11 bytes from offset mis
+                        A0[t] = __funnelshift_r(w0, w1, 8 * mis);
+                        A1[t] = __funnelshift_r(w1, w2, 8 * mis);
+                        A2[t] = __funnelshift_r(w2, w3, 8 * mis);
+                    }
                 }
-                // the right strip: lane's pixels at the 11 shifts (offsets offR[t] - 5 .. offR[t] + 5)
+                const unsigned onMask = (lane + 96 < 121) ? 0xfu : 0x7u;                 // which t are patch pixels for this lane
+                unsigned c0, c1, c2;                                                      // the centre row's bytes: cR[-5..5]
+                {
+                    const uint8_t* rp = cR - Ls;
+                    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(rp) & 3);
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(rp - mis);
+                    const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = mis >= 2 ? __ldg(q + 3) : 0u;   // 11 bytes from offset mis
+                    c0 = __funnelshift_r(w0, w1, 8 * mis); c1 = __funnelshift_r(w1, w2, 8 * mis); c2 = __funnelshift_r(w2, w3, 8 * mis);
+                }
                 int bestSad = 0x7fffffff, bestInc = 0;
-                int sads[11];
+                int mySad = 0;                                                            // lane k keeps the SAD of shift k - 5
 #pragma unroll
                 for (int inc = -Ls; inc <= Ls; inc++) {
-                    const int centreR = cR[inc];
+                    const int k = inc + Ls;
+                    const unsigned sel = 0x4440u | (unsigned)(k & 3);                     // byte k & 3 of the word, zero extended
+                    const int centreR = (int)__byte_perm(k < 4 ? c0 : k < 8 ? c1 : c2, 0u, sel);
                     int s = 0;
 #pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if (offR[t] != 0x7fffffff) s += abs(lv[t] - ((int)cR[offR[t] + inc] - centreR));
+                    for (int t = 0; t < 4; t++) {
+                        const int r = (int)__byte_perm(k < 4 ? A0[t] : k < 8 ? A1[t] : A2[t], 0u, sel);
+                        if (t < 3 || onMask == 0xfu) s = (int)__sad(lv[t] + centreR, r, (unsigned)s);
+                    }
                     s = __reduce_add_sync(0xffffffffu, s);
-                    sads[inc + Ls] = s;
+                    if (lane == k) mySad = s;
                     if (s < bestSad) { bestSad = s; bestInc = inc; }
                 }
                 if (bestInc != -Ls && bestInc != Ls) {
-                    float d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-                    for (int k = 1; k < 10; k++)
-                        if (k == bestInc + Ls) { d1 = (float)sads[k - 1]; d2 = (float)sads[k]; d3 = (float)sads[k + 1]; }
+                    const float d1 = (float)__shfl_sync(0xffffffffu, mySad, bestInc + Ls - 1);
+                    const float d2 = (float)__shfl_sync(0xffffffffu, mySad, bestInc + Ls);
+                    const float d3 = (float)__shfl_sync(0xffffffffu, mySad, bestInc + Ls + 1);
                     const float deltaR = __fdiv_rn(__fsub_rn(d1, d3),
                                                    __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
                     if (!(deltaR < -1 || deltaR > 1)) {
