@@ -395,6 +395,18 @@ int obs_search_for_triangulation(obs_matcher* m, const obs_bow_side* side1, cons
 int obs_distinctive_descriptors(obs_matcher* m, const uint8_t* descriptors, const int32_t* start, int n_points,
                                 int32_t* best);
 
+/* Keypoint-to-mask assignment at the head of Frame::BuildObject2DsRGBD (src/Frame.cc:240-311, min_keypoints = 5) and
+ * Frame::BuildObject2DsStereo (:314-385, min_keypoints = 10): the semantic masks (n_masks 8-bit images of w x h, 255 = object) are
+ * visited in order; a keypoint not taken by an earlier mask goes to the mask if mask(int(y + row), int(x + col)) == 255 for all
+ * row, col in [-10, 10) and 0 < depth <= th_depth (mThDepth); a mask with more than min_keypoints keypoints becomes the next
+ * Object2D.  mask_of_kp (n, may be NULL): the mask that took the keypoint or -1; object_kp_indices (n x 2): mvObjectKpIndices =
+ * (Object2D index, index inside the object's keypoint list) or (-1, -1); object_of_mask (n_masks, may be NULL); n_objects: N_O.
+ * Windows that leave the image (undefined behaviour in the reference) reject.  Host or device arrays. */
+int obs_assign_keypoints_to_masks(obs_matcher* m, const obs_keypoint* keys_un, const float* depth, int n, const uint8_t* masks,
+                                  int n_masks, int w, int h, size_t mask_stride, size_t mask_image_stride, float th_depth,
+                                  int min_keypoints, int32_t* mask_of_kp, int32_t* object_kp_indices, int32_t* object_of_mask,
+                                  int32_t* n_objects);
+
 /* ---------------------------------------------------------------------------------------
  * Multi-GPU exchange step of batched keyframe-vs-keyframe matching: every rank (one process per GPU)
  * owns a contiguous shard of the keyframes as queries and needs all descriptor sets as database.

@@ -151,3 +151,18 @@ struct TriSearchArgs {        // SearchForTriangulation (ORBmatcher.cc:657-823)
 cudaError_t launch_tri_search(const TriSearchArgs& a, int nPairs, cudaStream_t st);
 // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:345-410) over a CSR of descriptor lists
 cudaError_t launch_distinctive(const uint4* desc, const int* start, int nPoints, int* best, cudaStream_t st);
+
+// ---- object layer (objects.cu): keypoint-to-mask assignment of Frame::BuildObject2DsRGBD / BuildObject2DsStereo (src/Frame.cc:240-311, :314-385)
+struct MaskAssignArgs {
+    const float* keys;        // [n][7] cv::KeyPoint words (mvKeysUn)
+    const float* depth;       // [n] mvDepth
+    int n;
+    const uint8_t* masks;     // n_masks images, rowStride bytes per row, imageStride bytes per mask
+    int nMasks, w, h; size_t rowStride, imageStride;
+    float thDepth; int minKeypoints;
+    int* maskOfKp;            // [n] first mask whose 20x20 window is all 255 (and 0 < depth <= thDepth), else -1
+    int* objectKp;            // [n][2] mvObjectKpIndices: (Object2D index, index inside the object) or (-1, -1)
+    int* objectOfMask;        // [nMasks] Object2D index created for the mask, or -1
+    int* nObjects;            // [1]
+};
+cudaError_t launch_mask_assign(const MaskAssignArgs& a, cudaStream_t st);

@@ -698,4 +698,40 @@ int obs_distinctive_descriptors(obs_matcher* m, const uint8_t* descriptors, cons
     return OBS_OK;
 }
 
+int obs_assign_keypoints_to_masks(obs_matcher* m, const obs_keypoint* keys_un, const float* depth, int n, const uint8_t* masks,
+                                  int n_masks, int w, int h, size_t mask_stride, size_t mask_image_stride, float th_depth,
+                                  int min_keypoints, int32_t* mask_of_kp, int32_t* object_kp_indices, int32_t* object_of_mask,
+                                  int32_t* n_objects) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!keys_un || !depth || !masks || !object_kp_indices || !n_objects) return fail(OBS_ERR_INVALID, "null argument");
+    if (n < 1 || n_masks < 1 || w < 1 || h < 1 || mask_stride < (size_t)w || mask_image_stride < mask_stride * (size_t)h)
+        return fail(OBS_ERR_INVALID, "sizes / strides out of range");
+    if (mask_stride * (size_t)h > 0x7fffffffu) return fail(OBS_ERR_INVALID, "mask too large");
+    MaskAssignArgs a;
+    memset(&a, 0, sizeof(a));
+    const obs_keypoint* dk = nullptr;
+    if ((rc = dev_in(m, 0, keys_un, (size_t)n, &dk))) return rc;
+    a.keys = reinterpret_cast<const float*>(dk);
+    if ((rc = dev_in(m, 1, depth, (size_t)n, &a.depth))) return rc;
+    if ((rc = dev_in(m, 2, masks, (size_t)n_masks * mask_image_stride, &a.masks))) return rc;
+    a.n = n; a.nMasks = n_masks; a.w = w; a.h = h; a.rowStride = mask_stride; a.imageStride = mask_image_stride;
+    a.thDepth = th_depth; a.minKeypoints = min_keypoints;
+    CU(m->choice.ensure((size_t)n + n_masks));
+    if ((rc = dev_out(m, 20, mask_of_kp, (size_t)n, &a.maskOfKp))) return rc;
+    if (!a.maskOfKp) a.maskOfKp = m->choice.p;
+    if ((rc = dev_out(m, 21, object_kp_indices, (size_t)n * 2, &a.objectKp))) return rc;
+    if ((rc = dev_out(m, 22, object_of_mask, (size_t)n_masks, &a.objectOfMask))) return rc;
+    if (!a.objectOfMask) a.objectOfMask = m->choice.p + n;
+    if ((rc = dev_out(m, 23, n_objects, 1, &a.nObjects))) return rc;
+    CU(launch_mask_assign(a, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, mask_of_kp, a.maskOfKp, (size_t)n, &queued))) return rc;
+    if ((rc = host_back(m, object_kp_indices, a.objectKp, (size_t)n * 2, &queued))) return rc;
+    if ((rc = host_back(m, object_of_mask, a.objectOfMask, (size_t)n_masks, &queued))) return rc;
+    if ((rc = host_back(m, n_objects, a.nObjects, 1, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,112 @@
+// Object-layer pixel ops that read the same frame as the ORB front end: the keypoint-to-mask assignment at the head of
+// Frame::BuildObject2DsRGBD (src/Frame.cc:240-311) and Frame::BuildObject2DsStereo (:314-385).
+//
+// The reference walks the semantic masks in order and, for each, the keypoints not yet taken by an earlier mask: a keypoint goes to
+// the mask if the 20 x 20 window mask(int(y + row), int(x + col)), row, col in [-10, 10), is 255 everywhere and 0 < depth <= mThDepth.
+// Taken keypoints are erased from the pool whether or not the mask ends up with enough keypoints to become an Object2D
+// (> 5 for RGB-D, > 10 for stereo).  So "first mask that accepts the keypoint" is a per-keypoint question (k_mask_first, one
+// warp per keypoint), and the Object2D numbering / in-object indices are counts and ranks over that answer (k_mask_number).
+// Windows that leave the image are undefined behaviour in the reference (cv::Mat::at without a bounds check); they reject here.
+#include "matcher.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_mask_first(const __grid_constant__ MaskAssignArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= A.n) return;
+    const float x = A.keys[k * 7], y = A.keys[k * 7 + 1];
+    const float z = A.depth[k];
+    int first = -1;
+    if (z > 0.0f && z <= A.thDepth) {
+        // the lane's window pixels (row, col) = (e / 20 - 10, e % 20 - 10), e = lane + 32 t; indices as the reference forms them:
+        // float addition, then truncation
+        int off[13];
+#pragma unroll
+        for (int t = 0; t < 13; t++) {
+            const int e = lane + 32 * t;
+            off[t] = -1;
+            if (e < 400) {
+                const int row = e / 20 - 10, col = e - (e / 20) * 20 - 10;
+                const int iy = (int)__fadd_rn(y, (float)row), ix = (int)__fadd_rn(x, (float)col);
+                if (iy >= 0 && iy < A.h && ix >= 0 && ix < A.w) off[t] = iy * (int)A.rowStride + ix;
+                else off[t] = -2;                                  // outside the image: rejects
+            }
+        }
+        for (int m = 0; m < A.nMasks && first < 0; m++) {
+            const uint8_t* mk = A.masks + (size_t)m * A.imageStride;
+            bool ok = true;
+#pragma unroll
+            for (int t = 0; t < 13; t++) {
+                if (off[t] == -2) ok = false;
+                else if (off[t] >= 0 && __ldg(mk + off[t]) != 255) ok = false;
+            }
+            if (__all_sync(0xffffffffu, ok)) first = m;
+        }
+    }
+    if (lane == 0) A.maskOfKp[k] = first;
+}
+
+// One CTA: per mask, the keypoints assigned to it in ascending index order -> (object, j); objects are numbered in mask order.
+__global__ void __launch_bounds__(1024) k_mask_number(const __grid_constant__ MaskAssignArgs A) {
+    __shared__ int sWarp[33];
+    __shared__ int sObj;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sObj = 0;
+    for (int i = tid; i < A.n; i += 1024) { A.objectKp[2 * i] = -1; A.objectKp[2 * i + 1] = -1; }
+    __syncthreads();
+    for (int m = 0; m < A.nMasks; m++) {
+        // pass 1: count
+        int mine = 0;
+        for (int i = tid; i < A.n; i += 1024) mine += A.maskOfKp[i] == m;
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0) sWarp[warp] = mine;
+        __syncthreads();
+        if (warp == 0) {
+            int v = sWarp[lane];
+            v = __reduce_add_sync(0xffffffffu, v);
+            if (lane == 0) sWarp[32] = v;
+        }
+        __syncthreads();
+        const int total = sWarp[32];
+        const int obj = sObj;
+        __syncthreads();
+        if (total > A.minKeypoints) {
+            // pass 2: rank in ascending keypoint order (chunks of 1024 with a running carry)
+            int carry = 0;
+            for (int base = 0; base < A.n; base += 1024) {
+                const int i = base + tid;
+                const int f = (i < A.n && A.maskOfKp[i] == m) ? 1 : 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, f);
+                if (lane == 0) sWarp[warp] = __popc(bal);
+                __syncthreads();
+                if (warp == 0) {
+                    const int v = sWarp[lane];
+                    int incl = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                    sWarp[lane] = incl - v;
+                    if (lane == 31) sWarp[32] = incl;
+                }
+                __syncthreads();
+                if (f) {
+                    A.objectKp[2 * i] = obj;
+                    A.objectKp[2 * i + 1] = carry + sWarp[warp] + __popc(bal & ((1u << lane) - 1));
+                }
+                carry += sWarp[32];
+                __syncthreads();
+            }
+            if (tid == 0) { A.objectOfMask[m] = obj; sObj = obj + 1; }
+        } else if (tid == 0) A.objectOfMask[m] = -1;
+        __syncthreads();
+    }
+    if (tid == 0) *A.nObjects = sObj;
+}
+
+}  // namespace
+
+cudaError_t launch_mask_assign(const MaskAssignArgs& a, cudaStream_t st) {
+    if (a.n > 0) k_mask_first<<<(a.n + 7) / 8, 256, 0, st>>>(a);
+    k_mask_number<<<1, 1024, 0, st>>>(a);
+    return cudaGetLastError();
+}

@@ -335,3 +335,13 @@ class ORBmatcher:
         best = np.empty(max(n_points, 1), np.int32)
         check(lib().obs_distinctive_descriptors(self._h, ptr(d), ptr(st), n_points, ptr(best)))
         return best[:n_points]
+
+    # ---- object layer: Frame::BuildObject2DsRGBD / BuildObject2DsStereo, src/Frame.cc:240-385 (keypoint-to-mask assignment)
+    def AssignKeypointsToMasks(self, keys_un, depth, masks, th_depth, min_keypoints=5):
+        """masks: [n_masks, h, w] uint8 (255 = object).  Returns (mask_of_kp [n], mvObjectKpIndices [n, 2], object_of_mask [n_masks], N_O)."""
+        k = np.ascontiguousarray(keys_un); d = _f32(depth); mk = _u8(masks)
+        n, (nm, h, w) = len(k), mk.shape
+        mo = np.empty(n, np.int32); ok = np.empty((n, 2), np.int32); om = np.empty(nm, np.int32); no = np.zeros(1, np.int32)
+        check(lib().obs_assign_keypoints_to_masks(self._h, ptr(k), ptr(d), n, ptr(mk), nm, w, h, w, w * h, float(th_depth), int(min_keypoints),
+                                                  ptr(mo), ptr(ok), ptr(om), ptr(no)))
+        return mo, ok, om, int(no[0])

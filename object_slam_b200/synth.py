@@ -393,3 +393,22 @@ def sim3_pair(shape, n, seed, nlevels=8, bf=TUM_BF):
     pts2 = points(Pw2, keys2["octave"], desc2, R1, t1, seed + 2)
     poses = dict(t1w=f32(R1, t1), t2w=f32(R2, t2), t21=f32(sR21, t21), t12=f32(sR12, t12))
     return (keys1, desc1, ur1), (keys2, desc2, ur2), pts1, pts2, poses
+
+
+def semantic_masks(shape, n_masks, seed):
+    """n_masks instance masks (255 = object) as a detector would return them: filled ellipses and boxes of assorted sizes, some
+    overlapping (a keypoint then belongs to the first), some too small to hold a 20 x 20 window."""
+    h, w = shape
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    out = np.zeros((n_masks, h, w), np.uint8)
+    for m in range(n_masks):
+        cx, cy = rng.uniform(0.1 * w, 0.9 * w), rng.uniform(0.1 * h, 0.9 * h)
+        rx, ry = rng.uniform(8, 0.3 * w), rng.uniform(8, 0.35 * h)
+        if rng.random() < 0.5:
+            out[m][((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2 <= 1.0] = 255
+        else:
+            out[m][(abs(xx - cx) <= rx) & (abs(yy - cy) <= ry)] = 255
+        if rng.random() < 0.3:                                # a hole
+            out[m][(abs(xx - cx) <= rx * 0.2) & (abs(yy - cy) <= ry * 0.2)] = 0
+    return out

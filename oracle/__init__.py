@@ -104,6 +104,7 @@ def _bind_match(L):
     L.orc_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.orc_fuse_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p]
     L.orc_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 5 + ([C.c_int] + [C.c_void_p] * 6) * 2 + [C.c_float, C.c_void_p]
+    L.orc_assign_keypoints_to_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_logf.restype = C.c_float
     L.orc_logf.argtypes = [C.c_float]
     L.orc_norm3.restype = C.c_float
@@ -554,3 +555,13 @@ def search_by_sim3(frame1, frame2, scale, cam, t1w, t2w, t21, t12, pts1, pts2, t
     n = lib().orc_search_by_sim3(frame1._h, frame2._h, _ptr(scale), len(scale), logf(scale[1]), _ptr(cam), *[_ptr(t) for t in T],
                                  len(a[0]), *[_ptr(x) for x in a], len(b[0]), *[_ptr(x) for x in b], float(th), _ptr(m12))
     return n, m12[:len(a[0])]
+
+
+def assign_keypoints_to_masks(keys_un, depth, masks, th_depth, min_keypoints=5):
+    """Head of Frame::BuildObject2DsRGBD / BuildObject2DsStereo (src/Frame.cc:240-385).  masks: [n_masks, h, w] uint8.
+    Returns (mask_of_kp, mvObjectKpIndices [n, 2], object_of_mask, N_O)."""
+    k = np.ascontiguousarray(keys_un); d = np.ascontiguousarray(depth, np.float32); mk = np.ascontiguousarray(masks, np.uint8)
+    n, (nm, h, w) = len(k), mk.shape
+    mo = np.empty(max(n, 1), np.int32); ok = np.empty((max(n, 1), 2), np.int32); om = np.empty(max(nm, 1), np.int32)
+    no = lib().orc_assign_keypoints_to_masks(_ptr(k), _ptr(d), n, _ptr(mk), nm, w, h, float(th_depth), int(min_keypoints), _ptr(mo), _ptr(ok), _ptr(om))
+    return mo[:n], ok[:n], om[:nm], no

@@ -966,6 +966,45 @@ int orc_search_by_sim3(const void* f1, const void* f2, const float* scale, int n
     return nFound;
 }
 
+// Head of Frame::BuildObject2DsRGBD (Frame.cc:240-311, minKeypoints = 5) / BuildObject2DsStereo (:314-385, minKeypoints = 10): the
+// pool of (index, keypoint) pairs, the masks in order, erase on acceptance, Object2D numbering.  Windows that leave the image are
+// undefined in the reference (cv::Mat::at) and reject here.
+int orc_assign_keypoints_to_masks(const void* keysUn, const float* depth, int n, const uint8_t* masks, int nMasks, int w, int h,
+                                  float thDepth, int minKeypoints, int* maskOfKp, int* objectKp, int* objectOfMask) {
+    const KeyPt* kps = (const KeyPt*)keysUn;
+    std::vector<std::pair<int, KeyPt>> vIndex_Kp;
+    for (int i = 0; i < n; i++) { vIndex_Kp.push_back(std::make_pair(i, kps[i])); maskOfKp[i] = -1; objectKp[2 * i] = objectKp[2 * i + 1] = -1; }
+    int nObjects = 0;
+    for (int i = 0; i < nMasks; i++) {
+        const uint8_t* mask = masks + (size_t)i * w * h;
+        std::vector<int> vFrameKpIndices;
+        auto it = vIndex_Kp.begin();
+        while (it != vIndex_Kp.end()) {
+            const KeyPt kp = it->second;
+            const float kp_z = depth[it->first];
+            bool semantic_flag = true;
+            for (int row = -10; row < 10; row++)
+                for (int col = -10; col < 10; col++) {
+                    const int iy = (int)(kp.y + row), ix = (int)(kp.x + col);
+                    if (iy < 0 || iy >= h || ix < 0 || ix >= w) { semantic_flag = false; continue; }
+                    if ((int)mask[(size_t)iy * w + ix] != 255) semantic_flag = false;
+                }
+            if (semantic_flag && kp_z > 0 && kp_z <= thDepth) {
+                vFrameKpIndices.push_back(it->first);
+                maskOfKp[it->first] = i;
+                it = vIndex_Kp.erase(it);
+            } else ++it;
+        }
+        const int VaildKpNum = (int)vFrameKpIndices.size();
+        objectOfMask[i] = -1;
+        if (VaildKpNum > minKeypoints) {
+            for (int j = 0; j < VaildKpNum; j++) { objectKp[2 * vFrameKpIndices[j]] = nObjects; objectKp[2 * vFrameKpIndices[j] + 1] = j; }
+            objectOfMask[i] = nObjects++;
+        }
+    }
+    return nObjects;
+}
+
 float orc_logf(float x) { return logf(x); }
 float orc_norm3(const float* v) { return norm3(v); }
 int orc_predict_scale(float maxDistRaw, float dist, float logScaleFactor, int nLevels) { return predict_scale(maxDistRaw, dist, logScaleFactor, nLevels); }

@@ -281,3 +281,52 @@ def test_gpu_bow_matches_golden(matcher):
     matcher.mfNNratio = 0.7
     d, s = synth.observation_descriptors(500, 13)
     assert np.array_equal(matcher.ComputeDistinctiveDescriptors(d, s), want["distinctive"])
+
+
+# ------------------------------------------------------------------------------------------------ object layer
+def py_assign(keys, depth, masks, th_depth, min_kp):
+    """independent restatement: per keypoint the first accepting mask, then counts / ranks"""
+    n = len(keys); nm, h, w = masks.shape
+    first = -np.ones(n, np.int32)
+    for k in range(n):
+        if not (depth[k] > 0 and depth[k] <= th_depth):
+            continue
+        iy = (np.float32(keys["y"][k]) + np.arange(-10, 10, dtype=np.float32)).astype(np.int64)
+        ix = (np.float32(keys["x"][k]) + np.arange(-10, 10, dtype=np.float32)).astype(np.int64)
+        if iy.min() < 0 or iy.max() >= h or ix.min() < 0 or ix.max() >= w:
+            continue
+        for m in range(nm):
+            if (masks[m][np.ix_(iy, ix)] == 255).all():
+                first[k] = m
+                break
+    okp = -np.ones((n, 2), np.int32); om = -np.ones(nm, np.int32); nobj = 0
+    for m in range(nm):
+        idx = np.flatnonzero(first == m)
+        if len(idx) > min_kp:
+            okp[idx, 0] = nobj; okp[idx, 1] = np.arange(len(idx)); om[m] = nobj; nobj += 1
+    return first, okp, om, nobj
+
+
+def _mask_case(seed, n=1500, n_masks=9):
+    keys, _, _ = synth.synthetic_frame(synth.TUM_SHAPE, n, seed)
+    rng = np.random.default_rng(seed)
+    depth = rng.uniform(-0.5, 6.0, n).astype(np.float32)
+    return keys, depth, synth.semantic_masks(synth.TUM_SHAPE, n_masks, seed + 1)
+
+
+@pytest.mark.parametrize("seed,min_kp", [(1, 5), (2, 10), (3, 5)])
+def test_oracle_vs_python_mask_assignment(seed, min_kp):
+    keys, depth, masks = _mask_case(seed)
+    got = oracle.assign_keypoints_to_masks(keys, depth, masks, 3.5, min_kp)
+    want = py_assign(keys, depth, masks, 3.5, min_kp)
+    assert all(np.array_equal(a, b) for a, b in zip(got[:3], want[:3])) and got[3] == want[3]
+    assert got[3] >= 1 and (got[0] >= 0).sum() > 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,min_kp,n", [(1, 5, 1500), (2, 10, 1500), (4, 5, 2500), (5, 5, 40)])
+def test_gpu_mask_assignment(matcher, seed, min_kp, n):
+    keys, depth, masks = _mask_case(seed, n=n)
+    got = matcher.AssignKeypointsToMasks(keys, depth, masks, 3.5, min_kp)
+    want = oracle.assign_keypoints_to_masks(keys, depth, masks, 3.5, min_kp)
+    assert all(np.array_equal(a, b) for a, b in zip(got[:3], want[:3])) and got[3] == want[3]
