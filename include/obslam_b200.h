@@ -407,6 +407,12 @@ int obs_assign_keypoints_to_masks(obs_matcher* m, const obs_keypoint* keys_un, c
                                   int min_keypoints, int32_t* mask_of_kp, int32_t* object_kp_indices, int32_t* object_of_mask,
                                   int32_t* n_objects);
 
+/* Frame::ExtractHSVHistogramsFromMask, src/Frame.cc:388-414, for n_masks masks over one 8-bit 3-channel image (the reference
+ * converts with CV_BGR2HSV whatever the channel order of imRGB): hist receives n_masks x 94 floats = the L1-normalised
+ * concatenation V (32 bins) | S (32 bins) | H (30 bins), the order the reference's hconcat calls leave.  Mask pixels != 0 count. */
+int obs_hsv_histograms(obs_matcher* m, const uint8_t* bgr, size_t bgr_stride, const uint8_t* masks, int n_masks, int w, int h,
+                       size_t mask_stride, size_t mask_image_stride, float* hist);
+
 /* ---------------------------------------------------------------------------------------
  * Multi-GPU exchange step of batched keyframe-vs-keyframe matching: every rank (one process per GPU)
  * owns a contiguous shard of the keyframes as queries and needs all descriptor sets as database.

@@ -166,3 +166,9 @@ struct MaskAssignArgs {
     int* nObjects;            // [1]
 };
 cudaError_t launch_mask_assign(const MaskAssignArgs& a, cudaStream_t st);
+
+// Frame::ExtractHSVHistogramsFromMask (src/Frame.cc:388-414) for n_masks masks over one colour image
+#define OBS_HSV_BINS 94           // 32 (V) + 32 (S) + 30 (H), in the order hconcat leaves them
+cudaError_t hsv_tables_upload();
+cudaError_t launch_hsv_hist(const uint8_t* bgr, size_t bgrStride, const uint8_t* masks, size_t maskStride, size_t maskImageStride,
+                            int nMasks, int w, int h, int* counts, float* hist, cudaStream_t st);

@@ -23,6 +23,7 @@ struct obs_matcher {
     DevBuf<uint32_t> initList;
     DevBuf<int> initCount;
     DevBuf<int> sim3Idx[2], sim3Dist[2];
+    bool hsvTables = false;
     std::vector<int> lastRounds;
     std::vector<obs_frame_set*> sets;   // frame sets created on this matcher (orphaned, not freed, when it is destroyed first)
 };
@@ -730,6 +731,27 @@ int obs_assign_keypoints_to_masks(obs_matcher* m, const obs_keypoint* keys_un, c
     if ((rc = host_back(m, object_kp_indices, a.objectKp, (size_t)n * 2, &queued))) return rc;
     if ((rc = host_back(m, object_of_mask, a.objectOfMask, (size_t)n_masks, &queued))) return rc;
     if ((rc = host_back(m, n_objects, a.nObjects, 1, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
+int obs_hsv_histograms(obs_matcher* m, const uint8_t* bgr, size_t bgr_stride, const uint8_t* masks, int n_masks, int w, int h,
+                       size_t mask_stride, size_t mask_image_stride, float* hist) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!bgr || !masks || !hist) return fail(OBS_ERR_INVALID, "null argument");
+    if (n_masks < 1 || w < 1 || h < 1 || bgr_stride < (size_t)w * 3 || mask_stride < (size_t)w || mask_image_stride < mask_stride * (size_t)h)
+        return fail(OBS_ERR_INVALID, "sizes / strides out of range");
+    if (!m->hsvTables) { CU(hsv_tables_upload()); m->hsvTables = true; }
+    const uint8_t *dImg = nullptr, *dMask = nullptr;
+    float* dHist = nullptr;
+    if ((rc = dev_in(m, 0, bgr, bgr_stride * (size_t)h, &dImg))) return rc;
+    if ((rc = dev_in(m, 1, masks, (size_t)n_masks * mask_image_stride, &dMask))) return rc;
+    if ((rc = dev_out(m, 20, hist, (size_t)n_masks * OBS_HSV_BINS, &dHist))) return rc;
+    CU(m->choice.ensure((size_t)n_masks * OBS_HSV_BINS));
+    CU(launch_hsv_hist(dImg, bgr_stride, dMask, mask_stride, mask_image_stride, n_masks, w, h, m->choice.p, dHist, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, hist, dHist, (size_t)n_masks * OBS_HSV_BINS, &queued))) return rc;
     if (queued) CU(cudaStreamSynchronize(m->stream));
     return OBS_OK;
 }

@@ -8,6 +8,7 @@
 // warp per keypoint), and the Object2D numbering / in-object indices are counts and ranks over that answer (k_mask_number).
 // Windows that leave the image are undefined behaviour in the reference (cv::Mat::at without a bounds check); they reject here.
 #include "matcher.h"
+#include <cmath>
 
 namespace {
 
@@ -108,5 +109,92 @@ __global__ void __launch_bounds__(1024) k_mask_number(const __grid_constant__ Ma
 cudaError_t launch_mask_assign(const MaskAssignArgs& a, cudaStream_t st) {
     if (a.n > 0) k_mask_first<<<(a.n + 7) / 8, 256, 0, st>>>(a);
     k_mask_number<<<1, 1024, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame::ExtractHSVHistogramsFromMask, src/Frame.cc:388-414: cvtColor(CV_BGR2HSV) on 8-bit pixels, three calcHist
+// calls under the mask (H: 30 bins over [0,180), S and V: 32 bins over [0,256)), hconcat in the order V | S | H,
+// normalize(NORM_L1).  OpenCV's 8-bit BGR->HSV is fixed point (hsv_shift = 12, division tables rounded half to even);
+// reproduced exactly (oracle/orc_primitives.h hsv_from_bgr, pinned on all 2^24 colours against cv2 4.13).
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__constant__ int c_sdiv[256];
+__constant__ int c_hdiv[256];
+
+__device__ __forceinline__ void hsv_from_bgr(int b, int g, int r, int& h, int& s, int& v) {
+    v = max(max(b, g), r);
+    const int vmin = min(min(b, g), r), diff = v - vmin;
+    const int vr = v == r ? -1 : 0, vg = v == g ? -1 : 0;
+    s = (diff * c_sdiv[v] + (1 << 11)) >> 12;
+    h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+    h = (h * c_hdiv[diff] + (1 << 11)) >> 12;
+    h += h < 0 ? 180 : 0;
+}
+
+// grid (row chunks, masks): shared-memory histogram of the CTA's rows, then one global atomic per non-empty bin
+__global__ void __launch_bounds__(256) k_hsv_hist(const uint8_t* __restrict__ bgr, size_t bgrStride, const uint8_t* __restrict__ masks,
+                                                  size_t maskStride, size_t maskImageStride, int w, int h, int rowsPerCta,
+                                                  int* __restrict__ counts) {
+    __shared__ int sH[OBS_HSV_BINS];
+    const int m = blockIdx.y;
+    if (threadIdx.x < OBS_HSV_BINS) sH[threadIdx.x] = 0;
+    __syncthreads();
+    const int y0 = blockIdx.x * rowsPerCta, y1 = min(y0 + rowsPerCta, h);
+    const uint8_t* mk = masks + (size_t)m * maskImageStride;
+    for (int y = y0; y < y1; y++) {
+        const uint8_t* mrow = mk + (size_t)y * maskStride;
+        const uint8_t* prow = bgr + (size_t)y * bgrStride;
+        for (int x = threadIdx.x; x < w; x += 256) {
+            if (mrow[x] == 0) continue;
+            int hh, ss, vv;
+            hsv_from_bgr(prow[3 * x], prow[3 * x + 1], prow[3 * x + 2], hh, ss, vv);
+            atomicAdd(&sH[vv >> 3], 1);                       // V: 32 bins over [0, 256)
+            atomicAdd(&sH[32 + (ss >> 3)], 1);                // S
+            if (hh < 180) atomicAdd(&sH[64 + hh / 6], 1);      // H: 30 bins over [0, 180)
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < OBS_HSV_BINS && sH[threadIdx.x]) atomicAdd(&counts[m * OBS_HSV_BINS + threadIdx.x], sH[threadIdx.x]);
+}
+
+// normalize(NORM_L1): scale = (float)(1.0 / sum) (binary64 sum and reciprocal, binary32 scale and products)
+__global__ void __launch_bounds__(128) k_hsv_normalize(const int* __restrict__ counts, float* __restrict__ hist) {
+    __shared__ int sSum[4];
+    const int m = blockIdx.x, t = threadIdx.x;
+    int v = t < OBS_HSV_BINS ? counts[m * OBS_HSV_BINS + t] : 0;
+    const int ws = __reduce_add_sync(0xffffffffu, v);
+    if ((t & 31) == 0) sSum[t >> 5] = ws;
+    __syncthreads();
+    const int total = sSum[0] + sSum[1] + sSum[2] + sSum[3];
+    if (t < OBS_HSV_BINS) {
+        // cv::normalize leaves an all-zero histogram untouched (norm < DBL_EPSILON -> scale 0)
+        const float scale = total > 0 ? __double2float_rn(__ddiv_rn(1.0, (double)total)) : 0.0f;
+        hist[m * OBS_HSV_BINS + t] = __fmul_rn((float)v, scale);
+    }
+}
+
+}  // namespace
+
+cudaError_t hsv_tables_upload() {
+    int sdiv[256], hdiv[256];
+    sdiv[0] = hdiv[0] = 0;
+    for (int i = 1; i < 256; i++) {
+        sdiv[i] = (int)nearbyint((255 << 12) / (1. * i));     // saturate_cast<int>(double) = cvRound: half to even
+        hdiv[i] = (int)nearbyint((180 << 12) / (6. * i));
+    }
+    cudaError_t e = cudaMemcpyToSymbol(c_sdiv, sdiv, sizeof(sdiv));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_hdiv, hdiv, sizeof(hdiv));
+}
+
+cudaError_t launch_hsv_hist(const uint8_t* bgr, size_t bgrStride, const uint8_t* masks, size_t maskStride, size_t maskImageStride,
+                            int nMasks, int w, int h, int* counts, float* hist, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)nMasks * OBS_HSV_BINS * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    const int rowsPerCta = 8;
+    k_hsv_hist<<<dim3((h + rowsPerCta - 1) / rowsPerCta, nMasks), 256, 0, st>>>(bgr, bgrStride, masks, maskStride, maskImageStride, w, h, rowsPerCta, counts);
+    k_hsv_normalize<<<nMasks, 128, 0, st>>>(counts, hist);
     return cudaGetLastError();
 }

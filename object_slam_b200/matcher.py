@@ -345,3 +345,12 @@ class ORBmatcher:
         check(lib().obs_assign_keypoints_to_masks(self._h, ptr(k), ptr(d), n, ptr(mk), nm, w, h, w, w * h, float(th_depth), int(min_keypoints),
                                                   ptr(mo), ptr(ok), ptr(om), ptr(no)))
         return mo, ok, om, int(no[0])
+
+    # ---- Frame::ExtractHSVHistogramsFromMask, src/Frame.cc:388-414
+    def ExtractHSVHistogramsFromMasks(self, im_bgr, masks):
+        """im_bgr: [h, w, 3] uint8; masks: [n_masks, h, w] uint8.  Returns [n_masks, 94] float32 (V | S | H bins, L1-normalised)."""
+        im = _u8(im_bgr); mk = _u8(masks)
+        nm, h, w = mk.shape
+        hist = np.empty((nm, 94), np.float32)
+        check(lib().obs_hsv_histograms(self._h, ptr(im), 3 * w, ptr(mk), nm, w, h, w, w * h, ptr(hist)))
+        return hist

@@ -105,6 +105,8 @@ def _bind_match(L):
     L.orc_fuse_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p]
     L.orc_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 5 + ([C.c_int] + [C.c_void_p] * 6) * 2 + [C.c_float, C.c_void_p]
     L.orc_assign_keypoints_to_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_hsv_from_bgr.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_hsv_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.orc_logf.restype = C.c_float
     L.orc_logf.argtypes = [C.c_float]
     L.orc_norm3.restype = C.c_float
@@ -565,3 +567,21 @@ def assign_keypoints_to_masks(keys_un, depth, masks, th_depth, min_keypoints=5):
     mo = np.empty(max(n, 1), np.int32); ok = np.empty((max(n, 1), 2), np.int32); om = np.empty(max(nm, 1), np.int32)
     no = lib().orc_assign_keypoints_to_masks(_ptr(k), _ptr(d), n, _ptr(mk), nm, w, h, float(th_depth), int(min_keypoints), _ptr(mo), _ptr(ok), _ptr(om))
     return mo[:n], ok[:n], om[:nm], no
+
+
+def hsv_from_bgr(bgr):
+    """cv::cvtColor(CV_BGR2HSV) on 8-bit pixels; bgr: [..., 3] uint8."""
+    a = np.ascontiguousarray(bgr, np.uint8)
+    out = np.empty_like(a)
+    lib().orc_hsv_from_bgr(_ptr(a), a.size // 3, _ptr(out))
+    return out
+
+
+def hsv_histograms(im_bgr, masks):
+    """Frame::ExtractHSVHistogramsFromMask (src/Frame.cc:388-414) per mask: [n_masks, 94] float32, V | S | H."""
+    im = np.ascontiguousarray(im_bgr, np.uint8); mk = np.ascontiguousarray(masks, np.uint8)
+    nm, h, w = mk.shape
+    out = np.empty((nm, 94), np.float32)
+    for m in range(nm):
+        lib().orc_hsv_histogram(_ptr(im), _ptr(mk[m]), w, h, out[m].ctypes.data_as(C.c_void_p))
+    return out

@@ -1005,6 +1005,46 @@ int orc_assign_keypoints_to_masks(const void* keysUn, const float* depth, int n,
     return nObjects;
 }
 
+// Frame::ExtractHSVHistogramsFromMask, Frame.cc:388-414.  OpenCV is un-vendored; its 8-bit BGR->HSV (imgproc color_hsv: RGB2HSV_b,
+// hsv_shift = 12, division tables by saturate_cast<int> = round half to even), calcHist's uniform bins (value * size / range for
+// 8-bit data) and normalize(NORM_L1) (binary32 scale 1/sum) are restated here and pinned against cv2 4.13 by
+// tests/test_bow_matchers.py (all 2^24 colours).  out: 94 floats, V (32) | S (32) | H (30).
+void orc_hsv_from_bgr(const uint8_t* bgr, int n, uint8_t* hsv) {
+    static int sdiv[256], hdiv[256];
+    static bool init = false;
+    if (!init) {
+        sdiv[0] = hdiv[0] = 0;
+        for (int i = 1; i < 256; i++) { sdiv[i] = (int)nearbyint((255 << 12) / (1. * i)); hdiv[i] = (int)nearbyint((180 << 12) / (6. * i)); }
+        init = true;
+    }
+    for (int i = 0; i < n; i++) {
+        const int b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
+        int v = std::max(std::max(b, g), r);
+        const int vmin = std::min(std::min(b, g), r), diff = v - vmin;
+        const int vr = v == r ? -1 : 0, vg = v == g ? -1 : 0;
+        const int s = (diff * sdiv[v] + (1 << 11)) >> 12;
+        int h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+        h = (h * hdiv[diff] + (1 << 11)) >> 12;
+        h += h < 0 ? 180 : 0;
+        hsv[3 * i] = (uint8_t)h; hsv[3 * i + 1] = (uint8_t)s; hsv[3 * i + 2] = (uint8_t)v;
+    }
+}
+void orc_hsv_histogram(const uint8_t* bgr, const uint8_t* mask, int w, int h, float* out) {
+    std::vector<uint8_t> hsv((size_t)w * h * 3);
+    orc_hsv_from_bgr(bgr, w * h, hsv.data());
+    int cnt[94] = {0};
+    for (int i = 0; i < w * h; i++) {
+        if (!mask[i]) continue;
+        cnt[hsv[3 * i + 2] * 32 / 256]++;
+        cnt[32 + hsv[3 * i + 1] * 32 / 256]++;
+        if (hsv[3 * i] < 180) cnt[64 + hsv[3 * i] * 30 / 180]++;
+    }
+    double sum = 0;
+    for (int i = 0; i < 94; i++) sum += cnt[i];
+    const float scale = sum > 0 ? (float)(1.0 / sum) : 0.0f;
+    for (int i = 0; i < 94; i++) out[i] = (float)cnt[i] * scale;
+}
+
 float orc_logf(float x) { return logf(x); }
 float orc_norm3(const float* v) { return norm3(v); }
 int orc_predict_scale(float maxDistRaw, float dist, float logScaleFactor, int nLevels) { return predict_scale(maxDistRaw, dist, logScaleFactor, nLevels); }

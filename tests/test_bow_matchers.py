@@ -330,3 +330,53 @@ def test_gpu_mask_assignment(matcher, seed, min_kp, n):
     got = matcher.AssignKeypointsToMasks(keys, depth, masks, 3.5, min_kp)
     want = oracle.assign_keypoints_to_masks(keys, depth, masks, 3.5, min_kp)
     assert all(np.array_equal(a, b) for a, b in zip(got[:3], want[:3])) and got[3] == want[3]
+
+
+def _cv2():
+    try:
+        import cv2
+        return cv2
+    except Exception:
+        pytest.skip("cv2 not importable")
+
+
+def test_oracle_hsv_matches_cv2_on_all_colours():
+    """the restated 8-bit BGR->HSV against cv2.cvtColor over all 2^24 colours"""
+    cv2 = _cv2()
+    g, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    for r in range(0, 256):
+        img = np.stack([b, g, np.full_like(b, r)], -1)
+        assert np.array_equal(oracle.hsv_from_bgr(img), cv2.cvtColor(img, cv2.COLOR_BGR2HSV)), r
+
+
+def _colour_image(shape, seed):
+    rng = np.random.default_rng(seed)
+    base = synth.blocky_image(shape, seed)
+    return np.stack([base, np.roll(base, 7, 1) // 2 + rng.integers(0, 90, shape).astype(np.uint8),
+                     255 - np.roll(base, 13, 0)], -1).astype(np.uint8)
+
+
+def test_oracle_hsv_histogram_matches_cv2():
+    """ExtractHSVHistogramsFromMask restated vs the same cv2 calls (cvtColor, calcHist x3, hconcat order, normalize L1)"""
+    cv2 = _cv2()
+    img = _colour_image(synth.TUM_SHAPE, 3)
+    masks = synth.semantic_masks(synth.TUM_SHAPE, 6, 8)
+    masks[5] = 0                                               # an empty mask: all-zero histogram
+    got = oracle.hsv_histograms(img, masks)
+    hsv = cv2.cvtColor(img.copy(), cv2.COLOR_BGR2HSV)
+    for m in range(len(masks)):
+        H = None
+        for ch, size, rng in ((0, 30, [0, 180]), (1, 32, [0, 256]), (2, 32, [0, 256])):
+            hist = cv2.calcHist([hsv], [ch], masks[m], [size], rng, accumulate=False).reshape(1, -1)
+            H = hist.copy() if H is None else cv2.hconcat([hist, H])
+        H = cv2.normalize(H, None, norm_type=cv2.NORM_L1) if H.sum() > 0 else H
+        assert np.array_equal(got[m], H.reshape(-1)), m
+
+
+@pytest.mark.gpu
+def test_gpu_hsv_histograms(matcher):
+    for seed, shape in ((3, synth.TUM_SHAPE), (4, synth.KITTI_SHAPE)):
+        img = _colour_image(shape, seed)
+        masks = synth.semantic_masks(shape, 7, seed + 5)
+        masks[6] = 0
+        assert np.array_equal(matcher.ExtractHSVHistogramsFromMasks(img, masks), oracle.hsv_histograms(img, masks))
