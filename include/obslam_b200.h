@@ -413,6 +413,15 @@ int obs_assign_keypoints_to_masks(obs_matcher* m, const obs_keypoint* keys_un, c
 int obs_hsv_histograms(obs_matcher* m, const uint8_t* bgr, size_t bgr_stride, const uint8_t* masks, int n_masks, int w, int h,
                        size_t mask_stride, size_t mask_image_stride, float* hist);
 
+/* Frame::UndistortKeyPoints, src/Frame.cc:644-674: cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) over the keypoints
+ * (mvKeysUn[i] = mvKeys[i] with pt replaced; a plain copy when mDistCoef[0] == 0, :646-650).  dist_coef: k1, k2, p1, p2[, k3 ...]
+ * (host array, n_dist <= 14).  OpenCV's scalar algorithm in binary64 (5 iterations), pinned against cv2 4.13. */
+int obs_undistort_keypoints(obs_matcher* m, const obs_keypoint* keys, int n, float fx, float fy, float cx, float cy,
+                            const float* dist_coef, int n_dist, obs_keypoint* keys_un);
+/* The same on n packed (x, y) points, e.g. the four image corners of Frame::ComputeImageBounds (:676-704). */
+int obs_undistort_points(obs_matcher* m, const float* pts, int n, float fx, float fy, float cx, float cy, const float* dist_coef,
+                         int n_dist, float* out);
+
 /* ---------------------------------------------------------------------------------------
  * Multi-GPU exchange step of batched keyframe-vs-keyframe matching: every rank (one process per GPU)
  * owns a contiguous shard of the keyframes as queries and needs all descriptor sets as database.

@@ -172,3 +172,9 @@ cudaError_t launch_mask_assign(const MaskAssignArgs& a, cudaStream_t st);
 cudaError_t hsv_tables_upload();
 cudaError_t launch_hsv_hist(const uint8_t* bgr, size_t bgrStride, const uint8_t* masks, size_t maskStride, size_t maskImageStride,
                             int nMasks, int w, int h, int* counts, float* hist, cudaStream_t st);
+
+// Frame::UndistortKeyPoints (src/Frame.cc:644-674) / the corner undistortion of ComputeImageBounds (:676-704):
+// cv::undistortPoints(pts, pts, K, distCoef, Mat(), K) over n points; ptStride / outStride in floats (2 = packed points,
+// 7 = the pt fields of cv::KeyPoint records).
+struct UndistortArgs { double fx, fy, cx, cy, k[14]; };
+cudaError_t launch_undistort(const UndistortArgs& a, const float* pts, int ptStride, float* out, int outStride, int n, cudaStream_t st);

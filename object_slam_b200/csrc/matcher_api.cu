@@ -756,4 +756,50 @@ int obs_hsv_histograms(obs_matcher* m, const uint8_t* bgr, size_t bgr_stride, co
     return OBS_OK;
 }
 
+static int undistort_args(float fx, float fy, float cx, float cy, const float* dist, int n_dist, UndistortArgs* a) {
+    if (n_dist < 0 || n_dist > 14 || (n_dist > 0 && !dist)) return fail(OBS_ERR_INVALID, "0..14 distortion coefficients");
+    if (n_dist > 0 && is_device(dist)) return fail(OBS_ERR_INVALID, "distortion coefficients are a host array");
+    memset(a, 0, sizeof(*a));
+    a->fx = fx; a->fy = fy; a->cx = cx; a->cy = cy;
+    for (int i = 0; i < n_dist; i++) a->k[i] = dist[i];
+    return OBS_OK;
+}
+
+int obs_undistort_points(obs_matcher* m, const float* pts, int n, float fx, float fy, float cx, float cy, const float* dist_coef,
+                         int n_dist, float* out) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!pts || !out || n < 1) return fail(OBS_ERR_INVALID, "null argument or n < 1");
+    UndistortArgs a;
+    if ((rc = undistort_args(fx, fy, cx, cy, dist_coef, n_dist, &a))) return rc;
+    const float* dp = nullptr; float* dout = nullptr;
+    if ((rc = dev_in(m, 0, pts, (size_t)n * 2, &dp))) return rc;
+    if ((rc = dev_out(m, 20, out, (size_t)n * 2, &dout))) return rc;
+    CU(launch_undistort(a, dp, 2, dout, 2, n, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, out, dout, (size_t)n * 2, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
+int obs_undistort_keypoints(obs_matcher* m, const obs_keypoint* keys, int n, float fx, float fy, float cx, float cy,
+                            const float* dist_coef, int n_dist, obs_keypoint* keys_un) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!keys || !keys_un || n < 1) return fail(OBS_ERR_INVALID, "null argument or n < 1");
+    UndistortArgs a;
+    if ((rc = undistort_args(fx, fy, cx, cy, dist_coef, n_dist, &a))) return rc;
+    const obs_keypoint* dk = nullptr; obs_keypoint* dout = nullptr;
+    if ((rc = dev_in(m, 0, keys, (size_t)n, &dk))) return rc;
+    if ((rc = dev_out(m, 20, keys_un, (size_t)n, &dout))) return rc;
+    if ((const void*)dk != (const void*)dout)
+        CU(cudaMemcpyAsync(dout, dk, (size_t)n * sizeof(obs_keypoint), cudaMemcpyDeviceToDevice, m->stream));      // mvKeysUn[i] = mvKeys[i] with pt replaced
+    if (n_dist > 0 && dist_coef[0] != 0.0f)                    // mDistCoef.at<float>(0) == 0.0: mvKeysUn = mvKeys, Frame.cc:646-650
+        CU(launch_undistort(a, reinterpret_cast<const float*>(dk), 7, reinterpret_cast<float*>(dout), 7, n, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, keys_un, dout, (size_t)n, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
 }  // extern "C"

@@ -198,3 +198,46 @@ cudaError_t launch_hsv_hist(const uint8_t* bgr, size_t bgrStride, const uint8_t*
     k_hsv_normalize<<<nMasks, 128, 0, st>>>(counts, hist);
     return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------
+// cv::undistortPoints(src, dst, K, distCoeffs, noArray(), K) as Frame::UndistortKeyPoints calls it: normalise, five fixed-point
+// iterations of the inverse distortion (TermCriteria(COUNT, 5, 0.01)), reproject with P = K; all in binary64 with every
+// operation rounded on its own (OpenCV's scalar loop; pinned against cv2 4.13 on 2 M points, tests/test_bow_matchers.py).
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) k_undistort(const __grid_constant__ UndistortArgs A, const float* __restrict__ pts, int ptStride,
+                                                   float* __restrict__ out, int outStride, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double* k = A.k;
+    const double u = (double)pts[(size_t)i * ptStride], v = (double)pts[(size_t)i * ptStride + 1];
+    const double ifx = __ddiv_rn(1.0, A.fx), ify = __ddiv_rn(1.0, A.fy);
+    double x = __dmul_rn(__dsub_rn(u, A.cx), ifx), y = __dmul_rn(__dsub_rn(v, A.cy), ify);
+    const double x0 = x, y0 = y;
+#define MUL __dmul_rn
+#define ADD __dadd_rn
+    for (int j = 0; j < 5; j++) {
+        const double r2 = ADD(MUL(x, x), MUL(y, y));
+        const double num = ADD(1.0, MUL(ADD(MUL(ADD(MUL(k[7], r2), k[6]), r2), k[5]), r2));
+        const double den = ADD(1.0, MUL(ADD(MUL(ADD(MUL(k[4], r2), k[1]), r2), k[0]), r2));
+        const double icdist = __ddiv_rn(num, den);
+        if (icdist < 0) { x = x0; y = y0; break; }
+        const double dX = ADD(ADD(ADD(MUL(MUL(MUL(2.0, k[2]), x), y), MUL(k[3], ADD(r2, MUL(MUL(2.0, x), x)))), MUL(k[8], r2)), MUL(MUL(k[9], r2), r2));
+        const double dY = ADD(ADD(ADD(MUL(k[2], ADD(r2, MUL(MUL(2.0, y), y))), MUL(MUL(MUL(2.0, k[3]), x), y)), MUL(k[10], r2)), MUL(MUL(k[11], r2), r2));
+        x = MUL(__dsub_rn(x0, dX), icdist);
+        y = MUL(__dsub_rn(y0, dY), icdist);
+    }
+    out[(size_t)i * outStride] = __double2float_rn(ADD(MUL(A.fx, x), A.cx));
+    out[(size_t)i * outStride + 1] = __double2float_rn(ADD(MUL(A.fy, y), A.cy));
+#undef MUL
+#undef ADD
+}
+
+}  // namespace
+
+cudaError_t launch_undistort(const UndistortArgs& a, const float* pts, int ptStride, float* out, int outStride, int n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_undistort<<<(n + 255) / 256, 256, 0, st>>>(a, pts, ptStride, out, outStride, n);
+    return cudaGetLastError();
+}

@@ -354,3 +354,17 @@ class ORBmatcher:
         hist = np.empty((nm, 94), np.float32)
         check(lib().obs_hsv_histograms(self._h, ptr(im), 3 * w, ptr(mk), nm, w, h, w, w * h, ptr(hist)))
         return hist
+
+    # ---- Frame::UndistortKeyPoints, src/Frame.cc:644-674
+    def UndistortKeyPoints(self, keys, K, dist_coef):
+        """keys: KeyPoint array (mvKeys); K = (fx, fy, cx, cy); dist_coef = (k1, k2, p1, p2[, k3]).  Returns mvKeysUn."""
+        k = np.ascontiguousarray(keys); d = np.ascontiguousarray(dist_coef, np.float32)
+        out = np.empty_like(k)
+        check(lib().obs_undistort_keypoints(self._h, ptr(k), len(k), *[float(v) for v in K], ptr(d), len(d), ptr(out)))
+        return out
+
+    def UndistortPoints(self, pts, K, dist_coef):
+        p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2); d = np.ascontiguousarray(dist_coef, np.float32)
+        out = np.empty_like(p)
+        check(lib().obs_undistort_points(self._h, ptr(p), len(p), *[float(v) for v in K], ptr(d), len(d), ptr(out)))
+        return out

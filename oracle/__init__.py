@@ -107,6 +107,7 @@ def _bind_match(L):
     L.orc_assign_keypoints_to_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_hsv_from_bgr.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.orc_hsv_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.orc_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]
     L.orc_logf.restype = C.c_float
     L.orc_logf.argtypes = [C.c_float]
     L.orc_norm3.restype = C.c_float
@@ -584,4 +585,12 @@ def hsv_histograms(im_bgr, masks):
     out = np.empty((nm, 94), np.float32)
     for m in range(nm):
         lib().orc_hsv_histogram(_ptr(im), _ptr(mk[m]), w, h, out[m].ctypes.data_as(C.c_void_p))
+    return out
+
+
+def undistort_points(pts, K, dist_coef):
+    """cv::undistortPoints(pts, pts, K, distCoef, Mat(), K) as Frame::UndistortKeyPoints (src/Frame.cc:644-674) calls it; K = (fx, fy, cx, cy)."""
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2); d = np.ascontiguousarray(dist_coef, np.float32)
+    out = np.empty_like(p)
+    lib().orc_undistort_points(_ptr(p), len(p), *[float(np.float32(v)) for v in K], _ptr(d), len(d), _ptr(out))
     return out

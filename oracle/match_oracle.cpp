@@ -1045,6 +1045,31 @@ void orc_hsv_histogram(const uint8_t* bgr, const uint8_t* mask, int w, int h, fl
     for (int i = 0; i < 94; i++) out[i] = (float)cnt[i] * scale;
 }
 
+// cv::undistortPoints(src, dst, K, distCoeffs, noArray(), K) (OpenCV calib3d / imgproc undistort.dispatch.cpp, cvUndistortPointsInternal,
+// un-vendored): binary64 scalar loop, TermCriteria(COUNT, 5, 0.01), identity tilt and rectification, P = K.  Pinned against cv2 4.13.
+void orc_undistort_points(const float* pts, int n, float fxf, float fyf, float cxf, float cyf, const float* dist, int nDist, float* out) {
+    const double fx = fxf, fy = fyf, cx = cxf, cy = cyf;
+    double k[14] = {0};
+    for (int i = 0; i < nDist && i < 14; i++) k[i] = dist[i];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; i++) {
+        const double u = pts[2 * i], v = pts[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = x0; y = y0; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        out[2 * i] = (float)(fx * x + cx);
+        out[2 * i + 1] = (float)(fy * y + cy);
+    }
+}
+
 float orc_logf(float x) { return logf(x); }
 float orc_norm3(const float* v) { return norm3(v); }
 int orc_predict_scale(float maxDistRaw, float dist, float logScaleFactor, int nLevels) { return predict_scale(maxDistRaw, dist, logScaleFactor, nLevels); }

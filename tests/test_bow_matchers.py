@@ -380,3 +380,33 @@ def test_gpu_hsv_histograms(matcher):
         masks = synth.semantic_masks(shape, 7, seed + 5)
         masks[6] = 0
         assert np.array_equal(matcher.ExtractHSVHistogramsFromMasks(img, masks), oracle.hsv_histograms(img, masks))
+
+
+TUM1_K = (517.306408, 516.469215, 318.643040, 255.313989)                  # Examples/RGB-D/TUM1.yaml
+DISTORTIONS = [np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32),     # TUM1.yaml k1 k2 p1 p2 k3
+               np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32)]    # EuRoC.yaml k1 k2 p1 p2
+
+
+@pytest.mark.parametrize("dist", DISTORTIONS, ids=["tum1", "euroc"])
+def test_oracle_undistort_matches_cv2(dist):
+    cv2 = _cv2()
+    rng = np.random.default_rng(1)
+    pts = np.stack([rng.uniform(0, 640, 200000), rng.uniform(0, 480, 200000)], 1).astype(np.float32)
+    fx, fy, cx, cy = TUM1_K
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+    ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, dist, None, K).reshape(-1, 2)
+    assert np.array_equal(oracle.undistort_points(pts, TUM1_K, dist), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dist", DISTORTIONS + [np.zeros(5, np.float32)], ids=["tum1", "euroc", "none"])
+def test_gpu_undistort_keypoints(matcher, dist):
+    keys, _, _ = synth.synthetic_frame(synth.TUM_SHAPE, 2000, 9)
+    un = matcher.UndistortKeyPoints(keys, TUM1_K, dist)
+    want = keys.copy()
+    if dist[0] != 0:
+        p = oracle.undistort_points(np.stack([keys["x"], keys["y"]], 1), TUM1_K, dist)
+        want["x"], want["y"] = p[:, 0], p[:, 1]
+    assert un.tobytes() == want.tobytes()
+    corners = np.array([[0, 0], [640, 0], [0, 480], [640, 480]], np.float32)            # Frame::ComputeImageBounds
+    assert np.array_equal(matcher.UndistortPoints(corners, TUM1_K, dist), oracle.undistort_points(corners, TUM1_K, dist))
