@@ -362,10 +362,15 @@ def main():
     serial_ms = sum((2 * v if k != "stereo" else v) for k, v in per_launch_ms.items())
     shares = {k: (2 * v if k != "stereo" else v) / serial_ms for k, v in per_launch_ms.items()}
     dominant = max(shares, key=shares.get)
-    traffic = None
+    traffic, pipes = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(dominant)
+            tj = json.load(f)
+        # the ncu capture ran with tj["_images_per_launch"] images per launch; DRAM traffic scales with the batch
+        traffic = tj.get(dominant)
+        if traffic is not None:
+            traffic = traffic * F / float(tj.get("_images_per_launch", F))
+        pipes = tj.get("_pipes", {}).get(dominant)
     except Exception:
         pass
     if alg[dominant] is not None:
@@ -374,6 +379,9 @@ def main():
         achieved = 0.0
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "ncu_pipes": pipes,
+                "bound_note": "every stage is integer-issue bound before it is HBM bound (DESIGN.md section 4): ncu_pipes holds the ncu "
+                              "pipe utilisation of the dominant kernel (ALU pipe: one warp instruction per 2 cycles per SM sub-partition)",
                 "per_launch_ms": per_launch_ms, "share_of_step": shares,
                 "serialised_step_ms": serial_ms,
                 "note": "per_launch_ms: CUDA-event brackets of a profiling pass run directly after the timed region with every kernel "
