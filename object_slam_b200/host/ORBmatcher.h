@@ -13,6 +13,7 @@
 #define OBS_B200_ORBMATCHER_H
 
 #include <cstring>
+#include <stdint.h>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -117,12 +118,63 @@ public:
         return n;
     }
 
+    // include/ORBmatcher.h:54, src/ORBmatcher.cc:159-288.  KeyFrameT / FrameT carry mFeatVec (DBoW2::FeatureVector, any
+    // std::map<NodeId, std::vector<unsigned int> >-like container), mDescriptors, mvKeysUn, N; the keyframe GetMapPointMatches().
+    template<class KeyFrameT, class FrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT* pKF, FrameT &F, std::vector<MapPointT*> &vpMapPointMatches)
+    {
+        const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
+        BowCsr a, b;
+        FeatVecToCsr(pKF->mFeatVec, a); FeatVecToCsr(F.mFeatVec, b);
+        const int32_t nA = pKF->N, nB = F.N;
+        std::vector<uint8_t> valid(nA > 0 ? nA : 1), dA((size_t)(nA > 0 ? nA : 1)*32), dB((size_t)(nB > 0 ? nB : 1)*32);
+        for(int i=0; i<nA; i++) { valid[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad(); memcpy(&dA[(size_t)i*32], pKF->mDescriptors.ptr(i), 32); }
+        for(int i=0; i<nB; i++) memcpy(&dB[(size_t)i*32], F.mDescriptors.ptr(i), 32);
+        obs_bow_side s1 = MakeSide(nA, a, dA, pKF->mvKeysUn, valid.data());
+        obs_bow_side s2 = MakeSide(nB, b, dB, F.mvKeysUn, nullptr);
+        std::vector<int32_t> m12(s1.cap), m21(s2.cap);
+        int32_t n = 0;
+        ObsCheck(obs_search_by_bow(ThreadMatcher(), &s1, &s2, 1, TH_LOW, 0, mfNNratio, mbCheckOrientation, m12.data(), m21.data(), &n));
+        vpMapPointMatches = std::vector<MapPointT*>(F.N, static_cast<MapPointT*>(NULL));
+        for(int i=0; i<F.N; i++) if(m21[i]>=0) vpMapPointMatches[i] = vpMapPointsKF[m21[i]];
+        return n;
+    }
+
     static const int TH_LOW = 50;
     static const int TH_HIGH = 100;
     static const int HISTO_LENGTH = 30;
 
 protected:
     static int Capacity(int n) { return ((n > 0 ? n : 1) + 31) & ~31; }
+
+    // DBoW2::FeatureVector -> CSR (node ids ascending = the map's iteration order)
+    struct BowCsr { std::vector<uint32_t> id; std::vector<int32_t> start, idx; int32_t n, nNodes; };
+    template<class FeatVecT>
+    static void FeatVecToCsr(const FeatVecT &fv, BowCsr &c)
+    {
+        c.start.assign(1, 0);
+        for(typename FeatVecT::const_iterator it=fv.begin(); it!=fv.end(); ++it)
+        {
+            c.id.push_back((uint32_t)it->first);
+            c.idx.insert(c.idx.end(), it->second.begin(), it->second.end());
+            c.start.push_back((int32_t)c.idx.size());
+        }
+        c.nNodes = (int32_t)c.id.size();
+        if(c.id.empty()) { c.id.push_back(0); c.start.push_back(0); }
+        if(c.idx.empty()) c.idx.push_back(0);
+    }
+    static obs_bow_side MakeSide(const int32_t &n, BowCsr &c, const std::vector<uint8_t> &desc, const std::vector<cv::KeyPoint> &keys,
+                                 const uint8_t* valid)
+    {
+        c.n = n;
+        c.idx.resize(n > 0 ? n : 1, 0);
+        obs_bow_side s;
+        s.cap = n > 0 ? n : 1; s.node_cap = c.nNodes > 0 ? c.nNodes : 1;
+        s.n = &c.n; s.descriptors = desc.data(); s.keys_un = reinterpret_cast<const obs_keypoint*>(keys.data());
+        s.valid = valid; s.u_right = nullptr; s.n_nodes = &c.nNodes;
+        s.node_id = c.id.data(); s.node_start = c.start.data(); s.node_idx = c.idx.data();
+        return s;
+    }
 
     // src/ORBmatcher.cc:1601-1642 over the bin sizes
     void ComputeThreeMaxima(std::vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3)

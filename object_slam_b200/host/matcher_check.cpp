@@ -5,6 +5,7 @@
 #include "ORBmatcher.h"
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 
 struct MapPoint {                              // include/MapPoint.h: the members the matcher reads
     bool mbTrackInView = false, bad = false;
@@ -16,7 +17,10 @@ struct MapPoint {                              // include/MapPoint.h: the member
     cv::Mat GetDescriptor() const { return mDescriptor; }
 };
 
+typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;      // DBoW2::FeatureVector
+
 struct Frame {                                 // include/Frame.h: the members the matcher reads
+    FeatureVector mFeatVec;
     int N = 0;
     std::vector<cv::KeyPoint> mvKeysUn;
     cv::Mat mDescriptors;
@@ -26,6 +30,15 @@ struct Frame {                                 // include/Frame.h: the members t
     int mnScaleLevels = 8;
     std::vector<float> mvScaleFactors;
     obs_frame_set* mpDevFrame = nullptr;
+};
+
+struct KeyFrame {                              // include/KeyFrame.h: the members SearchByBoW reads
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    cv::Mat mDescriptors;
+    FeatureVector mFeatVec;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
 };
 
 static FILE* g_in;
@@ -84,6 +97,39 @@ int main(int argc, char** argv) {
         fwrite(res.data(), 4, res.size(), out);
         printf("SearchByProjection: %d matches, DescriptorDistance(d0,d1)=%d\n", n,
                ORB_SLAM2::ORBmatcher::DescriptorDistance(pts[0].mDescriptor, pts[1].mDescriptor));
+    } else if (mode == "bow") {
+        // keyframe side: N, keys, descriptors, valid flags, node of every keypoint; then the frame side without the flags
+        KeyFrame KF; Frame F;
+        std::vector<unsigned char> dk, df;
+        std::vector<MapPoint> pts;
+        float ratio;
+        rd(&ratio, 1);
+        for (int side = 0; side < 2; side++) {
+            int N; rd(&N, 1);
+            std::vector<cv::KeyPoint> keys(N);
+            rd(reinterpret_cast<unsigned char*>(keys.data()), (size_t)N * sizeof(cv::KeyPoint));
+            std::vector<unsigned char>& ds = side ? df : dk;
+            ds.resize((size_t)N * 32); rd(ds.data(), ds.size());
+            std::vector<unsigned char> valid(N); rd(valid.data(), N);
+            std::vector<int> node(N); rd(node.data(), N);
+            FeatureVector fv;
+            for (int i = 0; i < N; i++) fv[(unsigned)node[i]].push_back((unsigned)i);
+            if (side == 0) {
+                KF.N = N; KF.mvKeysUn = keys; KF.mDescriptors = cv::Mat(N, 32, CV_8UC1, ds.data(), 32); KF.mFeatVec = fv;
+                pts.resize(N); KF.mvpMapPoints.assign(N, nullptr);
+                for (int i = 0; i < N; i++) { pts[i].id = i; if (valid[i]) KF.mvpMapPoints[i] = &pts[i]; }
+            } else {
+                F.N = N; F.mvKeysUn = keys; F.mDescriptors = cv::Mat(N, 32, CV_8UC1, ds.data(), 32); F.mFeatVec = fv;
+            }
+        }
+        ORB_SLAM2::ORBmatcher matcher(ratio, true);
+        std::vector<MapPoint*> vpMatches;
+        const int n = matcher.SearchByBoW(&KF, F, vpMatches);
+        std::vector<int> res(F.N);
+        for (int i = 0; i < F.N; i++) res[i] = vpMatches[i] ? vpMatches[i]->id : -1;
+        fwrite(&n, 4, 1, out);
+        fwrite(res.data(), 4, res.size(), out);
+        printf("SearchByBoW: %d matches\n", n);
     } else {
         Frame F1, F2;
         std::vector<unsigned char> d1, d2;

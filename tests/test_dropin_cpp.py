@@ -96,7 +96,7 @@ def test_matcher_mirror_compiles_and_names_match_reference_header():
     if os.path.exists(ref):
         theirs, mine = open(ref).read(), open(os.path.join(HOST, "ORBmatcher.h")).read()
         for name in ("ORBmatcher(float nnratio=0.6, bool checkOri=true)", "static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b)",
-                     "int SearchByProjection(", "int SearchForInitialization(", "TH_LOW", "TH_HIGH", "HISTO_LENGTH", "ComputeThreeMaxima",
+                     "int SearchByProjection(", "int SearchForInitialization(", "int SearchByBoW(", "TH_LOW", "TH_HIGH", "HISTO_LENGTH", "ComputeThreeMaxima",
                      "mfNNratio", "mbCheckOrientation"):
             assert name in theirs and name in mine, name
 
@@ -131,3 +131,18 @@ def test_matcher_mirror_matches_oracle(gpu):
         pm = np.frombuffer(raw[4 + 4000:], np.float32).reshape(-1, 2)
         on, om12, opm = mc.oracle_init(f1, f2, shape, prev, 100, 0.9)
         assert n == on and np.array_equal(m12, om12) and np.array_equal(pm, opm)
+        # SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) through std::map feature vectors
+        import oracle
+        a, b, _ = synth.bow_pair(shape, 1000, 13, n_nodes=80)
+        blob = np.array([0.7], np.float32).tobytes()
+        for sd in (a, b):
+            node = np.zeros(sd["n"], np.int32)
+            for k in range(len(sd["node_id"])):
+                node[sd["node_idx"][sd["node_start"][k]:sd["node_start"][k + 1]]] = sd["node_id"][k]
+            blob += np.array([sd["n"]], np.int32).tobytes() + np.ascontiguousarray(sd["keys_un"]).tobytes() + \
+                np.ascontiguousarray(sd["descriptors"]).tobytes() + np.ascontiguousarray(sd["valid"], np.uint8).tobytes() + node.tobytes()
+        open(os.path.join(d, "bow.bin"), "wb").write(blob)
+        subprocess.check_call([exe, "bow", os.path.join(d, "bow.bin"), os.path.join(d, "bow.out")])
+        res = np.fromfile(os.path.join(d, "bow.out"), np.int32)
+        on, _, om21 = oracle.search_by_bow(a, dict(b, valid=None), 50, False, 0.7, True)
+        assert res[0] == on and np.array_equal(res[1:], om21)
