@@ -422,6 +422,12 @@ int obs_undistort_keypoints(obs_matcher* m, const obs_keypoint* keys, int n, flo
 int obs_undistort_points(obs_matcher* m, const float* pts, int n, float fx, float fy, float cx, float cy, const float* dist_coef,
                          int n_dist, float* out);
 
+/* cv::distanceTransform(~mask, mDistTransImg, cv::DIST_L2, cv::DIST_MASK_PRECISE) of the Object2D constructor, src/ObjectTypes.cc:23,
+ * for n_masks masks: dist (n_masks x h x w floats, packed) = exact Euclidean distance to the nearest pixel with mask == 255
+ * (65536 everywhere for a mask without such a pixel, like OpenCV's own code path).  OpenCV built with IPP may differ in the last bit. */
+int obs_distance_transform(obs_matcher* m, const uint8_t* masks, int n_masks, int w, int h, size_t mask_stride,
+                           size_t mask_image_stride, float* dist);
+
 /* ---------------------------------------------------------------------------------------
  * Multi-GPU exchange step of batched keyframe-vs-keyframe matching: every rank (one process per GPU)
  * owns a contiguous shard of the keyframes as queries and needs all descriptor sets as database.

@@ -178,3 +178,7 @@ cudaError_t launch_hsv_hist(const uint8_t* bgr, size_t bgrStride, const uint8_t*
 // 7 = the pt fields of cv::KeyPoint records).
 struct UndistortArgs { double fx, fy, cx, cy, k[14]; };
 cudaError_t launch_undistort(const UndistortArgs& a, const float* pts, int ptStride, float* out, int outStride, int n, cudaStream_t st);
+
+// Object2D::Object2D, src/ObjectTypes.cc:23: cv::distanceTransform(~mask, dist, DIST_L2, DIST_MASK_PRECISE) for n_masks masks
+cudaError_t launch_distance_transform(const uint8_t* masks, size_t maskStride, size_t maskImageStride, int nMasks, int w, int h,
+                                      float* out, cudaStream_t st);

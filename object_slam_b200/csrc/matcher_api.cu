@@ -802,4 +802,22 @@ int obs_undistort_keypoints(obs_matcher* m, const obs_keypoint* keys, int n, flo
     return OBS_OK;
 }
 
+int obs_distance_transform(obs_matcher* m, const uint8_t* masks, int n_masks, int w, int h, size_t mask_stride,
+                           size_t mask_image_stride, float* dist) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!masks || !dist) return fail(OBS_ERR_INVALID, "null argument");
+    if (n_masks < 1 || w < 1 || h < 1 || w > 4096 || h > 32767 || mask_stride < (size_t)w || mask_image_stride < mask_stride * (size_t)h)
+        return fail(OBS_ERR_INVALID, "sizes / strides out of range (w <= 4096)");
+    const uint8_t* dMask = nullptr; float* dOut = nullptr;
+    const size_t cnt = (size_t)n_masks * w * h;
+    if ((rc = dev_in(m, 1, masks, (size_t)n_masks * mask_image_stride, &dMask))) return rc;
+    if ((rc = dev_out(m, 20, dist, cnt, &dOut))) return rc;
+    CU(launch_distance_transform(dMask, mask_stride, mask_image_stride, n_masks, w, h, dOut, m->stream));
+    bool queued = false;
+    if ((rc = host_back(m, dist, dOut, cnt, &queued))) return rc;
+    if (queued) CU(cudaStreamSynchronize(m->stream));
+    return OBS_OK;
+}
+
 }  // extern "C"

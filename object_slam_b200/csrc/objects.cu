@@ -241,3 +241,94 @@ cudaError_t launch_undistort(const UndistortArgs& a, const float* pts, int ptStr
     k_undistort<<<(n + 255) / 256, 256, 0, st>>>(a, pts, ptStride, out, outStride, n);
     return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------
+// cv::distanceTransform(~mask, dst, DIST_L2, DIST_MASK_PRECISE) (Object2D constructor, src/ObjectTypes.cc:23): exact Euclidean
+// distance to the nearest pixel with mask == 255, OpenCV's trueDistTrans (imgproc/distransform.cpp, un-vendored) in two stages:
+// per column the vertical distance d to the nearest zero of ~mask, stored as (float)(d*d) (2^32 where the column has none within
+// reach); per row the lower envelope of the parabolas f[p] + (q - p)^2 with OpenCV's binary32 intersection arithmetic, then
+// sqrt.  Pinned against cv2 4.13 with IPP disabled (IPP builds differ in the last bit on some sizes).
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr float DT_INF = 4294967296.0f;
+
+// stage 1: one thread per (mask, column)
+__global__ void __launch_bounds__(128) k_dt_columns(const uint8_t* __restrict__ masks, size_t maskStride, size_t maskImageStride,
+                                                    int w, int h, float* __restrict__ out) {
+    const int x = blockIdx.x * 128 + threadIdx.x, m = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t* src = masks + (size_t)m * maskImageStride + x;
+    float* dst = out + (size_t)m * w * h + x;
+    int dist = h - 1;
+    for (int j = h - 1; j >= 0; j--) {                          // distance to the nearest object pixel below
+        dist = src[(size_t)j * maskStride] == 255 ? 0 : dist + 1;
+        dst[(size_t)j * w] = __int_as_float(dist);
+    }
+    dist = h - 1;
+    for (int j = 0; j < h; j++) {
+        const int below = __float_as_int(dst[(size_t)j * w]);
+        dist = min(dist + 1, below);
+        dst[(size_t)j * w] = dist < h ? (float)(dist * dist) : DT_INF;
+    }
+}
+
+// stage 2: one warp per (mask, row); lane 0 builds the envelope in shared memory, all lanes evaluate it
+__global__ void __launch_bounds__(128) k_dt_rows(int w, int h, int nRows, float* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t dtsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * 4 + warp;
+    if (row >= nRows) return;
+    float* f = reinterpret_cast<float*>(dtsm) + (size_t)warp * (3 * w + 2);
+    float* z = f + w;                                           // w + 1 entries
+    int* v = reinterpret_cast<int*>(z + w + 1);
+    float* d = out + (size_t)row * w;
+    for (int q = lane; q < w; q += 32) f[q] = d[q];
+    __syncwarp();
+    int K = 0;
+    if (lane == 0) {
+        int k = 0;
+        v[0] = 0; z[0] = -DT_INF; z[1] = DT_INF;
+        for (int q = 1; q < w; q++) {
+            const float fq = f[q];
+            const float a = __fadd_rn(fq, (float)(q * q));
+            for (;; k--) {
+                const int p = v[k];
+                const float s = __fmul_rn(__fsub_rn(__fsub_rn(a, f[p]), (float)(p * p)), (float)(0.5 / (q - p)));
+                if (s > z[k]) { k++; v[k] = q; z[k] = s; z[k + 1] = DT_INF; break; }
+            }
+        }
+        K = k;
+    }
+    K = __shfl_sync(0xffffffffu, K, 0);
+    __syncwarp();
+    for (int q = lane; q < w; q += 32) {
+        // smallest k with z[k + 1] >= q (the reference's running "while (z[k+1] < q) k++")
+        int lo = 0, hi = K;
+        const float fq = (float)q;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (z[mid + 1] < fq) lo = mid + 1; else hi = mid;
+        }
+        const int p = v[lo];
+        const int dq = abs(q - p);
+        d[q] = __fsqrt_rn(__fadd_rn((float)(dq * dq), f[p]));
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_distance_transform(const uint8_t* masks, size_t maskStride, size_t maskImageStride, int nMasks, int w, int h,
+                                      float* out, cudaStream_t st) {
+    k_dt_columns<<<dim3((w + 127) / 128, nMasks), 128, 0, st>>>(masks, maskStride, maskImageStride, w, h, out);
+    const size_t smem = (size_t)4 * (3 * w + 2) * 4;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_dt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int nRows = nMasks * h;
+    k_dt_rows<<<(nRows + 3) / 4, 128, smem, st>>>(w, h, nRows, out);
+    return cudaGetLastError();
+}

@@ -368,3 +368,12 @@ class ORBmatcher:
         out = np.empty_like(p)
         check(lib().obs_undistort_points(self._h, ptr(p), len(p), *[float(v) for v in K], ptr(d), len(d), ptr(out)))
         return out
+
+    # ---- Object2D::Object2D, src/ObjectTypes.cc:23
+    def DistanceTransform(self, masks):
+        """cv::distanceTransform(~mask, DIST_L2, DIST_MASK_PRECISE) per mask; masks [n_masks, h, w] uint8 -> [n_masks, h, w] float32."""
+        mk = _u8(masks)
+        nm, h, w = mk.shape
+        out = np.empty((nm, h, w), np.float32)
+        check(lib().obs_distance_transform(self._h, ptr(mk), nm, w, h, w, w * h, ptr(out)))
+        return out

@@ -108,6 +108,7 @@ def _bind_match(L):
     L.orc_hsv_from_bgr.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.orc_hsv_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.orc_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_distance_transform.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.orc_logf.restype = C.c_float
     L.orc_logf.argtypes = [C.c_float]
     L.orc_norm3.restype = C.c_float
@@ -593,4 +594,14 @@ def undistort_points(pts, K, dist_coef):
     p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2); d = np.ascontiguousarray(dist_coef, np.float32)
     out = np.empty_like(p)
     lib().orc_undistort_points(_ptr(p), len(p), *[float(np.float32(v)) for v in K], _ptr(d), len(d), _ptr(out))
+    return out
+
+
+def distance_transform(masks):
+    """cv::distanceTransform(~mask, DIST_L2, DIST_MASK_PRECISE) (src/ObjectTypes.cc:23) per mask: [n_masks, h, w] float32."""
+    mk = np.ascontiguousarray(masks, np.uint8)
+    nm, h, w = mk.shape
+    out = np.empty((nm, h, w), np.float32)
+    for m in range(nm):
+        lib().orc_distance_transform(_ptr(mk[m]), w, h, out[m].ctypes.data_as(C.c_void_p))
     return out

@@ -1070,6 +1070,47 @@ void orc_undistort_points(const float* pts, int n, float fxf, float fyf, float c
     }
 }
 
+// cv::distanceTransform(~mask, dst, DIST_L2, DIST_MASK_PRECISE), ObjectTypes.cc:23: OpenCV's trueDistTrans (imgproc/distransform.cpp,
+// un-vendored) restated: column pass (vertical distance to the nearest zero of ~mask, squared, 2^32 beyond reach), row pass (lower
+// envelope of parabolas with binary32 intersections, sqrt).  Pinned against cv2 4.13 with IPP disabled.
+void orc_distance_transform(const uint8_t* mask, int w, int h, float* out) {
+    const int m = h, n = w;
+    const float inf = 4294967296.0f;
+    std::vector<int> d(m);
+    for (int x = 0; x < n; x++) {
+        int dist = m - 1;
+        for (int j = m - 1; j >= 0; j--) { dist = (dist + 1) & (mask[(size_t)j * n + x] == 255 ? 0 : -1); d[j] = dist; }
+        dist = m - 1;
+        for (int j = 0; j < m; j++) {
+            dist = std::min(dist + 1, d[j]);
+            out[(size_t)j * n + x] = dist < m ? (float)(dist * dist) : inf;
+        }
+    }
+    std::vector<float> f(n), z(n + 1), sqr(n), inv(n);
+    std::vector<int> v(n);
+    sqr[0] = inv[0] = 0.f;
+    for (int i = 1; i < n; i++) { inv[i] = (float)(0.5 / i); sqr[i] = (float)(i * i); }
+    for (int y = 0; y < m; y++) {
+        float* dr = out + (size_t)y * n;
+        int k = 0;
+        v[0] = 0; z[0] = -inf; z[1] = inf; f[0] = dr[0];
+        for (int q = 1; q < n; q++) {
+            const float fq = dr[q];
+            f[q] = fq;
+            for (;; k--) {
+                const int p = v[k];
+                const float s = (fq + sqr[q] - dr[p] - sqr[p]) * inv[q - p];
+                if (s > z[k]) { k++; v[k] = q; z[k] = s; z[k + 1] = inf; break; }
+            }
+        }
+        for (int q = 0, kk = 0; q < n; q++) {
+            while (z[kk + 1] < q) kk++;
+            const int p = v[kk];
+            dr[q] = std::sqrt(sqr[std::abs(q - p)] + f[p]);
+        }
+    }
+}
+
 float orc_logf(float x) { return logf(x); }
 float orc_norm3(const float* v) { return norm3(v); }
 int orc_predict_scale(float maxDistRaw, float dist, float logScaleFactor, int nLevels) { return predict_scale(maxDistRaw, dist, logScaleFactor, nLevels); }

@@ -410,3 +410,34 @@ def test_gpu_undistort_keypoints(matcher, dist):
     assert un.tobytes() == want.tobytes()
     corners = np.array([[0, 0], [640, 0], [0, 480], [640, 480]], np.float32)            # Frame::ComputeImageBounds
     assert np.array_equal(matcher.UndistortPoints(corners, TUM1_K, dist), oracle.undistort_points(corners, TUM1_K, dist))
+
+
+def _dt_masks(shape, seed):
+    masks = synth.semantic_masks(shape, 6, seed)
+    masks = np.concatenate([masks, np.zeros((1,) + shape, np.uint8), np.full((1,) + shape, 255, np.uint8)])
+    masks[2][masks[2] == 0] = 100                             # values other than 0 / 255 are background too (~100 != 0)
+    masks[3, 5, 7] = 255                                       # an isolated object pixel
+    return masks
+
+
+@pytest.mark.parametrize("shape", [(90, 130), (61, 77), (120, 160)])
+def test_oracle_distance_transform_matches_cv2(shape):
+    """trueDistTrans restated vs cv2.distanceTransform with IPP off (IPP's variant differs in the last bit on some sizes)"""
+    cv2 = _cv2()
+    ipp = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        masks = _dt_masks(shape, 5)
+        got = oracle.distance_transform(masks)
+        for m in range(len(masks)):
+            ref = cv2.distanceTransform(~masks[m], cv2.DIST_L2, cv2.DIST_MASK_PRECISE)
+            assert np.array_equal(got[m], ref), m
+    finally:
+        cv2.ipp.setUseIPP(ipp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [synth.TUM_SHAPE, (61, 77), synth.KITTI_SHAPE])
+def test_gpu_distance_transform(matcher, shape):
+    masks = _dt_masks(shape, 6)
+    assert np.array_equal(matcher.DistanceTransform(masks), oracle.distance_transform(masks))
