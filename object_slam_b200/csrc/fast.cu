@@ -88,6 +88,7 @@ __device__ __forceinline__ unsigned pretest_word(unsigned C, unsigned up, unsign
 }
 
 struct FastShared {
+    // the first two members are cleared together with 128-bit stores (both 2112 bytes)
     uint32_t bitmap[FT_ROWS][8];               // emitted keypoints, one bit per tile pixel
     int rowOfs[FT_MAXCELLS][FT_ROWS];          // per cell: keypoints per row, then keypoints in the rows above
     uint8_t colCell[FT_PITCH];                 // tile column -> cell of the run
@@ -95,6 +96,8 @@ struct FastShared {
     uint8_t colOK[FT_PITCH];                   // 0x80: the column takes part in the current phase
     int cellAny[FT_MAXCELLS];
     int qCount;
+    int nSurv;                                 // suppressed keypoints so far; they are listed from the top of the queue downwards
+    int overflow;                              // the list ran into the queue (white-noise images): emission walks the bitmap instead
 };
 
 // One detection phase at threshold t over the columns enabled in sh.colOK:
@@ -160,6 +163,7 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
 
     // ---- pass 2
     const int total = sh.qCount;
+    if (tid == 0 && total > FT_LIST - sh.nSurv) sh.overflow = 1;          // the queue reached the keypoints listed by the previous phase
     const int per = ((total + FT_THREADS - 1) / FT_THREADS) * 32;
     const int start = warp * per, end = min(start + per, total);
     int nC = 0;
@@ -198,6 +202,8 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
             atomicOr(&sh.bitmap[pos >> 8][c >> 5], 1u << (c & 31));
             const int cl = sh.colCell[c];
             atomicAdd(&sh.rowOfs[cl][pos >> 8], 1);
+            const int slot = FT_LIST - 1 - atomicAdd(&sh.nSurv, 1);
+            if (slot >= total) Q[slot] = (uint16_t)pos; else sh.overflow = 1;
             if (markCells) sh.cellAny[cl] = 1;
         }
     }
@@ -247,7 +253,9 @@ __global__ void __launch_bounds__(FT_THREADS, 5) k_fast_cells(const __grid_const
             if (ld) *reinterpret_cast<uint4*>(tile + r * FT_PITCH + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src));
             *reinterpret_cast<uint4*>(score + r * FT_PITCH + 16 * v) = make_uint4(0, 0, 0, 0);
         }
-        for (int i = tid; i < shh * 8; i += FT_THREADS) (&sh.bitmap[0][0])[i] = 0;
+        static_assert((sizeof(sh.bitmap) + sizeof(sh.rowOfs)) % 16 == 0 && (sizeof(sh.bitmap) + sizeof(sh.rowOfs)) / 16 <= 2 * FT_THREADS, "clear");
+        for (int i = tid; i < (int)((sizeof(sh.bitmap) + sizeof(sh.rowOfs)) / 16); i += FT_THREADS)
+            reinterpret_cast<uint4*>(&sh.bitmap[0][0])[i] = make_uint4(0, 0, 0, 0);
         const int lastCol = maxBX - 4 - xa;               // tile column of the level's last interior column
         int inCell = max(tid - (X0 + 3 - xa), 0);         // column relative to the first interior column of the run
         int cc = 0;                                       // cell of the run (< 8): three compare-subtract steps
@@ -258,8 +266,7 @@ __global__ void __launch_bounds__(FT_THREADS, 5) k_fast_cells(const __grid_const
         sh.colFlags[tid] = (uint8_t)((inCell > 0 ? 1 : 0) | ((inCell < wCell - 1 && tid < lastCol) ? 2 : 0));
         sh.colOK[tid] = (tid >= cLo && tid < cHi) ? 0x80 : 0;
         if (tid < FT_MAXCELLS) sh.cellAny[tid] = 0;
-        if (tid == 0) sh.qCount = 0;
-        for (int i = tid; i < FT_MAXCELLS * FT_ROWS; i += FT_THREADS) (&sh.rowOfs[0][0])[i] = 0;
+        if (tid == 0) { sh.qCount = 0; sh.nSurv = 0; sh.overflow = 0; }
     }
     __syncthreads();
 
@@ -293,19 +300,31 @@ __global__ void __launch_bounds__(FT_THREADS, 5) k_fast_cells(const __grid_const
     }
     __syncthreads();
 
-    // ---- write the keypoints in row-major order inside each cell (cv::FAST's order)
-    for (int i = tid; i < shh * 8; i += FT_THREADS) {
-        const int r = i >> 3;
-        uint32_t word = sh.bitmap[r][i & 7];
-        while (word) {
-            const int c = ((i & 7) << 5) + __ffs(word) - 1;
-            word &= word - 1;
-            const int cl = sh.colCell[c];
-            const int cx0 = OBS_EDGE + (j0 + cl) * wCell - xa;
-            const int pos = sh.rowOfs[cl][r] + (c > cx0 ? row_bits(sh.bitmap[r], cx0, c) : 0);
-            uint32_t* slot = cand + (size_t)img * g.slotTotal + lg.slotBase + (size_t)(ci * lg.nCols + j0 + cl) * lg.cellCap;
-            // coordinates relative to the 16-px border origin, :820-825
-            slot[pos] = pack_key(xa + c - OBS_BORDER, Y0 + r - OBS_BORDER, score[r * FT_PITCH + c]);
+    // ---- write the keypoints in row-major order inside each cell (cv::FAST's order): position = keypoints of the cell in the rows
+    // above + keypoints of the cell to the left in the same row
+    uint32_t* slots = cand + (size_t)img * g.slotTotal + lg.slotBase + (size_t)(ci * lg.nCols + j0) * lg.cellCap;
+    auto emit = [&](int r, int c) {
+        const int cl = sh.colCell[c];
+        const int cx0 = OBS_EDGE + (j0 + cl) * wCell - xa;
+        const int pos = sh.rowOfs[cl][r] + (c > cx0 ? row_bits(sh.bitmap[r], cx0, c) : 0);
+        // coordinates relative to the 16-px border origin, :820-825
+        slots[cl * lg.cellCap + pos] = pack_key(xa + c - OBS_BORDER, Y0 + r - OBS_BORDER, score[r * FT_PITCH + c]);
+    };
+    if (!sh.overflow) {
+        const int K = sh.nSurv;
+        for (int i = tid; i < K; i += FT_THREADS) {
+            const int e = Q[FT_LIST - 1 - i];
+            emit(e >> 8, e & 255);
+        }
+    } else {
+        for (int i = tid; i < shh * 8; i += FT_THREADS) {
+            const int r = i >> 3;
+            uint32_t word = sh.bitmap[r][i & 7];
+            while (word) {
+                const int c = ((i & 7) << 5) + __ffs(word) - 1;
+                word &= word - 1;
+                emit(r, c);
+            }
         }
     }
 }
