@@ -373,6 +373,16 @@ def main():
         pipes = tj.get("_pipes", {}).get(dominant)
     except Exception:
         pass
+    issue = None
+    if pipes and pipes.get("warp_instructions"):
+        # warp instructions of one launch (ncu count at 64 images, scaled to this batch) over the live launch time, against
+        # 148 SMs x 4 schedulers x SM clock
+        wi = pipes["warp_instructions"] * F / 64.0
+        sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+        pk = 148 * 4 * sm_hz
+        issue = {"achieved": wi / (per_launch_ms[dominant] * 1e-3) / 1e12, "peak": pk / 1e12, "unit": "T warp-instructions/s",
+                 "frac": wi / (per_launch_ms[dominant] * 1e-3) / pk,
+                 "source": "instruction count from profiles/traffic.json (_pipes, ncu smsp__inst_executed.sum), time measured live"}
     if alg[dominant] is not None:
         achieved = alg[dominant] / (per_launch_ms[dominant] * 1e-3) / 1e9
     else:
@@ -380,6 +390,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "ncu_pipes": pipes,
+                "issue": issue,
                 "bound_note": "every stage is integer-issue bound before it is HBM bound (DESIGN.md section 4): ncu_pipes holds the ncu "
                               "pipe utilisation of the dominant kernel (ALU pipe: one warp instruction per 2 cycles per SM sub-partition)",
                 "per_launch_ms": per_launch_ms, "share_of_step": shares,
