@@ -12,6 +12,8 @@
 // next when the vertical taps allow; the vertical blend is two IMAD.HI per pixel.
 #include "kernels.h"
 #include <algorithm>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -146,15 +148,17 @@ __device__ __forceinline__ void hrow_tile(const uint8_t* row, int shift, const u
     for (int i = 0; i < 4; i++) hs[i] = __dp2a_lo(w[i], __byte_perm(U0, U1, sel[i]), 0u) >> 4;
 }
 
-__global__ void __launch_bounds__(32 * RT_BANDS) k_resize_tile(const __grid_constant__ Geom g, const PyrPtrs p,
-                                                               const ResizeTap* __restrict__ xtab,
-                                                               const ResizeTap* __restrict__ ytab, int level) {
-    extern __shared__ __align__(16) uint8_t tile[];
-    __shared__ YTap sY[RESIZE_TILE_H];
+// One 128 x 64 output tile of level `level` of image `img`.  CHAIN: the source level may have been written by another CTA of
+// the same cluster moments ago (k_resize_chain), so it is read through L2 (ld.global.cg) instead of the non-coherent path, and the
+// function ends with a barrier because the caller reuses the shared buffers for its next tile.
+template <bool CHAIN>
+__device__ __forceinline__ void resize_tile_body(const Geom& g, const PyrPtrs& p, const ResizeTap* __restrict__ xtab,
+                                                 const ResizeTap* __restrict__ ytab, int level, int img, int tileX, int tileY,
+                                                 uint8_t* tile, YTap* sY) {
     const LevelGeom& D = g.lv[level];
     const LevelGeom& S = g.lv[level - 1];
-    const int img = blockIdx.z, tid = threadIdx.y * 32 + threadIdx.x;
-    const int tx0 = blockIdx.x * RESIZE_TILE_W, ty0 = blockIdx.y * RESIZE_TILE_H;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int tx0 = tileX * RESIZE_TILE_W, ty0 = tileY * RESIZE_TILE_H;
     const int tw = min(RESIZE_TILE_W, D.w - tx0), th = min(RESIZE_TILE_H, D.h - ty0);
     const ResizeTap* xt = xtab + D.xtab;
     const ResizeTap* yt = ytab + D.ytab;
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(32 * RT_BANDS) k_resize_tile(const __grid_cons
     const int xs0 = xt[tx0].ofs & ~15, xs1 = xt[tx0 + tw - 1].ofs + 1;
     const int ys0 = min(max(yt[ty0].ofs, 0), S.h - 1), ys1 = min(max(yt[ty0 + th - 1].ofs + 1, 0), S.h - 1);
     const int pitch = D.rsPitch;
+    auto ld = [](const uint4* q) { return CHAIN ? __ldcg(q) : __ldg(q); };
     {
         // rows of the source are padded to a multiple of 16 bytes (slab pitch 128; level 0: 16-byte aligned stride)
         const int nVec = min((xs1 - xs0) / 16 + 1, (spitch - xs0) >> 4), nRows = ys1 - ys0 + 1;
@@ -174,13 +179,13 @@ __global__ void __launch_bounds__(32 * RT_BANDS) k_resize_tile(const __grid_cons
             const size_t gstep = (size_t)spitch * RSTEP / 16;
             int r = tid >> 4;
             for (; r + 3 * RSTEP < nRows; r += 4 * RSTEP, gp += 4 * gstep, tp += 4 * RSTEP * pitch) {
-                const uint4 a = __ldg(gp), b = __ldg(gp + gstep), c = __ldg(gp + 2 * gstep), d = __ldg(gp + 3 * gstep);
+                const uint4 a = ld(gp), b = ld(gp + gstep), c = ld(gp + 2 * gstep), d = ld(gp + 3 * gstep);
                 *reinterpret_cast<uint4*>(tp) = a;
                 *reinterpret_cast<uint4*>(tp + RSTEP * pitch) = b;
                 *reinterpret_cast<uint4*>(tp + 2 * RSTEP * pitch) = c;
                 *reinterpret_cast<uint4*>(tp + 3 * RSTEP * pitch) = d;
             }
-            for (; r < nRows; r += RSTEP, gp += gstep, tp += RSTEP * pitch) *reinterpret_cast<uint4*>(tp) = __ldg(gp);
+            for (; r < nRows; r += RSTEP, gp += gstep, tp += RSTEP * pitch) *reinterpret_cast<uint4*>(tp) = ld(gp);
         }
         if (tid < th) {
             const ResizeTap t = yt[ty0 + tid];
@@ -193,39 +198,68 @@ __global__ void __launch_bounds__(32 * RT_BANDS) k_resize_tile(const __grid_cons
     }
     __syncthreads();
     const int dx0 = tx0 + 4 * threadIdx.x, r0 = threadIdx.y * RT_ROWS;
-    if (dx0 >= D.w || r0 >= th) return;
-    const int nOut = min(RT_ROWS, th - r0);
-
-    unsigned w[4], sel[4];
-    int ofs0;
-    {
-        const ResizeTap t0 = xt[dx0];
-        ofs0 = t0.ofs;
+    if (dx0 < D.w && r0 < th) {
+        const int nOut = min(RT_ROWS, th - r0);
+        unsigned w[4], sel[4];
+        int ofs0;
+        {
+            const ResizeTap t0 = xt[dx0];
+            ofs0 = t0.ofs;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const ResizeTap tx = i ? xt[min(dx0 + i, D.w - 1)] : t0;
-            const int o = tx.ofs - ofs0;                    // 0..6 (host-checked)
-            w[i] = (unsigned)(unsigned short)tx.a0 | ((unsigned)(unsigned short)tx.a1 << 16);
-            sel[i] = (unsigned)o | ((unsigned)(o + 1) << 4);
+            for (int i = 0; i < 4; i++) {
+                const ResizeTap tx = i ? xt[min(dx0 + i, D.w - 1)] : t0;
+                const int o = tx.ofs - ofs0;                    // 0..6 (host-checked)
+                w[i] = (unsigned)(unsigned short)tx.a0 | ((unsigned)(unsigned short)tx.a1 << 16);
+                sel[i] = (unsigned)o | ((unsigned)(o + 1) << 4);
+            }
+        }
+        const int rel = ofs0 - xs0;
+        const uint8_t* col = tile + (rel & ~3);
+        const int shift = 8 * (rel & 3);
+        uint8_t* out = dst + (size_t)(ty0 + r0) * dpitch + dx0;
+        // Every output row filters its two source rows afresh: at scale 1.2 that is 2 row filters per output row
+        // instead of 1.2, but the loop carries no state, no branches and no register shuffling.
+#pragma unroll 4
+        for (int r = 0; r < nOut; r++, out += dpitch) {
+            const YTap y = sY[r0 + r];
+            unsigned hA[4], hB[4];
+            hrow_tile(col + y.off0, shift, w, sel, hA);
+            hrow_tile(col + y.off1, shift, w, sel, hB);
+            unsigned o = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) o += ((__umulhi(y.b0, hA[i]) + __umulhi(y.b1, hB[i]) + 2u) >> 2) << (8 * i);
+            *reinterpret_cast<uint32_t*>(out) = o;          // rows are padded to the pitch
         }
     }
-    const int rel = ofs0 - xs0;
-    const uint8_t* col = tile + (rel & ~3);
-    const int shift = 8 * (rel & 3);
-    uint8_t* out = dst + (size_t)(ty0 + r0) * dpitch + dx0;
+    if (CHAIN) __syncthreads();
+}
 
-    // Every output row filters its two source rows afresh: at scale 1.2 that is 2 row filters per output row
-    // instead of 1.2, but the loop carries no state, no branches and no register shuffling.
-#pragma unroll 4
-    for (int r = 0; r < nOut; r++, out += dpitch) {
-        const YTap y = sY[r0 + r];
-        unsigned hA[4], hB[4];
-        hrow_tile(col + y.off0, shift, w, sel, hA);
-        hrow_tile(col + y.off1, shift, w, sel, hB);
-        unsigned o = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) o += ((__umulhi(y.b0, hA[i]) + __umulhi(y.b1, hB[i]) + 2u) >> 2) << (8 * i);
-        *reinterpret_cast<uint32_t*>(out) = o;          // rows are padded to the pitch
+__global__ void __launch_bounds__(32 * RT_BANDS) k_resize_tile(const __grid_constant__ Geom g, const PyrPtrs p,
+                                                               const ResizeTap* __restrict__ xtab,
+                                                               const ResizeTap* __restrict__ ytab, int level) {
+    extern __shared__ __align__(16) uint8_t tile[];
+    __shared__ YTap sY[RESIZE_TILE_H];
+    resize_tile_body<false>(g, p, xtab, ytab, level, blockIdx.z, blockIdx.x, blockIdx.y, tile, sY);
+}
+
+// The small levels of the pyramid in one launch: a thread-block cluster of RC_CTAS CTAs owns one image and walks the levels
+// firstLevel .. n-1; the tiles of a level are dealt round-robin to the CTAs of the cluster, and a cluster barrier (release /
+// acquire at cluster scope) separates the levels.  Replaces 4 dependent launches of a few dozen CTAs each per image batch.
+constexpr int RC_CTAS = 8;
+
+__global__ void __launch_bounds__(32 * RT_BANDS) k_resize_chain(const __grid_constant__ Geom g, const PyrPtrs p,
+                                                                const ResizeTap* __restrict__ xtab,
+                                                                const ResizeTap* __restrict__ ytab, int firstLevel) {
+    extern __shared__ __align__(16) uint8_t tile[];
+    __shared__ YTap sY[RESIZE_TILE_H];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), img = blockIdx.y;
+    for (int level = firstLevel; level < g.nlevels; level++) {
+        const LevelGeom& D = g.lv[level];
+        const int tilesX = (D.w + RESIZE_TILE_W - 1) / RESIZE_TILE_W, tilesY = (D.h + RESIZE_TILE_H - 1) / RESIZE_TILE_H;
+        for (int t = rank; t < tilesX * tilesY; t += RC_CTAS)
+            resize_tile_body<true>(g, p, xtab, ytab, level, img, t % tilesX, t / tilesX, tile, sY);
+        if (level + 1 < g.nlevels) cluster.sync();
     }
 }
 
@@ -266,15 +300,43 @@ cudaError_t launch_repack(const uint8_t* src, size_t srcImgStride, size_t srcPit
     return cudaGetLastError();
 }
 
+// First level of the cluster-chained tail: the smallest l >= 1 from which every level uses the tiled kernel and has at most
+// 2 * RC_CTAS tiles, provided at least two levels remain; 0 = no chain.
+static int chain_first_level(const Geom& g) {
+    int first = 0;
+    for (int l = g.nlevels - 1; l >= 1; l--) {
+        const int tiles = ((g.lv[l].w + RESIZE_TILE_W - 1) / RESIZE_TILE_W) * ((g.lv[l].h + RESIZE_TILE_H - 1) / RESIZE_TILE_H);
+        if (g.lv[l].rsPitch <= 0 || tiles > 2 * RC_CTAS) break;
+        first = l;
+    }
+    return (first > 0 && g.nlevels - first >= 2) ? first : 0;
+}
+
 cudaError_t pyramid_prepare(const Geom& g) {
     size_t need = 0;
     for (int l = 1; l < g.nlevels; l++) need = std::max(need, (size_t)g.lv[l].rsPitch * g.lv[l].rsRows);
     if (need <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(k_resize_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    cudaError_t e = cudaFuncSetAttribute(k_resize_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_resize_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
 }
 
 cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, const ResizeTap* ytab, int nimg, cudaStream_t st) {
+    const int chain = chain_first_level(g);
     for (int l = 1; l < g.nlevels; l++) {
+        if (chain && l == chain) {
+            size_t smem = 0;
+            for (int k = chain; k < g.nlevels; k++) smem = std::max(smem, (size_t)g.lv[k].rsPitch * g.lv[k].rsRows);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(RC_CTAS, nimg); cfg.blockDim = dim3(32, RT_BANDS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = RC_CTAS; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, k_resize_chain, g, p, xtab, ytab, chain);
+            if (e != cudaSuccess) return e;
+            break;
+        }
         if (g.lv[l].rsPitch > 0) {
             dim3 block(32, RT_BANDS);
             dim3 grid((g.lv[l].w + RESIZE_TILE_W - 1) / RESIZE_TILE_W, (g.lv[l].h + RESIZE_TILE_H - 1) / RESIZE_TILE_H, nimg);
