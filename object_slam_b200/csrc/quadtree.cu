@@ -162,13 +162,16 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
             }
             __syncthreads();
             const int ofs = carry + S.warpTmp[warp] + incl - v;
-            // copy: the lanes of a warp cooperate on each of the warp's 32 cells
-            for (int src = 0; src < 32; src++) {
-                const int cv = __shfl_sync(0xffffffffu, v, src);
-                const int co = __shfl_sync(0xffffffffu, ofs, src);
-                if (cv == 0) continue;
-                const uint32_t* slot = slots + (size_t)(base + warp * 32 + src) * lg.cellCap;
-                for (int e = lane; e < cv; e += 32) keys[co + e] = slot[e];
+            // copy: a thread moves the (few) candidates of its own cell; four loads in flight at a time
+            if (v > 0) {
+                const uint32_t* slot = slots + (size_t)c * lg.cellCap;
+                uint32_t* dstk = keys + ofs;
+                int e = 0;
+                for (; e + 4 <= v; e += 4) {
+                    const uint32_t a0 = slot[e], a1 = slot[e + 1], a2 = slot[e + 2], a3 = slot[e + 3];
+                    dstk[e] = a0; dstk[e + 1] = a1; dstk[e + 2] = a2; dstk[e + 3] = a3;
+                }
+                for (; e < v; e++) dstk[e] = slot[e];
             }
             carry += S.warpTmp[32];
             __syncthreads();
@@ -274,12 +277,16 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
         const int Ctot = S.scanA[nsplit - 1] + S.neArr[nsplit - 1];
 
         // 2.4 new positions: children in reverse creation order, then the unsplit nodes in old order
-        for (int i = tid; i < L; i += QT_THREADS) S.scanB[i] = !(C[i] > 1 && S.rank[i] < nsplit);
-        __syncthreads();
-        block_scan_excl(S.scanB, L, S.warpTmp);
+        // (in a sweep every splittable node splits and scanB still holds "splittable nodes before i" from 2.1, so the unsplit
+        // nodes before i number i - scanB[i]; a largest-first pass needs a scan over the nodes it actually split)
+        if (largestFirst) {
+            for (int i = tid; i < L; i += QT_THREADS) S.scanB[i] = !(C[i] > 1 && S.rank[i] < nsplit);
+            __syncthreads();
+            block_scan_excl(S.scanB, L, S.warpTmp);
+        }
         for (int i = tid; i < L; i += QT_THREADS) {
             if (!(C[i] > 1 && S.rank[i] < nsplit)) {
-                const int pos = Ctot + S.scanB[i];
+                const int pos = Ctot + (largestFirst ? S.scanB[i] : i - S.scanB[i]);
                 S.selfPos[i] = (uint16_t)pos;
                 Rn[pos] = R[i];
                 Cn[pos] = C[i];
