@@ -423,7 +423,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "obs_extract_batch x2 (two host threads) + obs_stereo_match, page-locked host buffers in and out; "
                                             f"{WORKERS} pipelines take alternate steps (transfers of one overlap kernels of the other)"},
-        "gpu_launches": 24 * args.steps,
+        # per eye: 3 tiled resize levels + the cluster-chained tail, FAST, quadtree, blur, describe; per frame batch: stereo rows / match / filter
+        "gpu_launches": (2 * 8 + 3) * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
