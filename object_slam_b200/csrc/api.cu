@@ -193,7 +193,7 @@ void build_geometry(obs_extractor* e, int w, int h) {
     g.iniTh = e->prm.ini_th_fast; g.minTh = e->prm.min_th_fast;
     memcpy(g.umax, e->umax, sizeof(g.umax));
     unsigned off = 0, slot = 0;
-    int cells = 0, xt = 0, yt = 0, tiles = 0, maxFeat = 0, nodeCap = 0, fastCtas = 0, edgeItems = 0;
+    int cells = 0, xt = 0, yt = 0, tiles = 0, maxFeat = 0, nodeCap = 0, fastCtas = 0, edgeItems = 0, kpWorst = 0;
     for (int l = 0; l < nl; l++) {
         LevelGeom& L = g.lv[l];
         L.w = cv_round_f((float)w * e->invScale[l]);
@@ -243,12 +243,15 @@ void build_geometry(obs_extractor* e, int w, int h) {
         int nIni = 0;
         if (width > 0 && height > 0) nIni = (int)roundf((float)width / (float)height);
         nodeCap = std::max(nodeCap, std::max(L.nfeat + 4, 4 * nIni + 4));
+        // DistributeOctTree leaves at most N + 3 nodes, except that its first sweep always splits every root: very wide
+        // levels (nIni roots of one cell height) can end with up to 4 nIni nodes whatever the quota (:606-669)
+        kpWorst += std::max(L.nfeat + 3, 4 * nIni);
     }
     g.nCellsTotal = cells;
     g.slotTotal = std::max(slot, 1u);
     g.slabBytes = off;
     g.selCap = round_up(nodeCap, 4);
-    g.kpCap = round_up(e->prm.nfeatures + 4 * nl, 32);
+    g.kpCap = round_up(std::max(e->prm.nfeatures + 4 * nl, kpWorst), 32);
     g.blurTilesTotal = tiles;
     g.blurEdgeCtas = (edgeItems + 127) / 128;
     g.fastCtasTotal = fastCtas;

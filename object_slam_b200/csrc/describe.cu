@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
 
     for (int it = 0; it < DESC_PER_WARP; it++) {
         const int j = (blockIdx.x * DESC_PER_WARP + it) * DESC_WARPS + warp;     // output index of the keypoint (level-major)
-        if (j >= total) break;
+        if (j >= total || j >= g.kpCap) break;            // (the capacity covers the extractor's worst case; never write past it)
         const int level = __popc(__ballot_sync(0xffffffffu, lane < g.nlevels - 1 && j >= levelEnd[min(lane, OBS_MAX_LEVELS)]));
         const int local = j - (level ? levelEnd[level - 1] : 0);
         const LevelGeom& lg = g.lv[level];
