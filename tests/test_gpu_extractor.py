@@ -211,6 +211,7 @@ def test_pinned_host_buffers_take_the_dma_path(gpu):
 def test_very_wide_image_capacity(gpu):
     """A level much wider than high starts DistributeOctTree with many roots and its first sweep always splits them all, so a level
     can end far above its quota (src/ORBextractor.cc:606-669): 402 keypoints for nFeatures = 300 here.  The capacity must follow."""
+    from object_slam_b200.extractor import ORBextractor
     shape = (118, 1121)
     img = synth.blocky_image(shape, 651119381)
     e = ORBextractor(300, 1.1, 8, 20, 5, max_size=(shape[1], shape[0]))
