@@ -26,7 +26,15 @@
 
 namespace {
 
-constexpr int FT_PITCH = 256;          // bytes per staged row
+constexpr int FT_PITCH = 256;          // columns of a staged row
+#ifndef FT_PAD
+#define FT_PAD 16
+#endif
+#ifndef FT_MINCTAS
+#define FT_MINCTAS 4
+#endif
+constexpr int FT_SP = FT_PITCH + FT_PAD;   // shared-memory pitch of the tile and the score map: consecutive rows start 4 banks apart, so lanes
+                                       // that score pixels of neighbouring rows (same columns) do not collide
 constexpr int FT_ROWS = 66;            // hCell <= 60, + 6
 constexpr int FT_THREADS = 256;
 constexpr int FT_LIST = 8192;          // queue capacity == max interior pixels per CTA (host enforces)
@@ -48,7 +56,7 @@ __device__ __forceinline__ int fast_contrast(const uint8_t* c) {
     const unsigned v = c[0];
     const unsigned Vc = (v + 255u) | ((255u - v) << 16);
     unsigned P[16];
-#define RING(k, dx, dy) P[k] = (unsigned)c[(dy) * FT_PITCH + (dx)] * 0xFFFFu + Vc
+#define RING(k, dx, dy) P[k] = (unsigned)c[(dy) * FT_SP + (dx)] * 0xFFFFu + Vc
     RING(0, 0, 3); RING(1, 1, 3); RING(2, 2, 2); RING(3, 3, 1); RING(4, 3, 0); RING(5, 3, -1); RING(6, 2, -2); RING(7, 1, -3);
     RING(8, 0, -3); RING(9, -1, -3); RING(10, -2, -2); RING(11, -3, -1); RING(12, -3, 0); RING(13, -3, 1); RING(14, -2, 2); RING(15, -1, 3);
 #undef RING
@@ -122,13 +130,13 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
             unsigned acc = 0;
             if (r < rHi) {
                 if (cheap) {
-                    const uint8_t* rowp = tile + r * FT_PITCH + 16 * l8;
+                    const uint8_t* rowp = tile + r * FT_SP + 16 * l8;
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
                         const uint8_t* cp = rowp + 128 * q;
                         const uint4 C = *reinterpret_cast<const uint4*>(cp);
-                        const uint4 U = *reinterpret_cast<const uint4*>(cp + 3 * FT_PITCH);
-                        const uint4 D = *reinterpret_cast<const uint4*>(cp - 3 * FT_PITCH);
+                        const uint4 U = *reinterpret_cast<const uint4*>(cp + 3 * FT_SP);
+                        const uint4 D = *reinterpret_cast<const uint4*>(cp - 3 * FT_SP);
                         const unsigned L = *reinterpret_cast<const unsigned*>(cp - 4);
                         const unsigned R = *reinterpret_cast<const unsigned*>(cp + 16);
                         const uint4 ok = q ? okB : okA;
@@ -175,12 +183,12 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
             // entry: row << 8 | l8 << 5 | j << 3 | q << 2 | i  ->  column = q << 7 | l8 << 4 | i << 2 | j
             const unsigned c = ((e & 4u) << 5) | ((e >> 1) & 0x70u) | ((e & 3u) << 2) | ((e >> 3) & 3u);
             pos = (int)((e & 0xff00u) | c);
-            const int contrast = fast_contrast(tile + pos);
+            const int contrast = fast_contrast(tile + (pos >> 8) * FT_SP + (pos & 255));
             if (contrast > t && contrast > 1) s = contrast - 1;            // OpenCV: score = corner contrast - 1
         }
         const unsigned bal = __ballot_sync(0xffffffffu, s > 0);
         if (s > 0) {
-            score[pos] = (uint8_t)s;
+            score[(pos >> 8) * FT_SP + (pos & 255)] = (uint8_t)s;
             Q[start + nC + __popc(bal & ltMask)] = (uint16_t)pos;
         }
         nC += __popc(bal);
@@ -191,11 +199,11 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
     for (int i = lane; i < nC; i += 32) {
         const int pos = Q[start + i];
         const int c = pos & 255;
-        const uint8_t* sc = score + pos;
+        const uint8_t* sc = score + (pos >> 8) * FT_SP + c;
         const int fl = sh.colFlags[c];
-        int m = max(sc[-FT_PITCH], sc[FT_PITCH]);
-        const int mL = max(max(sc[-FT_PITCH - 1], sc[-1]), sc[FT_PITCH - 1]);
-        const int mR = max(max(sc[-FT_PITCH + 1], sc[1]), sc[FT_PITCH + 1]);
+        int m = max(sc[-FT_SP], sc[FT_SP]);
+        const int mL = max(max(sc[-FT_SP - 1], sc[-1]), sc[FT_SP - 1]);
+        const int mR = max(max(sc[-FT_SP + 1], sc[1]), sc[FT_SP + 1]);
         if (fl & 1) m = max(m, mL);
         if (fl & 2) m = max(m, mR);
         if (sc[0] > m) {
@@ -210,13 +218,13 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(FT_THREADS, 5) k_fast_cells(const __grid_constant__ Geom g, const PyrPtrs p,
+__global__ void __launch_bounds__(FT_THREADS, FT_MINCTAS) k_fast_cells(const __grid_constant__ Geom g, const PyrPtrs p,
                                                            const FastCta* __restrict__ ctaTab, int tileRows,
                                                            uint32_t* __restrict__ cand, int* __restrict__ cellCount) {
     extern __shared__ __align__(16) uint8_t sm[];
     uint8_t* tile = sm;                                   // tileRows x FT_PITCH pixels
-    uint8_t* score = sm + tileRows * FT_PITCH;            // same geometry, 0 = not a corner
-    uint16_t* Q = reinterpret_cast<uint16_t*>(sm + 2 * tileRows * FT_PITCH);    // pixel queue of the CTA
+    uint8_t* score = sm + tileRows * FT_SP;            // same geometry, 0 = not a corner
+    uint16_t* Q = reinterpret_cast<uint16_t*>(sm + 2 * tileRows * FT_SP);    // pixel queue of the CTA
     __shared__ __align__(16) FastShared sh;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -250,8 +258,8 @@ __global__ void __launch_bounds__(FT_THREADS, 5) k_fast_cells(const __grid_const
         const size_t srcStep = (size_t)pitch * (FT_THREADS / 16);
         const bool ld = v < nVec;
         for (int r = tid >> 4; r < shh; r += FT_THREADS / 16, src += srcStep) {
-            if (ld) *reinterpret_cast<uint4*>(tile + r * FT_PITCH + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src));
-            *reinterpret_cast<uint4*>(score + r * FT_PITCH + 16 * v) = make_uint4(0, 0, 0, 0);
+            if (ld) *reinterpret_cast<uint4*>(tile + r * FT_SP + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src));
+            *reinterpret_cast<uint4*>(score + r * FT_SP + 16 * v) = make_uint4(0, 0, 0, 0);
         }
         static_assert((sizeof(sh.bitmap) + sizeof(sh.rowOfs)) % 16 == 0 && (sizeof(sh.bitmap) + sizeof(sh.rowOfs)) / 16 <= 2 * FT_THREADS, "clear");
         for (int i = tid; i < (int)((sizeof(sh.bitmap) + sizeof(sh.rowOfs)) / 16); i += FT_THREADS)
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(FT_THREADS, 5) k_fast_cells(const __grid_const
         const int cx0 = OBS_EDGE + (j0 + cl) * wCell - xa;
         const int pos = sh.rowOfs[cl][r] + (c > cx0 ? row_bits(sh.bitmap[r], cx0, c) : 0);
         // coordinates relative to the 16-px border origin, :820-825
-        slots[cl * lg.cellCap + pos] = pack_key(xa + c - OBS_BORDER, Y0 + r - OBS_BORDER, score[r * FT_PITCH + c]);
+        slots[cl * lg.cellCap + pos] = pack_key(xa + c - OBS_BORDER, Y0 + r - OBS_BORDER, score[r * FT_SP + c]);
     };
     if (!sh.overflow) {
         const int K = sh.nSurv;
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(FT_THREADS, 5) k_fast_cells(const __grid_const
 
 }  // namespace
 
-size_t fast_smem_bytes(int tileRows) { return (size_t)2 * tileRows * FT_PITCH + (size_t)FT_LIST * 2; }
+size_t fast_smem_bytes(int tileRows) { return (size_t)2 * tileRows * FT_SP + (size_t)FT_LIST * 2; }
 
 cudaError_t fast_prepare(int tileRows) {
     return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(tileRows));
