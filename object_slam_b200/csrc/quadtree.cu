@@ -19,7 +19,10 @@
 
 namespace {
 
-constexpr int QT_THREADS = 512;
+#ifndef QT_NT
+#define QT_NT 512
+#endif
+constexpr int QT_THREADS = QT_NT;
 constexpr int QT_SMEM_KEYS = 4096;       // problems with at most this many candidates keep keys + node ids in shared memory
 
 struct Smem {
