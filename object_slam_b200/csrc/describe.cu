@@ -16,7 +16,10 @@ __device__ const int8_t d_pattern[256 * 4] = {
 #include "orb_pattern.inc"
 };
 
-constexpr int DESC_WARPS = 8;
+#ifndef DESC_NW
+#define DESC_NW 4
+#endif
+constexpr int DESC_WARPS = DESC_NW;
 
 // cv::fastAtan2 (OpenCV core, atanImpl scalar path): degrees in [0, 360).
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
@@ -74,7 +77,10 @@ __device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp)
     if (n & 1) { *sinp = cv; *cosp = sv; } else { *sinp = sv; *cosp = cv; }
 }
 
-constexpr int DESC_PER_WARP = 8;     // keypoints per warp: tables and the level offsets are set up once per 64 keypoints
+#ifndef DESC_NPW
+#define DESC_NPW 8
+#endif
+constexpr int DESC_PER_WARP = DESC_NPW;     // keypoints per warp: tables and the level offsets are set up once per 64 keypoints
 constexpr int PR = 18, PP = 40;      // rBRIEF window radius (pattern radius <= 18.39), staged row pitch (10 words)
 
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Geom g, const PyrPtrs p,
@@ -94,8 +100,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
         const int pr = (i & 31) * 8 + (i >> 5);
         pat[i] = make_float4((float)d_pattern[4 * pr], (float)d_pattern[4 * pr + 1], (float)d_pattern[4 * pr + 2], (float)d_pattern[4 * pr + 3]);
     }
-    if (tid < (OBS_HALF_PATCH + 2) * 8) {
-        const int av = tid >> 3, wi = tid & 7;
+    for (int t = tid; t < (OBS_HALF_PATCH + 2) * 8; t += DESC_WARPS * 32) {
+        const int av = t >> 3, wi = t & 7;
         uint32_t m = 0;
         if (av <= OBS_HALF_PATCH)
             for (int k = 0; k < 4; k++) if (abs(-OBS_HALF_PATCH + 4 * wi + k) <= g.umax[av]) m |= 0xffu << (8 * k);

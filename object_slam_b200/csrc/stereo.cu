@@ -16,7 +16,10 @@
 
 namespace {
 
-constexpr int ST_WARPS = 8;
+#ifndef ST_NW
+#define ST_NW 4
+#endif
+constexpr int ST_WARPS = ST_NW;
 constexpr int TH_HIGH = 100, TH_LOW = 50;
 
 __device__ __forceinline__ int hamming256(const uint32_t* a, const uint4 b0, const uint4 b1) {
