@@ -160,12 +160,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-pipelines", type=int, default=3, help="host-buffer pipelines of the e2e leg (each: an extractor pair + pinned buffers)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (0 = min(steps, 12))")
-    ap.add_argument("--workload", default="stereo", choices=["stereo", "knn2", "projection", "bow"],
+    ap.add_argument("--workload", default="stereo", choices=["stereo", "knn2", "projection", "bow", "extract"],
                     help="stereo = configs[1] (the headline); knn2 = configs[4] keyframe-vs-keyframe Hamming matching; "
-                         "projection = configs[2] TUM-shape extraction + SearchByProjection against a 20k-point map")
+                         "projection = configs[2] TUM-shape extraction + SearchByProjection against a 20k-point map; "
+                         "extract = configs[3] batched offline extraction of --total-frames KITTI-shape frames")
     ap.add_argument("--keyframes", type=int, default=4096, help="knn2: keyframes in total (sharded over the GPUs)")
     ap.add_argument("--window", type=int, default=8, help="knn2: every keyframe is matched against the +-window neighbours")
     ap.add_argument("--map-points", type=int, default=20000, help="projection: map points per frame")
+    ap.add_argument("--total-frames", type=int, default=32768, help="extract: frames of the whole offline job (configs[3]), sharded over the GPUs")
+    ap.add_argument("--pool-batches", type=int, default=4, help="extract: batches of distinct synthetic frames resident per GPU (cycled)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -1,4 +1,4 @@
-"""The matcher workloads of bench.py (`--workload knn2|projection`); same JSON contract as the headline line.
+"""The other workloads of bench.py (`--workload knn2|projection|bow|extract`); same JSON contract as the headline line.
 
 knn2        configs[4]: K keyframes x 2000 descriptors, every keyframe matched against its +-window neighbours
             (best / second best / ratio test).  Query keyframes are sharded over the ranks (strong scaling: the
@@ -7,6 +7,8 @@ knn2        configs[4]: K keyframes x 2000 descriptors, every keyframe matched a
             while it is in flight.
 projection  configs[2]: TUM-shape frames: extraction + frame-set (grid) build + SearchByProjection against a
             20k-point map per frame.  Frames are sharded over the ranks, no collective (weak scaling).
+extract     configs[3]: batched offline extraction of 32768 KITTI-shape frames, contiguous frame shards per rank, no
+            collective; a step is one batch of F frames per rank.
 """
 import ctypes as C
 import json
@@ -559,9 +561,196 @@ def run_bow(args, rank, local_rank, world, ClockSampler):
         dist.destroy_process_group()
 
 
+def cpu_extract(imgs, cores, nfeat):
+    """The reference extractor (oracle/_ref) on every image, `cores` host threads.  Returns (seconds, kind)."""
+    import oracle
+    import threading
+    use_ref = oracle.ref_available()
+    tl = threading.local()
+
+    def one(img):
+        if not hasattr(tl, "ex"):
+            tl.ex = oracle.ReferenceExtractor(nfeat) if use_ref else oracle.OracleExtractor(nfeat)
+        return len(tl.ex(img)[0])
+
+    with ThreadPoolExecutor(cores) as pool:
+        list(pool.map(one, imgs[:cores]))
+        t0 = time.perf_counter()
+        list(pool.map(one, imgs))
+        return time.perf_counter() - t0, ("reference" if use_ref else "port")
+
+
+def run_extract(args, rank, local_rank, world, ClockSampler):
+    """configs[3]: batched offline ORB extraction of `--total-frames` (32768) KITTI-shape frames.  The frame range is cut into
+    contiguous shards, one per rank (sharding.shard_range), no collective; a step is one batch of F frames per rank, so the job
+    is total / (F * world) steps per rank.  The frames are a resident pool of distinct synthetic images (seed = global frame
+    index of the first `pool` frames of the shard) cycled over the shard: 32768 KITTI frames are 15 GB of numpy generation."""
+    Himg, Wimg, NF, PITCH = 376, 1241, 2000, 1280
+    F = args.frames
+    T = args.total_frames
+    metric = "frames/s, batched offline ORB extraction, KITTI 1241x376, 2000 kp"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        imgs = [synth.blocky_image((Himg, Wimg), i) for i in range(2 * cores)]
+        for _ in range(args.warmup):
+            cpu_extract(imgs[:cores], cores, NF)
+        total, kind = 0.0, "port"
+        for _ in range(args.steps):
+            dt, kind = cpu_extract(imgs, cores, NF)
+            total += dt
+        v = len(imgs) * args.steps / total
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "configs[3] batched offline ORB extraction, KITTI shape", "frames_per_step": len(imgs)},
+                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
+                                           "sample": f"{len(imgs)} frames per step; reference ORBextractor.cc compiled in place, {cores} host threads"},
+                          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    import threading
+    import torch
+    import torch.distributed as dist
+    from object_slam_b200._capi import pinned_empty, KEYPOINT_DTYPE
+    from object_slam_b200.extractor import ORBextractor
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: object_slam_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lo, hi = sharding.shard_range(T, rank, world)
+    POOL = min(args.pool_batches * F, hi - lo)
+    POOL = max(POOL // F, 1) * F
+    with ThreadPoolExecutor(os.cpu_count() or 1) as tp:
+        imgs = list(tp.map(lambda i: synth.blocky_image((Himg, Wimg), lo + i), range(POOL)))
+    host = np.zeros((POOL, Himg, PITCH), np.uint8)
+    for i, im in enumerate(imgs):
+        host[i, :, :Wimg] = im
+    dimg = torch.from_numpy(host).to(dev)
+    NB = POOL // F
+    mk = lambda: ORBextractor(NF, 1.2, 8, 20, 7, max_size=(Wimg, Himg), max_batch=F, device=local_rank)
+    NPIPES = int(os.environ.get("OBS_BENCH_PIPES", "3"))
+    dpipes = [(mk(), torch.cuda.Stream()) for _ in range(NPIPES)]
+    main_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(main_stream)
+    step_no = [0]
+
+    def step_device():
+        ex, st = dpipes[step_no[0] % NPIPES]
+        b = step_no[0] % NB
+        step_no[0] += 1
+        ex.extract_device(dimg.data_ptr() + b * F * Himg * PITCH, F, Wimg, Himg, PITCH, Himg * PITCH, st.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, NPIPES, 3)):
+        step_device()
+    step_no[0] = 0
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _, st in dpipes:
+        st.wait_stream(main_stream)
+    for _ in range(args.steps):
+        step_device()
+    for _, st in dpipes:
+        main_stream.wait_stream(st)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    counts = dpipes[0][0].fetch_counts()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * F * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: page-locked host images in, keypoints + descriptors out; WORKERS pipelines take alternate batches
+    WORKERS = args.e2e_pipelines
+    cap = dpipes[0][0].capacity
+
+    class Pipe:
+        def __init__(self, ex, b):
+            self.ex = ex
+            self.pin = pinned_empty((F, Himg, Wimg), np.uint8)
+            for i in range(F):
+                self.pin[i] = imgs[(b * F + i) % POOL]
+            self.out = (pinned_empty((F, cap), KEYPOINT_DTYPE), pinned_empty((F, cap, 32), np.uint8), pinned_empty((F,), np.int32))
+
+        def step(self):
+            return self.ex.extract_batch(self.pin, out=self.out, copy=False)
+
+    pipes = [Pipe(dpipes[i % NPIPES][0] if i < NPIPES else mk(), i) for i in range(WORKERS)]
+    e2e_steps = max(WORKERS, (args.e2e_steps or max(4, min(args.steps, 12))) // WORKERS * WORKERS)
+
+    def run_pipes(nsteps):
+        ths = [threading.Thread(target=lambda p=p: [p.step() for _ in range(nsteps // WORKERS)]) for p in pipes[1:]]
+        for th in ths:
+            th.start()
+        for _ in range(nsteps // WORKERS):
+            pipes[0].step()
+        for th in ths:
+            th.join()
+
+    run_pipes(2 * WORKERS)
+    barrier()
+    t0 = time.perf_counter()
+    run_pipes(e2e_steps)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * F * e2e_steps / float(t.item())
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            sample = [imgs[i % POOL] for i in range(16 * cores)]
+            dt, kind = cpu_extract(sample, cores, NF)
+            cpu = {"value": len(sample) / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+                   "sample": f"{len(sample)} frames of the pool: reference src/ORBextractor.cc compiled in place (oracle/_ref) on {cores} host threads, {dt:.1f} s"}
+        step_ms = ms_total / args.steps
+        eye_bytes = 9359539.0
+        peak = _hbm_peak()
+        print(json.dumps({
+            "metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"configs[3]: batched offline ORB extraction of {T} synthetic KITTI-shape 1241x376 frames, nFeatures=2000, "
+                                   f"nLevels=8, scale 1.2, FAST 20/7, contiguous frame shards over the ranks",
+                       "frames_per_step_per_gpu": F, "job_steps_per_gpu": (hi - lo + F - 1) // F,
+                       "job_seconds_at_this_rate": T / value,
+                       "pool": f"{POOL} distinct frames per rank resident in HBM ({POOL * Himg * PITCH / 1e6:.0f} MB), cycled over the shard",
+                       "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                       "l2": f"working set per step {F * 4.0:.0f} MB of images, pyramids and blurred levels (> 126 MB L2), pool of inputs larger than L2",
+                       "mean_keypoints": float(counts.mean())},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * Himg * Wimg, "d2h_bytes_per_step": F * (cap * 60 + 4) + F * 4,
+                    "steps": e2e_steps, "api": f"obs_extract_batch, page-locked host images in, keypoints + descriptors out; {WORKERS} pipelines "
+                                               "take alternate batches from their own host threads"},
+            "gpu_launches": 8 * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": F * eye_bytes / (step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": F * eye_bytes / (step_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "note": "9,359,539 algorithmic bytes per KITTI image (SURVEY 8d); the kernels are integer-issue bound (DESIGN.md section 4), "
+                                 "the per-kernel roofline is on the headline line (--workload stereo)"},
+            "cpu_baseline": cpu}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run(args, rank, local_rank, world, ClockSampler):
     if args.workload == "bow":
         return run_bow(args, rank, local_rank, world, ClockSampler)
+    if args.workload == "extract":
+        return run_extract(args, rank, local_rank, world, ClockSampler)
     if args.workload == "knn2":
         return run_knn2(args, rank, local_rank, world, ClockSampler)
     return run_projection(args, rank, local_rank, world, ClockSampler)

@@ -93,3 +93,54 @@ def test_two_rank_keyframe_matching_equals_single_process():
         bi, bd, sd = oracle.hamming_knn2(D[a], D[b], 50, 0.6)
         g = merged[(int(a), int(b))]
         assert np.array_equal(g[0], bi) and np.array_equal(g[1], bd) and np.array_equal(g[2], sd)
+
+
+def _frame_worker(rank, world, port, q):
+    """The frame-sharded schedule of bench.py (stereo / extract workloads): contiguous shard per rank, no data-path
+    collective, the step time is the max over the ranks (all_reduce MAX) -- with the oracle standing in for the kernels."""
+    import time
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T, shape = 7, (120, 160)
+    lo, hi = sharding.shard_range(T, rank, world)
+    ex = oracle.OracleExtractor(200)
+    dist.barrier()
+    t0 = time.perf_counter()
+    res = {i: tuple(a.copy() for a in ex(synth.blocky_image(shape, i))) for i in range(lo, hi)}
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
+    mine = float(t.item())
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    q.put((rank, res, mine, float(t.item())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_frame_sharding_equals_single_process():
+    import multiprocessing as mp
+    import oracle
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_frame_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    merged = {}
+    for rank, res, mine, mx in outs:
+        assert not (set(res) & set(merged))
+        merged.update(res)
+        assert mx >= mine
+    assert len({mx for _, _, _, mx in outs}) == 1          # every rank reports the same (max) time
+    assert sorted(merged) == list(range(7))
+    ex = oracle.OracleExtractor(200)
+    for i in range(7):
+        k, d = ex(synth.blocky_image((120, 160), i))
+        assert merged[i][0].tobytes() == k.tobytes() and np.array_equal(merged[i][1], d)
