@@ -67,6 +67,27 @@ __device__ __forceinline__ const uint8_t* level_ptr(const PyrPtrs& p, const Geom
     return p.slab + (size_t)img * p.slabStride + g.lv[l].off;
 }
 
+// ---- helpers against ptxas rematerialisation.  Under a register bound (__launch_bounds__) ptxas prefers recomputing loop
+// invariants -- the lane index, shared-window bases (S2R CgaCtaId + LEA), loop bounds -- in every iteration over keeping them in
+// registers; in issue-bound loops that is 10-20 % of the instructions.  A value that went through an opaque shuffle (per-lane
+// values) or a volatile shared-memory load (warp-uniform values: a shuffle of those is folded away) cannot be recomputed.
+__device__ __forceinline__ unsigned pin(unsigned x) {
+    unsigned y;
+    asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(y) : "r"(x), "r"(threadIdx.x & 31u));
+    return y;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_volatile_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
+    return v;
+}
+template <int OFS> __device__ __forceinline__ unsigned lds_u8(uint32_t a) {      // LDS.U8 [R + imm] on a shared-window address
+    unsigned v;
+    asm("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFS));
+    return v;
+}
+
 // Candidate / key record: x (12 bits) | y (12 bits) << 12 | FAST response (8 bits) << 24,
 // x and y relative to the 16-px border origin as the reference hands them to DistributeOctTree.
 __device__ __forceinline__ uint32_t pack_key(int x, int y, int r) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)r << 24); }

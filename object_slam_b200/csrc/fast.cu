@@ -54,15 +54,15 @@ __host__ __device__ inline int fast_cells_per_cta(int wCell, int hCell) {
 // contiguous ring pixels of the minimum of (v - r) [ring darker] and of (r - v) [ring brighter].
 // Both polarities ride in one register as two 16-bit lanes, biased by +255 so that one IMAD per
 // ring pixel builds the pair: r * 0xFFFF + (v + 255 | (255 - v) << 16) = (v - r + 255, r - v + 255).
-__device__ __forceinline__ int fast_contrast(const uint8_t* c) {
-    const unsigned v = c[0];
+// c is an address in the shared window (every ring pixel is one LDS.U8 [R + imm]); returns the contrast + 255.
+__device__ __forceinline__ int fast_contrast_s(uint32_t c) {
+    const unsigned v = lds_u8<0>(c);
     const unsigned Vc = (v + 255u) | ((255u - v) << 16);
     unsigned P[16];
-#define RING(k, dx, dy) P[k] = (unsigned)c[(dy) * FT_SP + (dx)] * 0xFFFFu + Vc
+#define RING(k, dx, dy) P[k] = lds_u8<(dy) * FT_SP + (dx)>(c) * 0xFFFFu + Vc
     RING(0, 0, 3); RING(1, 1, 3); RING(2, 2, 2); RING(3, 3, 1); RING(4, 3, 0); RING(5, 3, -1); RING(6, 2, -2); RING(7, 1, -3);
     RING(8, 0, -3); RING(9, -1, -3); RING(10, -2, -2); RING(11, -3, -1); RING(12, -3, 0); RING(13, -3, 1); RING(14, -2, 2); RING(15, -1, 3);
 #undef RING
-    // min over every run of 3, then of 9 (three runs of 3), then the max over the 16 arcs: 40 three-input ops
     unsigned m3[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) m3[i] = __vimin3_u16x2(P[i], P[(i + 1) & 15], P[(i + 2) & 15]);
@@ -73,7 +73,7 @@ __device__ __forceinline__ int fast_contrast(const uint8_t* c) {
         const unsigned b = __vimin3_u16x2(m3[i + 1], m3[(i + 4) & 15], m3[(i + 7) & 15]);
         best = __vimax3_u16x2(best, a, b);
     }
-    return (int)max(best & 0xffffu, best >> 16) - 255;
+    return (int)max(best & 0xffffu, best >> 16);           // corner contrast + 255
 }
 
 // number of set bits of a 256-bit row bitmap (8 words) inside columns [a, b), a < b
@@ -108,6 +108,7 @@ struct FastShared {
     int qCount;
     int nSurv;                                 // suppressed keypoints so far; they are listed from the top of the queue downwards
     int overflow;                              // the list ran into the queue (white-noise images): emission walks the bitmap instead
+    uint32_t pinTile, pinThr;                  // loop invariants of pass 2, fetched back with volatile loads (see pass 2)
 };
 
 // One detection phase at threshold t over the columns enabled in sh.colOK:
@@ -169,31 +170,43 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
             }
         }
     }
+    if (tid == 0) { sh.pinTile = smem_u32(tile); sh.pinThr = 255u + (unsigned)max(t, 1); }
     __syncthreads();
 
     // ---- pass 2
     const int total = sh.qCount;
     if (tid == 0 && total > FT_LIST - sh.nSurv) sh.overflow = 1;          // the queue reached the keypoints listed by the previous phase
     const int per = ((total + FT_THREADS - 1) / FT_THREADS) * 32;
-    const int start = warp * per, end = min(start + per, total);
+    const int start = warp * per;
+    int end = min(start + per, total);
+    unsigned ltm = ltMask;
+    end = (int)pin((unsigned)end);
+    ltm = pin(ltm);
     int nC = 0;
-    for (int i0 = start; i0 < end; i0 += 32) {
-        const int i = i0 + lane;
-        int pos = 0, s = 0;
-        if (i < end) {
-            const unsigned e = Q[i];
+    {
+        // Uniform values ptxas would recompute in every iteration (a shuffle of a uniform value is folded away): a volatile load is not.
+        uint32_t tile_s, thr;         // thr: corner at t <=> contrast > t, and OpenCV's score = contrast - 1 must be > 0; contrasts are biased by 255
+        tile_s = lds_volatile_u32(&sh.pinTile);
+        thr = lds_volatile_u32(&sh.pinThr);
+        const uint32_t Q_s = smem_u32(Q) + 2u * (unsigned)start;
+        const unsigned scoreOfs = (unsigned)(score - tile);
+#pragma unroll 1
+        for (int i = start + lane, i0 = start; i0 < end; i += 32, i0 += 32) {
+            unsigned e = 3u << 8;                                         // lanes past the end score a harmless pixel and drop it
+            if (i < end) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(Q_s + 2u * (unsigned)(i - start)));
             // entry: row << 8 | l8 << 5 | j << 3 | q << 2 | i  ->  column = q << 7 | l8 << 4 | i << 2 | j
             const unsigned c = ((e & 4u) << 5) | ((e >> 1) & 0x70u) | ((e & 3u) << 2) | ((e >> 3) & 3u);
-            pos = (int)((e & 0xff00u) | c);
-            const int contrast = fast_contrast(tile + (pos >> 8) * FT_SP + (pos & 255));
-            if (contrast > t && contrast > 1) s = contrast - 1;            // OpenCV: score = corner contrast - 1
+            const unsigned pos = (e & 0xff00u) | c;
+            const uint32_t a = tile_s + (e >> 8) * FT_SP + c;
+            const int m = fast_contrast_s(a);
+            const bool ok = i < end && (unsigned)m > thr;
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                asm volatile("st.shared.u8 [%0], %1;" :: "r"(a + scoreOfs), "r"(m - 256) : "memory");   // OpenCV: score = corner contrast - 1
+                asm volatile("st.shared.u16 [%0], %1;" :: "r"(Q_s + 2u * (unsigned)(nC + __popc(bal & ltm))), "r"(pos) : "memory");
+            }
+            nC += __popc(bal);
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, s > 0);
-        if (s > 0) {
-            score[(pos >> 8) * FT_SP + (pos & 255)] = (uint8_t)s;
-            Q[start + nC + __popc(bal & ltMask)] = (uint16_t)pos;
-        }
-        nC += __popc(bal);
     }
     __syncthreads();
 
