@@ -20,6 +20,9 @@ __device__ const int8_t d_pattern[256 * 4] = {
 #define DESC_NW 4
 #endif
 constexpr int DESC_WARPS = DESC_NW;
+#ifndef DESC_MINCTAS
+#define DESC_MINCTAS 12          // 40 registers: the kernel lives on resident warps (its loads are gathers), not on instruction count
+#endif
 
 // cv::fastAtan2 (OpenCV core, atanImpl scalar path): degrees in [0, 360).
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
@@ -83,7 +86,7 @@ __device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp)
 constexpr int DESC_PER_WARP = DESC_NPW;     // keypoints per warp: tables and the level offsets are set up once per 64 keypoints
 constexpr int PR = 18, PP = 40;      // rBRIEF window radius (pattern radius <= 18.39), staged row pitch (10 words)
 
-__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Geom g, const PyrPtrs p,
+__global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(const __grid_constant__ Geom g, const PyrPtrs p,
                                                               const uint8_t* __restrict__ blurSlab, size_t blurStride,
                                                               const uint32_t* __restrict__ sel, const int* __restrict__ selCount,
                                                               uint8_t* __restrict__ records, size_t recordBytes) {
@@ -145,10 +148,14 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
             const uint8_t* gp = win - bmis + (size_t)(r3 * bpitch) + 4 * wi;
             uint32_t* sp = reinterpret_cast<uint32_t*>(mp) + r3 * (PP / 4) + wi;
             if (r3 < 3) {
+                // one 64-bit add per load: left to itself the compiler rebuilds every row address with IMAD.WIDE + IADD3 + IADD3.X
+                const uint64_t step = 3ull * bpitch;
 #pragma unroll
-                for (int r = 0; r < 2 * PR + 1; r += 3)
+                for (int r = 0; r < 2 * PR + 1; r += 3) {
                     if (r + 2 < 2 * PR + 1 || r + r3 < 2 * PR + 1)
-                        sp[r * (PP / 4)] = __ldg(reinterpret_cast<const uint32_t*>(gp + (size_t)bpitch * (unsigned)r));
+                        sp[r * (PP / 4)] = __ldg(reinterpret_cast<const uint32_t*>(gp));
+                    asm("add.u64 %0, %0, %1;" : "+l"(gp) : "l"(step));
+                }
             }
         }
 
@@ -164,13 +171,14 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
             const int wi = lane & 7, r4 = lane >> 3;
             const uint8_t* rowp = im + (size_t)(cy - OBS_HALF_PATCH + r4) * pitch + (cx - OBS_HALF_PATCH);
             const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(rowp) & 3);
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp - mis) + wi;
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(rowp - mis) + wi;
             const unsigned uw = 0x03020100u + 0x04040404u * wi;
+            const uint64_t step = 4ull * (unsigned)pitch;
             int s0 = 0, s1 = 0;
 #pragma unroll
             for (int t = 0; t < 8; t++) {
                 const int v = 4 * t + r4 - OBS_HALF_PATCH;
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(wp) + (size_t)(unsigned)pitch * (unsigned)(4 * t));
+                if (t) asm("add.u64 %0, %0, %1;" : "+l"(q) : "l"(step));
                 const unsigned W = __funnelshift_r(__ldg(q), __ldg(q + 1), 8 * mis) & rowMask[abs(v)][wi];
                 const int rs = (int)__dp4a(W, 0x01010101u, 0u);
                 s0 += rs;

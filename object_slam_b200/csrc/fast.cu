@@ -159,12 +159,14 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             int base = 0;
-            if (lane == 31 && incl > 0) base = atomicAdd(&sh.qCount, incl);
+            // (plain PTX: for an atomicAdd under a lane predicate the compiler emits its own warp aggregation, a second scan)
+            if (lane == 31 && incl > 0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(smem_u32(&sh.qCount)), "r"(incl) : "memory");
             base = __shfl_sync(0xffffffffu, base, 31);
             uint16_t* out = Q + base + incl - n;
             const unsigned e0 = (unsigned)(r << 8) | (unsigned)(l8 << 5);
             while (acc) {
-                const int b = 31 - __clz(acc);
+                unsigned b;
+                asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(acc));             // index of the highest flag
                 acc ^= 1u << b;
                 *out++ = (uint16_t)(e0 + b);
             }
