@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
                                                               const uint8_t* __restrict__ blurSlab, size_t blurStride,
                                                               const uint32_t* __restrict__ sel, const int* __restrict__ selCount,
                                                               uint8_t* __restrict__ records, size_t recordBytes) {
-    __shared__ float4 pat[256];                 // (x0, y0, x1, y1) of point pair 8*lane + k at [k * 32 + lane] (conflict-free)
+    // (x0, y0 | x1, y1) of point pair 8*lane + k at [k * 32 + lane] as four bfloat16 (|coordinate| <= 13 is exact; a bfloat16 is the upper
+    // half of the binary32): one LDS.64 instead of an LDS.128 per pair -- the kernel is bound by shared-memory wavefronts
+    __shared__ uint2 pat[256];
     // rowMask[|v|][i]: 0xff in the bytes of patch word i (columns u = -15 + 4 i + k) that lie inside the circular patch
     // (row OBS_HALF_PATCH + 1 is empty: the 32nd row slot of the warp's sweep)
     __shared__ uint32_t rowMask[OBS_HALF_PATCH + 2][8];
@@ -101,7 +103,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
     uint8_t* rec = records + (size_t)img * recordBytes;
     for (int i = tid; i < 256; i += DESC_WARPS * 32) {
         const int pr = (i & 31) * 8 + (i >> 5);
-        pat[i] = make_float4((float)d_pattern[4 * pr], (float)d_pattern[4 * pr + 1], (float)d_pattern[4 * pr + 2], (float)d_pattern[4 * pr + 3]);
+        const unsigned f0 = __float_as_uint((float)d_pattern[4 * pr]) >> 16, f1 = __float_as_uint((float)d_pattern[4 * pr + 1]) & 0xffff0000u;
+        const unsigned f2 = __float_as_uint((float)d_pattern[4 * pr + 2]) >> 16, f3 = __float_as_uint((float)d_pattern[4 * pr + 3]) & 0xffff0000u;
+        pat[i] = make_uint2(f0 | f1, f2 | f3);
     }
     for (int t = tid; t < (OBS_HALF_PATCH + 2) * 8; t += DESC_WARPS * 32) {
         const int av = t >> 3, wi = t & 7;
@@ -127,6 +131,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
     uint8_t* kpOut = rec + OBS_HDR_INTS * 4;
     uint8_t* descOut = kpOut + (size_t)g.kpCap * 28;
     uint8_t* mp = patch[warp];
+    unsigned rm[8];                               // the lane's eight row masks of the moment sweep, fixed for all keypoints (pinned in registers)
+#pragma unroll
+    for (int t = 0; t < 8; t++) rm[t] = pin(rowMask[abs(4 * t + (lane >> 3) - OBS_HALF_PATCH)][lane & 7]);
 
     for (int it = 0; it < DESC_PER_WARP; it++) {
         const int j = (blockIdx.x * DESC_PER_WARP + it) * DESC_WARPS + warp;     // output index of the keypoint (level-major)
@@ -152,8 +159,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
                 const uint64_t step = 3ull * bpitch;
 #pragma unroll
                 for (int r = 0; r < 2 * PR + 1; r += 3) {
-                    if (r + 2 < 2 * PR + 1 || r + r3 < 2 * PR + 1)
+                    if (r + 2 < 2 * PR + 1 || r + r3 < 2 * PR + 1) {
                         sp[r * (PP / 4)] = __ldg(reinterpret_cast<const uint32_t*>(gp));
+                    }
                     asm("add.u64 %0, %0, %1;" : "+l"(gp) : "l"(step));
                 }
             }
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
             for (int t = 0; t < 8; t++) {
                 const int v = 4 * t + r4 - OBS_HALF_PATCH;
                 if (t) asm("add.u64 %0, %0, %1;" : "+l"(q) : "l"(step));
-                const unsigned W = __funnelshift_r(__ldg(q), __ldg(q + 1), 8 * mis) & rowMask[abs(v)][wi];
+                const unsigned W = __funnelshift_r(__ldg(q), __ldg(q + 1), 8 * mis) & rm[t];
                 const int rs = (int)__dp4a(W, 0x01010101u, 0u);
                 s0 += rs;
                 s1 = (int)__dp4a(W, uw, (unsigned)s1);
@@ -200,7 +208,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
         unsigned val = 0;
 #pragma unroll
         for (int k = 7; k >= 0; k--) {
-            const float4 q = pat[k * 32 + lane];
+            const uint2 qw = pat[k * 32 + lane];
+            const float4 q = make_float4(__uint_as_float(qw.x << 16), __uint_as_float(qw.x & 0xffff0000u),
+                                         __uint_as_float(qw.y << 16), __uint_as_float(qw.y & 0xffff0000u));
             const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)));
             const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, b), __fmul_rn(q.w, a)));
