@@ -90,6 +90,10 @@ struct obs_extractor {
     PinBuf<uint8_t> stageIn, stageOut;
     size_t recordBytes = 0;
     PyrPtrs ptrs{};
+    DescMaps blurMaps{};           // TMA descriptors of the blur slab's levels, valid for (mapsPtr, mapsB, geometry)
+    DevBuf<CUtensorMap> dMaps;     // ... and their device copy, which the descriptor kernel reads
+    const uint8_t* mapsPtr = nullptr;
+    size_t mapsB = 0;
     int lastN = 0;                 // images in the last batch (0 = nothing extracted yet)
     cudaStream_t lastStream = nullptr;
 
@@ -267,7 +271,40 @@ void build_geometry(obs_extractor* e, int w, int h) {
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int encode_blur_maps(obs_extractor* e, size_t B) {
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) return fail(OBS_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        enc = (EncodeTiledFn)fn;
+    }
+    const Geom& g = e->g;
+    for (int l = 0; l < g.nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)std::max(L.h, 1), (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.slabBytes};       // bytes, dimensions 1 and 2
+        const cuuint32_t box[3] = {DESC_BOX_W, DESC_BOX_H, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&e->blurMaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, e->blur.p + L.off, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(OBS_ERR_CUDA, "cuTensorMapEncodeTiled(level %d) failed with %d", l, (int)r);
+    }
+    CU(e->dMaps.ensure(OBS_MAX_LEVELS));
+    CU(cudaMemcpy(e->dMaps.p, e->blurMaps.m, sizeof(e->blurMaps.m), cudaMemcpyHostToDevice));
+    e->mapsPtr = e->blur.p;
+    e->mapsB = B;
+    return OBS_OK;
+}
+
 int set_shape(obs_extractor* e, int w, int h, int nimg, cudaStream_t st) {
+    const bool newGeom = !e->geomValid || e->g.w != w || e->g.h != h;
     if (!e->geomValid || e->g.w != w || e->g.h != h) {
         build_geometry(e, w, h);
         if (e->g.lv[e->g.nlevels - 1].w < 1 || e->g.lv[e->g.nlevels - 1].h < 1)
@@ -304,6 +341,10 @@ int set_shape(obs_extractor* e, int w, int h, int nimg, cudaStream_t st) {
     CU(e->sel.ensure(B * g.nlevels * g.selCap));
     CU(e->selCount.ensure(B * g.nlevels));
     CU(e->records.ensure(B * e->recordBytes));
+    if (newGeom || e->mapsPtr != e->blur.p || e->mapsB != e->blur.n / g.slabBytes) {
+        const int rc = encode_blur_maps(e, e->blur.n / g.slabBytes);
+        if (rc != OBS_OK) return rc;
+    }
     return OBS_OK;
 }
 
@@ -342,7 +383,7 @@ int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st, int img0 = 0, bool
     if (ev) CU(cudaEventRecord(ev[5], st));
     if (forkBlur) CU(cudaStreamWaitEvent(st, e->join, 0));
     if (ev) CU(cudaEventRecord(ev[8], st));
-    CU(launch_describe(g, P, blurP, g.slabBytes, selP, selCountP, e->records.p + o * e->recordBytes, e->recordBytes, nimg, st));
+    CU(launch_describe(g, P, e->dMaps.p, img0, selP, selCountP, e->records.p + o * e->recordBytes, e->recordBytes, nimg, st));
     if (ev) { CU(cudaEventRecord(ev[9], st)); e->profCalls++; }
     e->lastN = img0 + nimg;
     e->lastStream = st;
@@ -413,7 +454,7 @@ int obs_extractor_destroy(obs_extractor* e) {
     if (!e) return OBS_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    e->pyr.release(); e->blur.release(); e->records.release(); e->rawIn.release(); e->cand.release(); e->keyScratch.release();
+    e->pyr.release(); e->blur.release(); e->dMaps.release(); e->records.release(); e->rawIn.release(); e->cand.release(); e->keyScratch.release();
     e->sel.release(); e->nodeScratch.release(); e->cellCount.release(); e->selCount.release();
     e->uRight.release(); e->depth.release(); e->sad.release(); e->rowStart.release(); e->rowIdx.release(); e->rightXO.release(); e->dXtab.release(); e->dYtab.release(); e->dFastCtas.release();
     e->stageIn.release(); e->stageOut.release();

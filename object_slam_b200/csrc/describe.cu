@@ -84,10 +84,12 @@ __device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp)
 #define DESC_NPW 8
 #endif
 constexpr int DESC_PER_WARP = DESC_NPW;     // keypoints per warp: tables and the level offsets are set up once per 64 keypoints
-constexpr int PR = 18, PP = 40;      // rBRIEF window radius (pattern radius <= 18.39), staged row pitch (10 words)
+constexpr int PR = 18, PP = DESC_BOX_W;      // rBRIEF window radius (pattern radius <= 18.39), row pitch of the TMA box
+constexpr int PATCH_BYTES = (DESC_BOX_W * DESC_BOX_H + 127) / 128 * 128;
+static_assert(DESC_BOX_H == 2 * PR + 1 && DESC_BOX_W >= 2 * PR + 1 + 15 && DESC_BOX_W % 16 == 0, "TMA box");
 
 __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(const __grid_constant__ Geom g, const PyrPtrs p,
-                                                              const uint8_t* __restrict__ blurSlab, size_t blurStride,
+                                                              const CUtensorMap* __restrict__ maps, int img0,
                                                               const uint32_t* __restrict__ sel, const int* __restrict__ selCount,
                                                               uint8_t* __restrict__ records, size_t recordBytes) {
     // (x0, y0 | x1, y1) of point pair 8*lane + k at [k * 32 + lane] as four bfloat16 (|coordinate| <= 13 is exact; a bfloat16 is the upper
@@ -97,7 +99,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
     // (row OBS_HALF_PATCH + 1 is empty: the 32nd row slot of the warp's sweep)
     __shared__ uint32_t rowMask[OBS_HALF_PATCH + 2][8];
     __shared__ int levelEnd[OBS_MAX_LEVELS + 1];  // keypoints up to and including level l (level-major output order)
-    __shared__ __align__(16) uint8_t patch[DESC_WARPS][(2 * PR + 1) * PP];
+    __shared__ __align__(128) uint8_t patch[DESC_WARPS][PATCH_BYTES];     // one TMA box per warp
+    __shared__ __align__(8) uint64_t mbar[DESC_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.y;
     uint8_t* rec = records + (size_t)img * recordBytes;
@@ -114,6 +117,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
             for (int k = 0; k < 4; k++) if (abs(-OBS_HALF_PATCH + 4 * wi + k) <= g.umax[av]) m |= 0xffu << (8 * k);
         rowMask[av][wi] = m;
     }
+    const uint32_t mbar_s = smem_u32(&mbar[warp]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned phase = 0;
     if (warp == DESC_WARPS - 1) {
         // lanes 0..nlevels-1 hold the per-level counts, a warp scan gives the offsets
         const int myCnt = lane < g.nlevels ? selCount[(size_t)img * g.nlevels + lane] : 0;
@@ -144,27 +153,16 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
         const uint32_t key = sel[((size_t)img * g.nlevels + level) * g.selCap + local];
         const int cx = key_x(key) + OBS_BORDER, cy = key_y(key) + OBS_BORDER;       // :837-838
 
-        // ---- stage the 37 x 37 window of the blurred level around the keypoint (the rotated pattern stays within
-        // 18 px): 10 aligned words per row, three rows per warp-wide load; the 16 gathers of a lane then hit
-        // shared memory instead of 16 x 32 scattered sectors.  Issued first so that it overlaps the moments.
-        const uint8_t* win = blurSlab + (size_t)img * blurStride + lg.off + (size_t)(cy - PR) * lg.pitch + (cx - PR);
-        const int bmis = (int)(reinterpret_cast<uintptr_t>(win) & 3);
-        {
-            const int r3 = lane / 10, wi = lane - 10 * r3;                     // lanes 30, 31 idle
-            const unsigned bpitch = (unsigned)lg.pitch;
-            const uint8_t* gp = win - bmis + (size_t)(r3 * bpitch) + 4 * wi;
-            uint32_t* sp = reinterpret_cast<uint32_t*>(mp) + r3 * (PP / 4) + wi;
-            if (r3 < 3) {
-                // one 64-bit add per load: left to itself the compiler rebuilds every row address with IMAD.WIDE + IADD3 + IADD3.X
-                const uint64_t step = 3ull * bpitch;
-#pragma unroll
-                for (int r = 0; r < 2 * PR + 1; r += 3) {
-                    if (r + 2 < 2 * PR + 1 || r + r3 < 2 * PR + 1) {
-                        sp[r * (PP / 4)] = __ldg(reinterpret_cast<const uint32_t*>(gp));
-                    }
-                    asm("add.u64 %0, %0, %1;" : "+l"(gp) : "l"(step));
-                }
-            }
+        // ---- the 37 x 37 window of the blurred level around the keypoint (the rotated pattern stays within 18 px), fetched by one
+        // TMA box load (64 x 37 bytes from the 16-byte aligned column at or before cx - 18, row cy - 18, image img0 + img): no
+        // per-lane addresses, no LSU traffic, and the copy runs while the warp computes the moments; the warp waits on its mbarrier
+        // before the gathers.  The previous keypoint's gathers are behind the __syncwarp at the loop's end.
+        const int bmis = (cx - PR) & 15;
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_s), "r"(DESC_BOX_W * DESC_BOX_H) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         :: "r"(smem_u32(mp)), "l"(reinterpret_cast<uint64_t>(maps + level)), "r"((cx - PR) & ~15), "r"(cy - PR), "r"(img0 + img), "r"(mbar_s)
+                         : "memory");
         }
 
         // ---- IC_Angle on the unblurred level (:77-104): integer moments over the circular patch.
@@ -203,7 +201,14 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
         const float factorPI = (float)(3.14159265358979323846 / 180.f);
         float a, b;
         sincosf_glibc(__fmul_rn(angle, factorPI), &b, &a);
-        __syncwarp();
+        {
+            unsigned ok;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(ok) : "r"(mbar_s), "r"(phase) : "memory");
+            } while (!ok);
+            phase ^= 1u;
+        }
         const uint8_t* cb = mp + PR * PP + PR + bmis;
         unsigned val = 0;
 #pragma unroll
@@ -239,10 +244,10 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
 
 }  // namespace
 
-cudaError_t launch_describe(const Geom& g, PyrPtrs p, const uint8_t* blurSlab, size_t blurStride,
+cudaError_t launch_describe(const Geom& g, PyrPtrs p, const CUtensorMap* maps, int img0,
                             const uint32_t* sel, const int* selCount, uint8_t* records, size_t recordBytes,
                             int nimg, cudaStream_t st) {
     dim3 grid((g.kpCap + DESC_WARPS * DESC_PER_WARP - 1) / (DESC_WARPS * DESC_PER_WARP), nimg);
-    k_describe<<<grid, DESC_WARPS * 32, 0, st>>>(g, p, blurSlab, blurStride, sel, selCount, records, recordBytes);
+    k_describe<<<grid, DESC_WARPS * 32, 0, st>>>(g, p, maps, img0, sel, selCount, records, recordBytes);
     return cudaGetLastError();
 }

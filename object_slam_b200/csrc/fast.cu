@@ -194,7 +194,7 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
         const unsigned scoreOfs = (unsigned)(score - tile);
 #pragma unroll 1
         for (int i = start + lane, i0 = start; i0 < end; i += 32, i0 += 32) {
-            unsigned e = 3u << 8;                                         // lanes past the end score a harmless pixel and drop it
+            unsigned e = (3u << 8) | (1u << 5);                           // lanes past the end score a harmless pixel (row 3, column 16) and drop it
             if (i < end) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(Q_s + 2u * (unsigned)(i - start)));
             // entry: row << 8 | l8 << 5 | j << 3 | q << 2 | i  ->  column = q << 7 | l8 << 4 | i << 2 | j
             const unsigned c = ((e & 4u) << 5) | ((e >> 1) & 0x70u) | ((e & 3u) << 2) | ((e >> 3) & 3u);

@@ -2,6 +2,7 @@
 // `st` and return the launch status; none synchronises.
 #pragma once
 #include "common.cuh"
+#include <cuda.h>                  // CUtensorMap (type only: the encoder is fetched with cudaGetDriverEntryPoint, nothing links libcuda)
 
 // K1  pyramid.cu   -- ComputePyramid (src/ORBextractor.cc:1107-1132), levels 1..n-1
 #define RESIZE_TILE_W 128          // output tile of the tiled resize kernel
@@ -30,7 +31,14 @@ cudaError_t launch_blur(const Geom& g, PyrPtrs p, uint8_t* blurSlab, size_t blur
 
 // K4+K6+K7 describe.cu -- IC_Angle (:77-104), computeOrbDescriptor (:108-147), keypoint
 // finalisation (:837-847, :1094-1103) into the per-image result record
-cudaError_t launch_describe(const Geom& g, PyrPtrs p, const uint8_t* blurSlab, size_t blurStride,
+// One TMA descriptor per level of the blur slab: 3-D tensors (pitch bytes x rows x images), box 64 x 37 x 1 -- the descriptor stage
+// pulls each keypoint's 37 x 37 window into shared memory with one cp.async.bulk.tensor instead of 13 gathered loads and stores.
+// The box starts at a 16-byte aligned column (the TMA unit rejects other start addresses with "illegal instruction", measured with
+// tools/tma_probe), so it is 15 + 37 <= 64 bytes wide.
+#define DESC_BOX_W 64
+#define DESC_BOX_H 37
+struct DescMaps { CUtensorMap m[OBS_MAX_LEVELS]; };      // host copy; the kernel reads the descriptors from global memory
+cudaError_t launch_describe(const Geom& g, PyrPtrs p, const CUtensorMap* maps /* device copy of DescMaps::m */, int img0,
                             const uint32_t* sel, const int* selCount, uint8_t* records, size_t recordBytes,
                             int nimg, cudaStream_t st);
 
