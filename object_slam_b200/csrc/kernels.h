@@ -31,11 +31,13 @@ cudaError_t launch_blur(const Geom& g, PyrPtrs p, uint8_t* blurSlab, size_t blur
 
 // K4+K6+K7 describe.cu -- IC_Angle (:77-104), computeOrbDescriptor (:108-147), keypoint
 // finalisation (:837-847, :1094-1103) into the per-image result record
-// One TMA descriptor per level of the blur slab: 3-D tensors (pitch bytes x rows x images), box 64 x 37 x 1 -- the descriptor stage
+// One TMA descriptor per level of the blur slab: 3-D tensors (pitch bytes x rows x images), box 80 x 37 x 1 -- the descriptor stage
 // pulls each keypoint's 37 x 37 window into shared memory with one cp.async.bulk.tensor instead of 13 gathered loads and stores.
 // The box starts at a 16-byte aligned column (the TMA unit rejects other start addresses with "illegal instruction", measured with
-// tools/tma_probe), so it is 15 + 37 <= 64 bytes wide.
-#define DESC_BOX_W 64
+// tools/tma_probe), so it needs 15 + 37 = 52 bytes; it is 80 wide because the box width is the shared-memory row pitch: with 64
+// (16 words) every second row falls on the same banks and the rBRIEF gathers, which cluster around the centre, collide; 20 words
+// spread eight consecutive rows over all banks (A/B: +0.2 % for the whole step).
+#define DESC_BOX_W 80
 #define DESC_BOX_H 37
 struct DescMaps { CUtensorMap m[OBS_MAX_LEVELS]; };      // host copy; the kernel reads the descriptors from global memory
 cudaError_t launch_describe(const Geom& g, PyrPtrs p, const CUtensorMap* maps /* device copy of DescMaps::m */, int img0,
