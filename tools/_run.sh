@@ -1,4 +1,3 @@
-cp variants/lib_w80.so object_slam_b200/libobslam_b200.so
-timeout 120 python -m pytest tests/test_gpu_extractor.py -m gpu -x -q 2>&1 | tail -1
-cp variants/lib_base.so object_slam_b200/libobslam_b200.so
-timeout 400 bash tools/ab.sh 2 base w80 2>&1 | grep -E "^(base|w80)"
+( time timeout 600 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -5
+( time timeout 300 python bench.py ) > gpurun_out/bench_r01p.json 2> gpurun_out/bench_r01p.err; tail -4 gpurun_out/bench_r01p.err; cut -c1-260 gpurun_out/bench_r01p.json
+timeout 100 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
