@@ -1,4 +1,5 @@
-// K4 + K6 + K7 -- orientation, rBRIEF descriptor and keypoint finalisation, one warp per keypoint.
+// K4 + K6 + K7 -- orientation, rBRIEF descriptor and keypoint finalisation, one warp per keypoint; the
+// keypoint's window of the blurred level arrives in shared memory by one TMA box load per keypoint.
 // Replaces IC_Angle / computeOrientation (src/ORBextractor.cc:77-104, :472-479),
 // computeOrbDescriptor / computeDescriptors (:108-147, :1034-1041) and the keypoint bookkeeping of
 // ComputeKeyPointsOctTree (:837-847) and operator() (:1094-1103).

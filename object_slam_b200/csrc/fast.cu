@@ -18,7 +18,8 @@
 //     pixels (a necessary condition for a 9-arc), leaves one bit per pixel in a bitmap, and pass 1b
 //     expands the bitmap into a dense queue of pixels;
 //   * pass 2 gives each queued pixel to one lane: exact score with both polarities packed as u16x2
-//     (v-r+255, r-v+255) through a min/max network of VIMNMX(3).U16x2; corners are re-queued densely;
+//     (v-r+255, r-v+255) through a min/max network of VIMNMX(3).U16x2; corners are re-queued densely
+//     (a third of the kernel's instructions: its loop invariants are pinned in registers, common.cuh);
 //   * pass 3 suppresses non-maxima among the corners only and re-queues the survivors; passes 4-6
 //     apply the per-cell threshold fallback and write the survivors in row-major order per cell,
 //     positions coming from popcounts over a bitmap of the emitted pixels.
