@@ -276,14 +276,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int encode_blur_maps(obs_extractor* e, size_t B) {
-    static EncodeTiledFn enc = nullptr;
-    if (!enc) {
+    // resolved once per process (the initialisation of a function-local static is thread safe: handles are created and reshaped from
+    // several host threads)
+    static const EncodeTiledFn enc = [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qr;
-        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
-        if (!fn || qr != cudaDriverEntryPointSuccess) return fail(OBS_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-        enc = (EncodeTiledFn)fn;
-    }
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) fn = nullptr;
+        return (EncodeTiledFn)fn;
+    }();
+    if (!enc) return fail(OBS_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
     const Geom& g = e->g;
     for (int l = 0; l < g.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
