@@ -350,6 +350,15 @@ int obs_hamming_knn2(obs_matcher* m, const uint8_t* descriptors, int n_keyframes
                      const int32_t* pairs, int n_pairs, int th_low, float nnratio,
                      int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
 
+/* Which kernel obs_hamming_knn2 runs: the exact int8 tensor-core contraction (tcgen05.mma kind::i8 on +-1 operands,
+ * hamming = (256 - a.b) / 2, csrc/knn2_tc.cu) or the POPC kernel (csrc/matcher.cu).  Both give identical results;
+ * AUTO (the default) takes the tensor cores from 192 descriptors per keyframe on.  The tensor path keeps a
+ * 256-byte-per-descriptor expansion of the descriptor sets in device memory (n_keyframes x n_desc x 256 bytes). */
+#define OBS_KNN2_AUTO 0
+#define OBS_KNN2_POPC 1
+#define OBS_KNN2_TENSOR 2
+int obs_matcher_set_knn2_engine(obs_matcher* m, int engine);
+
 /* One side of a DBoW2-gated search for a batch of n_pairs keyframes / frames with `cap` keypoint slots and
  * `node_cap` feature-vector slots each.  DBoW2 is an un-vendored third-party dependency of the reference
  * (Thirdparty/DBoW2); its FeatureVector (std::map<NodeId, std::vector<unsigned> >, KeyFrame::mFeatVec /

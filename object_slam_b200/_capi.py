@@ -130,6 +130,7 @@ _PROTOS = {
     "obs_undistort_keypoints": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _vp, C.c_int, _vp]),
     "obs_undistort_points": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _vp, C.c_int, _vp]),
     "obs_distance_transform": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, _vp]),
+    "obs_matcher_set_knn2_engine": (C.c_int, [_vp, C.c_int]),
     "obs_hamming_knn2": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp]),
 }
 

@@ -1,0 +1,340 @@
+// K11 on the 5th-generation tensor cores: brute-force keyframe-vs-keyframe Hamming search
+// (the candidate loop of ORBmatcher::SearchByBoW, /root/reference/src/ORBmatcher.cc:205-226, on
+// DescriptorDistance, :1647-1663) as an exact integer GEMM.
+//
+// With every descriptor bit b stored as the int8 value 1 - 2b, the dot product of two 256-element rows is
+//     a . b = (#equal bits) - (#different bits) = 256 - 2 * hamming(a, b),
+// so hamming = (256 - a.b) / 2, exact in the int32 accumulators of tcgen05.mma kind::i8 (|a.b| <= 256).
+//
+//   k_knn2_expand   bits -> +-1 int8 rows of 256 bytes (one pass over the descriptor sets per call)
+//   k_knn2_tc       persistent, one CTA per SM, warp specialised:
+//       warp 0      TMA producer: query tile (128 rows) and database tiles (256 rows) as two 128-byte swizzle atoms each
+//                   (cp.async.bulk.tensor.3d on a [keyframe][descriptor][256 B] tensor map, SWIZZLE_128B; rows past the end
+//                   of a keyframe are zero-filled by the TMA unit)
+//       warp 1      TMEM allocation; one lane issues 8 x tcgen05.mma.cta_group::1.kind::i8 (M 128, N 256, K 32) per database
+//                   tile into one of two 256-column accumulators and commits to the mbarriers of the pipeline
+//       warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns; thread = one query row and one 128-column half of the tile.
+//                   Distances become 16-bit keys dist << 7 | column-in-half, two per register (two IMAD), and the running
+//                   (best, second best) of every 16-bit lane is three packed VIMNMX.U16x2 per register -- 1.5 ALU
+//                   instructions per distance.  Keys are distinct, so the two smallest keys are the reference's best / second
+//                   best under its strict-< first-wins update; halves, tiles and the two threads of a row merge exactly.
+// The POPC kernel (matcher.cu k_knn2) remains the path for tiny descriptor sets; obs_hamming_knn2 picks per call.
+#include "matcher.h"
+#include "knn2_tc.h"
+
+#include <cuda.h>
+#include <algorithm>
+
+namespace {
+
+constexpr int TC_M = 128;                 // query rows of a work item (= TMEM lanes)
+constexpr int TC_N = 256;                 // database rows of one accumulator
+constexpr int TC_KB = 256;                // bytes of an expanded descriptor = K of the contraction
+constexpr int ATOM_B = 128;               // swizzle atom width in bytes
+constexpr int A_ATOM_BYTES = TC_M * ATOM_B;       // 16 KB
+constexpr int B_ATOM_BYTES = TC_N * ATOM_B;       // 32 KB
+constexpr int A_BYTES = 2 * A_ATOM_BYTES;         // 32 KB
+constexpr int B_BYTES = 2 * B_ATOM_BYTES;         // 64 KB
+constexpr int TC_THREADS = 320;
+constexpr int EPI_THREADS = 256;
+constexpr uint32_t SENT32 = (256u << 16) | 0xffffu;
+constexpr size_t TC_SMEM = 2 * A_BYTES + 2 * B_BYTES + 1024;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+// K-major operand tile of 128-byte rows under SWIZZLE_128B: groups of 8 rows 1024 bytes apart (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p; }"
+                 :: "r"(tmemD), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&d)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+                   "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]),
+                   "=r"(d[16]), "=r"(d[17]), "=r"(d[18]), "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]),
+                   "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]), "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// instruction descriptor of kind::i8: D = S32 (bits 4-5 = 2), A and B signed 8 bit (bits 7-9, 10-12 = 1), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+// ---- bits -> +-1 int8 -------------------------------------------------------------------------------------------------
+// thread = 16 descriptor bits -> 16 bytes; bit k of the descriptor (bit k%8 of byte k/8) becomes element k: 0 -> +1, 1 -> -1
+__device__ __forceinline__ uint32_t expand4(uint32_t b) {
+    const uint32_t x = (b * 0x00204081u) & 0x01010101u;       // bit i of b -> byte i
+    return x * 0xfeu + 0x01010101u;                             // 1 -> 0xff (-1), 0 -> 0x01 (+1)
+}
+__global__ void __launch_bounds__(256) k_knn2_expand(const uint16_t* __restrict__ bits, uint4* __restrict__ out, size_t nChunks) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= nChunks) return;
+    const uint32_t v = bits[i];
+    out[i] = make_uint4(expand4(v & 15u), expand4((v >> 4) & 15u), expand4((v >> 8) & 15u), expand4(v >> 12));
+}
+
+// ---- epilogue helpers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t key16_to_32(uint32_t k16, uint32_t colBase) {
+    const uint32_t dist = k16 >> 7;
+    return dist > 256u ? SENT32 : ((dist << 16) | (colBase + (k16 & 127u)));
+}
+__device__ __forceinline__ void merge2(uint32_t& best, uint32_t& second, uint32_t b, uint32_t s) {
+    const uint32_t hi = max(best, b);
+    best = min(best, b);
+    second = min(hi, min(second, s));
+}
+
+struct Knn2TcArgs {
+    const int2* pairs;
+    int nPairs, n, mTiles, nTiles;
+    int thLow; float nnratio;
+    int* bestIdx; int* bestDist; int* secondDist;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_knn2_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Knn2TcArgs A) {
+    extern __shared__ uint8_t smemRaw[];
+    __shared__ __align__(8) uint64_t bars[12];     // aFull[2] aEmpty[2] bFull[2] bEmpty[2] accFull[2] accEmpty[2]
+    __shared__ uint32_t tmemBaseS;
+    __shared__ uint2 sMerge[2][TC_M];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smemRaw) + 1023u) & ~1023u;
+    const uint32_t sA0 = base, sB0 = base + 2 * A_BYTES;
+    const uint32_t bar0 = smem_u32(bars);
+    auto aFull = [&](int s) { return bar0 + 8u * (0 + s); };
+    auto aEmpty = [&](int s) { return bar0 + 8u * (2 + s); };
+    auto bFull = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto bEmpty = [&](int s) { return bar0 + 8u * (6 + s); };
+    auto accFull = [&](int s) { return bar0 + 8u * (8 + s); };
+    auto accEmpty = [&](int s) { return bar0 + 8u * (10 + s); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; s++) {
+            mbar_init(aFull(s), 1); mbar_init(aEmpty(s), 1);
+            mbar_init(bFull(s), 1); mbar_init(bEmpty(s), 1);
+            mbar_init(accFull(s), 1); mbar_init(accEmpty(s), EPI_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmemBaseS)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmemBase = tmemBaseS;
+
+    const long long total = (long long)A.nPairs * A.mTiles;
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&mapB) : "memory");
+            uint32_t ai = 0, bi = 0;
+            for (long long w = blockIdx.x; w < total; w += gridDim.x, ai++) {
+                const int pair = (int)(w / A.mTiles), mt = (int)(w - (long long)pair * A.mTiles);
+                const int2 pr = A.pairs[pair];
+                const uint32_t sa = ai & 1u;
+                mbar_wait(aEmpty(sa), ((ai >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(aFull(sa), A_BYTES);
+                tma_load_3d(sA0 + sa * A_BYTES, &mapA, 0, mt * TC_M, pr.x, aFull(sa));
+                tma_load_3d(sA0 + sa * A_BYTES + A_ATOM_BYTES, &mapA, ATOM_B, mt * TC_M, pr.x, aFull(sa));
+                for (int nt = 0; nt < A.nTiles; nt++, bi++) {
+                    const uint32_t sb = bi & 1u;
+                    mbar_wait(bEmpty(sb), ((bi >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(bFull(sb), B_BYTES);
+                    tma_load_3d(sB0 + sb * B_BYTES, &mapB, 0, nt * TC_N, pr.y, bFull(sb));
+                    tma_load_3d(sB0 + sb * B_BYTES + B_ATOM_BYTES, &mapB, ATOM_B, nt * TC_N, pr.y, bFull(sb));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t ai = 0, bi = 0;
+            for (long long w = blockIdx.x; w < total; w += gridDim.x, ai++) {
+                const uint32_t sa = ai & 1u;
+                mbar_wait(aFull(sa), (ai >> 1) & 1u);
+                for (int nt = 0; nt < A.nTiles; nt++, bi++) {
+                    const uint32_t sb = bi & 1u, ph = (bi >> 1) & 1u;
+                    mbar_wait(accEmpty(sb), ph ^ 1u);
+                    mbar_wait(bFull(sb), ph);
+                    tc_fence_after();
+                    const uint32_t d = tmemBase + sb * TC_N;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint32_t ka = (uint32_t)(k >> 2) * A_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
+                        const uint32_t kb = (uint32_t)(k >> 2) * B_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
+                        umma_i8(d, umma_desc(sA0 + sa * A_BYTES + ka), umma_desc(sB0 + sb * B_BYTES + kb), IDESC_I8, k != 0);
+                    }
+                    umma_commit(bEmpty(sb));        // the database stage is free once these MMAs have read it
+                    umma_commit(accFull(sb));       // ... and the accumulator is complete
+                }
+                umma_commit(aEmpty(sa));
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int quad = warp & 3;                  // a warp reads the TMEM lanes 32 * (warp id % 4) ...
+        const int half = ew >> 2;                   // ... and this 128-column half of every accumulator
+        const int row = quad * 32 + lane;
+        uint32_t ai = 0, bi = 0;
+        for (long long w = blockIdx.x; w < total; w += gridDim.x, ai++) {
+            const int pair = (int)(w / A.mTiles), mt = (int)(w - (long long)pair * A.mTiles);
+            uint32_t best = SENT32, second = SENT32;
+            for (int nt = 0; nt < A.nTiles; nt++, bi++) {
+                const uint32_t sb = bi & 1u;
+                mbar_wait(accFull(sb), (bi >> 1) & 1u);
+                tc_fence_after();
+                const int colBase = nt * TC_N + half * 128;
+                const int valid = A.n - colBase;                       // columns of this half that exist
+                const uint32_t taddr = tmemBase + ((uint32_t)(quad * 32) << 16) + sb * TC_N + half * 128;
+                uint32_t b0 = 0xffffffffu, s0 = 0xffffffffu, b1 = 0xffffffffu, s1 = 0xffffffffu;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    int d[32];
+                    tmem_ld32(taddr + c * 32, d);
+                    tmem_ld_wait();
+                    if (c == 3) {                                      // the accumulator is in registers: hand it back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(accEmpty(sb));
+                    }
+                    if (valid >= c * 32 + 32) {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            const uint32_t C = (uint32_t)(16384 + c * 32 + 2 * k) | ((uint32_t)(16384 + c * 32 + 2 * k + 1) << 16);
+                            const uint32_t p = C + (uint32_t)d[2 * k] * (uint32_t)(-64) + (uint32_t)d[2 * k + 1] * (uint32_t)(-4194304);
+                            if (k & 1) { const uint32_t hi = __vmaxu2(p, b1); b1 = __vminu2(p, b1); s1 = __vminu2(s1, hi); }
+                            else       { const uint32_t hi = __vmaxu2(p, b0); b0 = __vminu2(p, b0); s0 = __vminu2(s0, hi); }
+                        }
+                    } else if (valid > c * 32) {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            const uint32_t C = (uint32_t)(16384 + c * 32 + 2 * k) | ((uint32_t)(16384 + c * 32 + 2 * k + 1) << 16);
+                            uint32_t p = C + (uint32_t)d[2 * k] * (uint32_t)(-64) + (uint32_t)d[2 * k + 1] * (uint32_t)(-4194304);
+                            if (c * 32 + 2 * k >= valid) p |= 0x0000ffffu;
+                            if (c * 32 + 2 * k + 1 >= valid) p |= 0xffff0000u;
+                            if (k & 1) { const uint32_t hi = __vmaxu2(p, b1); b1 = __vminu2(p, b1); s1 = __vminu2(s1, hi); }
+                            else       { const uint32_t hi = __vmaxu2(p, b0); b0 = __vminu2(p, b0); s0 = __vminu2(s0, hi); }
+                        }
+                    }
+                }
+                // two accumulators -> one, 16-bit lanes -> one, half-tile keys -> global keys
+                const uint32_t bb = __vminu2(b0, b1), ss = __vminu2(__vmaxu2(b0, b1), __vminu2(s0, s1));
+                const uint32_t bl = bb & 0xffffu, bh = bb >> 16, sl = ss & 0xffffu, sh = ss >> 16;
+                const uint32_t kb = min(bl, bh), ks = min(max(bl, bh), min(sl, sh));
+                merge2(best, second, key16_to_32(kb, (uint32_t)colBase), key16_to_32(ks, (uint32_t)colBase));
+            }
+            // the two threads of a row (column halves) meet in shared memory
+            if (half == 1) sMerge[ai & 1u][row] = make_uint2(best, second);
+            asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
+            if (half == 0) {
+                const uint2 o = sMerge[ai & 1u][row];
+                merge2(best, second, o.x, o.y);
+                const int qi = mt * TC_M + row;
+                if (qi < A.n) {
+                    const int bd = (int)(best >> 16), sd = (int)(second >> 16);
+                    const size_t o2 = (size_t)pair * A.n + qi;
+                    int idx = -1;
+                    if (bd <= A.thLow && (float)bd < __fmul_rn(A.nnratio, (float)sd)) idx = (int)(best & 0xffffu);
+                    A.bestIdx[o2] = idx;
+                    if (A.bestDist) A.bestDist[o2] = bd;
+                    if (A.secondDist) A.secondDist[o2] = sd;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(512u) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tma_encoder() {
+    static const EncodeTiledFn enc = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) fn = nullptr;
+        return (EncodeTiledFn)fn;
+    }();
+    return enc;
+}
+
+}  // namespace
+
+size_t knn2_tc_expanded_bytes(int nKeyframes, int n) { return (size_t)nKeyframes * (size_t)n * TC_KB; }
+
+cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded, cudaStream_t st) {
+    if (a.nPairs <= 0 || a.n <= 0) return cudaSuccess;
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc) return cudaErrorNotSupported;
+    // per device, and only ever the one size: safe to repeat from any thread
+    cudaError_t e = cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+
+    const size_t nChunks = (size_t)nKeyframes * a.n * 16;
+    k_knn2_expand<<<(unsigned)((nChunks + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(a.desc), reinterpret_cast<uint4*>(expanded), nChunks);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+
+    CUtensorMap mapA, mapB;
+    const cuuint64_t dims[3] = {(cuuint64_t)TC_KB, (cuuint64_t)a.n, (cuuint64_t)nKeyframes};
+    const cuuint64_t strides[2] = {(cuuint64_t)TC_KB, (cuuint64_t)a.n * TC_KB};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t boxA[3] = {ATOM_B, TC_M, 1}, boxB[3] = {ATOM_B, TC_N, 1};
+    if (enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, expanded, dims, strides, boxA, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    if (enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, expanded, dims, strides, boxB, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+
+    Knn2TcArgs k;
+    k.pairs = a.pairs; k.nPairs = a.nPairs; k.n = a.n;
+    k.mTiles = (a.n + TC_M - 1) / TC_M; k.nTiles = (a.n + TC_N - 1) / TC_N;
+    k.thLow = a.thLow; k.nnratio = a.nnratio;
+    k.bestIdx = a.bestIdx; k.bestDist = a.bestDist; k.secondDist = a.secondDist;
+    const long long total = (long long)k.nPairs * k.mTiles;
+    const unsigned grid = (unsigned)std::min<long long>(total, sms);
+    k_knn2_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(mapA, mapB, k);
+    return cudaGetLastError();
+}

@@ -1,0 +1,7 @@
+// Tensor-core brute-force Hamming search (knn2_tc.cu): launcher used by obs_hamming_knn2.
+#pragma once
+#include "matcher.h"
+// bytes of the +-1 int8 expansion of nKeyframes x n descriptors (256 per descriptor)
+size_t knn2_tc_expanded_bytes(int nKeyframes, int n);
+// expands a.desc into `expanded` and runs the tcgen05 kernel over a.pairs; same outputs as launch_knn2
+cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded, cudaStream_t st);

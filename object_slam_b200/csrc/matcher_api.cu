@@ -3,6 +3,7 @@
 #include "../../include/obslam_b200.h"
 #include "matcher.h"
 #include "matcher_api.h"
+#include "knn2_tc.h"
 #include "host_util.h"
 
 #include <cmath>
@@ -23,6 +24,8 @@ struct obs_matcher {
     DevBuf<uint32_t> initList;
     DevBuf<int> initCount;
     DevBuf<int> sim3Idx[2], sim3Dist[2];
+    DevBuf<uint8_t> knnExpanded;         // +-1 int8 expansion of the descriptor sets of the last tensor-core knn2 call
+    int knnEngine = OBS_KNN2_AUTO;
     bool hsvTables = false;
     std::vector<int> lastRounds;
     std::vector<obs_frame_set*> sets;   // frame sets created on this matcher (orphaned, not freed, when it is destroyed first)
@@ -149,7 +152,7 @@ int obs_matcher_destroy(obs_matcher* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (obs_frame_set* fs : m->sets) fs->m = nullptr;     // their buffers stay valid until obs_frame_set_destroy
     for (auto& s : m->slot) s.release();
-    m->cand.release(); m->pool.release(); m->poolCursor.release(); m->choice.release(); m->rounds.release(); m->initList.release(); m->initCount.release();
+    m->knnExpanded.release(); m->cand.release(); m->pool.release(); m->poolCursor.release(); m->choice.release(); m->rounds.release(); m->initList.release(); m->initCount.release();
     if (m->ev) cudaEventDestroy(m->ev);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -571,6 +574,13 @@ int obs_descriptor_distance(obs_matcher* m, const uint8_t* a, const uint8_t* b, 
     return OBS_OK;
 }
 
+int obs_matcher_set_knn2_engine(obs_matcher* m, int engine) {
+    if (!m) return fail(OBS_ERR_INVALID, "null matcher handle");
+    if (engine != OBS_KNN2_AUTO && engine != OBS_KNN2_POPC && engine != OBS_KNN2_TENSOR) return fail(OBS_ERR_INVALID, "unknown knn2 engine %d", engine);
+    m->knnEngine = engine;
+    return OBS_OK;
+}
+
 int obs_hamming_knn2(obs_matcher* m, const uint8_t* descriptors, int n_keyframes, int n_desc, const int32_t* pairs, int n_pairs,
                      int th_low, float nnratio, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist) {
     int rc = check_matcher(m);
@@ -592,7 +602,14 @@ int obs_hamming_knn2(obs_matcher* m, const uint8_t* descriptors, int n_keyframes
     if ((rc = dev_out(m, 2, best_idx, cnt, &a.bestIdx))) return rc;
     if ((rc = dev_out(m, 3, best_dist, best_dist ? cnt : 0, &a.bestDist))) return rc;
     if ((rc = dev_out(m, 4, second_dist, second_dist ? cnt : 0, &a.secondDist))) return rc;
-    CU(launch_knn2(a, m->stream));
+    // tensor cores (knn2_tc.cu) once a keyframe fills at least one 128 x 256 tile reasonably; the POPC kernel below that
+    const bool tensor = m->knnEngine == OBS_KNN2_TENSOR || (m->knnEngine == OBS_KNN2_AUTO && n_desc >= 192);
+    if (tensor) {
+        CU(m->knnExpanded.ensure(knn2_tc_expanded_bytes(n_keyframes, n_desc)));
+        CU(launch_knn2_tc(a, n_keyframes, m->knnExpanded.p, m->stream));
+    } else {
+        CU(launch_knn2(a, m->stream));
+    }
     bool queued = false;
     if ((rc = host_back(m, best_idx, a.bestIdx, cnt, &queued))) return rc;
     if ((rc = host_back(m, best_dist, a.bestDist, cnt, &queued))) return rc;

@@ -249,6 +249,12 @@ class ORBmatcher:
                                                   self.mfNNratio, int(self.mbCheckOrientation), ptr(n_matches)))
         return n_matches, matches12
 
+    KNN2_AUTO, KNN2_POPC, KNN2_TENSOR = 0, 1, 2
+
+    def set_knn2_engine(self, engine):
+        """Which kernel knn2 runs: KNN2_TENSOR (tcgen05 int8 contraction), KNN2_POPC, or KNN2_AUTO (by size)."""
+        check(lib().obs_matcher_set_knn2_engine(self._h, int(engine)))
+
     # ---- brute force best / second best + ratio (candidate loop of SearchByBoW, ORBmatcher.cc:200-229)
     def knn2(self, descriptors, pairs, n_keyframes=None, n_desc=None, th_low=None, best_idx=None, best_dist=None,
              second_dist=None, want_dists=True):

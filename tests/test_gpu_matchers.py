@@ -208,6 +208,46 @@ def test_knn2_matches_oracle(M):
     M.mfNNratio = 0.8
 
 
+@pytest.mark.parametrize("engine", ["tensor", "popc"])
+def test_knn2_engines_match_oracle(M, engine):
+    """The tcgen05 int8 contraction (hamming = (256 - a.b) / 2) and the POPC kernel against the oracle: sizes that are not
+    multiples of the 128 x 256 tile, a size below one tile, duplicates (lowest index wins, second best counts duplicates),
+    complementary descriptors (distance 256), an all-equal keyframe."""
+    M.set_knn2_engine(M.KNN2_TENSOR if engine == "tensor" else M.KNN2_POPC)
+    M.mfNNratio = 0.6
+    try:
+        for n, seed in ((2000, 11), (333, 12), (129, 13), (257, 14), (70, 15), (1, 16), (1024, 17)):
+            D = synth.keyframe_descriptors(3, n, seed)
+            if n >= 70:
+                D[1, 40] = D[1, 7]                  # duplicate database rows
+                D[0, 5] = D[1, 7]                   # ... matched exactly: best = second = 0
+                D[2, 3] = ~D[1, 9]                  # complement: distance 256
+                D[2, n - 1] = D[1, n - 1]           # last row / last column of the ragged tiles
+            pairs = np.array([(0, 1), (1, 0), (2, 1), (1, 1), (2, 2)], np.int32)
+            bi, bd, sd = M.knn2(D, pairs)
+            for p, (a, b) in enumerate(pairs):
+                obi, obd, osd = oracle.hamming_knn2(D[a], D[b], 50, 0.6)
+                assert np.array_equal(bd[p], obd), (engine, n, p)
+                assert np.array_equal(sd[p], osd), (engine, n, p)
+                assert np.array_equal(bi[p], obi), (engine, n, p)
+            if n >= 70:
+                assert bd[0, 5] == 0 and sd[0, 5] == 0 and bi[0, 5] == -1 and bd[2, n - 1] == 0
+        # every descriptor equal: all distances 0, the first database row wins everywhere
+        D = np.repeat(synth.keyframe_descriptors(1, 1, 18), 300, axis=1).repeat(2, axis=0)
+        bi, bd, sd = M.knn2(D, np.array([(0, 1)], np.int32))
+        assert (bd == 0).all() and (sd == 0).all() and (bi == -1).all()
+        # many pairs: more work items than SMs, every accumulator / stage parity exercised
+        D = synth.keyframe_descriptors(12, 600, 19)
+        pairs = np.array([(i, j) for i in range(12) for j in range(12) if abs(i - j) in (1, 2, 3)], np.int32)
+        bi, bd, sd = M.knn2(D, pairs)
+        for p, (a, b) in enumerate(pairs):
+            obi, obd, osd = oracle.hamming_knn2(D[a], D[b], 50, 0.6)
+            assert np.array_equal(bi[p], obi) and np.array_equal(bd[p], obd) and np.array_equal(sd[p], osd), (engine, p)
+    finally:
+        M.set_knn2_engine(M.KNN2_AUTO)
+        M.mfNNratio = 0.8
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "match_*.npz"))), ids=os.path.basename)
 def test_golden_fixtures(M, path):
     g = np.load(path)
