@@ -144,6 +144,25 @@ int obs_extractor_stage_ms(obs_extractor* e, float* stage_ms, float* stereo_ms, 
  * --------------------------------------------------------------------------------------- */
 int obs_stereo_match(obs_extractor* left, obs_extractor* right, float mbf, float min_d, float max_d,
                      float* u_right, float* depth, int cap);
+/* Whole stereo frames in one call -- what the stereo Frame constructor does (src/Frame.cc:78-90: ExtractORB on two threads,
+ * then ComputeStereoMatches) for n_frames frames: both eyes are uploaded, extracted and downloaded in overlapping chunks on the
+ * handles' own streams and the stereo match follows on the device, all enqueued by the calling thread.  Every buffer of
+ * obs_stereo_io must be page-locked (obs_host_alloc); image i of an eye starts at base + i * h * stride.
+ * obs_stereo_frames_submit returns once everything is enqueued; obs_stereo_frames_wait sleeps (blocking-sync event, no spinning)
+ * until all results have landed and checks the counts against cap.  One submission per handle pair may be in flight; several
+ * handle pairs driven round-robin by one thread overlap each other's transfers and kernels.  obs_stereo_frames = submit + wait. */
+typedef struct obs_stereo_io {
+    const uint8_t* left;  const uint8_t* right;                     /* n_frames x h x stride bytes each */
+    obs_keypoint* kp_left;  uint8_t* desc_left;  int32_t* n_left;   /* n_frames x cap, n_frames x cap x 32, n_frames */
+    obs_keypoint* kp_right; uint8_t* desc_right; int32_t* n_right;
+    float* u_right; float* depth;                                   /* n_frames x cap each (-1 = no match) */
+} obs_stereo_io;
+int obs_stereo_frames_submit(obs_extractor* left, obs_extractor* right, const obs_stereo_io* io, int n_frames, int w, int h,
+                             size_t stride, int cap, float mbf, float min_d, float max_d);
+int obs_stereo_frames_wait(obs_extractor* left, obs_extractor* right);
+int obs_stereo_frames(obs_extractor* left, obs_extractor* right, const obs_stereo_io* io, int n_frames, int w, int h,
+                      size_t stride, int cap, float mbf, float min_d, float max_d);
+
 /* Device-resident form: results stay in HBM (n_images x cap floats each, cap =
  * obs_extractor_max_keypoints(left)); pointers valid until the next call. */
 int obs_stereo_match_device(obs_extractor* left, obs_extractor* right, float mbf, float min_d, float max_d,

@@ -60,6 +60,13 @@ class BowSide(C.Structure):
                 ("node_start", C.c_void_p), ("node_idx", C.c_void_p)]
 
 
+class StereoIO(C.Structure):
+    _fields_ = [("left", C.c_void_p), ("right", C.c_void_p),
+                ("kp_left", C.c_void_p), ("desc_left", C.c_void_p), ("n_left", C.c_void_p),
+                ("kp_right", C.c_void_p), ("desc_right", C.c_void_p), ("n_right", C.c_void_p),
+                ("u_right", C.c_void_p), ("depth", C.c_void_p)]
+
+
 class ObsError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"obslam_b200 error {code}: {msg}")
@@ -91,6 +98,9 @@ _PROTOS = {
     "obs_extractor_set_profiling": (C.c_int, [_vp, C.c_int]),
     "obs_extractor_stage_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "obs_stereo_match": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_float, _vp, _vp, C.c_int]),
+    "obs_stereo_frames_submit": (C.c_int, [_vp, _vp, C.POINTER(StereoIO), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_float]),
+    "obs_stereo_frames_wait": (C.c_int, [_vp, _vp]),
+    "obs_stereo_frames": (C.c_int, [_vp, _vp, C.POINTER(StereoIO), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_float]),
     "obs_stereo_match_device": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_float, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "obs_gray_from_color": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, _vp, C.c_size_t, C.c_size_t, _vp]),
     "obs_depth_to_float": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_float, _vp, C.c_size_t, C.c_size_t, _vp]),

@@ -6,7 +6,6 @@
 #include "host_util.h"
 #include "matcher_api.h"
 
-#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstdarg>
@@ -40,6 +39,27 @@ bool is_device(const void* p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+int max_dynamic_smem(const void* kernel) {
+    int dev = 0, optin = 0;
+    cudaFuncAttributes fa;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return optin - (int)fa.sharedSizeBytes;
+}
+
+cudaError_t allow_max_smem(const void* kernel, std::atomic<unsigned long long>& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const int lim = max_dynamic_smem(kernel);
+    if (lim <= 0) return cudaErrorInvalidValue;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
 }  // namespace obsdetail
 
 namespace {
@@ -61,6 +81,10 @@ struct obs_extractor {
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;    // the blur runs here, beside FAST + quadtree (both only need the pyramid)
     cudaEvent_t done = nullptr, fork = nullptr, join = nullptr;
+    cudaEvent_t hostDone = nullptr;    // cudaEventBlockingSync: the host thread sleeps on it instead of spinning in a stream synchronise
+    bool pending = false;              // obs_stereo_frames_submit without its obs_stereo_frames_wait
+    const int* pendingCounts[2] = {nullptr, nullptr};
+    int pendingN = 0, pendingCap = 0;
     cudaStream_t cin = nullptr, cout = nullptr;       // host path: upload / download streams of the chunk pipeline
     std::vector<cudaEvent_t> chunkIn, chunkDone;
 
@@ -391,6 +415,60 @@ int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st, int img0 = 0, bool
     return OBS_OK;
 }
 
+// Host path of a batch whose images are one page-locked block and whose outputs are page-locked too: upload of chunk c+1
+// (copy-in stream), extraction of chunk c and download of chunk c-1 (copy-out stream) overlap; no staging.  Consecutive chunks
+// alternate between the handle's two compute streams, so one chunk's latency-bound quadtree runs beside the next chunk's
+// FAST / blur instead of serialising the pipeline.  Nothing here waits for the device: the caller synchronises on e->cout.
+// counts: page-locked ints, one per image.
+int enqueue_chunks(obs_extractor* e, const uint8_t* images0, int n_images, int w, int h, size_t stride,
+                   obs_keypoint* keypoints, uint8_t* descriptors, int cap, int* counts) {
+    const Geom& g = e->g;
+    cudaStream_t st = e->stream;
+    const size_t p0 = (size_t)g.lv[0].pitch;
+    const size_t imgBytes = stride * (size_t)h;
+    e->ptrs.l0 = e->pyr.p;
+    e->ptrs.l0ImgStride = g.slabBytes;
+    e->ptrs.l0Pitch = g.lv[0].pitch;
+    e->ptrs.slab = e->pyr.p;
+    e->ptrs.slabStride = g.slabBytes;
+    const int nChunks = n_images >= 32 ? 4 : n_images >= 8 ? 2 : 1;
+    while ((int)e->chunkIn.size() < nChunks) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        e->chunkIn.push_back(a); e->chunkDone.push_back(b);
+    }
+    CU(e->rawIn.ensure((size_t)e->maxBatch * imgBytes + 16));
+    const int m = cap < g.kpCap ? cap : g.kpCap;
+    // the previous call's device work (a stereo match may still read the pyramids) precedes the first upload
+    CU(cudaEventRecord(e->done, st));
+    CU(cudaStreamWaitEvent(e->cin, e->done, 0));
+    CU(cudaStreamWaitEvent(e->aux, e->done, 0));
+    for (int c = 0; c < nChunks; c++) {
+        const int c0 = (int)((long long)n_images * c / nChunks), c1 = (int)((long long)n_images * (c + 1) / nChunks);
+        if (c1 <= c0) continue;
+        CU(cudaMemcpyAsync(e->rawIn.p + (size_t)c0 * imgBytes, images0 + (size_t)c0 * imgBytes, (size_t)(c1 - c0) * imgBytes, cudaMemcpyHostToDevice, e->cin));
+        CU(cudaEventRecord(e->chunkIn[c], e->cin));
+        cudaStream_t cs = (c & 1) ? e->aux : st;
+        CU(cudaStreamWaitEvent(cs, e->chunkIn[c], 0));
+        CU(launch_repack(e->rawIn.p + (size_t)c0 * imgBytes, imgBytes, stride, e->pyr.p + (size_t)c0 * g.slabBytes, g.slabBytes, (int)p0, w, h, c1 - c0, cs));
+        int rc = run_pipeline(e, c1 - c0, cs, c0, false, false);
+        if (rc) return rc;
+        CU(cudaEventRecord(e->chunkDone[c], cs));
+        CU(cudaStreamWaitEvent(e->cout, e->chunkDone[c], 0));
+        const uint8_t* rec = e->records.p + (size_t)c0 * e->recordBytes;
+        CU(cudaMemcpy2DAsync(counts + c0, sizeof(int), rec, e->recordBytes, sizeof(int), c1 - c0, cudaMemcpyDeviceToHost, e->cout));
+        CU(cudaMemcpy2DAsync(keypoints + (size_t)c0 * cap, (size_t)cap * 28, rec + OBS_HDR_INTS * 4, e->recordBytes, (size_t)m * 28, c1 - c0, cudaMemcpyDeviceToHost, e->cout));
+        CU(cudaMemcpy2DAsync(descriptors + (size_t)c0 * cap * 32, (size_t)cap * 32, rec + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28, e->recordBytes, (size_t)m * 32, c1 - c0, cudaMemcpyDeviceToHost, e->cout));
+    }
+    // later consumers (stereo match, frame-set build) order themselves after the handle stream
+    CU(cudaEventRecord(e->join, e->aux));
+    CU(cudaStreamWaitEvent(st, e->join, 0));
+    e->lastN = n_images;
+    e->lastStream = st;
+    return OBS_OK;
+}
+
 int check_handle(const obs_extractor* e) {
     if (!e) return fail(OBS_ERR_INVALID, "null extractor handle");
     cudaError_t ce = cudaSetDevice(e->device);
@@ -442,6 +520,7 @@ int obs_extractor_create(const obs_orb_params* params, int max_w, int max_h, int
     if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming);
     if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming);
     if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->join, cudaEventDisableTiming);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->hostDone, cudaEventDisableTiming | cudaEventBlockingSync);
     if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&e->cin, cudaStreamNonBlocking);
     if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&e->cout, cudaStreamNonBlocking);
     if (se != cudaSuccess) { delete e; return fail(OBS_ERR_CUDA, "stream/event creation: %s", cudaGetErrorString(se)); }
@@ -464,6 +543,7 @@ int obs_extractor_destroy(obs_extractor* e) {
     if (e->done) cudaEventDestroy(e->done);
     if (e->fork) cudaEventDestroy(e->fork);
     if (e->join) cudaEventDestroy(e->join);
+    if (e->hostDone) cudaEventDestroy(e->hostDone);
     for (cudaEvent_t ev : e->chunkIn) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->chunkDone) cudaEventDestroy(ev);
     if (e->cin) cudaStreamDestroy(e->cin);
@@ -582,71 +662,13 @@ int obs_extract_batch(obs_extractor* e, const uint8_t* const* images, int n_imag
     e->ptrs.slabStride = g.slabBytes;
     const bool pinnedOut = keypoints && descriptors && is_pinned(keypoints) && is_pinned(descriptors) && cap > 0;
     if (oneBlock && pinnedOut && n_images >= 8) {
-        // Chunk pipeline: upload of chunk c+1 (copy-in stream), extraction of chunk c and download of chunk c-1
-        // (copy-out stream) overlap; page-locked memory on both sides, no staging.  Consecutive chunks alternate
-        // between the handle's two compute streams, so one chunk's latency-bound quadtree runs beside the next
-        // chunk's FAST / blur instead of serialising the pipeline.
-        const int nChunks = n_images >= 32 ? 4 : 2;
-        while ((int)e->chunkIn.size() < nChunks) {
-            cudaEvent_t a, b;
-            CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-            e->chunkIn.push_back(a); e->chunkDone.push_back(b);
-        }
-        CU(e->rawIn.ensure((size_t)e->maxBatch * imgBytes + 16));
         CU(e->stageOut.ensure((size_t)e->maxBatch * sizeof(int)));
         int* cnts = reinterpret_cast<int*>(e->stageOut.p);
-        const int m = cap < g.kpCap ? cap : g.kpCap;
-        // the previous call's device work (a stereo match may still read the pyramids) precedes the first upload
-        CU(cudaEventRecord(e->done, st));
-        CU(cudaStreamWaitEvent(e->cin, e->done, 0));
-        CU(cudaStreamWaitEvent(e->aux, e->done, 0));
-        static const bool trace = getenv("OBS_TRACE") != nullptr;
-        cudaEvent_t tev[6 * 4];
-        if (trace) for (auto& t : tev) cudaEventCreate(&t);
-        const auto tHost0 = std::chrono::steady_clock::now();
-        for (int c = 0; c < nChunks; c++) {
-            const int c0 = (int)((long long)n_images * c / nChunks), c1 = (int)((long long)n_images * (c + 1) / nChunks);
-            if (c1 <= c0) continue;
-            if (trace) cudaEventRecord(tev[6 * c + 0], e->cin);
-            CU(cudaMemcpyAsync(e->rawIn.p + (size_t)c0 * imgBytes, images[c0], (size_t)(c1 - c0) * imgBytes, cudaMemcpyHostToDevice, e->cin));
-            if (trace) cudaEventRecord(tev[6 * c + 1], e->cin);
-            CU(cudaEventRecord(e->chunkIn[c], e->cin));
-            cudaStream_t cs = (c & 1) ? e->aux : st;
-            CU(cudaStreamWaitEvent(cs, e->chunkIn[c], 0));
-            if (trace) cudaEventRecord(tev[6 * c + 2], cs);
-            CU(launch_repack(e->rawIn.p + (size_t)c0 * imgBytes, imgBytes, stride, e->pyr.p + (size_t)c0 * g.slabBytes, g.slabBytes, (int)p0, w, h, c1 - c0, cs));
-            rc = run_pipeline(e, c1 - c0, cs, c0, false, false);
-            if (rc) return rc;
-            if (trace) cudaEventRecord(tev[6 * c + 3], cs);
-            CU(cudaEventRecord(e->chunkDone[c], cs));
-            CU(cudaStreamWaitEvent(e->cout, e->chunkDone[c], 0));
-            if (trace) cudaEventRecord(tev[6 * c + 4], e->cout);
-            const uint8_t* rec = e->records.p + (size_t)c0 * e->recordBytes;
-            CU(cudaMemcpy2DAsync(cnts + c0, sizeof(int), rec, e->recordBytes, sizeof(int), c1 - c0, cudaMemcpyDeviceToHost, e->cout));
-            CU(cudaMemcpy2DAsync(keypoints + (size_t)c0 * cap, (size_t)cap * 28, rec + OBS_HDR_INTS * 4, e->recordBytes, (size_t)m * 28, c1 - c0, cudaMemcpyDeviceToHost, e->cout));
-            CU(cudaMemcpy2DAsync(descriptors + (size_t)c0 * cap * 32, (size_t)cap * 32, rec + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28, e->recordBytes, (size_t)m * 32, c1 - c0, cudaMemcpyDeviceToHost, e->cout));
-            if (trace) cudaEventRecord(tev[6 * c + 5], e->cout);
-        }
-        // later consumers (stereo match, frame-set build) order themselves after the handle stream
-        CU(cudaEventRecord(e->join, e->aux));
-        CU(cudaStreamWaitEvent(st, e->join, 0));
-        e->lastN = n_images;
-        e->lastStream = st;
-        const auto tHost1 = std::chrono::steady_clock::now();
-        CU(cudaStreamSynchronize(e->cout));
-        if (trace) {
-            const auto tHost2 = std::chrono::steady_clock::now();
-            fprintf(stderr, "[obs trace %p] enqueue %.3f ms, total %.3f ms;", (void*)e,
-                    std::chrono::duration<double, std::milli>(tHost1 - tHost0).count(), std::chrono::duration<double, std::milli>(tHost2 - tHost0).count());
-            for (int c = 0; c < nChunks; c++) {
-                float t[6];
-                for (int k = 0; k < 6; k++) cudaEventElapsedTime(&t[k], tev[0], tev[6 * c + k]);
-                fprintf(stderr, " c%d in %.3f-%.3f run %.3f-%.3f out %.3f-%.3f;", c, t[0], t[1], t[2], t[3], t[4], t[5]);
-            }
-            fprintf(stderr, "\n");
-            for (auto& t : tev) cudaEventDestroy(t);
-        }
+        rc = enqueue_chunks(e, images[0], n_images, w, h, stride, keypoints, descriptors, cap, cnts);
+        if (rc) return rc;
+        // sleep until the last download has landed (blocking-sync event: no spinning host thread per handle)
+        CU(cudaEventRecord(e->hostDone, e->cout));
+        CU(cudaEventSynchronize(e->hostDone));
         int status = OBS_OK;
         for (int i = 0; i < n_images; i++) {
             n_out[i] = cnts[i];
@@ -897,6 +919,8 @@ int obs_frame_set_from_extractor(obs_frame_set* fs, obs_extractor* e, const floa
     if (obs_frame_set_capacity(fs) < e->g.kpCap)
         return fail(OBS_ERR_CAPACITY, "frame set keypoint capacity %d < extractor capacity %d", obs_frame_set_capacity(fs), e->g.kpCap);
     if (d_u_right && !is_device(d_u_right)) return fail(OBS_ERR_INVALID, "d_u_right must be device memory");
+    if (obs_frame_set_device(fs) != e->device)
+        return fail(OBS_ERR_INVALID, "the frame set lives on device %d, the extractor on device %d", obs_frame_set_device(fs), e->device);
     const uint8_t* rec = e->records.p;
     return obs_frame_set_build_device(fs, rec + OBS_HDR_INTS * 4, e->recordBytes, rec + OBS_HDR_INTS * 4 + (size_t)e->g.kpCap * 28,
                                       e->recordBytes, d_u_right, (size_t)e->g.kpCap, reinterpret_cast<const int*>(rec),
@@ -946,6 +970,65 @@ int obs_stereo_from_rgbd(obs_extractor* e, const float* d_depth, size_t depth_st
     if (d_u_right) *d_u_right = e->uRight.p;
     if (d_depth_out) *d_depth_out = e->depth.p;
     return OBS_OK;
+}
+
+// ---- whole stereo frames in one call (Frame::Frame for stereo, src/Frame.cc:78-90: two ExtractORB threads + ComputeStereoMatches)
+int obs_stereo_frames_submit(obs_extractor* L, obs_extractor* R, const obs_stereo_io* io, int n_frames, int w, int h, size_t stride,
+                             int cap, float mbf, float min_d, float max_d) {
+    int rc = check_handle(L);
+    if (rc) return rc;
+    if (!R || !io) return fail(OBS_ERR_INVALID, "null argument");
+    if (L == R) return fail(OBS_ERR_INVALID, "the two eyes need two extractor handles");
+    if (L->device != R->device) return fail(OBS_ERR_INVALID, "both eyes must live on one device");
+    if (L->pending || R->pending) return fail(OBS_ERR_STATE, "obs_stereo_frames_submit: the previous submission on these handles has not been waited for");
+    if (n_frames < 1 || n_frames > L->maxBatch || n_frames > R->maxBatch) return fail(OBS_ERR_CAPACITY, "batch of %d exceeds max_batch", n_frames);
+    if (w < 1 || h < 1 || w > L->maxW || h > L->maxH || w > R->maxW || h > R->maxH) return fail(OBS_ERR_INVALID, "image %dx%d outside the handles' limits", w, h);
+    if (stride < (size_t)w || cap < 1) return fail(OBS_ERR_INVALID, "stride smaller than width, or cap < 1");
+    const void* need[] = {io->left, io->right, io->kp_left, io->desc_left, io->n_left, io->kp_right, io->desc_right, io->n_right, io->u_right, io->depth};
+    for (const void* p : need)
+        if (!p || !is_pinned(p)) return fail(OBS_ERR_INVALID, "obs_stereo_frames_submit takes page-locked host buffers (obs_host_alloc) for every field of obs_stereo_io");
+    if ((rc = set_shape(L, w, h, n_frames, L->stream))) return rc;
+    if ((rc = set_shape(R, w, h, n_frames, R->stream))) return rc;
+    if (cap > L->g.kpCap) return fail(OBS_ERR_INVALID, "cap %d exceeds obs_extractor_max_keypoints (%d)", cap, L->g.kpCap);
+    // the two eyes on their own streams (the reference's two extraction threads), enqueued by this one host thread
+    if ((rc = enqueue_chunks(L, io->left, n_frames, w, h, stride, io->kp_left, io->desc_left, cap, io->n_left))) return rc;
+    if ((rc = enqueue_chunks(R, io->right, n_frames, w, h, stride, io->kp_right, io->desc_right, cap, io->n_right))) return rc;
+    if ((rc = obs_stereo_match_device(L, R, mbf, min_d, max_d, nullptr, nullptr, nullptr))) return rc;
+    const int kc = L->g.kpCap;
+    CU(cudaMemcpy2DAsync(io->u_right, (size_t)cap * 4, L->uRight.p, (size_t)kc * 4, (size_t)cap * 4, n_frames, cudaMemcpyDeviceToHost, L->stream));
+    CU(cudaMemcpy2DAsync(io->depth, (size_t)cap * 4, L->depth.p, (size_t)kc * 4, (size_t)cap * 4, n_frames, cudaMemcpyDeviceToHost, L->stream));
+    // one event behind everything: the downloads of both eyes and of the stereo result
+    CU(cudaEventRecord(L->fork, L->cout));
+    CU(cudaStreamWaitEvent(L->stream, L->fork, 0));
+    CU(cudaEventRecord(R->fork, R->cout));
+    CU(cudaStreamWaitEvent(L->stream, R->fork, 0));
+    CU(cudaEventRecord(L->hostDone, L->stream));
+    L->pending = R->pending = true;
+    L->pendingCounts[0] = io->n_left; L->pendingCounts[1] = io->n_right;
+    L->pendingN = n_frames; L->pendingCap = cap;
+    return OBS_OK;
+}
+
+int obs_stereo_frames_wait(obs_extractor* L, obs_extractor* R) {
+    int rc = check_handle(L);
+    if (rc) return rc;
+    if (!R) return fail(OBS_ERR_INVALID, "null argument");
+    if (!L->pending || !R->pending) return fail(OBS_ERR_STATE, "obs_stereo_frames_wait without a submission");
+    L->pending = R->pending = false;
+    CU(cudaEventSynchronize(L->hostDone));          // blocking-sync event: the thread sleeps
+    for (int s = 0; s < 2; s++)
+        for (int i = 0; i < L->pendingN; i++)
+            if (L->pendingCounts[s][i] > L->pendingCap)
+                return fail(OBS_ERR_CAPACITY, "caller capacity %d smaller than the keypoint count %d (frame %d, %s eye)", L->pendingCap,
+                            L->pendingCounts[s][i], i, s ? "right" : "left");
+    return OBS_OK;
+}
+
+int obs_stereo_frames(obs_extractor* L, obs_extractor* R, const obs_stereo_io* io, int n_frames, int w, int h, size_t stride,
+                      int cap, float mbf, float min_d, float max_d) {
+    int rc = obs_stereo_frames_submit(L, R, io, n_frames, w, h, stride, cap, mbf, min_d, max_d);
+    if (rc) return rc;
+    return obs_stereo_frames_wait(L, R);
 }
 
 int obs_host_alloc(size_t bytes, void** out) {

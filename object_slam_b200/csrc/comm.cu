@@ -28,11 +28,11 @@ struct NcclApi {
     ncclResult_t (*GetVersion)(int*) = nullptr;
 };
 
+// Resolved once per process; the initialisation of a function-local static is thread safe (communicators may be created
+// from several host threads).
 NcclApi* nccl_api() {
-    static NcclApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const NcclApi api = [] {
+        NcclApi api;
         void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (h) {
@@ -50,8 +50,9 @@ NcclApi* nccl_api() {
                 !api.GroupStart || !api.GroupEnd || !api.GetErrorString)
                 api.h = nullptr;
         }
-    }
-    return api.h ? &api : nullptr;
+        return api;
+    }();
+    return api.h ? const_cast<NcclApi*>(&api) : nullptr;
 }
 
 #define NC(call)                                                                                          \
@@ -129,6 +130,7 @@ int obs_comm_allgather(obs_comm* c, const uint8_t* d_local, size_t local_bytes, 
     if (!c || !d_local || !d_all) return fail(OBS_ERR_INVALID, "null argument");
     if (n_chunks < 1 || local_bytes == 0) return fail(OBS_ERR_INVALID, "n_chunks >= 1 and local_bytes > 0 required");
     if (!is_device(d_local) || !is_device(d_all)) return fail(OBS_ERR_INVALID, "both buffers must be device memory");
+    if (local_bytes % 32) return fail(OBS_ERR_INVALID, "local_bytes must be a multiple of 32 (whole descriptors)");
     NcclApi* N = nccl_api();
     if (!N) return fail(OBS_ERR_CUDA, "libnccl.so.2 cannot be loaded");
     CU(cudaSetDevice(c->device));
@@ -144,8 +146,7 @@ int obs_comm_allgather(obs_comm* c, const uint8_t* d_local, size_t local_bytes, 
     uint8_t* mine = d_all + (size_t)c->rank * local_bytes;
     if (mine != d_local) CU(cudaMemcpyAsync(mine, d_local, local_bytes, cudaMemcpyDeviceToDevice, c->stream));
     // chunk boundaries on 32-byte descriptors
-    const size_t nDesc = local_bytes / 32, rem = local_bytes % 32;
-    if (rem) return fail(OBS_ERR_INVALID, "local_bytes must be a multiple of 32");
+    const size_t nDesc = local_bytes / 32;
     for (int k = 0; k < n_chunks; k++) {
         const size_t lo = nDesc * k / n_chunks * 32, hi = nDesc * (k + 1) / n_chunks * 32;
         if (hi > lo && c->world > 1) {

@@ -360,7 +360,9 @@ __global__ void __launch_bounds__(FT_THREADS, FT_MINCTAS) k_fast_cells(const __g
 size_t fast_smem_bytes(int tileRows) { return (size_t)2 * tileRows * FT_SP + (size_t)FT_LIST * 2; }
 
 cudaError_t fast_prepare(int tileRows) {
-    return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes(tileRows));
+    cudaError_t e = OBS_ALLOW_MAX_SMEM(k_fast_cells);
+    if (e != cudaSuccess) return e;
+    return (int)fast_smem_bytes(tileRows) <= obsdetail::max_dynamic_smem((const void*)k_fast_cells) ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 int fast_cells_per_cta_host(int wCell, int hCell) { return fast_cells_per_cta(wCell, hCell); }

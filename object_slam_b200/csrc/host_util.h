@@ -1,12 +1,20 @@
 // Host-side helpers shared by the C-ABI translation units (api.cu, matcher_api.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstddef>
 
 namespace obsdetail {
 int fail(int code, const char* fmt, ...);     // records the thread-local message of obs_last_error(), returns code
 bool is_pinned(const void* p);                // page-locked host memory
 bool is_device(const void* p);                // device (or managed) memory
+
+// The dynamic shared-memory limit of a kernel (cudaFuncAttributeMaxDynamicSharedMemorySize) is process-wide per kernel and
+// device, not per handle: it is raised ONCE to the device's opt-in maximum (minus the kernel's static shared memory) and never
+// lowered, so handles with different shapes or capacities cannot invalidate each other's launches.  `done` is a per-call-site
+// bit mask of the devices already configured; racing threads write the same value.
+cudaError_t allow_max_smem(const void* kernel, std::atomic<unsigned long long>& done);
+int max_dynamic_smem(const void* kernel);      // that limit for the current device (bytes), 0 on error
 
 template <typename T> struct DevBuf {
     T* p = nullptr;
@@ -41,6 +49,12 @@ using obsdetail::is_pinned;
 using obsdetail::is_device;
 using obsdetail::DevBuf;
 using obsdetail::PinBuf;
+
+#define OBS_ALLOW_MAX_SMEM(kernel)                                                                  \
+    ([]() -> cudaError_t {                                                                          \
+        static std::atomic<unsigned long long> done_{0};                                            \
+        return obsdetail::allow_max_smem((const void*)(kernel), done_);                             \
+    }())
 
 #define CU(call)                                                                                   \
     do {                                                                                           \

@@ -2,6 +2,7 @@
 // `st` and return the launch status; none synchronises.
 #pragma once
 #include "common.cuh"
+#include "host_util.h"
 #include <cuda.h>                  // CUtensorMap (type only: the encoder is fetched with cudaGetDriverEntryPoint, nothing links libcuda)
 
 // K1  pyramid.cu   -- ComputePyramid (src/ORBextractor.cc:1107-1132), levels 1..n-1

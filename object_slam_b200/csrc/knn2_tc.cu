@@ -302,8 +302,7 @@ cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded,
     if (a.nPairs <= 0 || a.n <= 0) return cudaSuccess;
     EncodeTiledFn enc = tma_encoder();
     if (!enc) return cudaErrorNotSupported;
-    // per device, and only ever the one size: safe to repeat from any thread
-    cudaError_t e = cudaFuncSetAttribute(k_knn2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    cudaError_t e = OBS_ALLOW_MAX_SMEM(k_knn2_tc);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
     e = cudaGetDevice(&dev);

@@ -865,7 +865,7 @@ cudaError_t launch_proj_search(const ProjSearchArgs& a, int variant, int nFrames
     if (e != cudaSuccess) return e;
 #define OBS_PROJ_CASE(VV)                                                                                                   \
     case VV:                                                                                                                \
-        e = cudaFuncSetAttribute(k_proj_resolve<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+        e = OBS_ALLOW_MAX_SMEM(k_proj_resolve<VV>);                                                                         \
         if (e != cudaSuccess) return e;                                                                                     \
         k_proj_candidates<VV><<<grid, 128, 0, st>>>(a);                                                                     \
         k_proj_resolve<VV><<<nFrames, 1024, smem, st>>>(a);                                                                 \
@@ -896,7 +896,7 @@ cudaError_t launch_sim3_agree(const int* idx1, const int* dist1, int n1, const i
 
 cudaError_t launch_init_search(const InitSearchArgs& a, int nFrames, cudaStream_t st) {
     const size_t smem = ((size_t)a.F2.cap * 2 + (size_t)a.F1.cap * 2) * sizeof(int);
-    cudaError_t e = cudaFuncSetAttribute(k_init_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = OBS_ALLOW_MAX_SMEM(k_init_search);
     if (e != cudaSuccess) return e;
     k_init_search<<<nFrames, 512, smem, st>>>(a);
     return cudaGetLastError();

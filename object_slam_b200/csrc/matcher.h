@@ -1,6 +1,7 @@
 // Device-side argument blocks and launchers of the matcher kernels (matcher.cu).
 #pragma once
 #include "common.cuh"
+#include "host_util.h"
 
 #define OBS_GRID_COLS 64          // FRAME_GRID_COLS, include/Frame.h:41
 #define OBS_GRID_ROWS 48          // FRAME_GRID_ROWS, include/Frame.h:42

@@ -45,6 +45,8 @@ struct obs_frame_set {
     // upload staging
     PinBuf<uint8_t> hStage;
     DevBuf<uint8_t> dStage;
+    cudaEvent_t built = nullptr;      // recorded behind every build: searches issued from another matcher's stream wait for it
+    int device = 0;
 };
 
 namespace {
@@ -53,6 +55,15 @@ int check_matcher(const obs_matcher* m) {
     if (!m) return fail(OBS_ERR_INVALID, "null matcher handle");
     cudaError_t ce = cudaSetDevice(m->device);
     if (ce != cudaSuccess) return fail(OBS_ERR_CUDA, "cudaSetDevice(%d): %s", m->device, cudaGetErrorString(ce));
+    return OBS_OK;
+}
+
+// A frame set may be searched from any matcher of its device (the reference builds a Frame on the Tracking thread and searches it
+// from LocalMapping / LoopClosing): a foreign matcher's stream first waits for the set's last build.  Rebuilding a set while another
+// thread still searches it is the caller's race, as it would be for the reference's Frame.
+int adopt_set(obs_matcher* m, obs_frame_set* fs) {
+    if (fs->device != m->device) return fail(OBS_ERR_INVALID, "frame set lives on device %d, the matcher on device %d", fs->device, m->device);
+    if (fs->m != m && fs->built) CU(cudaStreamWaitEvent(m->stream, fs->built, 0));
     return OBS_OK;
 }
 
@@ -118,6 +129,7 @@ int obs_frame_set_build_device(obs_frame_set* fs, const uint8_t* keys, size_t ke
     a.uRight = uRight; a.uRightFrameStride = uRightFrameStride;
     a.count = count; a.countStrideInts = countStrideInts;
     CU(launch_frame_build(a, nFrames, m->stream));
+    CU(cudaEventRecord(fs->built, m->stream));
     fs->nFrames = nFrames;
     return OBS_OK;
 }
@@ -186,6 +198,7 @@ int obs_frame_set_create(obs_matcher* m, const obs_frame_params* params, int max
     obs_frame_set* fs = new (std::nothrow) obs_frame_set;
     if (!fs) return fail(OBS_ERR_INVALID, "out of host memory");
     fs->m = m;
+    fs->device = m->device;
     fs->prm = *params;
     fs->maxFrames = max_frames;
     fs->cap = (max_keypoints + 31) & ~31;
@@ -196,6 +209,7 @@ int obs_frame_set_create(obs_matcher* m, const obs_frame_params* params, int max
     if (e == cudaSuccess) e = fs->desc.ensure(B * cap * 2);
     if (e == cudaSuccess) e = fs->cellStart.ensure(B * (OBS_GRID_CELLS + 1));
     if (e == cudaSuccess) e = fs->cellIdx.ensure(B * cap);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fs->built, cudaEventDisableTiming);
     if (e != cudaSuccess) { obs_frame_set_destroy(fs); return fail(OBS_ERR_CUDA, "frame set allocation: %s", cudaGetErrorString(e)); }
     fs->d.cap = fs->cap;
     fs->d.n = fs->n.p; fs->d.kp = fs->kp.p; fs->d.angle = fs->angle.p; fs->d.desc = fs->desc.p;
@@ -208,14 +222,16 @@ int obs_frame_set_create(obs_matcher* m, const obs_frame_params* params, int max
 
 int obs_frame_set_destroy(obs_frame_set* fs) {
     if (!fs) return OBS_OK;
+    cudaSetDevice(fs->device);
+    if (fs->built) cudaEventSynchronize(fs->built);
     if (fs->m) {
-        cudaSetDevice(fs->m->device);
         cudaStreamSynchronize(fs->m->stream);
         for (size_t i = 0; i < fs->m->sets.size(); i++)
             if (fs->m->sets[i] == fs) { fs->m->sets.erase(fs->m->sets.begin() + i); break; }
     }
     fs->n.release(); fs->kp.release(); fs->angle.release(); fs->desc.release(); fs->cellStart.release(); fs->cellIdx.release();
     fs->hStage.release(); fs->dStage.release();
+    if (fs->built) cudaEventDestroy(fs->built);
     delete fs;
     return OBS_OK;
 }
@@ -223,6 +239,7 @@ int obs_frame_set_destroy(obs_frame_set* fs) {
 int obs_frame_set_count(const obs_frame_set* fs) { return fs ? fs->nFrames : -1; }
 }
 int obs_frame_set_capacity(const obs_frame_set* fs) { return fs ? fs->cap : -1; }
+int obs_frame_set_device(const obs_frame_set* fs) { return fs ? fs->device : -1; }
 extern "C" {
 
 int obs_frame_set_upload(obs_frame_set* fs, const obs_frame_view* frames, int n_frames) {
@@ -290,6 +307,9 @@ static int run_proj(obs_matcher* m, obs_frame_set* fs, ProjSearchArgs& a, int va
     CU(m->poolCursor.ensure((size_t)B));
     CU(m->choice.ensure((size_t)B * std::max(M, 1)));
     CU(m->rounds.ensure((size_t)B));
+    // k_proj_resolve keeps four ints per keypoint slot in shared memory (about 14.5 k keypoints per frame at most)
+    if ((size_t)fs->cap * 16 > 220 * 1024)
+        return fail(OBS_ERR_CAPACITY, "projection searches need max_keypoints <= %d (frame set was created with %d)", 220 * 1024 / 16, fs->cap);
     a.F = fs->d;
     a.cand = m->cand.p; a.pool = m->pool.p; a.poolCursor = m->poolCursor.p; a.choice = m->choice.p; a.kpMatch = dMatch; a.nMatches = dN; a.rounds = m->rounds.p;
     CU(launch_proj_search(a, variant, B, m->stream));
@@ -309,7 +329,7 @@ int obs_search_by_projection(obs_matcher* m, obs_frame_set* frames, const obs_ma
     int rc = check_matcher(m);
     if (rc) return rc;
     if (!frames || !pts || !kp_match || !n_matches) return fail(OBS_ERR_INVALID, "null argument");
-    if (frames->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if ((rc = adopt_set(m, frames))) return rc;
     if (frames->nFrames < 1) return fail(OBS_ERR_STATE, "frame set is empty");
     if (pts->n < 0) return fail(OBS_ERR_INVALID, "negative point count");
     if (pts->n > 0 && (!pts->in_view || !pts->proj_x || !pts->proj_y || !pts->proj_xr || !pts->scale_level || !pts->view_cos ||
@@ -340,7 +360,7 @@ int obs_search_by_projection_last(obs_matcher* m, obs_frame_set* cur, const obs_
     int rc = check_matcher(m);
     if (rc) return rc;
     if (!cur || !last || !kp_match || !n_matches) return fail(OBS_ERR_INVALID, "null argument");
-    if (cur->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if ((rc = adopt_set(m, cur))) return rc;
     if (cur->nFrames < 1) return fail(OBS_ERR_STATE, "frame set is empty");
     if (last->n < 0) return fail(OBS_ERR_INVALID, "negative point count");
     if (!last->tcw_last || !last->tcw_current) return fail(OBS_ERR_INVALID, "null pose");
@@ -372,7 +392,7 @@ static int run_keyframe_search(obs_matcher* m, obs_frame_set* fs, const obs_keyf
     int rc = check_matcher(m);
     if (rc) return rc;
     if (!fs || !pts || !kp_match || !n_matches) return fail(OBS_ERR_INVALID, "null argument");
-    if (fs->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if ((rc = adopt_set(m, fs))) return rc;
     if (fs->nFrames < 1) return fail(OBS_ERR_STATE, "frame set is empty");
     if (pts->n < 0 || !pts->tcw) return fail(OBS_ERR_INVALID, "negative point count or null pose");
     if (pts->n > 0 && (!pts->valid || !pts->world_pos || !pts->min_distance || !pts->max_distance || !pts->max_distance_raw ||
@@ -417,7 +437,7 @@ int obs_fuse_search(obs_matcher* m, obs_frame_set* fs, const obs_keyframe_points
     int rc = check_matcher(m);
     if (rc) return rc;
     if (!fs || !pts || !best_idx || !best_dist) return fail(OBS_ERR_INVALID, "null argument");
-    if (fs->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if ((rc = adopt_set(m, fs))) return rc;
     if (fs->nFrames < 1) return fail(OBS_ERR_STATE, "frame set is empty");
     if (pts->n < 1 || !pts->tcw) return fail(OBS_ERR_INVALID, "point count < 1 or null pose");
     if (!pts->valid || !pts->world_pos || !pts->min_distance || !pts->max_distance || !pts->max_distance_raw || !pts->descriptors || !pts->normal)
@@ -493,7 +513,7 @@ int obs_search_by_sim3(obs_matcher* m, obs_frame_set* kf1, obs_frame_set* kf2, c
     int rc = check_matcher(m);
     if (rc) return rc;
     if (!kf1 || !kf2 || !points1 || !points2 || !t21 || !t12 || !match12 || !n_found) return fail(OBS_ERR_INVALID, "null argument");
-    if (kf1->m != m || kf2->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if ((rc = adopt_set(m, kf1)) || (rc = adopt_set(m, kf2))) return rc;
     if (kf1->nFrames < 1 || kf1->nFrames != kf2->nFrames) return fail(OBS_ERR_STATE, "frame sets are empty or differ in size");
     const int B = kf1->nFrames;
     FuseSearchArgs a1, a2;
@@ -518,10 +538,17 @@ int obs_search_for_initialization(obs_matcher* m, obs_frame_set* f1, obs_frame_s
     int rc = check_matcher(m);
     if (rc) return rc;
     if (!f1 || !f2 || !prev_matched || !matches12 || !n_matches) return fail(OBS_ERR_INVALID, "null argument");
-    if (f1->m != m || f2->m != m) return fail(OBS_ERR_INVALID, "frame set belongs to another matcher");
+    if ((rc = adopt_set(m, f1)) || (rc = adopt_set(m, f2))) return rc;
     if (f1->nFrames < 1 || f1->nFrames != f2->nFrames) return fail(OBS_ERR_STATE, "both frame sets must hold the same number (>= 1) of frames");
     const int B = f1->nFrames;
     const size_t c1 = (size_t)B * f1->cap;
+    // k_init_search keeps two ints per keypoint slot of either frame in shared memory; the candidate lists are cap2 entries per
+    // keypoint of frame 1 (a window can hold every keypoint of frame 2)
+    if (((size_t)f1->cap + (size_t)f2->cap) * 8 > 220 * 1024)
+        return fail(OBS_ERR_CAPACITY, "SearchForInitialization needs max_keypoints1 + max_keypoints2 <= %d (got %d + %d)", 220 * 1024 / 8, f1->cap, f2->cap);
+    if (c1 * (size_t)f2->cap * 4 > ((size_t)4 << 30))
+        return fail(OBS_ERR_CAPACITY, "SearchForInitialization: %d frame pairs x %d x %d candidate slots exceed 4 GB; use smaller batches or frame sets "
+                    "created with a tighter max_keypoints", B, f1->cap, f2->cap);
     InitSearchArgs a;
     memset(&a, 0, sizeof(a));
     a.F1 = f1->d; a.F2 = f2->d;

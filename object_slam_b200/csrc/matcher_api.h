@@ -10,3 +10,4 @@ int obs_frame_set_build_device(obs_frame_set* fs, const uint8_t* keys, size_t ke
                                size_t descFrameStride, const float* uRight, size_t uRightFrameStride, const int* count,
                                size_t countStrideInts, int nFrames, cudaStream_t producer);
 int obs_frame_set_capacity(const obs_frame_set* fs);
+int obs_frame_set_device(const obs_frame_set* fs);       // device the set lives on

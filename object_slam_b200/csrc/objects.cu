@@ -322,11 +322,9 @@ cudaError_t launch_distance_transform(const uint8_t* masks, size_t maskStride, s
                                       float* out, cudaStream_t st) {
     k_dt_columns<<<dim3((w + 127) / 128, nMasks), 128, 0, st>>>(masks, maskStride, maskImageStride, w, h, out);
     const size_t smem = (size_t)4 * (3 * w + 2) * 4;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_dt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) {
+        cudaError_t e = OBS_ALLOW_MAX_SMEM(k_dt_rows);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     const int nRows = nMasks * h;
     k_dt_rows<<<(nRows + 3) / 4, 128, smem, st>>>(w, h, nRows, out);

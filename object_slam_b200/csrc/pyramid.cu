@@ -316,9 +316,9 @@ cudaError_t pyramid_prepare(const Geom& g) {
     size_t need = 0;
     for (int l = 1; l < g.nlevels; l++) need = std::max(need, (size_t)g.lv[l].rsPitch * g.lv[l].rsRows);
     if (need <= 48 * 1024) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_resize_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    cudaError_t e = OBS_ALLOW_MAX_SMEM(k_resize_tile);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_resize_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    return OBS_ALLOW_MAX_SMEM(k_resize_chain);
 }
 
 cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, const ResizeTap* ytab, int nimg, cudaStream_t st) {

@@ -352,7 +352,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
 size_t quadtree_smem_bytes(int nodeCap) { return smem_layout(nodeCap, nullptr, nullptr); }
 
 cudaError_t quadtree_prepare(int nodeCap) {
-    return cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)quadtree_smem_bytes(nodeCap));
+    cudaError_t e = OBS_ALLOW_MAX_SMEM(k_quadtree);
+    if (e != cudaSuccess) return e;
+    return (int)quadtree_smem_bytes(nodeCap) <= obsdetail::max_dynamic_smem((const void*)k_quadtree) ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 cudaError_t launch_quadtree(const Geom& g, int nodeCap, const uint32_t* cand, const int* cellCount,

@@ -287,11 +287,9 @@ __global__ void __launch_bounds__(256) k_stereo_filter(const __grid_constant__ S
 
 cudaError_t launch_stereo(const StereoArgs& a, int nimg, cudaStream_t st) {
     const size_t smemRows = (size_t)(a.g.lv[0].h + 1) * sizeof(int);
-    static thread_local size_t configured = 0;
-    if (smemRows > 48 * 1024 && smemRows > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRows);
+    if (smemRows > 48 * 1024) {
+        cudaError_t e = OBS_ALLOW_MAX_SMEM(k_stereo_rows);
         if (e != cudaSuccess) return e;
-        configured = smemRows;
     }
     k_stereo_rows<<<nimg, 256, smemRows, st>>>(a);
     dim3 grid((a.g.kpCap + ST_WARPS - 1) / ST_WARPS, nimg);

@@ -224,3 +224,56 @@ def stereo_match_device(left, right, mbf, minD, maxD, stream=None):
     check(lib().obs_stereo_match_device(left._h, right._h, float(mbf), float(minD), float(maxD),
                                         C.c_void_p(int(stream) if stream else 0), C.byref(pu), C.byref(pd)))
     return pu.value, pd.value
+
+
+class StereoFrames:
+    """The stereo ``Frame`` constructor's device work for batches of frames (src/Frame.cc:78-90: ExtractORB on both eyes, then
+    ComputeStereoMatches) through ``obs_stereo_frames_submit`` / ``obs_stereo_frames_wait``: one extractor pair, page-locked
+    input and output buffers, one C call per batch.  ``submit`` returns as soon as the batch is enqueued; several instances
+    driven round-robin from one thread overlap each other's transfers and kernels.
+
+    ``left`` / ``right``: page-locked [F, H, stride] uint8 arrays to fill (``self.left[i, :, :W] = image``)."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, size, frames, device=0):
+        from ._capi import StereoIO, pinned_empty
+        W, H = int(size[0]), int(size[1])
+        self.W, self.H, self.F = W, H, int(frames)
+        self.eL = ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_size=(W, H), max_batch=frames, device=device)
+        self.eR = ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_size=(W, H), max_batch=frames, device=device)
+        cap = self.cap = self.eL.capacity
+        self.stride = W
+        self.left = pinned_empty((frames, H, W), np.uint8)
+        self.right = pinned_empty((frames, H, W), np.uint8)
+        mk = lambda: (pinned_empty((frames, cap), KEYPOINT_DTYPE), pinned_empty((frames, cap, 32), np.uint8), pinned_empty((frames,), np.int32))
+        self.kpL, self.descL, self.nL = mk()
+        self.kpR, self.descR, self.nR = mk()
+        self.uRight = pinned_empty((frames, cap), np.float32)
+        self.depth = pinned_empty((frames, cap), np.float32)
+        a = _capi.addr
+        self._io = StereoIO(a(self.left), a(self.right), a(self.kpL), a(self.descL), a(self.nL), a(self.kpR), a(self.descR), a(self.nR),
+                            a(self.uRight), a(self.depth))
+        self.h2d_bytes = 2 * frames * H * W
+        self.d2h_bytes = 2 * frames * (cap * 60 + 4) + 2 * frames * cap * 4
+
+    def submit(self, mbf, minD, maxD, frames=None):
+        n = self.F if frames is None else int(frames)
+        check(lib().obs_stereo_frames_submit(self.eL._h, self.eR._h, C.byref(self._io), n, self.W, self.H, self.stride, self.cap,
+                                             float(mbf), float(minD), float(maxD)))
+        self.eL._last_n = self.eR._last_n = n
+
+    def wait(self):
+        check(lib().obs_stereo_frames_wait(self.eL._h, self.eR._h))
+
+    def __call__(self, mbf, minD, maxD, frames=None):
+        self.submit(mbf, minD, maxD, frames)
+        self.wait()
+        return self.results(self.F if frames is None else int(frames))
+
+    def results(self, n=None):
+        """[(keysL, descL, keysR, descR, uRight, depth)] per frame (views of the page-locked buffers)."""
+        n = self.F if n is None else n
+        out = []
+        for i in range(n):
+            a, b = int(self.nL[i]), int(self.nR[i])
+            out.append((self.kpL[i, :a], self.descL[i, :a], self.kpR[i, :b], self.descR[i, :b], self.uRight[i, :a], self.depth[i, :a]))
+        return out

@@ -13,8 +13,11 @@
 #ifndef OBS_MAX_HEIGHT
 #define OBS_MAX_HEIGHT 1536
 #endif
+// 1 (default): mvImagePyramid holds the level pixels after every call, as in the reference -- an unmodified
+// Frame::ComputeStereoMatches can keep reading them.  0: sizes only (saves the device-to-host copy) for trees whose
+// ComputeStereoMatches forwards to ComputeStereoMatchesB200; the Mats are then zero-filled, never stale.
 #ifndef OBS_DOWNLOAD_PYRAMID
-#define OBS_DOWNLOAD_PYRAMID 0
+#define OBS_DOWNLOAD_PYRAMID 1
 #endif
 #ifndef OBS_DEVICE
 #define OBS_DEVICE 0
@@ -88,6 +91,8 @@ void ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std:
 #if OBS_DOWNLOAD_PYRAMID
         obsCheck(obs_extractor_get_level(mpHandle, 0, level, 0, mvImagePyramid[level].data, mvImagePyramid[level].step, &w, &h),
                  "obs_extractor_get_level");
+#else
+        memset(mvImagePyramid[level].data, 0, (size_t)mvImagePyramid[level].step * h);
 #endif
     }
 }

@@ -27,12 +27,20 @@ namespace ORB_SLAM2
 
 inline void ObsCheck(int rc) { if (rc != OBS_OK) throw std::runtime_error(std::string("obslam_b200: ") + obs_last_error()); }
 
-// One matcher handle (stream + workspace) per thread, like the reference's stack-local ORBmatcher objects.
+// One matcher handle (stream + workspace) per thread, like the reference's stack-local ORBmatcher objects; destroyed when
+// the thread exits.  A frame uploaded on one thread (Tracking) can be searched from any other (LocalMapping, LoopClosing):
+// the library orders a foreign matcher's stream behind the frame set's last build.
+struct ThreadMatcherHolder
+{
+    obs_matcher* m;
+    ThreadMatcherHolder(): m(NULL) {}
+    ~ThreadMatcherHolder() { if(m) obs_matcher_destroy(m); }
+};
 inline obs_matcher* ThreadMatcher()
 {
-    static thread_local obs_matcher* m = nullptr;
-    if(!m) ObsCheck(obs_matcher_create(0, &m));
-    return m;
+    static thread_local ThreadMatcherHolder h;
+    if(!h.m) ObsCheck(obs_matcher_create(0, &h.m));
+    return h.m;
 }
 
 // Frame -> device, Frame.cc:103/164/224 (after AssignFeaturesToGrid; the device rebuilds the grid itself).
@@ -124,6 +132,9 @@ public:
     int SearchByBoW(KeyFrameT* pKF, FrameT &F, std::vector<MapPointT*> &vpMapPointMatches)
     {
         const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
+        vpMapPointMatches = std::vector<MapPointT*>(F.N, static_cast<MapPointT*>(NULL));
+        if(pKF->N <= 0 || F.N <= 0)       // nothing to walk: the reference's loops fall through and return 0
+            return 0;
         BowCsr a, b;
         FeatVecToCsr(pKF->mFeatVec, a); FeatVecToCsr(F.mFeatVec, b);
         const int32_t nA = pKF->N, nB = F.N;
@@ -135,7 +146,6 @@ public:
         std::vector<int32_t> m12(s1.cap), m21(s2.cap);
         int32_t n = 0;
         ObsCheck(obs_search_by_bow(ThreadMatcher(), &s1, &s2, 1, TH_LOW, 0, mfNNratio, mbCheckOrientation, m12.data(), m21.data(), &n));
-        vpMapPointMatches = std::vector<MapPointT*>(F.N, static_cast<MapPointT*>(NULL));
         for(int i=0; i<F.N; i++) if(m21[i]>=0) vpMapPointMatches[i] = vpMapPointsKF[m21[i]];
         return n;
     }

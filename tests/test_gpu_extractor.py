@@ -219,3 +219,21 @@ def test_very_wide_image_capacity(gpu):
     ok, od = oracle.OracleExtractor(300, 1.1, 8, 20, 5)(img)
     assert len(ok) > 300 + 4 * 8
     assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+
+
+def test_alternating_handles_with_different_settings(gpu):
+    """Handles with different nfeatures / shapes used alternately (the monocular drop-in: mpIniORBextractor at 2 x nFeatures beside
+    mpORBextractorLeft): the dynamic shared-memory limit of a kernel is process-wide, so a handle with smaller node or tile
+    capacities must not lower it under the other one's feet."""
+    big = _ex(2000, synth.KITTI_SHAPE)
+    small = _ex(500, synth.TUM_SHAPE)
+    huge = _ex(4000, synth.KITTI_SHAPE)
+    imgK = synth.blocky_image(synth.KITTI_SHAPE, 31)
+    imgT = synth.blocky_image(synth.TUM_SHAPE, 32)
+    want = {}
+    for name, e, img, nf in (("big", big, imgK, 2000), ("small", small, imgT, 500), ("huge", huge, imgK, 4000)):
+        want[name] = oracle.OracleExtractor(nf)(img)
+    for _ in range(3):                      # geometry unchanged between rounds: nothing is re-prepared
+        for name, e, img in (("big", big, imgK), ("small", small, imgT), ("huge", huge, imgK), ("small", small, imgT), ("big", big, imgK)):
+            k, d = e(img)
+            _assert_same(k, d, *want[name])

@@ -327,6 +327,34 @@ def test_errors(M):
         M.SearchByProjection(fs, *[np.zeros(1, np.uint8)] * 8)   # empty frame set
 
 
+def test_capacity_errors_are_explicit(M):
+    """Frame sets beyond what the searches can hold in shared memory fail with OBS_ERR_CAPACITY and a message, not with a
+    launch error."""
+    from object_slam_b200._capi import ObsError
+    fs = M.frame_set(synth.scale_factors(), bounds(TUM), max_frames=1, max_keypoints=20000)
+    f = synth.synthetic_frame(TUM, 300, 3)
+    fs.upload([f])
+    mp = synth.map_points_for_frame(f[0], f[1], TUM, 100, 1)
+    with pytest.raises(ObsError, match="max_keypoints"):
+        M.SearchByProjection(fs, *[mp[k] for k in MP_KEYS], th=3.0)
+    with pytest.raises(ObsError, match="max_keypoints"):
+        M.SearchForInitialization(fs, fs, np.zeros((1, fs.cap, 2), np.float32), 100)
+
+
+def test_frame_set_searched_from_another_matcher(M):
+    """A frame uploaded through one matcher (the Tracking thread's) is searched from another one (LocalMapping's): the second
+    matcher's stream is ordered behind the build."""
+    from object_slam_b200.matcher import ORBmatcher
+    shape = TUM
+    frame, mp, _ = map_case(shape, 800, 4000, 5)
+    other = ORBmatcher(0.8, True)
+    for _ in range(3):
+        fs = frame_set(M, shape, [frame])
+        n, match = other.SearchByProjection(fs, *[mp[k] for k in MP_KEYS], th=3.0, per_frame=False)
+        on, omatch = oracle_map(frame, shape, mp, 3.0, 0.8)
+        assert n[0] == on and np.array_equal(match[0, :800], omatch)
+
+
 def test_two_gpu_allgather_and_sharded_matching(gpu):
     """The NCCL exchange step (csrc/comm.cu) and sharded keyframe matching on 2 GPUs; skipped on a 1-GPU box."""
     import subprocess

@@ -91,3 +91,42 @@ def test_identical_eyes_give_zero_disparity_clamp(gpu):
     our, odp, _ = _oracle_stereo(img, img, 1000, 40.0, 0.0, 525.0)
     assert np.array_equal(ur, our) and np.array_equal(dp, odp)
     # every accepted match has SAD 0 here, so the median cut (thDist = 0) removes them all -- as in the reference
+
+
+@pytest.mark.parametrize("frames", [3, 12, 40])
+def test_stereo_frames_one_call_matches_oracle(gpu, frames):
+    """obs_stereo_frames_submit / _wait (both eyes + ComputeStereoMatches in one C call, page-locked buffers, chunked transfers):
+    keypoints, descriptors, uRight and depth of every frame equal the oracle's; two pipelines driven round-robin by one thread."""
+    from object_slam_b200.extractor import StereoFrames
+    shape = synth.TUM_SHAPE
+    H, W = shape
+    pipes = [StereoFrames(1000, 1.2, 8, 20, 7, (W, H), frames) for _ in range(2)]
+    pairs = [[synth.stereo_pair(shape, 100 * p + s) for s in range(frames)] for p in range(2)]
+    for pipe, pp in zip(pipes, pairs):
+        for i, (l, r) in enumerate(pp):
+            pipe.left[i] = l
+            pipe.right[i] = r
+    for rnd in range(2):                               # the second round reuses the handles and buffers
+        for pipe in pipes:
+            pipe.submit(40.0, 0.0, 525.0)
+        for pipe in pipes:
+            pipe.wait()
+        for pipe, pp in zip(pipes, pairs):
+            res = pipe.results()
+            for i in ([0, frames - 1] if frames > 12 else range(frames)):
+                L, R = pp[i]
+                oL, oR = oracle.OracleExtractor(1000), oracle.OracleExtractor(1000)
+                kL, dL = oL(L); kR, dR = oR(R)
+                t = oL.tables()
+                our, odp, _ = oracle.stereo_match(kL, dL, kR, dR, [oL.level(l) for l in range(8)], [oR.level(l) for l in range(8)],
+                                                  t["scale"], t["inv_scale"], 40.0, 0.0, 525.0)
+                gkL, gdL, gkR, gdR, ur, dp = res[i]
+                assert gkL.tobytes() == kL.tobytes() and np.array_equal(gdL, dL)
+                assert gkR.tobytes() == kR.tobytes() and np.array_equal(gdR, dR)
+                assert np.array_equal(ur, our) and np.array_equal(dp, odp)
+    # a second submit without a wait is refused
+    from object_slam_b200._capi import ObsError
+    pipes[0].submit(40.0, 0.0, 525.0)
+    with pytest.raises(ObsError):
+        pipes[0].submit(40.0, 0.0, 525.0)
+    pipes[0].wait()
