@@ -1,4 +1,5 @@
-"""The other workloads of bench.py (`--workload knn2|projection|bow|extract`); same JSON contract as the headline line.
+"""The other workloads of bench.py: configs[3] (extract) and configs[4] (knn2) -- measured as sub-results of the default line and
+available alone with `--workload` -- plus configs[2] (projection) and the BoW search; same JSON contract as the headline line.
 
 knn2        configs[4]: K keyframes x 2000 descriptors, every keyframe matched against its +-window neighbours
             (best / second best / ratio test).  Query keyframes are sharded over the ranks (strong scaling: the
@@ -58,175 +59,6 @@ def cpu_knn2(D, pairs, cores):
         t0 = time.perf_counter()
         list(pool.map(one, pairs))
         return time.perf_counter() - t0
-
-
-def run_knn2(args, rank, local_rank, world, ClockSampler):
-    K, Wn = args.keyframes, args.window
-    metric = "Hamming distance evaluations/s, brute-force keyframe-vs-keyframe matching (best + second best + ratio), 2000 descriptors per keyframe"
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        cores = os.cpu_count() or 1
-        D = synth.keyframe_descriptors(8, NDESC, 0)
-        pairs = sharding.window_pairs(0, 8, 8, 8)[:max(cores * 2, 8)]
-        total = 0.0
-        for _ in range(args.warmup):
-            cpu_knn2(D, pairs[:cores], cores)
-        for _ in range(args.steps):
-            total += cpu_knn2(D, pairs, cores)
-        v = len(pairs) * NDESC * NDESC * args.steps / total
-        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "distances/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
-                          "scaling": "strong", "vs_baseline": None, "dtype": "u32 popcount", "data": "synthetic",
-                          "config": {"workload": "configs[4] brute-force keyframe matching", "pairs_per_step": len(pairs)},
-                          "cpu_baseline": {"value": v, "unit": "distances/s", "cores": cores, "kind": "port",
-                                           "sample": f"{len(pairs)} keyframe pairs per step, restated SearchByBoW candidate loop with the reference's SWAR DescriptorDistance"},
-                          "e2e": {"value": v, "unit": "distances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
-        return
-    import torch
-    import torch.distributed as dist
-    from object_slam_b200._capi import check, lib, pinned_empty
-    from object_slam_b200.matcher import ORBmatcher
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    per = sharding.padded_shard(K, world)
-    lo, hi = rank * per, min(K, (rank + 1) * per)
-    full = _device_keyframes(torch, K, 1234, dev)              # every rank generates the same set, keeps only its shard
-    local = torch.zeros((per, NDESC, 32), dtype=torch.uint8, device=dev)
-    local[:hi - lo] = full[lo:hi]
-    del full
-    allD = torch.zeros((world * per, NDESC, 32), dtype=torch.uint8, device=dev)
-    pairs = sharding.window_pairs(lo, hi, K, Wn)
-    p_loc, p_rem = sharding.split_by_locality(pairs, lo, hi)
-    P = len(pairs)
-    dp_loc = torch.from_numpy(p_loc).to(dev); dp_rem = torch.from_numpy(p_rem).to(dev)
-    best = torch.empty((max(P, 1), NDESC), dtype=torch.int32, device=dev)
-    M = ORBmatcher(RATIO, True, device=local_rank)
-    mstream = M.stream
-    comm = None
-    if world > 1:
-        def bcast(raw):
-            t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
-            dist.broadcast(t, 0)
-            return bytes(t.cpu().tolist())
-        comm = sharding.Comm(rank, world, local_rank, bcast)
-    local_bytes = per * NDESC * 32
-
-    def knn(dpairs, n, out_off):
-        if n:
-            check(lib().obs_hamming_knn2(M._h, C.c_void_p(allD.data_ptr()), world * per, NDESC, C.c_void_p(dpairs.data_ptr()), n,
-                                         TH_LOW, RATIO, C.c_void_p(best.data_ptr() + out_off * NDESC * 4), None, None))
-
-    mine = allD[rank * per:(rank + 1) * per]                  # this rank's shard lives in its slot of the gathered set
-    mine.copy_(local)
-    torch.cuda.synchronize()
-
-    def step():
-        # the gather is ordered after everything queued on the matcher stream (the producer of `mine` and the
-        # previous step's readers of the remote slots) and runs on the communicator's stream; pairs whose
-        # database keyframe is local are matched meanwhile, the others wait for the gather
-        if comm:
-            comm.allgather(mine.data_ptr(), local_bytes, allD.data_ptr(), 1, mstream)
-        knn(dp_loc, len(p_loc), 0)
-        if comm:
-            comm.wait(0, mstream)
-        knn(dp_rem, len(p_rem), len(p_loc))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    ms_stream = torch.cuda.ExternalStream(mstream)
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(ms_stream):
-        e0.record()
-    for _ in range(args.steps):
-        step()
-    with torch.cuda.stream(ms_stream):
-        e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms_total, float(P)], dtype=torch.float64, device=dev)
-    if world > 1:
-        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        ms_total, P_all = float(tm[0]), int(ts[1])
-    else:
-        P_all = P
-    dist_per_step = P_all * NDESC * NDESC
-    value = dist_per_step * args.steps / (ms_total * 1e-3)
-    matches = int((best[:P] >= 0).sum())
-
-    # ---- end to end: descriptor shard from page-locked host memory in, best indices out, every step
-    h_local = pinned_empty((per, NDESC, 32), np.uint8)
-    h_local[:] = local.cpu().numpy()
-    h_best = pinned_empty((max(P, 1), NDESC), np.int32)
-    e2e_steps = max(3, min(args.steps, 5))
-
-    def step_host():
-        with torch.cuda.stream(ms_stream):
-            mine.copy_(torch.from_numpy(h_local), non_blocking=True)
-        step()
-        with torch.cuda.stream(ms_stream):
-            torch.from_numpy(h_best).copy_(best, non_blocking=True)
-        M.sync()
-
-    step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = dist_per_step * e2e_steps / float(t.item())
-    if rank == 0:
-        popc_only = _popc_peak(2)          # Gdist/s at 8 popc per distance == popc pipe ceiling / 8
-        kernel_ms = ms_total / args.steps
-        peak_popc = popc_only * 8e9        # popc/s of one GPU
-        ach_popc = 5.0 * (dist_per_step / world) / (kernel_ms * 1e-3)      # the kernel issues 5 popc per distance (carry-save folding)
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            Dh = synth.keyframe_descriptors(8, NDESC, 0)
-            sp = sharding.window_pairs(0, 8, 8, 8)[:max(2 * cores, 8)]
-            dt = cpu_knn2(Dh, sp, cores)
-            cpu = {"value": len(sp) * NDESC * NDESC / dt, "unit": "distances/s", "cores": cores, "kind": "port",
-                   "sample": f"{len(sp)} keyframe pairs (2000 x 2000 distances each) on {cores} host threads, {dt:.1f} s; restated "
-                             "SearchByBoW candidate loop with the reference's SWAR DescriptorDistance"}
-        print(json.dumps({
-            "metric": metric, "value": value, "unit": "distances/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32 popcount", "data": "synthetic (generated on the device)",
-            "config": {"workload": f"configs[4]: {K} keyframes x {NDESC} descriptors, window +-{Wn} ({P_all} ordered keyframe pairs per step), "
-                                   "ratio 0.6, TH_LOW 50", "parallelism": f"query keyframes sharded over {world} GPU(s); NCCL all-gather of the "
-                                   "descriptor shards every step" if world > 1 else "1 GPU, no collective",
-                       "l2": f"descriptor set {K * NDESC * 32 / 1e6:.0f} MB + {P_all * NDESC * 4 / 1e6:.0f} MB of results per step (> 126 MB L2)",
-                       "queries_per_s": value / NDESC, "accepted_matches_rank0": matches},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "distances/s", "h2d_bytes_per_step": world * local_bytes, "d2h_bytes_per_step": P_all * NDESC * 4,
-                    "steps": e2e_steps, "api": "descriptor shard H2D from page-locked memory, obs_comm_allgather, obs_hamming_knn2, best indices D2H"},
-            "gpu_launches": (2 if world > 1 else 1) * args.steps,
-            "roofline": {"bound": "int-popc", "kernel": "k_knn2", "achieved": ach_popc / 1e12, "peak": peak_popc / 1e12, "unit": "Tpopc/s",
-                         "frac": ach_popc / peak_popc, "traffic": None,
-                         "peak_source": "obs_microbench_popc mode 2 measured in this run (POPC pipe: 16 lanes/clk/SM)",
-                         "distances_per_s_vs_plain_ceiling": (value / world) / (popc_only * 1e9)},
-            "cpu_baseline": cpu}), flush=True)
-    if comm:
-        comm.close()
-    if world > 1:
-        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------ projection
@@ -292,7 +124,7 @@ def run_projection(args, rank, local_rank, world, ClockSampler):
     from object_slam_b200.matcher import ORBmatcher
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     imgs = [synth.blocky_image(synth.TUM_SHAPE, rank * F + i) for i in range(F)]
@@ -402,8 +234,6 @@ def run_projection(args, rank, local_rank, world, ClockSampler):
                          "peak": _hbm_peak(), "unit": "GB/s", "frac": F * 5.742474e6 / (ms_total / args.steps * 1e-3) / 1e9 / _hbm_peak(),
                          "traffic": None, "note": "extraction dominates; the search alone is reported in config.search_only_*"},
             "cpu_baseline": cpu}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def _hbm_peak():
@@ -458,7 +288,7 @@ def run_bow(args, rank, local_rank, world, ClockSampler):
     from object_slam_b200.matcher import ORBmatcher
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     M = ORBmatcher(RAT, True, device=local_rank)
@@ -557,8 +387,6 @@ def run_bow(args, rank, local_rank, world, ClockSampler):
                          "peak_source": "obs_microbench_popc mode 2 measured in this run; the kernel is latency bound (one warp per vocabulary "
                                         "node, sequential over the node's keypoints as the reference's order demands), not popc bound"},
             "cpu_baseline": cpu}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def cpu_extract(imgs, cores, nfeat):
@@ -580,177 +408,443 @@ def cpu_extract(imgs, cores, nfeat):
         return time.perf_counter() - t0, ("reference" if use_ref else "port")
 
 
-def run_extract(args, rank, local_rank, world, ClockSampler):
+def _expected_hash(key):
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_hashes.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+def _hash_check(key, value):
+    exp = _expected_hash(key)
+    return {"value": f"{value:016x}", "n1_hash": exp, "equals_n1_hash": (exp == f"{value:016x}") if exp else None,
+            "source": "tests/golden/bench_hashes.json (written from a 1-GPU run by tools/update_bench_hashes.py)"}
+
+
+# ------------------------------------------------------------------------------------------------ configs[3]
+EXTRACT_METRIC = "frames/s, batched offline ORB extraction, KITTI 1241x376, 2000 kp"
+
+
+def extract_workload(T):
+    return (f"configs[3]: batched offline ORB extraction of {T} synthetic KITTI-shape 1241x376 frames, nFeatures=2000, nLevels=8, "
+            "scale 1.2, FAST 20/7, contiguous frame shards over the ranks")
+
+
+def _record_hashes(torch, ex, F, dev):
+    """One 64-bit hash per image of the last extraction on `ex`, computed on the device from the result records: every valid
+    keypoint field and descriptor word times a position-dependent odd multiplier, summed modulo 2^64 (int64 wrap-around)."""
+    d_rec, rec_bytes, cap = ex.results_device()
+    ints = rec_bytes // 4
+    # view the library's record buffer without copying: a tensor over foreign device memory
+    rec = _foreign_i32(torch, d_rec, F * ints, dev).view(F, ints)
+    n = rec[:, 0].to(torch.int64)
+    kp = rec[:, 16:16 + cap * 7].view(F, cap, 7).to(torch.int64)
+    ds = rec[:, 16 + cap * 7:16 + cap * 15].view(F, cap, 8).to(torch.int64)
+    idx = torch.arange(cap, device=dev, dtype=torch.int64)
+    valid = (idx[None, :] < n[:, None]).to(torch.int64)
+    wk = (idx[:, None] * 7 + torch.arange(7, device=dev, dtype=torch.int64)[None, :]) * 2654435761 + 1
+    wd = (idx[:, None] * 8 + torch.arange(8, device=dev, dtype=torch.int64)[None, :]) * 40503 + 12345678901
+    h = ((kp * wk[None]).sum(2) * valid).sum(1) + ((ds * wd[None]).sum(2) * valid).sum(1) + n * 1099511628211
+    return h
+
+
+class _CudaArray:
+    """__cuda_array_interface__ over a raw device pointer (no ownership)."""
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+
+
+def _foreign_i32(torch, ptr, n, dev):
+    return torch.as_tensor(_CudaArray(ptr, n), device=dev)
+
+
+def measure_extract(args, ctx, ClockSampler):
     """configs[3]: batched offline ORB extraction of `--total-frames` (32768) KITTI-shape frames.  The frame range is cut into
-    contiguous shards, one per rank (sharding.shard_range), no collective; a step is one batch of F frames per rank, so the job
-    is total / (F * world) steps per rank.  The frames are a resident pool of distinct synthetic images (seed = global frame
-    index of the first `pool` frames of the shard) cycled over the shard: 32768 KITTI frames are 15 GB of numpy generation."""
-    Himg, Wimg, NF, PITCH = 376, 1241, 2000, 1280
-    F = args.frames
-    T = args.total_frames
-    metric = "frames/s, batched offline ORB extraction, KITTI 1241x376, 2000 kp"
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        cores = os.cpu_count() or 1
-        imgs = [synth.blocky_image((Himg, Wimg), i) for i in range(2 * cores)]
-        for _ in range(args.warmup):
-            cpu_extract(imgs[:cores], cores, NF)
-        total, kind = 0.0, "port"
-        for _ in range(args.steps):
-            dt, kind = cpu_extract(imgs, cores, NF)
-            total += dt
-        v = len(imgs) * args.steps / total
-        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "config": {"workload": "configs[3] batched offline ORB extraction, KITTI shape", "frames_per_step": len(imgs)},
-                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
-                                           "sample": f"{len(imgs)} frames per step; reference ORBextractor.cc compiled in place, {cores} host threads"},
-                          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
-        return
-    import threading
-    import torch
-    import torch.distributed as dist
+    contiguous shards, one per rank (sharding.shard_range), no data-path collective; a step is one batch of F frames and the job is
+    shard / F steps per rank.  Global frame g is the synthetic image of seed g mod POOL (POOL = 512 distinct images, generated once --
+    each rank makes POOL / world of them and the pool is all-gathered over NCCL -- and kept resident; 32768 distinct KITTI frames
+    would be 15 GB of numpy generation).  `value` times the WHOLE job (repeated to fill >= 1 s); the job hash is the sum over all
+    global frames of a per-frame hash of keypoints and descriptors, so it does not depend on the number of GPUs."""
+    torch, dist = ctx.torch, ctx.dist
     from object_slam_b200._capi import pinned_empty, KEYPOINT_DTYPE
     from object_slam_b200.extractor import ORBextractor
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: object_slam_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local_rank, world, dev = ctx.rank, ctx.local_rank, ctx.world, ctx.dev
+    Himg, Wimg, NF, PITCH = 376, 1241, 2000, 1280
+    F, T = args.frames, args.total_frames
+    POOL = max(args.pool // F, 1) * F
     lo, hi = sharding.shard_range(T, rank, world)
-    POOL = min(args.pool_batches * F, hi - lo)
-    POOL = max(POOL // F, 1) * F
-    with ThreadPoolExecutor(os.cpu_count() or 1) as tp:
-        imgs = list(tp.map(lambda i: synth.blocky_image((Himg, Wimg), lo + i), range(POOL)))
-    host = np.zeros((POOL, Himg, PITCH), np.uint8)
-    for i, im in enumerate(imgs):
-        host[i, :, :Wimg] = im
-    dimg = torch.from_numpy(host).to(dev)
+    # the pool: every rank generates its slice, NCCL spreads it
+    own_lo, own_hi = sharding.shard_range(POOL, rank, world)
+    with ThreadPoolExecutor(len(ctx.all_cpus) // max(world, 1) or 1) as tp:
+        mine = list(tp.map(lambda i: synth.blocky_image((Himg, Wimg), i), range(own_lo, own_hi)))
+    dimg = torch.zeros((POOL, Himg, PITCH), dtype=torch.uint8, device=dev)
+    if mine:
+        dimg[own_lo:own_hi, :, :Wimg] = torch.from_numpy(np.stack(mine)).to(dev)
+    if world > 1:
+        dist.all_reduce(dimg.view(torch.int32), op=dist.ReduceOp.SUM)        # slices are disjoint, the rest is zero
     NB = POOL // F
+    steps_job = max((hi - lo) // F, 1)
     mk = lambda: ORBextractor(NF, 1.2, 8, 20, 7, max_size=(Wimg, Himg), max_batch=F, device=local_rank)
     NPIPES = int(os.environ.get("OBS_BENCH_PIPES", "3"))
     dpipes = [(mk(), torch.cuda.Stream()) for _ in range(NPIPES)]
-    main_stream = torch.cuda.Stream()
-    torch.cuda.set_stream(main_stream)
-    step_no = [0]
+    main_stream = torch.cuda.current_stream()
+    first_batch = (lo // F) % NB
 
-    def step_device():
-        ex, st = dpipes[step_no[0] % NPIPES]
-        b = step_no[0] % NB
-        step_no[0] += 1
-        ex.extract_device(dimg.data_ptr() + b * F * Himg * PITCH, F, Wimg, Himg, PITCH, Himg * PITCH, st.cuda_stream)
+    def job_device(nrep):
+        for s in range(nrep * steps_job):
+            ex, st = dpipes[s % NPIPES]
+            b = (first_batch + s % steps_job) % NB
+            ex.extract_device(dimg.data_ptr() + b * F * Himg * PITCH, F, Wimg, Himg, PITCH, Himg * PITCH, st.cuda_stream)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def timed(nrep):
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _, st in dpipes:
+            st.wait_stream(main_stream)
+        job_device(nrep)
+        for _, st in dpipes:
+            main_stream.wait_stream(st)
+        e1.record()
+        ctx.barrier()
+        return e0.elapsed_time(e1)
 
-    for _ in range(max(args.warmup, NPIPES, 3)):
-        step_device()
-    step_no[0] = 0
-    barrier()
+    for s in range(max(args.warmup, NPIPES, 3)):
+        dpipes[s % NPIPES][0].extract_device(dimg.data_ptr(), F, Wimg, Himg, PITCH, Himg * PITCH, dpipes[s % NPIPES][1].cuda_stream)
+    reps = ctx.repeats(timed(1))
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _, st in dpipes:
-        st.wait_stream(main_stream)
-    for _ in range(args.steps):
-        step_device()
-    for _, st in dpipes:
-        main_stream.wait_stream(st)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = ctx.reduce([timed(reps)])[0]
     clocks = sampler.stop() if sampler else None
-    counts = dpipes[0][0].fetch_counts()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * F * args.steps / (ms_total * 1e-3)
+    value = T * reps / (ms_total * 1e-3)
 
-    # ---- end to end: page-locked host images in, keypoints + descriptors out; WORKERS pipelines take alternate batches
+    # ---- the job hash: per-image hashes of the POOL images, each weighted by how often the shard visits it
+    ex0, st0 = dpipes[0]
+    hsum = 0
+    kp_total = 0
+    with torch.cuda.stream(st0):
+        for b in range(NB):
+            ex0.extract_device(dimg.data_ptr() + b * F * Himg * PITCH, F, Wimg, Himg, PITCH, Himg * PITCH, st0.cuda_stream)
+            h = _record_hashes(torch, ex0, F, dev)
+            visits = sum(1 for s in range(steps_job) if (first_batch + s) % NB == b)
+            hsum = (hsum + visits * int(h.sum().item())) & 0xffffffffffffffff
+            kp_total += int(ex0.fetch_counts().sum())
+    job_hash = ctx.sum_u64(hsum)
+
+    # ---- end to end: the shard's frames from page-locked host memory in, keypoints + descriptors out to page-locked memory, the
+    # whole job; one host thread keeps WORKERS handles in flight (obs_extract_batch_submit / _wait)
     WORKERS = args.e2e_pipelines
-    cap = dpipes[0][0].capacity
+    cap = ex0.capacity
+    pool_host = pinned_empty((POOL, Himg, Wimg), np.uint8)
+    pool_host[:] = dimg[:, :, :Wimg].cpu().numpy()
+    outs = [(pinned_empty((F, cap), KEYPOINT_DTYPE), pinned_empty((F, cap, 32), np.uint8), pinned_empty((F,), np.int32)) for _ in range(WORKERS)]
+    exs = [dpipes[i % NPIPES][0] if i < NPIPES else mk() for i in range(WORKERS)]
 
-    class Pipe:
-        def __init__(self, ex, b):
-            self.ex = ex
-            self.pin = pinned_empty((F, Himg, Wimg), np.uint8)
-            for i in range(F):
-                self.pin[i] = imgs[(b * F + i) % POOL]
-            self.out = (pinned_empty((F, cap), KEYPOINT_DTYPE), pinned_empty((F, cap, 32), np.uint8), pinned_empty((F,), np.int32))
+    def job_host(nrep):
+        n = nrep * steps_job
+        for s in range(n + WORKERS):
+            k = s % WORKERS
+            if s >= WORKERS:
+                exs[k].wait_batch()
+            if s < n:
+                b = (first_batch + s % steps_job) % NB
+                exs[k].submit_batch(pool_host[b * F:(b + 1) * F], *outs[k])
 
-        def step(self):
-            return self.ex.extract_batch(self.pin, out=self.out, copy=False)
-
-    pipes = [Pipe(dpipes[i % NPIPES][0] if i < NPIPES else mk(), i) for i in range(WORKERS)]
-    e2e_steps = max(WORKERS, (args.e2e_steps or max(4, min(args.steps, 12))) // WORKERS * WORKERS)
-
-    def run_pipes(nsteps):
-        ths = [threading.Thread(target=lambda p=p: [p.step() for _ in range(nsteps // WORKERS)]) for p in pipes[1:]]
-        for th in ths:
-            th.start()
-        for _ in range(nsteps // WORKERS):
-            pipes[0].step()
-        for th in ths:
-            th.join()
-
-    run_pipes(2 * WORKERS)
-    barrier()
-    t0 = time.perf_counter()
-    run_pipes(e2e_steps)
     torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * F * e2e_steps / float(t.item())
-    if rank == 0:
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            sample = [imgs[i % POOL] for i in range(16 * cores)]
-            dt, kind = cpu_extract(sample, cores, NF)
-            cpu = {"value": len(sample) / dt, "unit": "frames/s", "cores": cores, "kind": kind,
-                   "sample": f"{len(sample)} frames of the pool: reference src/ORBextractor.cc compiled in place (oracle/_ref) on {cores} host threads, {dt:.1f} s"}
-        step_ms = ms_total / args.steps
-        eye_bytes = 9359539.0
-        peak = _hbm_peak()
-        print(json.dumps({
-            "metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"configs[3]: batched offline ORB extraction of {T} synthetic KITTI-shape 1241x376 frames, nFeatures=2000, "
-                                   f"nLevels=8, scale 1.2, FAST 20/7, contiguous frame shards over the ranks",
-                       "frames_per_step_per_gpu": F, "job_steps_per_gpu": (hi - lo + F - 1) // F,
-                       "job_seconds_at_this_rate": T / value,
-                       "pool": f"{POOL} distinct frames per rank resident in HBM ({POOL * Himg * PITCH / 1e6:.0f} MB), cycled over the shard",
-                       "parallelism": f"frames sharded over {world} GPU(s), no collective",
-                       "l2": f"working set per step {F * 4.0:.0f} MB of images, pyramids and blurred levels (> 126 MB L2), pool of inputs larger than L2",
-                       "mean_keypoints": float(counts.mean())},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * Himg * Wimg, "d2h_bytes_per_step": F * (cap * 60 + 4) + F * 4,
-                    "steps": e2e_steps, "api": f"obs_extract_batch, page-locked host images in, keypoints + descriptors out; {WORKERS} pipelines "
-                                               "take alternate batches from their own host threads"},
-            "gpu_launches": 8 * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": F * eye_bytes / (step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": F * eye_bytes / (step_ms * 1e-3) / 1e9 / peak, "traffic": None,
-                         "note": "9,359,539 algorithmic bytes per KITTI image (SURVEY 8d); the kernels are integer-issue bound (DESIGN.md section 4), "
-                                 "the per-kernel roofline is on the headline line (--workload stereo)"},
-            "cpu_baseline": cpu}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    job_host(1) if steps_job >= 2 * WORKERS else job_host(2)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    job_host(1)
+    e2e_reps = ctx.repeats(1e3 * (time.perf_counter() - t0))
+    ctx.barrier()
+    t0 = time.perf_counter()
+    job_host(e2e_reps)
+    torch.cuda.synchronize()
+    e2e_s = ctx.reduce([time.perf_counter() - t0])[0]
+    e2e_value = T * e2e_reps / e2e_s
+    if rank != 0:
+        return None
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        ctx.release_cpus()
+        cores = os.cpu_count() or 1
+        sample = [np.ascontiguousarray(pool_host[i % POOL]) for i in range(8 * cores)]
+        dt, kind = cpu_extract(sample, cores, NF)
+        cpu = {"value": len(sample) / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+               "sample": f"{len(sample)} frames of the pool: reference src/ORBextractor.cc compiled in place (oracle/_ref) on {cores} host threads, {dt:.1f} s"}
+    job_ms = ms_total / reps
+    eye_bytes = 9359539.0
+    peak = _hbm_peak()
+    return {
+        "metric": EXTRACT_METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps_job, "warmup": max(args.warmup, 3),
+        "ms_per_step": job_ms / steps_job, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": extract_workload(T), "frames_per_step_per_gpu": F, "job_steps_per_gpu": steps_job,
+                   "job_ms": job_ms, "repeats": reps, "timed_region_s": ms_total * 1e-3,
+                   "pool": f"{POOL} distinct frames (seed = global frame index mod {POOL}) resident in HBM ({POOL * Himg * PITCH / 1e6:.0f} MB), "
+                           "generated once across the ranks and spread over NCCL",
+                   "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                   "l2": f"working set per step {F * 4.0:.0f} MB of images, pyramids and blurred levels (> 126 MB L2), pool of inputs larger than L2",
+                   "mean_keypoints": kp_total / POOL},
+        "result_hash": _hash_check(f"extract:T={T}:pool={POOL}", job_hash),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * Himg * Wimg, "d2h_bytes_per_step": F * (cap * 60 + 4),
+                "steps": e2e_reps * steps_job, "seconds": e2e_s,
+                "api": f"obs_extract_batch_submit / _wait, page-locked host images in, keypoints + descriptors out; one host thread keeps "
+                       f"{WORKERS} handles in flight"},
+        "gpu_launches": 8 * reps * steps_job,
+        "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": T * eye_bytes / (job_ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                     "frac": T * eye_bytes / (job_ms * 1e-3) / 1e9 / world / peak, "traffic": None,
+                     "note": "per GPU; 9,359,539 algorithmic bytes per KITTI image (SURVEY 8d); the kernels are integer-issue bound (DESIGN.md "
+                             "section 4), the per-kernel fractions are on the headline line"},
+        "cpu_baseline": cpu}
 
 
-def run(args, rank, local_rank, world, ClockSampler):
-    if args.workload == "bow":
-        return run_bow(args, rank, local_rank, world, ClockSampler)
-    if args.workload == "extract":
-        return run_extract(args, rank, local_rank, world, ClockSampler)
+# ------------------------------------------------------------------------------------------------ configs[4]
+KNN2_METRIC = "Hamming distance evaluations/s, brute-force keyframe-vs-keyframe matching (best + second best + ratio), 2000 descriptors per keyframe"
+
+
+def knn2_workload(K, Wn):
+    return (f"configs[4]: {K} keyframes x {NDESC} descriptors, every keyframe against its +-{Wn} neighbours, ratio 0.6, TH_LOW 50, "
+            "query keyframes sharded over the ranks, NCCL all-gather of the descriptor sets")
+
+
+def _imma_peak(local_rank):
+    from object_slam_b200._capi import check, lib
+    g = C.c_double()
+    check(lib().obs_microbench_imma(int(local_rank), C.byref(g)))
+    return g.value
+
+
+def measure_knn2(args, ctx, ClockSampler):
+    """configs[4]: K keyframes x 2000 descriptors, every keyframe matched against its +-window neighbours (best / second best / ratio
+    test).  Query keyframes are sharded over the ranks (strong scaling: the total is fixed).  Every rank needs all descriptor sets, so
+    each step starts with the all-gather of the descriptor shards over NCCL (csrc/comm.cu) in `--gather-chunks` chunks; pairs whose
+    database keyframe is local are matched while the gather is in flight, the others as soon as their chunk has arrived.  The result
+    hash weights every best index with (query keyframe, database keyframe, row), so it does not depend on the sharding."""
+    torch, dist = ctx.torch, ctx.dist
+    from object_slam_b200._capi import check, lib, pinned_empty
+    from object_slam_b200.matcher import ORBmatcher
+    rank, local_rank, world, dev = ctx.rank, ctx.local_rank, ctx.world, ctx.dev
+    K, Wn = args.keyframes, args.window
+    NC = max(args.gather_chunks, 1) if world > 1 else 1
+    per = sharding.padded_shard(K, world)
+    while NC > 1 and per % NC:
+        NC -= 1                                                # chunk boundaries on whole keyframes
+    lo, hi = rank * per, min(K, (rank + 1) * per)
+    full = _device_keyframes(torch, K, 1234, dev)              # every rank generates the same set, keeps only its shard
+    local = torch.zeros((per, NDESC, 32), dtype=torch.uint8, device=dev)
+    local[:hi - lo] = full[lo:hi]
+    del full
+    allD = torch.zeros((world * per, NDESC, 32), dtype=torch.uint8, device=dev)
+    pairs = sharding.window_pairs(lo, hi, K, Wn)
+    groups = sharding.split_by_chunk(pairs, lo, hi, per, NC)   # [local, chunk 0, chunk 1, ...]
+    order = np.concatenate([g for g in groups if len(g)]) if len(pairs) else pairs
+    P = len(pairs)
+    dgroups = [torch.from_numpy(g).to(dev) if len(g) else None for g in groups]
+    best = torch.empty((max(P, 1), NDESC), dtype=torch.int32, device=dev)
+    M = ORBmatcher(RATIO, True, device=local_rank)
+    M.set_knn2_engine({"auto": M.KNN2_AUTO, "tensor": M.KNN2_TENSOR, "popc": M.KNN2_POPC}[args.knn2_engine])
+    tensor = args.knn2_engine != "popc"
+    mstream = M.stream
+    comm = None
+    if world > 1:
+        def bcast(raw):
+            t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        comm = sharding.Comm(rank, world, local_rank, bcast)
+    local_bytes = per * NDESC * 32
+
+    def knn(dpairs, out_off):
+        n = 0 if dpairs is None else dpairs.shape[0]
+        if n:
+            check(lib().obs_hamming_knn2(M._h, C.c_void_p(allD.data_ptr()), world * per, NDESC, C.c_void_p(dpairs.data_ptr()), n,
+                                         TH_LOW, RATIO, C.c_void_p(best.data_ptr() + out_off * NDESC * 4), None, None))
+        return n
+
+    mine = allD[rank * per:(rank + 1) * per]                  # this rank's shard lives in its slot of the gathered set
+    mine.copy_(local)
+    torch.cuda.synchronize()
+    launches = [0]
+
+    def step():
+        # the gather is ordered after everything queued on the matcher stream (the producer of `mine` and the previous step's
+        # readers of the remote slots) and runs on the communicator's stream; local pairs are matched meanwhile, the pairs of a
+        # remote chunk wait for that chunk only
+        if comm:
+            comm.allgather(mine.data_ptr(), local_bytes, allD.data_ptr(), NC, mstream)
+        off = knn(dgroups[0], 0)
+        for c in range(NC):
+            if comm:
+                comm.wait(c, mstream)
+            off += knn(dgroups[1 + c], off) if len(dgroups) > 1 + c else 0
+
+    ms_stream = torch.cuda.ExternalStream(mstream)
+
+    def timed(n):
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ms_stream):
+            e0.record()
+        for _ in range(n):
+            step()
+        with torch.cuda.stream(ms_stream):
+            e1.record()
+        ctx.barrier()
+        return e0.elapsed_time(e1)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    steps = max(min(args.steps, 10), 1)
+    reps = ctx.repeats(timed(steps))
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total = ctx.reduce([timed(reps * steps)])[0]
+    clocks = sampler.stop() if sampler else None
+    timed_steps = reps * steps
+    P_all = int(ctx.reduce([P], "sum")[0])
+    dist_per_step = P_all * NDESC * NDESC
+    value = dist_per_step * timed_steps / (ms_total * 1e-3)
+
+    # ---- result hash over (query keyframe, database keyframe, row, best index)
+    hsum = 0
+    if P:
+        dorder = torch.from_numpy(order.astype(np.int64)).to(dev)
+        pw = dorder[:, 0] * 1000003 + dorder[:, 1] * 7919 + 1
+        cw = torch.arange(NDESC, device=dev, dtype=torch.int64) * 2654435761 + 12345
+        for a in range(0, P, 2048):
+            b = min(P, a + 2048)
+            hsum = (hsum + int((((best[a:b].to(torch.int64) + 2) * cw[None, :]).sum(1) * pw[a:b]).sum().item())) & 0xffffffffffffffff
+    matches = int(ctx.reduce([int((best[:P] >= 0).sum())], "sum")[0])
+    job_hash = ctx.sum_u64(hsum)
+
+    # ---- end to end: descriptor shard from page-locked host memory in, best indices out to page-locked memory, every step
+    h_local = pinned_empty((per, NDESC, 32), np.uint8)
+    h_local[:] = local.cpu().numpy()
+    h_best = pinned_empty((max(P, 1), NDESC), np.int32)
+
+    def step_host():
+        with torch.cuda.stream(ms_stream):
+            mine.copy_(torch.from_numpy(h_local), non_blocking=True)
+        step()
+        with torch.cuda.stream(ms_stream):
+            torch.from_numpy(h_best).copy_(best, non_blocking=True)
+        M.sync()
+
+    step_host()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    step_host()
+    e2e_steps = ctx.repeats(1e3 * (time.perf_counter() - t0))
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    e2e_s = ctx.reduce([time.perf_counter() - t0])[0]
+    e2e_value = dist_per_step * e2e_steps / e2e_s
+    if comm:
+        comm.close()
+    if rank != 0:
+        return None
+    kernel_ms = ms_total / timed_steps
+    if tensor:
+        peak_tops = _imma_peak(local_rank)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                bf16 = float(json.load(f)["bf16_tflops"])
+        except Exception:
+            bf16 = 1590.0
+        ach = 512.0 * (dist_per_step / world) / (kernel_ms * 1e-3) / 1e12     # 256 multiply-adds = 512 operations per distance
+        roof = {"bound": "tensor", "kernel": "k_knn2_tc", "achieved": ach, "peak": peak_tops, "unit": "TOP/s (int8)", "frac": ach / peak_tops,
+                "traffic": None,
+                "peak_source": "obs_microbench_imma measured in this run: tcgen05.mma kind::i8 M128 N256 K32 from shared memory issued back to "
+                               "back on all SMs (MEASURED_PEAKS.json holds no int8 figure)",
+                "vs_2x_measured_bf16": ach / (2 * bf16), "measured_bf16_tflops": bf16,
+                "per_gpu_distances_per_s": value / world,
+                "popc_pipe_ceiling_distances_per_s": _popc_peak(2) * 1e9,
+                "note": "hamming = (256 - a.b) / 2 on +-1 int8 operands: 512 tensor operations per distance; the POPC pipe ceiling "
+                        "(8 popc per distance) is what the non-tensor kernel is bound by"}
+    else:
+        popc_only = _popc_peak(2)
+        peak_popc = popc_only * 8e9
+        ach_popc = 5.0 * (dist_per_step / world) / (kernel_ms * 1e-3)
+        roof = {"bound": "int-popc", "kernel": "k_knn2", "achieved": ach_popc / 1e12, "peak": peak_popc / 1e12, "unit": "Tpopc/s",
+                "frac": ach_popc / peak_popc, "traffic": None,
+                "peak_source": "obs_microbench_popc mode 2 measured in this run (POPC pipe: 16 lanes/clk/SM)"}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        ctx.release_cpus()
+        cores = os.cpu_count() or 1
+        Dh = synth.keyframe_descriptors(8, NDESC, 0)
+        sp = sharding.window_pairs(0, 8, 8, 8)[:max(2 * cores, 8)]
+        dt = cpu_knn2(Dh, sp, cores)
+        cpu = {"value": len(sp) * NDESC * NDESC / dt, "unit": "distances/s", "cores": cores, "kind": "port",
+               "sample": f"{len(sp)} keyframe pairs (2000 x 2000 distances each) on {cores} host threads, {dt:.1f} s; "
+                         "SearchByBoW candidate loop with the reference's SWAR DescriptorDistance"}
+    return {
+        "metric": KNN2_METRIC, "value": value, "unit": "distances/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int8 (+-1 per descriptor bit), int32 accumulate" if tensor else "u32 popcount", "data": "synthetic (generated on the device)",
+        "config": {"workload": knn2_workload(K, Wn), "pairs_per_step": P_all, "gather_chunks": NC,
+                   "timed_steps": timed_steps, "repeats": reps, "timed_region_s": ms_total * 1e-3,
+                   "parallelism": (f"query keyframes sharded over {world} GPU(s); obs_comm_allgather of the descriptor shards every step in {NC} "
+                                   f"chunks ({local_bytes * world / 1e6:.0f} MB gathered per rank per step), remote pairs wait per chunk")
+                                  if world > 1 else "1 GPU, no collective",
+                   "l2": f"descriptor set {K * NDESC * 32 / 1e6:.0f} MB + {P_all * NDESC * 4 / 1e6:.0f} MB of results per step (> 126 MB L2)",
+                   "queries_per_s": value / NDESC, "accepted_matches": matches},
+        "result_hash": _hash_check(f"knn2:K={K}:W={Wn}", job_hash),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "distances/s", "h2d_bytes_per_step": world * local_bytes, "d2h_bytes_per_step": P_all * NDESC * 4,
+                "steps": e2e_steps, "seconds": e2e_s,
+                "api": "descriptor shard H2D from page-locked memory, obs_comm_allgather, obs_hamming_knn2, best indices D2H to page-locked memory"},
+        "gpu_launches": (3 * (1 + NC) if tensor else (1 + NC)) * timed_steps,
+        "roofline": roof,
+        "cpu_baseline": cpu}
+
+
+def run_reference(args, ctx):
+    """`--impl reference` of the non-headline workloads: the CPU arm of that workload on all host cores, rank 0 only."""
+    if ctx.rank != 0:
+        return
+    cores = os.cpu_count() or 1
     if args.workload == "knn2":
-        return run_knn2(args, rank, local_rank, world, ClockSampler)
-    return run_projection(args, rank, local_rank, world, ClockSampler)
+        D = synth.keyframe_descriptors(8, NDESC, 0)
+        pairs = sharding.window_pairs(0, 8, 8, 8)[:max(cores * 2, 8)]
+        total = 0.0
+        for _ in range(args.warmup):
+            cpu_knn2(D, pairs[:cores], cores)
+        for _ in range(args.steps):
+            total += cpu_knn2(D, pairs, cores)
+        v = len(pairs) * NDESC * NDESC * args.steps / total
+        line = {"metric": KNN2_METRIC, "unit": "distances/s", "scaling": "strong", "dtype": "u32 popcount",
+                "config": {"workload": knn2_workload(args.keyframes, args.window), "pairs_per_step": len(pairs)},
+                "kind": "port", "sample": f"{len(pairs)} keyframe pairs per step, SearchByBoW candidate loop with the reference's SWAR DescriptorDistance"}
+    elif args.workload == "extract":
+        imgs = [synth.blocky_image((376, 1241), i) for i in range(2 * cores)]
+        for _ in range(args.warmup):
+            cpu_extract(imgs[:cores], cores, 2000)
+        total, kind = 0.0, "port"
+        for _ in range(args.steps):
+            dt, kind = cpu_extract(imgs, cores, 2000)
+            total += dt
+        v = len(imgs) * args.steps / total
+        line = {"metric": EXTRACT_METRIC, "unit": "frames/s", "scaling": "strong", "dtype": "u8",
+                "config": {"workload": extract_workload(args.total_frames), "frames_per_step": len(imgs)},
+                "kind": kind, "sample": f"{len(imgs)} frames per step; reference ORBextractor.cc compiled in place, {cores} host threads"}
+    else:
+        return (run_projection if args.workload == "projection" else run_bow)(args, ctx.rank, ctx.local_rank, ctx.world, None)
+    out = {"impl": "reference", "metric": line["metric"], "value": v, "unit": line["unit"], "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": line["scaling"],
+           "vs_baseline": None, "dtype": line["dtype"], "data": "synthetic", "config": line["config"],
+           "cpu_baseline": {"value": v, "unit": line["unit"], "cores": cores, "kind": line["kind"], "sample": line["sample"]},
+           "e2e": {"value": v, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def run(args, ctx, ClockSampler):
+    """One of the non-headline workloads as its own JSON line (returned on rank 0; projection / bow print theirs)."""
+    if args.workload == "extract":
+        return measure_extract(args, ctx, ClockSampler)
+    if args.workload == "knn2":
+        return measure_knn2(args, ctx, ClockSampler)
+    (run_bow if args.workload == "bow" else run_projection)(args, ctx.rank, ctx.local_rank, ctx.world, ClockSampler)
+    return None

@@ -144,6 +144,14 @@ int obs_extractor_stage_ms(obs_extractor* e, float* stage_ms, float* stereo_ms, 
  * --------------------------------------------------------------------------------------- */
 int obs_stereo_match(obs_extractor* left, obs_extractor* right, float mbf, float min_d, float max_d,
                      float* u_right, float* depth, int cap);
+/* Asynchronous obs_extract_batch for page-locked buffers (obs_host_alloc): image i starts at images + i * h * stride.
+ * _submit returns once upload, extraction and download are enqueued (in overlapping chunks on the handle's streams);
+ * _wait sleeps on a blocking-sync event until the results have landed and checks the counts.  One submission per handle
+ * may be in flight; several handles driven round-robin by one host thread overlap each other. */
+int obs_extract_batch_submit(obs_extractor* e, const uint8_t* images, int n_images, int w, int h, size_t stride,
+                             obs_keypoint* keypoints, uint8_t* descriptors, int cap, int32_t* n_out);
+int obs_extract_batch_wait(obs_extractor* e);
+
 /* Whole stereo frames in one call -- what the stereo Frame constructor does (src/Frame.cc:78-90: ExtractORB on two threads,
  * then ComputeStereoMatches) for n_frames frames: both eyes are uploaded, extracted and downloaded in overlapping chunks on the
  * handles' own streams and the stereo match follows on the device, all enqueued by the calling thread.  Every buffer of
@@ -482,6 +490,9 @@ int obs_comm_wait(obs_comm* c, int chunk, void* consumer_stream);
  * ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1647-1663, with hardware popc); mode 1: the same
  * through three carry-save adders (5 popc); mode 3: four carry-save adders (4 popc); mode 2: popc only. */
 int obs_microbench_popc(int device, int mode, double* gdist_per_s);
+/* Roofline denominator of the tensor-core knn2 path: int8 tcgen05.mma throughput (TOP/s) in the kernel's own MMA shape
+ * (kind::i8, M 128, N 256, K 32, both operands in shared memory), issued back to back on every SM with no loads or epilogue. */
+int obs_microbench_imma(int device, double* tops);
 
 #ifdef __cplusplus
 }

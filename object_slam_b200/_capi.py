@@ -98,6 +98,8 @@ _PROTOS = {
     "obs_extractor_set_profiling": (C.c_int, [_vp, C.c_int]),
     "obs_extractor_stage_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "obs_stereo_match": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_float, _vp, _vp, C.c_int]),
+    "obs_extract_batch_submit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, _vp, _vp, C.c_int, _vp]),
+    "obs_extract_batch_wait": (C.c_int, [_vp]),
     "obs_stereo_frames_submit": (C.c_int, [_vp, _vp, C.POINTER(StereoIO), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_float]),
     "obs_stereo_frames_wait": (C.c_int, [_vp, _vp]),
     "obs_stereo_frames": (C.c_int, [_vp, _vp, C.POINTER(StereoIO), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_float]),
@@ -131,6 +133,7 @@ _PROTOS = {
     "obs_comm_destroy": (C.c_int, [_vp]),
     "obs_comm_allgather": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int, _vp]),
     "obs_comm_wait": (C.c_int, [_vp, C.c_int, _vp]),
+    "obs_microbench_imma": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "obs_microbench_popc": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "obs_search_by_bow": (C.c_int, [_vp, C.POINTER(BowSide), C.POINTER(BowSide), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
     "obs_search_for_triangulation": (C.c_int, [_vp, C.POINTER(BowSide), C.POINTER(BowSide), C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),

@@ -972,6 +972,39 @@ int obs_stereo_from_rgbd(obs_extractor* e, const float* d_depth, size_t depth_st
     return OBS_OK;
 }
 
+// ---- asynchronous form of obs_extract_batch for page-locked buffers
+int obs_extract_batch_submit(obs_extractor* e, const uint8_t* images, int n_images, int w, int h, size_t stride,
+                             obs_keypoint* keypoints, uint8_t* descriptors, int cap, int32_t* n_out) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (e->pending) return fail(OBS_ERR_STATE, "obs_extract_batch_submit: the previous submission on this handle has not been waited for");
+    if (n_images < 1 || n_images > e->maxBatch) return fail(OBS_ERR_CAPACITY, "batch of %d exceeds max_batch %d", n_images, e->maxBatch);
+    if (w < 1 || h < 1 || w > e->maxW || h > e->maxH) return fail(OBS_ERR_INVALID, "image %dx%d outside [1,%d]x[1,%d]", w, h, e->maxW, e->maxH);
+    if (stride < (size_t)w || cap < 1) return fail(OBS_ERR_INVALID, "stride smaller than width, or cap < 1");
+    const void* need[] = {images, keypoints, descriptors, n_out};
+    for (const void* p : need)
+        if (!p || !is_pinned(p)) return fail(OBS_ERR_INVALID, "obs_extract_batch_submit takes page-locked host buffers (obs_host_alloc)");
+    if ((rc = set_shape(e, w, h, n_images, e->stream))) return rc;
+    if ((rc = enqueue_chunks(e, images, n_images, w, h, stride, keypoints, descriptors, cap, n_out))) return rc;
+    CU(cudaEventRecord(e->hostDone, e->cout));
+    e->pending = true;
+    e->pendingCounts[0] = n_out; e->pendingCounts[1] = nullptr;
+    e->pendingN = n_images; e->pendingCap = cap;
+    return OBS_OK;
+}
+
+int obs_extract_batch_wait(obs_extractor* e) {
+    int rc = check_handle(e);
+    if (rc) return rc;
+    if (!e->pending || !e->pendingCounts[0] || e->pendingCounts[1]) return fail(OBS_ERR_STATE, "obs_extract_batch_wait without an obs_extract_batch_submit");
+    e->pending = false;
+    CU(cudaEventSynchronize(e->hostDone));
+    for (int i = 0; i < e->pendingN; i++)
+        if (e->pendingCounts[0][i] > e->pendingCap)
+            return fail(OBS_ERR_CAPACITY, "caller capacity %d smaller than the keypoint count %d (image %d)", e->pendingCap, e->pendingCounts[0][i], i);
+    return OBS_OK;
+}
+
 // ---- whole stereo frames in one call (Frame::Frame for stereo, src/Frame.cc:78-90: two ExtractORB threads + ComputeStereoMatches)
 int obs_stereo_frames_submit(obs_extractor* L, obs_extractor* R, const obs_stereo_io* io, int n_frames, int w, int h, size_t stride,
                              int cap, float mbf, float min_d, float max_d) {
@@ -1013,7 +1046,7 @@ int obs_stereo_frames_wait(obs_extractor* L, obs_extractor* R) {
     int rc = check_handle(L);
     if (rc) return rc;
     if (!R) return fail(OBS_ERR_INVALID, "null argument");
-    if (!L->pending || !R->pending) return fail(OBS_ERR_STATE, "obs_stereo_frames_wait without a submission");
+    if (!L->pending || !R->pending || !L->pendingCounts[1]) return fail(OBS_ERR_STATE, "obs_stereo_frames_wait without an obs_stereo_frames_submit");
     L->pending = R->pending = false;
     CU(cudaEventSynchronize(L->hostDone));          // blocking-sync event: the thread sleeps
     for (int s = 0; s < 2; s++)

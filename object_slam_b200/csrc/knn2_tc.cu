@@ -96,11 +96,22 @@ __device__ __forceinline__ uint32_t expand4(uint32_t b) {
     const uint32_t x = (b * 0x00204081u) & 0x01010101u;       // bit i of b -> byte i
     return x * 0xfeu + 0x01010101u;                             // 1 -> 0xff (-1), 0 -> 0x01 (+1)
 }
-__global__ void __launch_bounds__(256) k_knn2_expand(const uint16_t* __restrict__ bits, uint4* __restrict__ out, size_t nChunks) {
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= nChunks) return;
-    const uint32_t v = bits[i];
-    out[i] = make_uint4(expand4(v & 15u), expand4((v >> 4) & 15u), expand4((v >> 8) & 15u), expand4(v >> 12));
+// only the keyframes a pair of this call names are expanded: k_knn2_mark flags them, one CTA per flagged keyframe expands it
+__global__ void __launch_bounds__(256) k_knn2_mark(const int2* __restrict__ pairs, int nPairs, int nKeyframes, uint8_t* __restrict__ used) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= nPairs) return;
+    const int2 p = pairs[i];
+    if ((unsigned)p.x < (unsigned)nKeyframes) used[p.x] = 1;
+    if ((unsigned)p.y < (unsigned)nKeyframes) used[p.y] = 1;
+}
+__global__ void __launch_bounds__(256) k_knn2_expand(const uint16_t* __restrict__ bits, uint4* __restrict__ out, int chunksPerKf,
+                                                     const uint8_t* __restrict__ used) {
+    if (!used[blockIdx.x]) return;
+    const size_t base = (size_t)blockIdx.x * chunksPerKf;
+    for (int i = threadIdx.x; i < chunksPerKf; i += 256) {
+        const uint32_t v = bits[base + i];
+        out[base + i] = make_uint4(expand4(v & 15u), expand4((v >> 4) & 15u), expand4((v >> 8) & 15u), expand4(v >> 12));
+    }
 }
 
 // ---- epilogue helpers ---------------------------------------------------------------------------------------------------
@@ -281,6 +292,44 @@ k_knn2_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(512u) : "memory");
 }
 
+// ---- measured denominator of the knn2 roofline: the same tcgen05.mma shape (kind::i8, M 128, N 256, K 32, operands in
+// SWIZZLE_128B shared memory, cta_group::1) issued back to back with no loads and no epilogue, one CTA per SM
+__global__ void __launch_bounds__(128, 1) k_imma_peak(int iters, int* sink) {
+    extern __shared__ uint8_t smemRaw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmemBaseS;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t base = (smem_u32(smemRaw) + 1023u) & ~1023u;
+    for (uint32_t i = threadIdx.x; i < (A_BYTES + B_BYTES) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smemRaw + (base - smem_u32(smemRaw)))[i] = 0x01ff01ffu;
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmemBaseS)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores above -> async-proxy reads of the MMA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmemBase = tmemBaseS;
+    if (threadIdx.x == 0) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t ka = (uint32_t)(k >> 2) * A_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
+                const uint32_t kb = (uint32_t)(k >> 2) * B_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
+                umma_i8(tmemBase + (uint32_t)(it & 1) * TC_N, umma_desc(base + ka), umma_desc(base + A_BYTES + kb), IDESC_I8, k != 0);
+            }
+        }
+        umma_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), 0);
+        if (sink && iters < 0) *sink = 1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(512u) : "memory");
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -296,9 +345,36 @@ EncodeTiledFn tma_encoder() {
 
 }  // namespace
 
+// int8 tensor-core throughput of this device in the shape k_knn2_tc uses: *tops = 2 * M * N * K operations per tcgen05.mma / time
+cudaError_t knn2_tc_peak(double* tops) {
+    cudaError_t e = OBS_ALLOW_MAX_SMEM(k_imma_peak);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    const int iters = 4096;
+    cudaEvent_t e0, e1;
+    if ((e = cudaEventCreate(&e0)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&e1)) != cudaSuccess) return e;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_imma_peak<<<sms, 128, A_BYTES + B_BYTES + 1024>>>(iters, nullptr);
+        cudaEventRecord(e1);
+        if ((e = cudaEventSynchronize(e1)) != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) return e;
+    *tops = 2.0 * TC_M * TC_N * 32 * 8.0 * iters * sms / (best * 1e-3) / 1e12;
+    return cudaGetLastError();
+}
+
 size_t knn2_tc_expanded_bytes(int nKeyframes, int n) { return (size_t)nKeyframes * (size_t)n * TC_KB; }
 
-cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded, cudaStream_t st) {
+cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded, uint8_t* used, cudaStream_t st) {
     if (a.nPairs <= 0 || a.n <= 0) return cudaSuccess;
     EncodeTiledFn enc = tma_encoder();
     if (!enc) return cudaErrorNotSupported;
@@ -310,8 +386,10 @@ cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded,
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
 
-    const size_t nChunks = (size_t)nKeyframes * a.n * 16;
-    k_knn2_expand<<<(unsigned)((nChunks + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(a.desc), reinterpret_cast<uint4*>(expanded), nChunks);
+    e = cudaMemsetAsync(used, 0, (size_t)nKeyframes, st);
+    if (e != cudaSuccess) return e;
+    k_knn2_mark<<<(a.nPairs + 255) / 256, 256, 0, st>>>(a.pairs, a.nPairs, nKeyframes, used);
+    k_knn2_expand<<<nKeyframes, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(a.desc), reinterpret_cast<uint4*>(expanded), a.n * 16, used);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 

@@ -24,6 +24,7 @@ struct obs_matcher {
     DevBuf<uint32_t> initList;
     DevBuf<int> initCount;
     DevBuf<int> sim3Idx[2], sim3Dist[2];
+    DevBuf<uint8_t> knnUsed;
     DevBuf<uint8_t> knnExpanded;         // +-1 int8 expansion of the descriptor sets of the last tensor-core knn2 call
     int knnEngine = OBS_KNN2_AUTO;
     bool hsvTables = false;
@@ -164,7 +165,7 @@ int obs_matcher_destroy(obs_matcher* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (obs_frame_set* fs : m->sets) fs->m = nullptr;     // their buffers stay valid until obs_frame_set_destroy
     for (auto& s : m->slot) s.release();
-    m->knnExpanded.release(); m->cand.release(); m->pool.release(); m->poolCursor.release(); m->choice.release(); m->rounds.release(); m->initList.release(); m->initCount.release();
+    m->knnExpanded.release(); m->knnUsed.release(); m->cand.release(); m->pool.release(); m->poolCursor.release(); m->choice.release(); m->rounds.release(); m->initList.release(); m->initCount.release();
     if (m->ev) cudaEventDestroy(m->ev);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -633,7 +634,8 @@ int obs_hamming_knn2(obs_matcher* m, const uint8_t* descriptors, int n_keyframes
     const bool tensor = m->knnEngine == OBS_KNN2_TENSOR || (m->knnEngine == OBS_KNN2_AUTO && n_desc >= 192);
     if (tensor) {
         CU(m->knnExpanded.ensure(knn2_tc_expanded_bytes(n_keyframes, n_desc)));
-        CU(launch_knn2_tc(a, n_keyframes, m->knnExpanded.p, m->stream));
+        CU(m->knnUsed.ensure((size_t)n_keyframes));
+        CU(launch_knn2_tc(a, n_keyframes, m->knnExpanded.p, m->knnUsed.p, m->stream));
     } else {
         CU(launch_knn2(a, m->stream));
     }

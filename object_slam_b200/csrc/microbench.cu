@@ -7,6 +7,7 @@
 //   mode 2: POPC only (8 per "distance"), the pipe ceiling.
 #include "../../include/obslam_b200.h"
 #include "host_util.h"
+#include "knn2_tc.h"
 
 namespace {
 
@@ -93,5 +94,13 @@ extern "C" int obs_microbench_popc(int device, int mode, double* gdist_per_s) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d); cudaFree(sink);
     *gdist_per_s = (double)blocks * 256 * iters * 8 / (best * 1e-3) / 1e9;
+    return OBS_OK;
+}
+
+// Measured int8 tensor-core rate in the shape of k_knn2_tc (csrc/knn2_tc.cu): the denominator of the knn2 roofline.
+extern "C" int obs_microbench_imma(int device, double* tops) {
+    if (!tops) return fail(OBS_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(device));
+    CU(knn2_tc_peak(tops));
     return OBS_OK;
 }

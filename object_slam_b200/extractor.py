@@ -117,6 +117,17 @@ class ORBextractor:
             return [(kps[i, :counts[i]].copy(), desc[i, :counts[i]].copy()) for i in range(nimg)]
         return [(kps[i, :counts[i]], desc[i, :counts[i]]) for i in range(nimg)]
 
+    def submit_batch(self, images, keypoints, descriptors, counts, n=None):
+        """obs_extract_batch_submit on page-locked arrays: images [F, H, stride] uint8, keypoints [F, cap] KEYPOINT_DTYPE,
+        descriptors [F, cap, 32] uint8, counts [F] int32.  Returns once enqueued; ``wait_batch`` sleeps until the results are there."""
+        n = images.shape[0] if n is None else int(n)
+        check(lib().obs_extract_batch_submit(self._h, ptr(images), n, images.shape[2], images.shape[1], images.strides[1],
+                                             ptr(keypoints), ptr(descriptors), keypoints.shape[1], ptr(counts)))
+        self._last_n = n
+
+    def wait_batch(self):
+        check(lib().obs_extract_batch_wait(self._h))
+
     def extract_device(self, d_images, n_images, w, h, stride, image_stride, stream=None):
         """Images already resident in HBM (``d_images`` = device address); results stay on the device."""
         check(lib().obs_extract_batch_device(self._h, C.c_void_p(int(d_images)), int(n_images), int(w), int(h),

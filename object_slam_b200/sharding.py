@@ -40,6 +40,17 @@ def split_by_locality(pairs, lo, hi):
     return pairs[local], pairs[~local]
 
 
+def split_by_chunk(pairs, lo, hi, per, n_chunks):
+    """[pairs with a local database keyframe, pairs of gather chunk 0, chunk 1, ...]: the chunked all-gather
+    (``Comm.allgather(..., n_chunks)``) delivers keyframes [per * c / n_chunks, per * (c + 1) / n_chunks) of EVERY rank's shard
+    with chunk c, so a remote pair can run as soon as the chunk of its database keyframe has arrived.  Needs per % n_chunks == 0."""
+    pairs = np.asarray(pairs, np.int32).reshape(-1, 2)
+    assert n_chunks >= 1 and per % n_chunks == 0
+    local = (pairs[:, 1] >= lo) & (pairs[:, 1] < hi)
+    chunk = (pairs[:, 1] % per) * n_chunks // per
+    return [pairs[local]] + [pairs[~local & (chunk == c)] for c in range(n_chunks)]
+
+
 class Comm:
     """NCCL communicator of the library (csrc/comm.cu); the 128-byte id travels through `broadcast_id`,
     a callable that takes rank 0's bytes and returns them on every rank (e.g. via torch.distributed)."""

@@ -144,3 +144,23 @@ def test_two_rank_frame_sharding_equals_single_process():
     for i in range(7):
         k, d = ex(synth.blocky_image((120, 160), i))
         assert merged[i][0].tobytes() == k.tobytes() and np.array_equal(merged[i][1], d)
+
+
+def test_split_by_chunk_partitions_the_pairs():
+    K, world, W, nc = 64, 4, 9, 4
+    per = sharding.padded_shard(K, world)
+    for rank in range(world):
+        lo, hi = rank * per, (rank + 1) * per
+        pairs = sharding.window_pairs(lo, hi, K, W)
+        groups = sharding.split_by_chunk(pairs, lo, hi, per, nc)
+        assert len(groups) == 1 + nc
+        assert sum(len(g) for g in groups) == len(pairs)
+        assert sorted(map(tuple, np.concatenate(groups))) == sorted(map(tuple, pairs))
+        assert all(lo <= d < hi for _, d in groups[0])
+        for c in range(nc):
+            for _, d in groups[1 + c]:
+                assert not (lo <= d < hi) and (d % per) * nc // per == c
+    # one rank: everything is local
+    pairs = sharding.window_pairs(0, K, K, W)
+    groups = sharding.split_by_chunk(pairs, 0, K, K, 1)
+    assert len(groups[0]) == len(pairs) and len(groups[1]) == 0
