@@ -68,6 +68,7 @@ struct obs_comm {
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ready = nullptr;            // producer of the local shard -> comm stream
+    cudaEvent_t started = nullptr;          // comm stream has reached the gather -> producer stream may continue
     std::vector<cudaEvent_t> chunkDone;
     int nChunks = 0;
 };
@@ -106,8 +107,14 @@ int obs_comm_create(const uint8_t* id128, int rank, int n_ranks, int device, obs
     memcpy(&id, id128, 128);
     ncclResult_t r = N->CommInitRank(&c->comm, n_ranks, id, rank);
     if (r != ncclSuccess) { delete c; return fail(OBS_ERR_CUDA, "ncclCommInitRank: %s", N->GetErrorString(r)); }
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    // The communicator's stream has the highest priority: NCCL's few CTAs must be scheduled ahead of the pending CTAs of a
+    // matching kernel whenever an SM frees up, or a rank whose NCCL kernel is resident spins -- holding its SMs -- on a peer
+    // whose NCCL kernel is queued behind a persistent matching kernel.
+    int prLow = 0, prHigh = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prHigh);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->started, cudaEventDisableTiming);
     if (e != cudaSuccess) { N->CommDestroy(c->comm); delete c; return fail(OBS_ERR_CUDA, "stream/event creation: %s", cudaGetErrorString(e)); }
     *out = c;
     return OBS_OK;
@@ -121,6 +128,7 @@ int obs_comm_destroy(obs_comm* c) {
     if (N && c->comm) N->CommDestroy(c->comm);
     for (cudaEvent_t ev : c->chunkDone) cudaEventDestroy(ev);
     if (c->ready) cudaEventDestroy(c->ready);
+    if (c->started) cudaEventDestroy(c->started);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return OBS_OK;
@@ -143,6 +151,10 @@ int obs_comm_allgather(obs_comm* c, const uint8_t* d_local, size_t local_bytes, 
     // the local shard must be complete before it is sent
     CU(cudaEventRecord(c->ready, (cudaStream_t)producer_stream));
     CU(cudaStreamWaitEvent(c->stream, c->ready, 0));
+    // ... and what the producer stream enqueues next (matching against the local shard) starts once the communicator's stream
+    // has arrived here, i.e. behind the launch of the first NCCL kernel on every rank rather than racing it
+    CU(cudaEventRecord(c->started, c->stream));
+    CU(cudaStreamWaitEvent((cudaStream_t)producer_stream, c->started, 0));
     uint8_t* mine = d_all + (size_t)c->rank * local_bytes;
     if (mine != d_local) CU(cudaMemcpyAsync(mine, d_local, local_bytes, cudaMemcpyDeviceToDevice, c->stream));
     // chunk boundaries on 32-byte descriptors

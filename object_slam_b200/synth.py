@@ -267,17 +267,21 @@ def keyframe_points(last, seed, camera_centre=(0.0, 0.0, 0.0)):
     d = np.linalg.norm(pos - np.asarray(camera_centre, np.float32), axis=1).astype(np.float32)
     # mfMaxDistance such that MapPoint::PredictScale lands on the keypoint's octave (70 %) or next to it
     delta = rng.choice([0, 0, 0, 0, 0, 0, 0, -1, 1, 2], n)
+    # the reference keeps two members per point, mfMinDistance / mfMaxDistance; the invariance limits are 0.8f / 1.2f times those and
+    # PredictScale reads mfMaxDistance (MapPoint.cc:475-519) -- the generated fields follow that relation exactly
     raw = (d * np.power(1.2, last["octave"] - 0.5 + delta)).astype(np.float32)
-    mind = (np.float32(0.8) * (raw / np.float32(1.2 ** 7))).astype(np.float32)
-    maxd = (np.float32(1.2) * raw).astype(np.float32)
     far = rng.random(n) < 0.05
-    maxd[far] = (d[far] * 0.5).astype(np.float32)                         # outside the invariance region
+    raw[far] = (d[far] * 0.4).astype(np.float32)                          # outside the invariance region
+    raw_min = (raw / np.float32(1.2 ** 7)).astype(np.float32)
+    mind = (np.float32(0.8) * raw_min).astype(np.float32)
+    maxd = (np.float32(1.2) * raw).astype(np.float32)
     nrm = pos / np.linalg.norm(pos, axis=1, keepdims=True) + rng.normal(0, 0.3, (n, 3))      # mean viewing direction (camera -> point)
     flip = rng.random(n) < 0.1
     nrm[flip] *= -1                                                        # seen from behind: fails the 60-degree test
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
     return dict(valid=(rng.random(n) < 0.9).astype(np.uint8), world_pos=pos, min_distance=mind, max_distance=maxd,
-                max_distance_raw=raw, normal=nrm.astype(np.float32), angle=last["angle"], descriptors=last["descriptors"])
+                min_distance_raw=raw_min, max_distance_raw=raw, normal=nrm.astype(np.float32), angle=last["angle"],
+                descriptors=last["descriptors"])
 
 
 def feature_vector(node_of_keypoint):
@@ -382,12 +386,13 @@ def sim3_pair(shape, n, seed, nlevels=8, bf=TUM_BF):
         d = np.linalg.norm(P @ Rt.T + tt, axis=1).astype(np.float32)          # distance from the camera it is projected into
         delta = r.choice([0, 0, 0, 0, 0, 0, 0, -1, 1, 2], len(P))
         raw = (d * np.power(1.2, octave - 0.5 + delta)).astype(np.float32)
-        mind = (np.float32(0.8) * (raw / np.float32(1.2 ** (nlevels - 1)))).astype(np.float32)
-        maxd = (np.float32(1.2) * raw).astype(np.float32)
         far = r.random(len(P)) < 0.05
-        maxd[far] = (d[far] * 0.5).astype(np.float32)
+        raw[far] = (d[far] * 0.4).astype(np.float32)          # mfMaxDistance so small that the point falls outside its invariance region
+        raw_min = (raw / np.float32(1.2 ** (nlevels - 1))).astype(np.float32)
+        mind = (np.float32(0.8) * raw_min).astype(np.float32)  # MapPoint::GetMinDistanceInvariance / GetMaxDistanceInvariance
+        maxd = (np.float32(1.2) * raw).astype(np.float32)
         return dict(valid=(r.random(len(P)) < 0.85).astype(np.uint8), world_pos=P.astype(np.float32), min_distance=mind, max_distance=maxd,
-                    max_distance_raw=raw, descriptors=flip_bits(desc, r.integers(0, 12, len(P)), r))
+                    min_distance_raw=raw_min, max_distance_raw=raw, descriptors=flip_bits(desc, r.integers(0, 12, len(P)), r))
 
     pts1 = points(Pw, keys1["octave"], desc1, R2, t2, seed + 1)
     pts2 = points(Pw2, keys2["octave"], desc2, R1, t1, seed + 2)

@@ -193,26 +193,53 @@ def test_oracle_vs_python_distinctive():
     assert np.array_equal(oracle.distinctive_descriptors(d, s), py_distinctive(d, s))
 
 
-def golden_cases():
+def golden_poses(seed):
+    """Keyframe poses of the triangulation fixture (the reference derives the epipole from them, ORBmatcher.cc:664-671)."""
+    rng = np.random.default_rng(seed)
+    t1 = np.hstack([synth._rot(*rng.normal(0, 0.02, 3)), rng.normal(0, 0.3, (3, 1))]).astype(np.float32)
+    t2 = np.hstack([synth._rot(*rng.normal(0, 0.02, 3)), rng.normal(0, 0.3, (3, 1))]).astype(np.float32)
+    return t1, t2
+
+
+def golden_cases(reference=False, stored=None):
+    """The fixture's cases through the restatement, or (reference=True, tools/make_golden_bow.py) through the reference's own
+    ORBmatcher.cc / MapPoint.cc compiled in place (oracle.refm).  stored: a loaded fixture, whose epipoles replay the triangulation
+    cases where the compiled reference is not available."""
+    from matcher_cases import bounds
     out = {}
+    shape = synth.TUM_SHAPE
     for n, seed, nodes in [(500, 11, 60), (1000, 12, 100)]:
-        a, b, x = synth.bow_pair(synth.TUM_SHAPE, n, seed, n_nodes=nodes)
+        a, b, x = synth.bow_pair(shape, n, seed, n_nodes=nodes)
         k = f"{n}_{seed}"
-        r = oracle.search_by_bow(a, dict(b, valid=None), 50, False, 0.7, True)
-        out[f"bowA_n_{k}"] = np.int32(r[0]); out[f"bowA_m21_{k}"] = r[2]
-        r = oracle.search_by_bow(a, b, 50, True, 0.8, True)
-        out[f"bowB_n_{k}"] = np.int32(r[0]); out[f"bowB_m12_{k}"] = r[1]
-        r = oracle.search_for_triangulation(a, b, x["f12"], x["epipole"], x["level_sigma2"], x["scale_factors"], False, True)
-        out[f"tri_n_{k}"] = np.int32(r[0]); out[f"tri_m12_{k}"] = r[1]
+        t1, t2 = golden_poses(seed)
+        if reference:
+            from oracle import refm
+            r = refm.search_by_bow(a, dict(b, valid=None), bounds(shape), False, 0.7, True)
+            out[f"bowA_n_{k}"] = np.int32(r[0]); out[f"bowA_m21_{k}"] = r[2]
+            r = refm.search_by_bow(a, b, bounds(shape), True, 0.8, True)
+            out[f"bowB_n_{k}"] = np.int32(r[0]); out[f"bowB_m12_{k}"] = r[1]
+            r = refm.search_for_triangulation(a, b, x["f12"], bounds(shape), synth.camera_for(shape), x["scale_factors"], t1, t2, False, True)
+            out[f"tri_n_{k}"] = np.int32(r[0]); out[f"tri_m12_{k}"] = r[1]; out[f"tri_epipole_{k}"] = r[2]
+        else:
+            r = oracle.search_by_bow(a, dict(b, valid=None), 50, False, 0.7, True)
+            out[f"bowA_n_{k}"] = np.int32(r[0]); out[f"bowA_m21_{k}"] = r[2]
+            r = oracle.search_by_bow(a, b, 50, True, 0.8, True)
+            out[f"bowB_n_{k}"] = np.int32(r[0]); out[f"bowB_m12_{k}"] = r[1]
+            ep = stored[f"tri_epipole_{k}"]
+            r = oracle.search_for_triangulation(a, b, x["f12"], ep, x["level_sigma2"], x["scale_factors"], False, True)
+            out[f"tri_n_{k}"] = np.int32(r[0]); out[f"tri_m12_{k}"] = r[1]; out[f"tri_epipole_{k}"] = np.asarray(ep, np.float32)
     d, s = synth.observation_descriptors(500, 13)
-    out["distinctive"] = oracle.distinctive_descriptors(d, s)
+    dd = np.asarray(d).reshape(-1, 32)
+    best = (oracle.refm.distinctive_descriptors(d, s) if reference else oracle.distinctive_descriptors(d, s))
+    # the chosen descriptor itself (an observation list may hold equal descriptors under different indices)
+    out["distinctive"] = np.stack([dd[s[p] + best[p]] if best[p] >= 0 else np.zeros(32, np.uint8) for p in range(len(s) - 1)])
     return out
 
 
 def test_oracle_matches_golden():
     """fixtures written by tools/make_golden_bow.py from this oracle at the commit that introduced it"""
     want = np.load(GOLDEN)
-    got = golden_cases()
+    got = golden_cases(stored=want)
     assert sorted(want.files) == sorted(got)
     for k in want.files:
         assert np.array_equal(want[k], got[k]), k
@@ -276,11 +303,15 @@ def test_gpu_bow_matches_golden(matcher):
         matcher.mfNNratio = 0.8
         nm, m12, m21 = matcher.SearchByBoW([a], [b], keyframe_pair=True)
         assert nm[0] == want[f"bowB_n_{k}"] and np.array_equal(m12[0, :n], want[f"bowB_m12_{k}"])
-        nm, m12 = matcher.SearchForTriangulation([a], [b], x["f12"], x["epipole"], x["level_sigma2"], x["scale_factors"])
+        # the fixture's epipole is the one the reference derived from the fixture's poses (ORBmatcher.cc:664-671)
+        nm, m12 = matcher.SearchForTriangulation([a], [b], x["f12"], want[f"tri_epipole_{k}"], x["level_sigma2"], x["scale_factors"])
         assert nm[0] == want[f"tri_n_{k}"] and np.array_equal(m12[0, :n], want[f"tri_m12_{k}"])
     matcher.mfNNratio = 0.7
     d, s = synth.observation_descriptors(500, 13)
-    assert np.array_equal(matcher.ComputeDistinctiveDescriptors(d, s), want["distinctive"])
+    best = matcher.ComputeDistinctiveDescriptors(d, s)
+    dd = np.asarray(d).reshape(-1, 32)
+    got = np.stack([dd[s[p] + best[p]] if best[p] >= 0 else np.zeros(32, np.uint8) for p in range(len(s) - 1)])
+    assert np.array_equal(got, want["distinctive"])
 
 
 # ------------------------------------------------------------------------------------------------ object layer

@@ -272,7 +272,7 @@ def test_knn2_equals_numpy_bruteforce():
 def test_oracle_reproduces_golden_fixtures(path):
     import make_golden_match
     g = np.load(path)
-    want = make_golden_match.compute(str(g["kind"]), int(g["seed"]))
+    want = make_golden_match.compute(str(g["kind"]), int(g["seed"]), g["rt_decomposed"] if "rt_decomposed" in g.files else None)
     for k in want:
         assert np.array_equal(g[k], want[k]), k
 

@@ -1,8 +1,9 @@
 """Generates tests/golden/*.npz from the reference itself: the reference's own, unmodified
 src/ORBextractor.cc compiled in place (oracle/_ref, bump allocator) run on seeded synthetic
 frames.  Needs /root/reference (or a prebuilt oracle/_ref); the fixtures it writes are what
-travels.  Stereo fixtures come from the restated ComputeStereoMatches (the reference's Frame.cc
-cannot be compiled here), fed with the reference extractor's outputs.
+travels.  Stereo fixtures come from the reference's own Frame::ComputeStereoMatches (src/Frame.cc compiled
+unmodified into oracle/_ref/libref_matcher.so, oracle/refm.py), fed with the reference extractor's outputs;
+the restatement must agree before a fixture is written (its `sad` array is kept as a diagnostic).
 
     python tools/make_golden.py
 """
@@ -33,14 +34,22 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"extract_{name}.npz"), keypoints=k, descriptors=d, level_checksums=cks,
                             shape=np.array(shape), nfeatures=nf, generator=gen, seed=seed)
         print(name, len(k))
-    # stereo: reference extractor outputs -> restated ComputeStereoMatches
+    # stereo: reference extractor outputs -> the reference's ComputeStereoMatches
+    from oracle import refm
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    from matcher_cases import bounds
     for seed in (0, 5):
         L, R = synth.stereo_pair(synth.KITTI_SHAPE, seed)
         rL, rR = oracle.ReferenceExtractor(2000), oracle.ReferenceExtractor(2000)
         kL, dL = rL(L); kR, dR = rR(R)
         sc = np.empty(8, np.float32); oracle.ref_lib().ref_get_scale_factors(rL._h, sc.ctypes.data_as(oracle.C.c_void_p))
-        ur, dp, sad = oracle.stereo_match(kL, dL, kR, dR, [rL.level(l) for l in range(8)], [rR.level(l) for l in range(8)],
-                                          sc, (1.0 / sc).astype(np.float32), synth.KITTI_BF, 0.0, synth.KITTI_FX)
+        pl, pr = [rL.level(l) for l in range(8)], [rR.level(l) for l in range(8)]
+        rur, rdp, used = refm.stereo_match(kL, dL, kR, dR, pl, pr, sc, synth.KITTI_BF, synth.KITTI_FX, bounds(synth.KITTI_SHAPE))
+        assert np.float32(used) == np.float32(synth.KITTI_FX), "mbf / mb must reproduce maxD = fx"
+        ur, dp, sad = oracle.stereo_match(kL, dL, kR, dR, pl, pr, sc, (1.0 / sc).astype(np.float32), synth.KITTI_BF, 0.0, synth.KITTI_FX)
+        assert np.array_equal(ur, rur) and np.array_equal(dp, rdp), "restatement differs from the compiled reference"
+        ur, dp = rur, rdp
         np.savez_compressed(os.path.join(OUT, f"stereo_kitti_s{seed}.npz"), uRight=ur, depth=dp, sad=sad,
                             n_left=len(kL), n_right=len(kR), seed=seed)
         print("stereo", seed, (ur >= 0).sum())
