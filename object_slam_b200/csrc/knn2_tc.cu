@@ -130,12 +130,14 @@ struct Knn2TcArgs {
     int nPairs, n, mTiles, nTiles;
     int thLow; float nnratio;
     int* bestIdx; int* bestDist; int* secondDist;
+    unsigned long long* workCounter;      // zeroed before the launch: next (pair, query tile) work item
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn2_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Knn2TcArgs A) {
     extern __shared__ uint8_t smemRaw[];
-    __shared__ __align__(8) uint64_t bars[12];     // aFull[2] aEmpty[2] bFull[2] bEmpty[2] accFull[2] accEmpty[2]
+    __shared__ __align__(8) uint64_t bars[16];     // aFull[2] aEmpty[2] bFull[2] bEmpty[2] accFull[2] accEmpty[2] qFull[2] qEmpty[2]
+    __shared__ long long workQ[2];                 // work items handed from the producer to the MMA and epilogue warps (-1 = done)
     __shared__ uint32_t tmemBaseS;
     __shared__ uint2 sMerge[2][TC_M];
 
@@ -149,12 +151,15 @@ k_knn2_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     auto bEmpty = [&](int s) { return bar0 + 8u * (6 + s); };
     auto accFull = [&](int s) { return bar0 + 8u * (8 + s); };
     auto accEmpty = [&](int s) { return bar0 + 8u * (10 + s); };
+    auto qFull = [&](int s) { return bar0 + 8u * (12 + s); };
+    auto qEmpty = [&](int s) { return bar0 + 8u * (14 + s); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) {
             mbar_init(aFull(s), 1); mbar_init(aEmpty(s), 1);
             mbar_init(bFull(s), 1); mbar_init(bEmpty(s), 1);
             mbar_init(accFull(s), 1); mbar_init(accEmpty(s), EPI_THREADS / 32);
+            mbar_init(qFull(s), 1); mbar_init(qEmpty(s), 1 + EPI_THREADS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -172,11 +177,19 @@ k_knn2_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" :: "l"(&mapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" :: "l"(&mapB) : "memory");
-            uint32_t ai = 0, bi = 0;
-            for (long long w = blockIdx.x; w < total; w += gridDim.x, ai++) {
+            // Work items come from a global counter, not from a fixed stride: a CTA that starts late (its SM was held by another
+            // kernel, e.g. NCCL's while the descriptor gather is in flight) simply takes fewer of them.
+            uint32_t bi = 0;
+            for (uint32_t ai = 0;; ai++) {
+                const uint32_t sa = ai & 1u;
+                mbar_wait(qEmpty(sa), ((ai >> 1) & 1u) ^ 1u);
+                long long w = (long long)atomicAdd(A.workCounter, 1ull);
+                if (w >= total) w = -1;
+                workQ[sa] = w;
+                mbar_arrive(qFull(sa));
+                if (w < 0) break;
                 const int pair = (int)(w / A.mTiles), mt = (int)(w - (long long)pair * A.mTiles);
                 const int2 pr = A.pairs[pair];
-                const uint32_t sa = ai & 1u;
                 mbar_wait(aEmpty(sa), ((ai >> 1) & 1u) ^ 1u);
                 mbar_expect_tx(aFull(sa), A_BYTES);
                 tma_load_3d(sA0 + sa * A_BYTES, &mapA, 0, mt * TC_M, pr.x, aFull(sa));
@@ -192,9 +205,13 @@ k_knn2_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            uint32_t ai = 0, bi = 0;
-            for (long long w = blockIdx.x; w < total; w += gridDim.x, ai++) {
+            uint32_t bi = 0;
+            for (uint32_t ai = 0;; ai++) {
                 const uint32_t sa = ai & 1u;
+                mbar_wait(qFull(sa), (ai >> 1) & 1u);
+                const long long w = *reinterpret_cast<volatile long long*>(&workQ[sa]);
+                mbar_arrive(qEmpty(sa));
+                if (w < 0) break;
                 mbar_wait(aFull(sa), (ai >> 1) & 1u);
                 for (int nt = 0; nt < A.nTiles; nt++, bi++) {
                     const uint32_t sb = bi & 1u, ph = (bi >> 1) & 1u;
@@ -219,8 +236,14 @@ k_knn2_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int quad = warp & 3;                  // a warp reads the TMEM lanes 32 * (warp id % 4) ...
         const int half = ew >> 2;                   // ... and this 128-column half of every accumulator
         const int row = quad * 32 + lane;
-        uint32_t ai = 0, bi = 0;
-        for (long long w = blockIdx.x; w < total; w += gridDim.x, ai++) {
+        uint32_t bi = 0;
+        for (uint32_t ai = 0;; ai++) {
+            const uint32_t sa = ai & 1u;
+            mbar_wait(qFull(sa), (ai >> 1) & 1u);
+            const long long w = *reinterpret_cast<volatile long long*>(&workQ[sa]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qEmpty(sa));
+            if (w < 0) break;
             const int pair = (int)(w / A.mTiles), mt = (int)(w - (long long)pair * A.mTiles);
             uint32_t best = SENT32, second = SENT32;
             for (int nt = 0; nt < A.nTiles; nt++, bi++) {
@@ -373,6 +396,7 @@ cudaError_t knn2_tc_peak(double* tops) {
 }
 
 size_t knn2_tc_expanded_bytes(int nKeyframes, int n) { return (size_t)nKeyframes * (size_t)n * TC_KB; }
+size_t knn2_tc_scratch_bytes(int nKeyframes) { return (((size_t)nKeyframes + 7) & ~(size_t)7) + 8; }
 
 cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded, uint8_t* used, cudaStream_t st) {
     if (a.nPairs <= 0 || a.n <= 0) return cudaSuccess;
@@ -386,7 +410,9 @@ cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded,
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
 
-    e = cudaMemsetAsync(used, 0, (size_t)nKeyframes, st);
+    // `used`: nKeyframes flags, then (8-byte aligned) the work counter of the tensor-core kernel
+    const size_t counterOff = ((size_t)nKeyframes + 7) & ~(size_t)7;
+    e = cudaMemsetAsync(used, 0, counterOff + 8, st);
     if (e != cudaSuccess) return e;
     k_knn2_mark<<<(a.nPairs + 255) / 256, 256, 0, st>>>(a.pairs, a.nPairs, nKeyframes, used);
     k_knn2_expand<<<nKeyframes, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(a.desc), reinterpret_cast<uint4*>(expanded), a.n * 16, used);
@@ -410,6 +436,7 @@ cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded,
     k.mTiles = (a.n + TC_M - 1) / TC_M; k.nTiles = (a.n + TC_N - 1) / TC_N;
     k.thLow = a.thLow; k.nnratio = a.nnratio;
     k.bestIdx = a.bestIdx; k.bestDist = a.bestDist; k.secondDist = a.secondDist;
+    k.workCounter = reinterpret_cast<unsigned long long*>(used + counterOff);
     const long long total = (long long)k.nPairs * k.mTiles;
     const unsigned grid = (unsigned)std::min<long long>(total, sms);
     k_knn2_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(mapA, mapB, k);

@@ -634,7 +634,7 @@ int obs_hamming_knn2(obs_matcher* m, const uint8_t* descriptors, int n_keyframes
     const bool tensor = m->knnEngine == OBS_KNN2_TENSOR || (m->knnEngine == OBS_KNN2_AUTO && n_desc >= 192);
     if (tensor) {
         CU(m->knnExpanded.ensure(knn2_tc_expanded_bytes(n_keyframes, n_desc)));
-        CU(m->knnUsed.ensure((size_t)n_keyframes));
+        CU(m->knnUsed.ensure(knn2_tc_scratch_bytes(n_keyframes)));
         CU(launch_knn2_tc(a, n_keyframes, m->knnExpanded.p, m->knnUsed.p, m->stream));
     } else {
         CU(launch_knn2(a, m->stream));
