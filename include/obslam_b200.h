@@ -129,7 +129,9 @@ int obs_extractor_get_selected(obs_extractor* e, int image_index, int level, int
  * calls of each stage's time in ms: stage_ms[OBS_NUM_STAGES] = {pyramid, FAST, quadtree, blur,
  * orientation+descriptors}; *stereo_ms = stereo match + outlier filter.  Without profiling the blur runs on an
  * auxiliary stream beside FAST + quadtree (both depend on the pyramid only); while profiling is on the stages
- * of a call are serialised so that their brackets do not overlap. */
+ * of a call are serialised so that their brackets do not overlap.  While profiling is on the enqueue of every stage
+ * is also wrapped in an NVTX range ("obs:ComputePyramid", "obs:FAST", "obs:DistributeOctTree", "obs:GaussianBlur",
+ * "obs:IC_Angle+computeOrbDescriptor", "obs:ComputeStereoMatches" inside "obs:extract") for Nsight timelines. */
 #define OBS_NUM_STAGES 5
 int obs_extractor_set_profiling(obs_extractor* e, int on);
 int obs_extractor_stage_ms(obs_extractor* e, float* stage_ms, float* stereo_ms, int* n_calls, int* n_stereo_calls);
@@ -170,6 +172,15 @@ int obs_stereo_frames_submit(obs_extractor* left, obs_extractor* right, const ob
 int obs_stereo_frames_wait(obs_extractor* left, obs_extractor* right);
 int obs_stereo_frames(obs_extractor* left, obs_extractor* right, const obs_stereo_io* io, int n_frames, int w, int h,
                       size_t stride, int cap, float mbf, float min_d, float max_d);
+
+/* Process-wide launch options, both on by default.
+ *   "pdl"    = 1: the kernels of the per-frame chain are launched with programmatic stream serialization (each kernel releases its
+ *              successor at entry -- griddepcontrol.launch_dependents -- and waits for its predecessor's results with
+ *              griddepcontrol.wait), so launch latency and prologues overlap the predecessor's tail;
+ *   "graphs" = 1: obs_stereo_frames_submit replays a CUDA graph once it has seen the same buffers, shape and parameters twice
+ *              (one cudaGraphLaunch instead of ~60 runtime calls per stereo frame; up to 8 argument sets per handle pair).
+ * Results are identical either way.  Returns OBS_ERR_INVALID for an unknown name. */
+int obs_set_option(const char* name, int value);
 
 /* Device-resident form: results stay in HBM (n_images x cap floats each, cap =
  * obs_extractor_max_keypoints(left)); pointers valid until the next call. */

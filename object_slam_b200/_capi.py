@@ -81,6 +81,7 @@ _PROTOS = {
     "obs_device_count": (C.c_int, []),
     "obs_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "obs_host_free": (C.c_int, [_vp]),
+    "obs_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "obs_extractor_create": (C.c_int, [C.POINTER(OrbParams), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "obs_extractor_destroy": (C.c_int, [_vp]),
     "obs_extractor_levels": (C.c_int, [_vp]),

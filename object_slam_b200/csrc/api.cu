@@ -6,6 +6,8 @@
 #include "host_util.h"
 #include "matcher_api.h"
 
+#include <nvtx3/nvToolsExt.h>          // header-only NVTX v3: the ranges cost nothing unless a tool is attached
+
 #include <cmath>
 #include <cstdlib>
 #include <cstdarg>
@@ -38,6 +40,14 @@ bool is_device(const void* p) {
     if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
+
+// process-wide launch options (obs_set_option)
+static std::atomic<int> g_pdl{1}, g_graphs{1};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+void set_pdl_enabled(bool on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+bool graphs_enabled() { return g_graphs.load(std::memory_order_relaxed) != 0; }
+void set_graphs_enabled(bool on) { g_graphs.store(on ? 1 : 0, std::memory_order_relaxed); }
+std::atomic<unsigned long long> g_allocEpoch{0};
 
 int max_dynamic_smem(const void* kernel) {
     int dev = 0, optin = 0;
@@ -72,6 +82,14 @@ inline short sat_short(float v) { int i = cv_round_f(v); return (short)(i < -327
 
 constexpr int PROF_SLOTS = 128;
 
+// NVTX range around the enqueue of one stage, only while obs_extractor_set_profiling is on (the reference's ad-hoc
+// std::chrono timers around the same stages: src/Tracking.cc:270-273)
+struct StageRange {
+    bool on;
+    StageRange(bool enabled, const char* name) : on(enabled) { if (on) nvtxRangePushA(name); }
+    ~StageRange() { if (on) nvtxRangePop(); }
+};
+
 }  // namespace
 
 struct obs_extractor {
@@ -82,6 +100,8 @@ struct obs_extractor {
     cudaStream_t aux = nullptr;    // the blur runs here, beside FAST + quadtree (both only need the pyramid)
     cudaEvent_t done = nullptr, fork = nullptr, join = nullptr;
     cudaEvent_t hostDone = nullptr;    // cudaEventBlockingSync: the host thread sleeps on it instead of spinning in a stream synchronise
+    cudaEvent_t hostDoneSpin = nullptr; // plain event for small batches (a live frame): the wake-up of a sleeping thread costs more than the frame
+    bool pendingSpin = false;
     bool pending = false;              // obs_stereo_frames_submit without its obs_stereo_frames_wait
     const int* pendingCounts[2] = {nullptr, nullptr};
     int pendingN = 0, pendingCap = 0;
@@ -120,6 +140,26 @@ struct obs_extractor {
     size_t mapsB = 0;
     int lastN = 0;                 // images in the last batch (0 = nothing extracted yet)
     cudaStream_t lastStream = nullptr;
+
+    // CUDA graphs of obs_stereo_frames_submit (owned by the left handle): one executable graph per distinct argument set
+    struct StereoGraph {
+        const void* io[10];
+        int n, w, h, cap;
+        size_t stride;
+        float mbf, minD, maxD;
+        obs_extractor* right;
+        unsigned long long epoch;      // g_allocEpoch at capture: any device reallocation since then invalidates the pointers inside
+        bool pdl;
+        cudaGraphExec_t exec;          // nullptr: arguments seen once (plain enqueue); captured when they come a second time
+        unsigned long long lastUse;
+        bool same_args(const StereoGraph& o) const {
+            return memcmp(io, o.io, sizeof(io)) == 0 && n == o.n && w == o.w && h == o.h && cap == o.cap && stride == o.stride &&
+                   mbf == o.mbf && minD == o.minD && maxD == o.maxD && right == o.right;
+        }
+    };
+    std::vector<StereoGraph> graphs;
+    unsigned long long graphClock = 0;
+    cudaEvent_t gjoin[3] = {nullptr, nullptr, nullptr};   // joins of the side streams at the end of a capture
 
     // optional per-stage CUDA-event timing (obs_extractor_set_profiling)
     bool prof = false;
@@ -389,8 +429,9 @@ int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st, int img0 = 0, bool
     int* selCountP = e->selCount.p + o * g.nlevels;
     cudaEvent_t* ev = nullptr;
     if (e->prof && e->profCalls < PROF_SLOTS && img0 == 0 && last) ev = e->pev.data() + (size_t)e->profCalls * (2 * OBS_NUM_STAGES);
+    StageRange whole(e->prof, "obs:extract");
     if (ev) CU(cudaEventRecord(ev[0], st));
-    CU(launch_pyramid(g, P, e->dXtab.p, e->dYtab.p, nimg, st));
+    { StageRange r(e->prof, "obs:ComputePyramid"); CU(launch_pyramid(g, P, e->dXtab.p, e->dYtab.p, nimg, st)); }
     if (ev) CU(cudaEventRecord(ev[1], st));
     cudaStream_t bs = forkBlur ? e->aux : st;
     if (forkBlur) {
@@ -398,17 +439,19 @@ int run_pipeline(obs_extractor* e, int nimg, cudaStream_t st, int img0 = 0, bool
         CU(cudaStreamWaitEvent(e->aux, e->fork, 0));
     }
     if (ev) CU(cudaEventRecord(ev[6], bs));
-    CU(launch_blur(g, P, blurP, g.slabBytes, nimg, bs));
+    { StageRange r(e->prof, "obs:GaussianBlur"); CU(launch_blur(g, P, blurP, g.slabBytes, nimg, bs)); }
     if (ev) CU(cudaEventRecord(ev[7], bs));
     if (forkBlur) CU(cudaEventRecord(e->join, e->aux));
     if (ev) CU(cudaEventRecord(ev[2], st));
-    CU(launch_fast(g, P, e->dFastCtas.p, candP, cellCountP, nimg, st));
+    { StageRange r(e->prof, "obs:FAST"); CU(launch_fast(g, P, e->dFastCtas.p, candP, cellCountP, nimg, st)); }
     if (ev) { CU(cudaEventRecord(ev[3], st)); CU(cudaEventRecord(ev[4], st)); }
-    CU(launch_quadtree(g, e->nodeCap, candP, cellCountP, e->keyScratch.p + o * g.slotTotal, e->nodeScratch.p + o * g.slotTotal, selP, selCountP, nimg, st));
+    { StageRange r(e->prof, "obs:DistributeOctTree");
+      CU(launch_quadtree(g, e->nodeCap, candP, cellCountP, e->keyScratch.p + o * g.slotTotal, e->nodeScratch.p + o * g.slotTotal, selP, selCountP, nimg, st)); }
     if (ev) CU(cudaEventRecord(ev[5], st));
     if (forkBlur) CU(cudaStreamWaitEvent(st, e->join, 0));
     if (ev) CU(cudaEventRecord(ev[8], st));
-    CU(launch_describe(g, P, e->dMaps.p, img0, selP, selCountP, e->records.p + o * e->recordBytes, e->recordBytes, nimg, st));
+    { StageRange r(e->prof, "obs:IC_Angle+computeOrbDescriptor");
+      CU(launch_describe(g, P, e->dMaps.p, img0, selP, selCountP, e->records.p + o * e->recordBytes, e->recordBytes, nimg, st)); }
     if (ev) { CU(cudaEventRecord(ev[9], st)); e->profCalls++; }
     e->lastN = img0 + nimg;
     e->lastStream = st;
@@ -521,6 +564,8 @@ int obs_extractor_create(const obs_orb_params* params, int max_w, int max_h, int
     if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming);
     if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->join, cudaEventDisableTiming);
     if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->hostDone, cudaEventDisableTiming | cudaEventBlockingSync);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->hostDoneSpin, cudaEventDisableTiming);
+    for (cudaEvent_t& ev : e->gjoin) if (se == cudaSuccess) se = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&e->cin, cudaStreamNonBlocking);
     if (se == cudaSuccess) se = cudaStreamCreateWithFlags(&e->cout, cudaStreamNonBlocking);
     if (se != cudaSuccess) { delete e; return fail(OBS_ERR_CUDA, "stream/event creation: %s", cudaGetErrorString(se)); }
@@ -544,6 +589,9 @@ int obs_extractor_destroy(obs_extractor* e) {
     if (e->fork) cudaEventDestroy(e->fork);
     if (e->join) cudaEventDestroy(e->join);
     if (e->hostDone) cudaEventDestroy(e->hostDone);
+    if (e->hostDoneSpin) cudaEventDestroy(e->hostDoneSpin);
+    for (cudaEvent_t ev : e->gjoin) if (ev) cudaEventDestroy(ev);
+    for (auto& sg : e->graphs) if (sg.exec) cudaGraphExecDestroy(sg.exec);
     for (cudaEvent_t ev : e->chunkIn) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->chunkDone) cudaEventDestroy(ev);
     if (e->cin) cudaStreamDestroy(e->cin);
@@ -872,7 +920,7 @@ int obs_stereo_match_device(obs_extractor* L, obs_extractor* R, float mbf, float
     cudaEvent_t* sev = nullptr;
     if (L->prof && L->stereoCalls < PROF_SLOTS) sev = L->sev.data() + (size_t)L->stereoCalls * 2;
     if (sev) CU(cudaEventRecord(sev[0], st));
-    CU(launch_stereo(a, n, st));
+    { StageRange r(L->prof, "obs:ComputeStereoMatches"); CU(launch_stereo(a, n, st)); }
     if (sev) { CU(cudaEventRecord(sev[1], st)); L->stereoCalls++; }
     // later work on either handle must not overwrite the inputs while the match runs
     CU(cudaEventRecord(L->done, st));
@@ -1023,19 +1071,108 @@ int obs_stereo_frames_submit(obs_extractor* L, obs_extractor* R, const obs_stere
     if ((rc = set_shape(L, w, h, n_frames, L->stream))) return rc;
     if ((rc = set_shape(R, w, h, n_frames, R->stream))) return rc;
     if (cap > L->g.kpCap) return fail(OBS_ERR_INVALID, "cap %d exceeds obs_extractor_max_keypoints (%d)", cap, L->g.kpCap);
-    // the two eyes on their own streams (the reference's two extraction threads), enqueued by this one host thread
-    if ((rc = enqueue_chunks(L, io->left, n_frames, w, h, stride, io->kp_left, io->desc_left, cap, io->n_left))) return rc;
-    if ((rc = enqueue_chunks(R, io->right, n_frames, w, h, stride, io->kp_right, io->desc_right, cap, io->n_right))) return rc;
-    if ((rc = obs_stereo_match_device(L, R, mbf, min_d, max_d, nullptr, nullptr, nullptr))) return rc;
-    const int kc = L->g.kpCap;
-    CU(cudaMemcpy2DAsync(io->u_right, (size_t)cap * 4, L->uRight.p, (size_t)kc * 4, (size_t)cap * 4, n_frames, cudaMemcpyDeviceToHost, L->stream));
-    CU(cudaMemcpy2DAsync(io->depth, (size_t)cap * 4, L->depth.p, (size_t)kc * 4, (size_t)cap * 4, n_frames, cudaMemcpyDeviceToHost, L->stream));
-    // one event behind everything: the downloads of both eyes and of the stereo result
-    CU(cudaEventRecord(L->fork, L->cout));
-    CU(cudaStreamWaitEvent(L->stream, L->fork, 0));
-    CU(cudaEventRecord(R->fork, R->cout));
-    CU(cudaStreamWaitEvent(L->stream, R->fork, 0));
-    CU(cudaEventRecord(L->hostDone, L->stream));
+    // Steady state of a live front end: the same pinned buffers, shape and parameters call after call.  The second call with one
+    // argument set is captured into a CUDA graph (both eyes' uploads, 2 x 9 kernels with their programmatic-dependency edges, the
+    // stereo kernels, every download), later calls are one cudaGraphLaunch instead of ~60 runtime calls.
+    obs_extractor::StereoGraph key{};
+    const void* iov[10] = {io->left, io->right, io->kp_left, io->desc_left, io->n_left, io->kp_right, io->desc_right, io->n_right, io->u_right, io->depth};
+    memcpy(key.io, iov, sizeof(iov));
+    key.n = n_frames; key.w = w; key.h = h; key.cap = cap; key.stride = stride; key.mbf = mbf; key.minD = min_d; key.maxD = max_d; key.right = R;
+    obs_extractor::StereoGraph* slot = nullptr;
+    const bool useGraphs = graphs_enabled() && !L->prof && !R->prof;
+    if (useGraphs) {
+        for (auto& sg : L->graphs) if (sg.same_args(key)) slot = &sg;
+        if (slot && slot->exec && (slot->epoch != g_allocEpoch.load(std::memory_order_relaxed) || slot->pdl != pdl_enabled())) {
+            cudaGraphExecDestroy(slot->exec);
+            slot->exec = nullptr;
+        }
+    }
+    // work still queued on the handles' streams by earlier calls precedes everything below (a graph runs on L->stream only)
+    {
+        cudaStream_t pre[3] = {R->stream, R->lastStream, L->lastStream};
+        for (int i = 0; i < 3; i++) {
+            if (!pre[i] || pre[i] == L->stream || (i == 1 && pre[1] == pre[0])) continue;
+            CU(cudaEventRecord(L->gjoin[i], pre[i]));
+            CU(cudaStreamWaitEvent(L->stream, L->gjoin[i], 0));
+        }
+    }
+    const bool launchGraph = slot && slot->exec;
+    const bool capture = slot && !slot->exec;
+    if (launchGraph) {
+        CU(cudaGraphLaunch(slot->exec, L->stream));
+        slot->lastUse = ++L->graphClock;
+        for (obs_extractor* e : {L, R}) {              // the state enqueue_chunks / obs_stereo_match_device leave behind
+            e->ptrs.l0 = e->pyr.p; e->ptrs.l0ImgStride = e->g.slabBytes; e->ptrs.l0Pitch = e->g.lv[0].pitch;
+            e->ptrs.slab = e->pyr.p; e->ptrs.slabStride = e->g.slabBytes;
+            e->lastN = n_frames;
+        }
+        L->lastStream = L->stream; R->lastStream = R->stream;
+    } else {
+        if (capture) {
+            CU(cudaStreamBeginCapture(L->stream, cudaStreamCaptureModeRelaxed));
+            cudaError_t fe = cudaEventRecord(L->fork, L->stream);
+            if (fe == cudaSuccess) fe = cudaStreamWaitEvent(R->stream, L->fork, 0);
+            if (fe != cudaSuccess) { cudaGraph_t g0 = nullptr; cudaStreamEndCapture(L->stream, &g0); if (g0) cudaGraphDestroy(g0); CU(fe); }
+        }
+        // the two eyes on their own streams (the reference's two extraction threads), enqueued by this one host thread
+        rc = enqueue_chunks(L, io->left, n_frames, w, h, stride, io->kp_left, io->desc_left, cap, io->n_left);
+        if (!rc) rc = enqueue_chunks(R, io->right, n_frames, w, h, stride, io->kp_right, io->desc_right, cap, io->n_right);
+        if (!rc) rc = obs_stereo_match_device(L, R, mbf, min_d, max_d, nullptr, nullptr, nullptr);
+        const int kc = L->g.kpCap;
+        cudaError_t ce = cudaSuccess;
+        auto step = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
+        if (!rc) {
+            step(cudaMemcpy2DAsync(io->u_right, (size_t)cap * 4, L->uRight.p, (size_t)kc * 4, (size_t)cap * 4, n_frames, cudaMemcpyDeviceToHost, L->stream));
+            step(cudaMemcpy2DAsync(io->depth, (size_t)cap * 4, L->depth.p, (size_t)kc * 4, (size_t)cap * 4, n_frames, cudaMemcpyDeviceToHost, L->stream));
+            // one stream behind everything: the downloads of both eyes and of the stereo result
+            step(cudaEventRecord(L->fork, L->cout));
+            step(cudaStreamWaitEvent(L->stream, L->fork, 0));
+            step(cudaEventRecord(R->fork, R->cout));
+            step(cudaStreamWaitEvent(L->stream, R->fork, 0));
+            if (capture) {                             // every stream that joined the capture returns to its origin
+                cudaStream_t side[3] = {R->stream, L->cin, R->cin};
+                for (int i = 0; i < 3; i++) { step(cudaEventRecord(L->gjoin[i], side[i])); step(cudaStreamWaitEvent(L->stream, L->gjoin[i], 0)); }
+            }
+        }
+        if (capture) {
+            cudaGraph_t graph = nullptr;
+            cudaError_t ee = cudaStreamEndCapture(L->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess || ee != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                return fail(OBS_ERR_CUDA, "obs_stereo_frames_submit: graph capture failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+            }
+            cudaGraphExec_t exec = nullptr;
+            cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) return fail(OBS_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+            slot->exec = exec;
+            slot->epoch = g_allocEpoch.load(std::memory_order_relaxed);
+            slot->pdl = pdl_enabled();
+            slot->lastUse = ++L->graphClock;
+            CU(cudaGraphLaunch(exec, L->stream));
+        } else {
+            if (rc) return rc;
+            CU(ce);
+            if (useGraphs && !slot) {                  // first time these arguments are seen: remember them (at most 8 sets, least recently used out)
+                if (L->graphs.size() >= 8) {
+                    size_t v = 0;
+                    for (size_t i = 1; i < L->graphs.size(); i++) if (L->graphs[i].lastUse < L->graphs[v].lastUse) v = i;
+                    if (L->graphs[v].exec) cudaGraphExecDestroy(L->graphs[v].exec);
+                    L->graphs.erase(L->graphs.begin() + v);
+                }
+                key.exec = nullptr; key.lastUse = ++L->graphClock;
+                L->graphs.push_back(key);
+            }
+        }
+    }
+    if (launchGraph || capture) {                      // later work on the right handle's stream waits for the graph
+        CU(cudaEventRecord(L->done, L->stream));
+        CU(cudaStreamWaitEvent(R->stream, L->done, 0));
+    }
+    L->pendingSpin = n_frames <= 4;
+    CU(cudaEventRecord(L->pendingSpin ? L->hostDoneSpin : L->hostDone, L->stream));
     L->pending = R->pending = true;
     L->pendingCounts[0] = io->n_left; L->pendingCounts[1] = io->n_right;
     L->pendingN = n_frames; L->pendingCap = cap;
@@ -1048,7 +1185,13 @@ int obs_stereo_frames_wait(obs_extractor* L, obs_extractor* R) {
     if (!R) return fail(OBS_ERR_INVALID, "null argument");
     if (!L->pending || !R->pending || !L->pendingCounts[1]) return fail(OBS_ERR_STATE, "obs_stereo_frames_wait without an obs_stereo_frames_submit");
     L->pending = R->pending = false;
-    CU(cudaEventSynchronize(L->hostDone));          // blocking-sync event: the thread sleeps
+    if (L->pendingSpin) {                           // a live frame (<= 4 frames): poll, the frame is shorter than a thread wake-up
+        cudaError_t q;
+        while ((q = cudaEventQuery(L->hostDoneSpin)) == cudaErrorNotReady) {}
+        CU(q);
+    } else {
+        CU(cudaEventSynchronize(L->hostDone));      // blocking-sync event: the thread sleeps
+    }
     for (int s = 0; s < 2; s++)
         for (int i = 0; i < L->pendingN; i++)
             if (L->pendingCounts[s][i] > L->pendingCap)
@@ -1062,6 +1205,13 @@ int obs_stereo_frames(obs_extractor* L, obs_extractor* R, const obs_stereo_io* i
     int rc = obs_stereo_frames_submit(L, R, io, n_frames, w, h, stride, cap, mbf, min_d, max_d);
     if (rc) return rc;
     return obs_stereo_frames_wait(L, R);
+}
+
+int obs_set_option(const char* name, int value) {
+    if (!name) return fail(OBS_ERR_INVALID, "null option name");
+    if (!strcmp(name, "pdl")) { obsdetail::set_pdl_enabled(value != 0); return OBS_OK; }
+    if (!strcmp(name, "graphs")) { obsdetail::set_graphs_enabled(value != 0); return OBS_OK; }
+    return fail(OBS_ERR_INVALID, "unknown option '%s' (known: pdl, graphs)", name);
 }
 
 int obs_host_alloc(size_t bytes, void** out) {

@@ -33,6 +33,7 @@ constexpr int BT_ROWS = BL_TH + 6;
 __global__ void __launch_bounds__(32 * BL_BANDS) k_blur_tile(const __grid_constant__ Geom g, const PyrPtrs p,
                                                               uint8_t* __restrict__ blurSlab, size_t blurStride) {
     extern __shared__ __align__(16) uint8_t tile[];
+    pdl_entry();
     const int img = blockIdx.y, tid = threadIdx.y * 32 + threadIdx.x;
     int t = (int)blockIdx.x, level = 0;
 #pragma unroll 1
@@ -142,6 +143,8 @@ cudaError_t launch_blur(const Geom& g, PyrPtrs p, uint8_t* blurSlab, size_t blur
     if (g.blurTilesTotal == 0) return cudaSuccess;
     dim3 grid(g.blurTilesTotal, nimg);
     dim3 block(32, BL_BANDS);
-    k_blur_tile<<<grid, block, BT_PITCH * (BT_ROWS + 2), st>>>   /* the 8-row blocks of the loop touch two rows past the apron */(g, p, blurSlab, blurStride);
+    /* the 8-row blocks of the loop touch two rows past the apron */
+    cudaError_t le = launch_k(pdl_enabled(), k_blur_tile, grid, block, (size_t)(BT_PITCH * (BT_ROWS + 2)), st, g, p, blurSlab, blurStride);
+    if (le != cudaSuccess) return le;
     return cudaGetLastError();
 }

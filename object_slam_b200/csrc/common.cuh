@@ -67,6 +67,16 @@ __device__ __forceinline__ const uint8_t* level_ptr(const PyrPtrs& p, const Geom
     return p.slab + (size_t)img * p.slabStride + g.lv[l].off;
 }
 
+// ---- programmatic dependent launch (PDL).  Every kernel of the per-frame chain starts with pdl_entry(): it lets the NEXT kernel of
+// the stream be scheduled right away (griddepcontrol.launch_dependents -- that kernel then runs its own prologue and parks in its
+// griddepcontrol.wait) and then waits until everything the PREVIOUS kernel wrote is complete and visible.  Nothing touches global
+// memory before the wait, so no kernel can overtake the data it depends on.  Without the launch attribute (host_util.h launch_k
+// with pdl = false) both instructions are no-ops.
+__device__ __forceinline__ void pdl_entry() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- helpers against ptxas rematerialisation.  Under a register bound (__launch_bounds__) ptxas prefers recomputing loop
 // invariants -- the lane index, shared-window bases (S2R CgaCtaId + LEA), loop bounds -- in every iteration over keeping them in
 // registers; in issue-bound loops that is 10-20 % of the instructions.  A value that went through an opaque shuffle (per-lane

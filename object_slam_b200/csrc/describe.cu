@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINCTAS) k_describe(cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     unsigned phase = 0;
+    pdl_entry();              // the pattern / mask tables above come from constant memory and the parameters: built while the quadtree finishes
     if (warp == DESC_WARPS - 1) {
         // lanes 0..nlevels-1 hold the per-level counts, a warp scan gives the offsets
         const int myCnt = lane < g.nlevels ? selCount[(size_t)img * g.nlevels + lane] : 0;
@@ -249,6 +250,7 @@ cudaError_t launch_describe(const Geom& g, PyrPtrs p, const CUtensorMap* maps, i
                             const uint32_t* sel, const int* selCount, uint8_t* records, size_t recordBytes,
                             int nimg, cudaStream_t st) {
     dim3 grid((g.kpCap + DESC_WARPS * DESC_PER_WARP - 1) / (DESC_WARPS * DESC_PER_WARP), nimg);
-    k_describe<<<grid, DESC_WARPS * 32, 0, st>>>(g, p, maps, img0, sel, selCount, records, recordBytes);
+    cudaError_t le = launch_k(pdl_enabled(), k_describe, grid, dim3(DESC_WARPS * 32), 0, st, g, p, maps, img0, sel, selCount, records, recordBytes);
+    if (le != cudaSuccess) return le;
     return cudaGetLastError();
 }

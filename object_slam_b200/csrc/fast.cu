@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(FT_THREADS, FT_MINCTAS) k_fast_cells(const __g
     uint16_t* Q = reinterpret_cast<uint16_t*>(sm + 2 * tileRows * FT_SP);    // pixel queue of the CTA
     __shared__ __align__(16) FastShared sh;
 
+    pdl_entry();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.y;
     const FastCta cta = ctaTab[blockIdx.x];
@@ -370,6 +371,5 @@ int fast_cells_per_cta_host(int wCell, int hCell) { return fast_cells_per_cta(wC
 cudaError_t launch_fast(const Geom& g, PyrPtrs p, const FastCta* ctaTab, uint32_t* cand, int* cellCount, int nimg, cudaStream_t st) {
     if (g.fastCtasTotal == 0) return cudaSuccess;
     dim3 grid(g.fastCtasTotal, nimg);
-    k_fast_cells<<<grid, FT_THREADS, fast_smem_bytes(g.fastTileRows), st>>>(g, p, ctaTab, g.fastTileRows, cand, cellCount);
-    return cudaGetLastError();
+    return launch_k(pdl_enabled(), k_fast_cells, grid, dim3(FT_THREADS), fast_smem_bytes(g.fastTileRows), st, g, p, ctaTab, g.fastTileRows, cand, cellCount);
 }

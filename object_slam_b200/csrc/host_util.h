@@ -16,6 +16,24 @@ bool is_device(const void* p);                // device (or managed) memory
 cudaError_t allow_max_smem(const void* kernel, std::atomic<unsigned long long>& done);
 int max_dynamic_smem(const void* kernel);      // that limit for the current device (bytes), 0 on error
 
+// Kernel launch with or without the programmatic-stream-serialization attribute (PDL): with it, the kernel may be scheduled while
+// its predecessor on the stream is still running and synchronises itself with griddepcontrol.wait (common.cuh pdl_entry).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+bool pdl_enabled();                 // process-wide switches (obs_set_option "pdl" / "graphs"), default on
+void set_pdl_enabled(bool on);
+bool graphs_enabled();
+void set_graphs_enabled(bool on);
+extern std::atomic<unsigned long long> g_allocEpoch;     // bumped by every device (re)allocation: captured graphs hold raw pointers
+
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
@@ -23,11 +41,12 @@ template <typename T> struct DevBuf {
         if (count <= n) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; n = 0;
+        g_allocEpoch.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
         if (e == cudaSuccess) n = count;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) { cudaFree(p); g_allocEpoch.fetch_add(1, std::memory_order_relaxed); } p = nullptr; n = 0; }
 };
 
 template <typename T> struct PinBuf {
@@ -48,6 +67,10 @@ using obsdetail::fail;
 using obsdetail::is_pinned;
 using obsdetail::is_device;
 using obsdetail::DevBuf;
+using obsdetail::launch_k;
+using obsdetail::pdl_enabled;
+using obsdetail::graphs_enabled;
+using obsdetail::g_allocEpoch;
 using obsdetail::PinBuf;
 
 #define OBS_ALLOW_MAX_SMEM(kernel)                                                                  \

@@ -916,9 +916,6 @@ cudaError_t launch_knn2(const Knn2Args& a, cudaStream_t st) {
     if (a.nPairs <= 0 || a.n <= 0) return cudaSuccess;
     const long long blocks = (long long)((a.n + KNN_THREADS - 1) / KNN_THREADS) * a.nPairs;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    static const int mode = getenv("OBS_KNN2_MODE") ? atoi(getenv("OBS_KNN2_MODE")) : 1;
-    if (mode == 0) k_knn2<0><<<(unsigned)blocks, KNN_THREADS, 0, st>>>(a);
-    else if (mode == 1) k_knn2<1><<<(unsigned)blocks, KNN_THREADS, 0, st>>>(a);
-    else k_knn2<3><<<(unsigned)blocks, KNN_THREADS, 0, st>>>(a);
+    k_knn2<1><<<(unsigned)blocks, KNN_THREADS, 0, st>>>(a);          // carry-save variant (5 POPC per distance)
     return cudaGetLastError();
 }

@@ -60,6 +60,7 @@ __device__ __forceinline__ void hrow(const RowWords& rw, const uint8_t* __restri
 __global__ void __launch_bounds__(32 * RS_BANDS) k_resize(const __grid_constant__ Geom g, const PyrPtrs p,
                                                           const ResizeTap* __restrict__ xtab,
                                                           const ResizeTap* __restrict__ ytab, int level) {
+    pdl_entry();
     const LevelGeom& D = g.lv[level];
     const LevelGeom& S = g.lv[level - 1];
     const int img = blockIdx.z;
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(32 * RT_BANDS) k_resize_tile(const __grid_cons
                                                                const ResizeTap* __restrict__ ytab, int level) {
     extern __shared__ __align__(16) uint8_t tile[];
     __shared__ YTap sY[RESIZE_TILE_H];
+    pdl_entry();
     resize_tile_body<false>(g, p, xtab, ytab, level, blockIdx.z, blockIdx.x, blockIdx.y, tile, sY);
 }
 
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(32 * RT_BANDS) k_resize_chain(const __grid_con
                                                                 const ResizeTap* __restrict__ ytab, int firstLevel) {
     extern __shared__ __align__(16) uint8_t tile[];
     __shared__ YTap sY[RESIZE_TILE_H];
+    pdl_entry();
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), img = blockIdx.y;
     for (int level = firstLevel; level < g.nlevels; level++) {
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(32 * RT_BANDS) k_resize_chain(const __grid_con
 // 128-byte row pitch so that every later stage can use aligned vector loads.
 __global__ void __launch_bounds__(256) k_repack(const uint8_t* __restrict__ src, size_t srcImgStride, size_t srcPitch,
                                                 uint8_t* __restrict__ dst, size_t dstImgStride, int dstPitch, int w, int h) {
+    pdl_entry();
     const int img = blockIdx.z;
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (y >= h) return;
@@ -296,8 +300,7 @@ __global__ void __launch_bounds__(256) k_repack(const uint8_t* __restrict__ src,
 cudaError_t launch_repack(const uint8_t* src, size_t srcImgStride, size_t srcPitch, uint8_t* dst, size_t dstImgStride,
                           int dstPitch, int w, int h, int nimg, cudaStream_t st) {
     dim3 grid((w + 4 * 32 * 4 - 1) / (4 * 32 * 4), (h + 7) / 8, nimg);
-    k_repack<<<grid, 256, 0, st>>>(src, srcImgStride, srcPitch, dst, dstImgStride, dstPitch, w, h);
-    return cudaGetLastError();
+    return launch_k(pdl_enabled(), k_repack, grid, dim3(256), 0, st, src, srcImgStride, srcPitch, dst, dstImgStride, dstPitch, w, h);
 }
 
 // First level of the cluster-chained tail: the smallest l >= 1 from which every level uses the tiled kernel and has at most
@@ -329,10 +332,12 @@ cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, cons
             for (int k = chain; k < g.nlevels; k++) smem = std::max(smem, (size_t)g.lv[k].rsPitch * g.lv[k].rsRows);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(RC_CTAS, nimg); cfg.blockDim = dim3(32, RT_BANDS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-            cudaLaunchAttribute attr;
-            attr.id = cudaLaunchAttributeClusterDimension;
-            attr.val.clusterDim.x = RC_CTAS; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-            cfg.attrs = &attr; cfg.numAttrs = 1;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = RC_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
             cudaError_t e = cudaLaunchKernelEx(&cfg, k_resize_chain, g, p, xtab, ytab, chain);
             if (e != cudaSuccess) return e;
             break;
@@ -340,12 +345,14 @@ cudaError_t launch_pyramid(const Geom& g, PyrPtrs p, const ResizeTap* xtab, cons
         if (g.lv[l].rsPitch > 0) {
             dim3 block(32, RT_BANDS);
             dim3 grid((g.lv[l].w + RESIZE_TILE_W - 1) / RESIZE_TILE_W, (g.lv[l].h + RESIZE_TILE_H - 1) / RESIZE_TILE_H, nimg);
-            k_resize_tile<<<grid, block, (size_t)g.lv[l].rsPitch * g.lv[l].rsRows, st>>>(g, p, xtab, ytab, l);
+            cudaError_t e = launch_k(pdl_enabled(), k_resize_tile, grid, block, (size_t)g.lv[l].rsPitch * g.lv[l].rsRows, st, g, p, xtab, ytab, l);
+            if (e != cudaSuccess) return e;
             continue;
         }
         dim3 block(32, RS_BANDS);
         dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + RS_ROWS * RS_BANDS - 1) / (RS_ROWS * RS_BANDS), nimg);
-        k_resize<<<grid, block, 0, st>>>(g, p, xtab, ytab, l);
+        cudaError_t e = launch_k(pdl_enabled(), k_resize, grid, block, 0, st, g, p, xtab, ytab, l);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }

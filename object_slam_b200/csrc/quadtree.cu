@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
     Smem S;
     smem_layout(nc, smraw, &S);
     __shared__ int sMisc[8];
+    pdl_entry();
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int level = g.nlevels - 1 - (int)blockIdx.x;      // any order is correct; this one just interleaves problem sizes
@@ -361,6 +362,7 @@ cudaError_t launch_quadtree(const Geom& g, int nodeCap, const uint32_t* cand, co
                             uint32_t* keyScratch, uint16_t* nodeScratch, uint32_t* sel, int* selCount,
                             int nimg, cudaStream_t st) {
     dim3 grid(g.nlevels, nimg);
-    k_quadtree<<<grid, QT_THREADS, quadtree_smem_bytes(nodeCap), st>>>(g, nodeCap, cand, cellCount, keyScratch, nodeScratch, sel, selCount);
+    cudaError_t le = launch_k(pdl_enabled(), k_quadtree, grid, dim3(QT_THREADS), quadtree_smem_bytes(nodeCap), st, g, nodeCap, cand, cellCount, keyScratch, nodeScratch, sel, selCount);
+    if (le != cudaSuccess) return le;
     return cudaGetLastError();
 }

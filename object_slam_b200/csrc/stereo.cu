@@ -32,6 +32,7 @@ __device__ __forceinline__ int hamming256(const uint32_t* a, const uint4 b0, con
 __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ StereoArgs A) {
     extern __shared__ int sRow[];                 // H + 1 counters, then cursors
     __shared__ int sWarp[9];
+    pdl_entry();
     const Geom& g = A.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.x;
     const int H = g.lv[0].h;
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
 }
 
 __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_constant__ StereoArgs A) {
+    pdl_entry();
     const Geom& g = A.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.y;
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
 // median of the accepted SADs (element [m/2] of the sorted list, :867) and the outlier cut
 __global__ void __launch_bounds__(256) k_stereo_filter(const __grid_constant__ StereoArgs A) {
     __shared__ int sCnt[2];
+    pdl_entry();
     const int tid = threadIdx.x, img = blockIdx.x;
     const int cap = A.g.kpCap;
     const int nL = min(*reinterpret_cast<const int*>(A.recL + (size_t)img * A.recordBytes), cap);
@@ -291,9 +294,12 @@ cudaError_t launch_stereo(const StereoArgs& a, int nimg, cudaStream_t st) {
         cudaError_t e = OBS_ALLOW_MAX_SMEM(k_stereo_rows);
         if (e != cudaSuccess) return e;
     }
-    k_stereo_rows<<<nimg, 256, smemRows, st>>>(a);
+    cudaError_t le = launch_k(pdl_enabled(), k_stereo_rows, dim3(nimg), dim3(256), smemRows, st, a);
+    if (le != cudaSuccess) return le;
     dim3 grid((a.g.kpCap + ST_WARPS - 1) / ST_WARPS, nimg);
-    k_stereo_match<<<grid, ST_WARPS * 32, 0, st>>>(a);
-    k_stereo_filter<<<nimg, 256, 0, st>>>(a);
+    le = launch_k(pdl_enabled(), k_stereo_match, grid, dim3(ST_WARPS * 32), 0, st, a);
+    if (le != cudaSuccess) return le;
+    le = launch_k(pdl_enabled(), k_stereo_filter, dim3(nimg), dim3(256), 0, st, a);
+    if (le != cudaSuccess) return le;
     return cudaGetLastError();
 }

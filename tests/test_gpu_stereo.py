@@ -130,3 +130,40 @@ def test_stereo_frames_one_call_matches_oracle(gpu, frames):
     with pytest.raises(ObsError):
         pipes[0].submit(40.0, 0.0, 525.0)
     pipes[0].wait()
+
+
+@pytest.mark.parametrize("frames", [1, 9])
+def test_stereo_frames_graph_replay_matches_oracle(gpu, frames):
+    """The steady state of obs_stereo_frames_submit is a CUDA graph replay (captured on the second call with the same buffers,
+    launched from the third on).  New images are written into the same page-locked buffers before every call; every round --
+    plain enqueue, capture, replays, and replays after toggling the "pdl" / "graphs" options -- equals the oracle."""
+    from object_slam_b200.extractor import StereoFrames
+    from object_slam_b200._capi import lib, check
+    shape = synth.TUM_SHAPE
+    H, W = shape
+    pipe = StereoFrames(1000, 1.2, 8, 20, 7, (W, H), frames)
+    options = [None, None, None, None, ("pdl", 0), None, ("graphs", 0), ("graphs", 1), ("pdl", 1), None]
+    try:
+        for rnd, opt in enumerate(options):
+            if opt:
+                check(lib().obs_set_option(opt[0].encode(), opt[1]))
+            pairs = [synth.stereo_pair(shape, 1000 + 37 * rnd + s) for s in range(frames)]
+            for i, (l, r) in enumerate(pairs):
+                pipe.left[i] = l
+                pipe.right[i] = r
+            res = pipe(40.0, 0.0, 525.0)
+            for i in sorted({0, frames - 1}):
+                our, odp, _ = _oracle_stereo(pairs[i][0], pairs[i][1], 1000, 40.0, 0.0, 525.0)
+                kL, dL = oracle.OracleExtractor(1000)(pairs[i][0])
+                gkL, gdL, gkR, gdR, ur, dp = res[i]
+                assert gkL.tobytes() == kL.tobytes() and np.array_equal(gdL, dL), f"round {rnd}"
+                assert np.array_equal(ur, our) and np.array_equal(dp, odp), f"round {rnd}"
+            # an extraction through another entry point between two replays must not disturb the next one
+            if rnd == 3:
+                pipe.eL(pairs[0][1])
+    finally:
+        check(lib().obs_set_option(b"pdl", 1))
+        check(lib().obs_set_option(b"graphs", 1))
+    from object_slam_b200._capi import ObsError
+    with pytest.raises(ObsError):
+        check(lib().obs_set_option(b"no_such_option", 1))
