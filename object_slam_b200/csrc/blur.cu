@@ -13,6 +13,9 @@
 
 namespace {
 
+#ifndef BL_OPT_STAGE
+#define BL_OPT_STAGE 1
+#endif
 constexpr int BL_ROWS = 32;                 // output rows per thread
 constexpr int BL_BANDS = 4;                 // row bands per CTA
 constexpr int BL_TW = 128, BL_TH = BL_ROWS * BL_BANDS;      // CTA tile: 128 x 128 pixels
@@ -52,6 +55,15 @@ __global__ void __launch_bounds__(32 * BL_BANDS) k_blur_tile(const __grid_consta
         const int v = tid % 10, r0 = tid / 10;                      // 12 rows per sweep, threads 120..127 idle
         const int gx = tx0 - 16 + 16 * v;
         if (r0 < 12 && gx >= 0 && gx + 16 <= pitch) {
+#if BL_OPT_STAGE
+            // every row of the thread's column of vectors is requested before the first one is waited for (cp.async, no registers):
+            // one DRAM round trip per CTA instead of one per sweep of 12 rows
+            uint32_t tp = smem_u32(tile + r0 * BT_PITCH + 16 * v);
+            for (int r = r0; r < nRows; r += 12, tp += 12 * BT_PITCH) {
+                const uint8_t* sp = src + (size_t)reflect101(ty0 - 3 + r, H) * pitch + gx;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(tp), "l"(sp) : "memory");
+            }
+#else
             uint8_t* tp = tile + r0 * BT_PITCH + 16 * v;
             if (ty0 >= 3 && ty0 - 3 + nRows <= H) {                // no row reflection in this tile
                 const uint8_t* sp = src + (size_t)(ty0 - 3 + r0) * pitch + gx;
@@ -62,7 +74,11 @@ __global__ void __launch_bounds__(32 * BL_BANDS) k_blur_tile(const __grid_consta
                 for (int r = r0; r < nRows; r += 12, tp += 12 * BT_PITCH)
                     *reinterpret_cast<uint4*>(tp) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(ty0 - 3 + r, H) * pitch + gx));
             }
+#endif
         }
+#if BL_OPT_STAGE
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
     }
     const bool border = tx0 == 0 || tx0 + BL_TW + 8 > W;          // CTA-uniform
     if (border) {

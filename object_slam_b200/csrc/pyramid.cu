@@ -136,6 +136,9 @@ __global__ void __launch_bounds__(32 * RS_BANDS) k_resize(const __grid_constant_
 // 128-bit loads; a thread owns four output columns of a 16-row band.  No clamping is left in the loop: rows
 // are rebased in a shared copy of the y taps, columns by the staged pitch.
 // (b * h) >> 16 == umulhi(b << 16, h); the result cannot exceed 255 because a pair of weights sums to at most 2049.
+#ifndef RS_OPT_STAGE
+#define RS_OPT_STAGE 1
+#endif
 constexpr int RT_ROWS = 16;          // output rows per thread
 constexpr int RT_BANDS = RESIZE_TILE_H / RT_ROWS;
 
@@ -174,6 +177,17 @@ __device__ __forceinline__ void resize_tile_body(const Geom& g, const PyrPtrs& p
         // rows of the source are padded to a multiple of 16 bytes (slab pitch 128; level 0: 16-byte aligned stride)
         const int nVec = min((xs1 - xs0) / 16 + 1, (spitch - xs0) >> 4), nRows = ys1 - ys0 + 1;
         constexpr int RSTEP = 32 * RT_BANDS / 16;
+#if RS_OPT_STAGE
+        // every row of the thread's column of vectors is requested before anything is waited for (cp.async through L2, which is
+        // also what the chained levels need): one DRAM / L2 round trip per tile instead of one per four sweeps
+        for (int v = tid & 15; v < nVec; v += 16) {
+            const uint8_t* gp = src + (size_t)(ys0 + (tid >> 4)) * spitch + xs0 + 16 * v;
+            uint32_t tp = smem_u32(tile + (tid >> 4) * pitch + 16 * v);
+            for (int r = tid >> 4; r < nRows; r += RSTEP, gp += (size_t)spitch * RSTEP, tp += RSTEP * pitch)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(tp), "l"(gp) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#else
         for (int v = tid & 15; v < nVec; v += 16) {
             const uint4* gp = reinterpret_cast<const uint4*>(src + (size_t)(ys0 + (tid >> 4)) * spitch + xs0) + v;
             uint8_t* tp = tile + (tid >> 4) * pitch + 16 * v;
@@ -188,6 +202,7 @@ __device__ __forceinline__ void resize_tile_body(const Geom& g, const PyrPtrs& p
             }
             for (; r < nRows; r += RSTEP, gp += gstep, tp += RSTEP * pitch) *reinterpret_cast<uint4*>(tp) = ld(gp);
         }
+#endif
         if (tid < th) {
             const ResizeTap t = yt[ty0 + tid];
             YTap y;
@@ -196,6 +211,9 @@ __device__ __forceinline__ void resize_tile_body(const Geom& g, const PyrPtrs& p
             y.b0 = (unsigned)t.a0 << 16; y.b1 = (unsigned)t.a1 << 16;
             sY[tid] = y;
         }
+#if RS_OPT_STAGE
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
     }
     __syncthreads();
     const int dx0 = tx0 + 4 * threadIdx.x, r0 = threadIdx.y * RT_ROWS;
