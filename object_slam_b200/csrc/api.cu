@@ -129,8 +129,7 @@ struct obs_extractor {
     DevBuf<int> cellCount, selCount;
     DevBuf<float> uRight, depth;
     DevBuf<int> sad, rowStart;
-    DevBuf<uint16_t> rowIdx;
-    DevBuf<float2> rightXO;
+    DevBuf<uint2> rowIdx;
     PinBuf<uint8_t> stageIn, stageOut;
     size_t recordBytes = 0;
     PyrPtrs ptrs{};
@@ -581,7 +580,7 @@ int obs_extractor_destroy(obs_extractor* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->pyr.release(); e->blur.release(); e->dMaps.release(); e->records.release(); e->rawIn.release(); e->cand.release(); e->keyScratch.release();
     e->sel.release(); e->nodeScratch.release(); e->cellCount.release(); e->selCount.release();
-    e->uRight.release(); e->depth.release(); e->sad.release(); e->rowStart.release(); e->rowIdx.release(); e->rightXO.release(); e->dXtab.release(); e->dYtab.release(); e->dFastCtas.release();
+    e->uRight.release(); e->depth.release(); e->sad.release(); e->rowStart.release(); e->rowIdx.release(); e->dXtab.release(); e->dYtab.release(); e->dFastCtas.release();
     e->stageIn.release(); e->stageOut.release();
     for (cudaEvent_t ev : e->pev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->sev) cudaEventDestroy(ev);
@@ -906,7 +905,6 @@ int obs_stereo_match_device(obs_extractor* L, obs_extractor* R, float mbf, float
     const int rowIdxCap = L->g.kpCap * bandMax;
     CU(L->rowStart.ensure((size_t)n * (L->g.h + 1)));
     CU(L->rowIdx.ensure((size_t)n * rowIdxCap));
-    CU(L->rightXO.ensure(cnt));
     // order after both extractions
     if (R->lastStream != st) { CU(cudaEventRecord(R->done, R->lastStream)); CU(cudaStreamWaitEvent(st, R->done, 0)); }
     if (L->lastStream != st) { CU(cudaEventRecord(L->done, L->lastStream)); CU(cudaStreamWaitEvent(st, L->done, 0)); }
@@ -916,7 +914,7 @@ int obs_stereo_match_device(obs_extractor* L, obs_extractor* R, float mbf, float
     a.recL = L->records.p; a.recR = R->records.p; a.recordBytes = L->recordBytes;
     a.mbf = mbf; a.minD = min_d; a.maxD = max_d;
     a.uRight = L->uRight.p; a.depth = L->depth.p; a.sad = L->sad.p;
-    a.rowStart = L->rowStart.p; a.rowIdx = L->rowIdx.p; a.rowIdxCap = rowIdxCap; a.rightXO = L->rightXO.p;
+    a.rowStart = L->rowStart.p; a.rowIdx = L->rowIdx.p; a.rowIdxCap = rowIdxCap;
     cudaEvent_t* sev = nullptr;
     if (L->prof && L->stereoCalls < PROF_SLOTS) sev = L->sev.data() + (size_t)L->stereoCalls * 2;
     if (sev) CU(cudaEventRecord(sev[0], st));

@@ -434,7 +434,13 @@ __global__ void __launch_bounds__(FT_THREADS, FT_MINCTAS) k_fast_cells(const __g
 
 }  // namespace
 
-size_t fast_smem_bytes(int tileRows) { return (size_t)2 * tileRows * FT_SP + (size_t)FT_LIST * 2; }
+#ifndef FT_SMEM_MIN
+#define FT_SMEM_MIN 0
+#endif
+size_t fast_smem_bytes(int tileRows) {
+    const size_t need = (size_t)2 * tileRows * FT_SP + (size_t)FT_LIST * 2;
+    return need < (size_t)FT_SMEM_MIN ? (size_t)FT_SMEM_MIN : need;       // (A/B knob: a larger footprint caps the CTAs per SM)
+}
 
 cudaError_t fast_prepare(int tileRows) {
     cudaError_t e = OBS_ALLOW_MAX_SMEM(k_fast_cells);

@@ -54,9 +54,8 @@ struct StereoArgs {
     float* uRight; float* depth;     // nimg x kpCap
     int* sad;                        // nimg x kpCap scratch (best SAD of accepted matches, -1 otherwise)
     int* rowStart;                   // nimg x (h + 1): CSR row table of the right keypoints
-    uint16_t* rowIdx;                // nimg x rowIdxCap
+    uint2* rowIdx;                   // nimg x rowIdxCap entries of the row table: (x as float bits, octave << 16 | right keypoint index)
     int rowIdxCap;
-    float2* rightXO;                 // nimg x kpCap: (x, octave bits) of the right keypoints
 };
 cudaError_t launch_stereo(const StereoArgs& a, int nimg, cudaStream_t st);
 

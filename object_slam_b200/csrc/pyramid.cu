@@ -211,27 +211,29 @@ __device__ __forceinline__ void resize_tile_body(const Geom& g, const PyrPtrs& p
             y.b0 = (unsigned)t.a0 << 16; y.b1 = (unsigned)t.a1 << 16;
             sY[tid] = y;
         }
-#if RS_OPT_STAGE
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
     }
-    __syncthreads();
+    // the thread's four column taps are fetched while the tile is in flight
     const int dx0 = tx0 + 4 * threadIdx.x, r0 = threadIdx.y * RT_ROWS;
-    if (dx0 < D.w && r0 < th) {
-        const int nOut = min(RT_ROWS, th - r0);
-        unsigned w[4], sel[4];
-        int ofs0;
-        {
-            const ResizeTap t0 = xt[dx0];
-            ofs0 = t0.ofs;
+    const bool active = dx0 < D.w && r0 < th;
+    unsigned w[4] = {0, 0, 0, 0}, sel[4] = {0, 0, 0, 0};
+    int ofs0 = 0;
+    if (active) {
+        const ResizeTap t0 = xt[dx0];
+        ofs0 = t0.ofs;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const ResizeTap tx = i ? xt[min(dx0 + i, D.w - 1)] : t0;
-                const int o = tx.ofs - ofs0;                    // 0..6 (host-checked)
-                w[i] = (unsigned)(unsigned short)tx.a0 | ((unsigned)(unsigned short)tx.a1 << 16);
-                sel[i] = (unsigned)o | ((unsigned)(o + 1) << 4);
-            }
+        for (int i = 0; i < 4; i++) {
+            const ResizeTap tx = i ? xt[min(dx0 + i, D.w - 1)] : t0;
+            const int o = tx.ofs - ofs0;                    // 0..6 (host-checked)
+            w[i] = (unsigned)(unsigned short)tx.a0 | ((unsigned)(unsigned short)tx.a1 << 16);
+            sel[i] = (unsigned)o | ((unsigned)(o + 1) << 4);
         }
+    }
+#if RS_OPT_STAGE
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+    __syncthreads();
+    if (active) {
+        const int nOut = min(RT_ROWS, th - r0);
         const int rel = ofs0 - xs0;
         const uint8_t* col = tile + (rel & ~3);
         const int shift = 8 * (rel & 3);

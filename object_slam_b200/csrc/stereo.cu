@@ -40,8 +40,7 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
     const int nR = min(*reinterpret_cast<const int*>(recR), g.kpCap);
     const float* kpR = reinterpret_cast<const float*>(recR + OBS_HDR_INTS * 4);
     int* rowStart = A.rowStart + (size_t)img * (g.h + 1);
-    uint16_t* rowIdx = A.rowIdx + (size_t)img * A.rowIdxCap;
-    float2* rk = A.rightXO + (size_t)img * g.kpCap;
+    uint2* rowIdx = A.rowIdx + (size_t)img * A.rowIdxCap;
 
     for (int i = tid; i <= H; i += 256) sRow[i] = 0;
     __syncthreads();
@@ -52,7 +51,6 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
         const int maxr = min((int)ceilf(__fadd_rn(y, r)), H - 1);
         const int minr = max((int)floorf(__fsub_rn(y, r)), 0);
         for (int yi = minr; yi <= maxr; yi++) atomicAdd(&sRow[yi], 1);
-        rk[i] = make_float2(kpR[i * 7], __int_as_float(oct));
     }
     __syncthreads();
     // exclusive scan of the H row counts (chunks of 256)
@@ -90,9 +88,11 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
         const float r = __fmul_rn(2.0f, g.lv[oct].scale);
         const int maxr = min((int)ceilf(__fadd_rn(y, r)), H - 1);
         const int minr = max((int)floorf(__fsub_rn(y, r)), 0);
+        // the entry carries what the match kernel filters on (x, octave), so that a candidate costs one dependent load, not two
+        const uint2 ent = make_uint2(__float_as_uint(kpR[i * 7]), ((unsigned)oct << 16) | (unsigned)i);
         for (int yi = minr; yi <= maxr; yi++) {
             const int pos = atomicAdd(&sRow[yi], 1);
-            if (pos < A.rowIdxCap) rowIdx[pos] = (uint16_t)i;
+            if (pos < A.rowIdxCap) rowIdx[pos] = ent;
         }
     }
 }
@@ -111,8 +111,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
     const uint8_t* descL = recL + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28;
     const uint8_t* descR = recR + OBS_HDR_INTS * 4 + (size_t)g.kpCap * 28;
     const int* rowStart = A.rowStart + (size_t)img * (g.h + 1);
-    const uint16_t* rowIdx = A.rowIdx + (size_t)img * A.rowIdxCap;
-    const float2* rk = A.rightXO + (size_t)img * g.kpCap;
+    const uint2* rowIdx = A.rowIdx + (size_t)img * A.rowIdxCap;
 
     float outU = -1.0f, outD = -1.0f;
     int outSad = -1;
@@ -122,6 +121,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
         const int row = (int)vL;                                  // vRowIndices[vL], :758
         const float minU = __fsub_rn(uL, A.maxD), maxU = __fsub_rn(uL, A.minD);
         uint32_t best = ((uint32_t)TH_HIGH << 16);                // dist << 16 | iR ; only dist < TH_HIGH can win
+        float bestX = 0.f;
         if (!(maxU < 0) && row >= 0 && row < g.lv[0].h) {
             uint32_t dl[8];
             {
@@ -131,22 +131,24 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_con
             }
             const int c0 = rowStart[row], c1 = min(rowStart[row + 1], A.rowIdxCap);
             for (int ci = c0 + lane; ci < c1; ci += 32) {
-                const int iR = rowIdx[ci];
-                const float2 k = rk[iR];
-                const int octR = __float_as_int(k.y);
+                const uint2 ent = __ldg(rowIdx + ci);
+                const float xR = __uint_as_float(ent.x);
+                const int octR = (int)(ent.y >> 16), iR = (int)(ent.y & 0xffffu);
                 if (octR < levelL - 1 || octR > levelL + 1) continue;
-                if (!(k.x >= minU && k.x <= maxU)) continue;
+                if (!(xR >= minU && xR <= maxU)) continue;
                 const uint4 b0 = *reinterpret_cast<const uint4*>(descR + (size_t)iR * 32);
                 const uint4 b1 = *reinterpret_cast<const uint4*>(descR + (size_t)iR * 32 + 16);
-                best = min(best, ((uint32_t)hamming256(dl, b0, b1) << 16) | (uint32_t)iR);
+                const uint32_t key = ((uint32_t)hamming256(dl, b0, b1) << 16) | (uint32_t)iR;
+                if (key < best) { best = key; bestX = xR; }
             }
         }
+        const uint32_t mine = best;
         best = __reduce_min_sync(0xffffffffu, best);
         const int bestDist = (int)(best >> 16);
-        const int bestIdxR = (int)(best & 0xffffu);
         if (bestDist < (TH_HIGH + TH_LOW) / 2) {
             // ---- sub-pixel refinement by correlation on level `levelL` (:794-862)
-            const float uR0 = rk[bestIdxR].x;
+            // (keys are unique -- they hold the keypoint index -- so exactly one lane owns the minimum and its x)
+            const float uR0 = __shfl_sync(0xffffffffu, bestX, __ffs(__ballot_sync(0xffffffffu, mine == best)) - 1);
             const float sf = g.lv[levelL].invScale;
             const float scaleduL = roundf(__fmul_rn(uL, sf));
             const float scaledvL = roundf(__fmul_rn(vL, sf));
