@@ -270,6 +270,8 @@ def load_pipe_counters():
 
 def measure_stereo(ctx, args):
     torch = ctx.torch
+    import ctypes as C
+    from object_slam_b200._capi import check, lib
     from object_slam_b200.extractor import ORBextractor, StereoFrames, stereo_match_device
     rank, local_rank, world = ctx.rank, ctx.local_rank, ctx.world
     F = args.frames
@@ -441,12 +443,14 @@ def measure_stereo(ctx, args):
     traffic = tj.get(dominant)
     if traffic is not None:
         traffic = traffic * F / per_img
-    sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
-    issue_peak = 148 * 4 * sm_hz
-    # per stage: achieved HBM fraction and achieved fraction of the binding pipe.  The pipe fractions come from instruction /
-    # wavefront counts of the committed ncu capture (profiles/traffic.json `_pipes`, per 64 images) over the LIVE launch time;
-    # peaks: issue = 1 warp instruction / clk / scheduler; ALU pipe = 1 per 2 clk per scheduler (B300_MICROARCH "fma vs alu split");
-    # LSU shared-memory wavefronts = 1 / clk / SM.
+    # Per stage: achieved HBM fraction and achieved fraction of the pipes the stage is bound by.  Numerators: warp-instruction /
+    # ALU-instruction / shared-memory-wavefront counts of the committed ncu capture (profiles/traffic.json `_pipes`, written by
+    # tools/ncu_pipes.py, per 64 images) over the LIVE launch time.  Denominators: measured here on this device by
+    # obs_microbench_pipes (issue rate with both integer pipes fed, ALU-pipe rate, conflict-free LDS wavefront rate).
+    gi, ga, gl = C.c_double(), C.c_double(), C.c_double()
+    check(lib().obs_microbench_pipes(local_rank, C.byref(gi), C.byref(ga), C.byref(gl)))
+    pipe_peaks = {"issue_ginst_per_s": gi.value, "alu_ginst_per_s": ga.value, "lds_gwavefronts_per_s": gl.value,
+                  "source": "obs_microbench_pipes on this device (csrc/microbench.cu), best of 3"}
     stage_fracs = {}
     for k, ms in per_launch_ms.items():
         ent = {"ms_per_launch": ms}
@@ -455,22 +459,25 @@ def measure_stereo(ctx, args):
             ent["hbm_frac"] = ent["hbm_gbs"] / peak
         pp = tj.get("_pipes", {}).get(k)
         if pp:
-            sc = F / 64.0
-            if pp.get("warp_instructions"):
-                ent["issue_frac"] = pp["warp_instructions"] * sc / (ms * 1e-3) / issue_peak
+            sc = F / per_img
+            t = ms * 1e-3
+            ent["issue_frac"] = pp["warp_instructions"] * sc / t / (gi.value * 1e9)
             if pp.get("alu_instructions"):
-                ent["alu_pipe_frac"] = pp["alu_instructions"] * sc / (ms * 1e-3) / (issue_peak / 2)
+                ent["alu_pipe_frac"] = pp["alu_instructions"] * sc / t / (ga.value * 1e9)
             if pp.get("lsu_wavefronts"):
-                ent["lsu_wavefront_frac"] = pp["lsu_wavefronts"] * sc / (ms * 1e-3) / (148 * sm_hz)
-            ent["binding_pipe"] = pp.get("binding")
+                ent["lds_wavefront_frac"] = pp["lsu_wavefronts"] * sc / t / (gl.value * 1e9)
+            fr = {"issue": ent["issue_frac"], "alu": ent.get("alu_pipe_frac", 0.0), "lds_wavefronts": ent.get("lds_wavefront_frac", 0.0),
+                  "hbm": ent.get("hbm_frac", 0.0)}
+            ent["binding_pipe"] = max(fr, key=fr.get)
+            ent["binding_frac"] = fr[ent["binding_pipe"]]
         stage_fracs[k] = ent
     achieved = alg[dominant] / (per_launch_ms[dominant] * 1e-3) / 1e9 if alg[dominant] is not None else 0.0
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "stages": stage_fracs,
-                "bound_note": "every stage is integer-issue / LSU bound before it is HBM bound (DESIGN.md section 4): `stages` holds, per "
-                              "kernel, the HBM fraction and the fraction of the binding pipe's peak (instruction counts of the committed ncu "
-                              "capture over the live launch time)",
+                "stages": stage_fracs, "pipe_peaks": pipe_peaks,
+                "bound_note": "every stage is bound inside the SM (instruction issue / ALU pipe / shared-memory wavefronts) before it is HBM "
+                              "bound (DESIGN.md section 4): `stages` holds, per stage, the HBM fraction and the fractions of the measured "
+                              "pipe peaks (`pipe_peaks`); counts from the committed ncu capture (profiles/traffic.json) over the live launch time",
                 "per_launch_ms": per_launch_ms, "share_of_step": shares,
                 "serialised_step_ms": serial_ms,
                 "note": "per_launch_ms: CUDA-event brackets of a profiling pass run directly after the timed region with every kernel "

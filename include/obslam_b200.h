@@ -504,6 +504,10 @@ int obs_microbench_popc(int device, int mode, double* gdist_per_s);
 /* Roofline denominator of the tensor-core knn2 path: int8 tcgen05.mma throughput (TOP/s) in the kernel's own MMA shape
  * (kind::i8, M 128, N 256, K 32, both operands in shared memory), issued back to back on every SM with no loads or epilogue. */
 int obs_microbench_imma(int device, double* tops);
+/* Roofline denominators of the extractor / stereo stages, which are bound inside the SM, in 1e9/s for the
+ * whole device: warp instructions issued per second with the ALU and FMA pipes fed 1:1, warp instructions per second of the ALU
+ * pipe alone (LOP3 chains), conflict-free shared-memory load wavefronts per second. */
+int obs_microbench_pipes(int device, double* issue_ginst_per_s, double* alu_ginst_per_s, double* lds_gwavefronts_per_s);
 
 #ifdef __cplusplus
 }

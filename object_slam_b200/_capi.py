@@ -135,6 +135,7 @@ _PROTOS = {
     "obs_comm_allgather": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int, _vp]),
     "obs_comm_wait": (C.c_int, [_vp, C.c_int, _vp]),
     "obs_microbench_imma": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "obs_microbench_pipes": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "obs_microbench_popc": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "obs_search_by_bow": (C.c_int, [_vp, C.POINTER(BowSide), C.POINTER(BowSide), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp]),
     "obs_search_for_triangulation": (C.c_int, [_vp, C.POINTER(BowSide), C.POINTER(BowSide), C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
