@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
     }
 }
 
-__global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(const __grid_constant__ StereoArgs A) {
+#ifndef ST_MINCTAS
+#define ST_MINCTAS 16       // 32 registers (a few spilled words): the kernel waits on dependent gathers, so resident warps are what counts
+#endif
+__global__ void __launch_bounds__(ST_WARPS * 32, ST_MINCTAS) k_stereo_match(const __grid_constant__ StereoArgs A) {
     pdl_entry();
     const Geom& g = A.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -22,6 +22,8 @@ KEYS = [
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
 ]
 
 def launches(path):
@@ -50,8 +52,13 @@ def full(path):
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
-    print(f"# {path}: ncu --set full, one block per captured launch")
+    print(f"# {path}: ncu --set full, one block per distinct kernel and grid (first captured launch of each)")
+    seen = set()
     for r in rows[2:]:
+        key = (r[idx["Kernel Name"]], r[idx["launch__grid_size"]] if "launch__grid_size" in idx else "")
+        if key in seen:
+            continue
+        seen.add(key)
         print("----", r[idx["Kernel Name"]].split("(")[0], "grid", r[idx.get("launch__grid_size", 0)] if "launch__grid_size" in idx else "")
         for k in KEYS:
             if k in idx:
