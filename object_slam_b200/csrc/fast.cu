@@ -226,6 +226,7 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
             const int m = fast_contrast_s(a);
             const bool ok = i < end && (unsigned)m > thr;
             const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            __syncwarp();                                 // every lane has read its queue entry before the corners are compacted over them
             if (ok) {
                 asm volatile("st.shared.u8 [%0], %1;" :: "r"(a + scoreOfs), "r"(m - 256) : "memory");   // OpenCV: score = corner contrast - 1
                 asm volatile("st.shared.u16 [%0], %1;" :: "r"(Q_s + 2u * (unsigned)(nC + __popc(bal & ltm))), "r"(pos) : "memory");
