@@ -754,7 +754,12 @@ def measure_knn2(args, ctx, ClockSampler):
         except Exception:
             bf16 = 1590.0
         ach = 512.0 * (dist_per_step / world) / (kernel_ms * 1e-3) / 1e12     # 256 multiply-adds = 512 operations per distance
-        roof = {"bound": "tensor", "kernel": "k_knn2_tc", "achieved": ach, "peak": peak_tops, "unit": "TOP/s (int8)", "frac": ach / peak_tops,
+        clk = (clocks or {})
+        clk_ratio = (clk.get("sm_mhz") or 0) / (clk.get("sm_max_mhz") or 1) if clk.get("sm_mhz") else None
+        roof = {"bound": "tensor", "kernel": "k_knn2_tc_pair (tcgen05.mma.cta_group::2)", "achieved": ach, "peak": peak_tops, "unit": "TOP/s (int8)",
+                "frac": ach / peak_tops,
+                # the run is power-capped (clocks.reasons: sw_power_cap): the same peak scaled to the SM clock the timed region ran at
+                "frac_at_sustained_clock": (ach / (peak_tops * clk_ratio)) if clk_ratio else None, "sustained_clock_ratio": clk_ratio,
                 "traffic": None,
                 "peak_source": "obs_microbench_imma measured in this run: tcgen05.mma kind::i8 M128 N256 K32 from shared memory issued back to "
                                "back on all SMs (MEASURED_PEAKS.json holds no int8 figure)",

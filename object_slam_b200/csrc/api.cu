@@ -5,6 +5,7 @@
 #include "kernels.h"
 #include "host_util.h"
 #include "matcher_api.h"
+#include "knn2_tc.h"
 
 #include <nvtx3/nvToolsExt.h>          // header-only NVTX v3: the ranges cost nothing unless a tool is attached
 
@@ -1209,7 +1210,8 @@ int obs_set_option(const char* name, int value) {
     if (!name) return fail(OBS_ERR_INVALID, "null option name");
     if (!strcmp(name, "pdl")) { obsdetail::set_pdl_enabled(value != 0); return OBS_OK; }
     if (!strcmp(name, "graphs")) { obsdetail::set_graphs_enabled(value != 0); return OBS_OK; }
-    return fail(OBS_ERR_INVALID, "unknown option '%s' (known: pdl, graphs)", name);
+    if (!strcmp(name, "knn2_cta_pair")) { knn2_tc_set_cta_pair(value != 0); return OBS_OK; }
+    return fail(OBS_ERR_INVALID, "unknown option '%s' (known: pdl, graphs, knn2_cta_pair)", name);
 }
 
 int obs_host_alloc(size_t bytes, void** out) {

@@ -24,8 +24,11 @@
 
 #include <cuda.h>
 #include <algorithm>
+#include <atomic>
 
 namespace {
+
+std::atomic<int> g_knn2Pair{1};       // obs_set_option("knn2_cta_pair"): k_knn2_tc_pair (default) or k_knn2_tc
 
 constexpr int TC_M = 128;                 // query rows of a work item (= TMEM lanes)
 constexpr int TC_N = 256;                 // database rows of one accumulator
@@ -50,11 +53,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
+// (suspend-time hint: a waiting thread sleeps in the barrier unit until the phase completes instead of re-issuing try_wait every few
+// cycles -- the producer and MMA lanes wait most of the time and would otherwise take ~15 % of the issue slots of the epilogue warps
+// they share a scheduler with)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(200000u) : "memory");
     } while (!done);
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
@@ -315,6 +321,290 @@ k_knn2_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(512u) : "memory");
 }
 
+// ---- CTA-pair variant (cta_group::2) -------------------------------------------------------------------------------------
+// k_knn2_tc pulls every 64 KB database tile through L2 for ONE 128-row query tile: ~53 B per cycle per SM, more than L2 delivers
+// to an SM (~42 B/clk), so the tensor pipe waits.  Here a cluster of two CTAs (the two SMs of a TPC) works on TWO query tiles
+// against the same database tile: one tcgen05.mma.cta_group::2 (M 256, N 256, K 32) per K step, issued by the leader CTA, reads
+// each CTA's own 128 query rows and each CTA's HALF of the database tile (128 rows, 32 KB) from both shared memories and leaves
+// every CTA its own 128 x 256 accumulator in its own TMEM.  Per SM the L2 traffic halves; the smaller stage buys a 4-deep ring.
+//   * work items = (pair, pair of query tiles) from the global counter, fetched by the leader's producer and published to both
+//     CTAs' queues (st.shared::cluster + cluster-scope release / acquire on the queue barriers);
+//   * both producers issue their own TMA loads with .cta_group::2 onto the LEADER's full barriers (expect_tx there counts both);
+//   * tcgen05.commit ... multicast::cluster frees the stages in / signals the accumulators of both CTAs;
+//   * both CTAs' epilogue warps hand accumulators and queue slots back by (remote) arrives on the leader's barriers.
+constexpr int B2_ATOM_BYTES = 128 * ATOM_B;        // 128 database rows x 128 bytes
+constexpr int B2_BYTES = 2 * B2_ATOM_BYTES;        // 32 KB: this CTA's half of a database tile
+constexpr int B2_STAGES = 4;
+constexpr size_t TC2_SMEM = 2 * A_BYTES + B2_STAGES * B2_BYTES + 1024;
+constexpr int EPI2_PARTS = 4;                     // epilogue warps per TMEM lane quarter: each takes 256 / 4 accumulator columns
+constexpr int EPI2_COLS = TC_N / EPI2_PARTS;
+constexpr int EPI2_THREADS = 128 * EPI2_PARTS, TC2_THREADS = 64 + EPI2_THREADS;
+constexpr uint32_t IDESC_I8_PAIR = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on a barrier given by its shared::cluster address (own or peer CTA).  _release: cluster-scope release, for the one barrier
+// that publishes data written with ordinary stores (the work queue); the others only hand back resources whose reads are complete
+// (TMEM accumulators behind tcgen05.fence, queue slots already read), and a cluster-scope fence per arrive would sit on the
+// accumulator hand-off path.
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cbar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cbar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cbar) : "memory");
+}
+// wait with acquire at cluster scope (the data behind the barrier may have been written by the peer CTA); bounded: a protocol error
+// must not hang the device
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    const long long t0 = clock64();
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(200000u) : "memory");
+        if (!done && clock64() - t0 > 20000000000ll) __trap();
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t leaderBar) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(leaderBar) : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p; }"
+                 :: "r"(tmemD), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {       // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+k_knn2_tc_pair(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ Knn2TcArgs A) {
+    extern __shared__ uint8_t smemRaw[];
+    // aFull[2] aEmpty[2] bFull[4] bEmpty[4] accFull[2] accEmpty[2] qFull[2] qEmpty[2]
+    __shared__ __align__(8) uint64_t bars[20];
+    __shared__ __align__(8) long long workQ[2];
+    __shared__ uint32_t tmemBaseS;
+    __shared__ uint2 sMerge[2][EPI2_PARTS - 1][TC_M];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the epilogue warps come first: the scheduler favours the higher warp id, and the two single-lane warps that feed the tensor
+    // pipe (TMA producer, MMA issuer) must not wait behind the epilogue warps they share a scheduler with
+    constexpr int W_PRODUCER = EPI2_THREADS / 32, W_MMA = W_PRODUCER + 1;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const uint32_t base = (smem_u32(smemRaw) + 1023u) & ~1023u;
+    const uint32_t sA0 = base, sB0 = base + 2 * A_BYTES;
+    const uint32_t bar0 = smem_u32(bars);
+    auto aFull = [&](int s) { return bar0 + 8u * (0 + s); };
+    auto aEmpty = [&](int s) { return bar0 + 8u * (2 + s); };
+    auto bFull = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto bEmpty = [&](int s) { return bar0 + 8u * (8 + s); };
+    auto accFull = [&](int s) { return bar0 + 8u * (12 + s); };
+    auto accEmpty = [&](int s) { return bar0 + 8u * (14 + s); };
+    auto qFull = [&](int s) { return bar0 + 8u * (16 + s); };
+    auto qEmpty = [&](int s) { return bar0 + 8u * (18 + s); };
+    constexpr uint32_t EPI_WARPS = EPI2_THREADS / 32;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; s++) {
+            mbar_init(aFull(s), 1); mbar_init(aEmpty(s), 1);
+            mbar_init(accFull(s), 1); mbar_init(accEmpty(s), 2 * EPI_WARPS);           // the epilogue warps of both CTAs
+            mbar_init(qFull(s), 1); mbar_init(qEmpty(s), 2 * EPI_WARPS + 2);           // ... + the leader's MMA lane + the peer's producer
+        }
+        for (int s = 0; s < B2_STAGES; s++) { mbar_init(bFull(s), 1); mbar_init(bEmpty(s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmemBaseS)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmemBase = tmemBaseS;
+    const int mPairs = (A.mTiles + 1) >> 1;
+    const long long total = (long long)A.nPairs * mPairs;
+
+    if (warp == W_PRODUCER) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&mapT) : "memory");
+            uint32_t bi = 0, ai = 0;
+            for (;; ai++) {
+                const uint32_t sa = ai & 1u, pa = (ai >> 1) & 1u;
+                long long w;
+                if (leader) {
+                    mbar_wait(qEmpty(sa), pa ^ 1u);                         // both CTAs have read the slot's previous item
+                    w = (long long)atomicAdd(A.workCounter, 1ull);
+                    if (w >= total) w = -1;
+                    workQ[sa] = w;
+                    asm volatile("st.shared::cluster.b64 [%0], %1;" :: "r"(map_to_cta(smem_u32(&workQ[sa]), 1)), "l"(w) : "memory");
+                    mbar_arrive_cluster_release(map_to_cta(qFull(sa), 0));
+                    mbar_arrive_cluster_release(map_to_cta(qFull(sa), 1));
+                } else {
+                    mbar_wait_cluster(qFull(sa), pa);
+                    w = *reinterpret_cast<volatile long long*>(&workQ[sa]);
+                    mbar_arrive_cluster(map_to_cta(qEmpty(sa), 0));
+                }
+                if (w < 0) break;
+                const int pair = (int)(w / mPairs), mt = 2 * (int)(w - (long long)pair * mPairs) + (int)rank;
+                const int2 pr = A.pairs[pair];
+                const uint32_t aBar = map_to_cta(aFull(sa), 0);
+                mbar_wait(aEmpty(sa), pa ^ 1u);
+                if (leader) mbar_expect_tx(aFull(sa), 2 * A_BYTES);        // this CTA's query tile and the peer's
+                tma_load_3d_pair(sA0 + sa * A_BYTES, &mapT, 0, mt * TC_M, pr.x, aBar);
+                tma_load_3d_pair(sA0 + sa * A_BYTES + A_ATOM_BYTES, &mapT, ATOM_B, mt * TC_M, pr.x, aBar);
+                for (int nt = 0; nt < A.nTiles; nt++, bi++) {
+                    const uint32_t sb = bi % B2_STAGES, pb = (bi / B2_STAGES) & 1u;
+                    const uint32_t bBar = map_to_cta(bFull(sb), 0);
+                    mbar_wait(bEmpty(sb), pb ^ 1u);
+                    if (leader) mbar_expect_tx(bFull(sb), 2 * B2_BYTES);   // both halves of the database tile
+                    const int y = nt * TC_N + (int)rank * 128;
+                    tma_load_3d_pair(sB0 + sb * B2_BYTES, &mapT, 0, y, pr.y, bBar);
+                    tma_load_3d_pair(sB0 + sb * B2_BYTES + B2_ATOM_BYTES, &mapT, ATOM_B, y, pr.y, bBar);
+                }
+            }
+            // every multicast commit aimed at this CTA's stage barriers has landed before the CTA may leave
+            for (uint32_t s = 0; s < (uint32_t)B2_STAGES; s++) {
+                const uint32_t uses = bi > s ? (bi - s + B2_STAGES - 1) / B2_STAGES : 0;
+                if (uses) mbar_wait(bEmpty(s), (uses - 1) & 1u);
+            }
+            for (uint32_t s = 0; s < 2; s++) {
+                const uint32_t uses = ai > s ? (ai - s + 1) / 2 : 0;      // items that used stage s (the terminating slot loaded nothing)
+                if (uses) mbar_wait(aEmpty(s), (uses - 1) & 1u);
+            }
+        }
+    } else if (warp == W_MMA) {
+        if (lane == 0 && leader) {
+            uint32_t bi = 0;
+            for (uint32_t ai = 0;; ai++) {
+                const uint32_t sa = ai & 1u, pa = (ai >> 1) & 1u;
+                mbar_wait_cluster(qFull(sa), pa);
+                const long long w = *reinterpret_cast<volatile long long*>(&workQ[sa]);
+                mbar_arrive_cluster(map_to_cta(qEmpty(sa), 0));
+                if (w < 0) break;
+                mbar_wait(aFull(sa), pa);
+                for (int nt = 0; nt < A.nTiles; nt++, bi++) {
+                    const uint32_t sb = bi % B2_STAGES, pb = (bi / B2_STAGES) & 1u;
+                    const uint32_t acc = bi & 1u, pacc = (bi >> 1) & 1u;
+                    mbar_wait(accEmpty(acc), pacc ^ 1u);
+                    mbar_wait(bFull(sb), pb);
+                    tc_fence_after();
+                    const uint32_t d = tmemBase + acc * TC_N;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint32_t ka = (uint32_t)(k >> 2) * A_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
+                        const uint32_t kb = (uint32_t)(k >> 2) * B2_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
+                        umma_i8_pair(d, umma_desc(sA0 + sa * A_BYTES + ka), umma_desc(sB0 + sb * B2_BYTES + kb), IDESC_I8_PAIR, k != 0);
+                    }
+                    umma_commit_pair(bEmpty(sb));       // both CTAs' database stages are free once these MMAs have read them
+                    umma_commit_pair(accFull(acc));     // ... and both accumulators are complete
+                }
+                umma_commit_pair(aEmpty(sa));
+            }
+        }
+    } else {
+        const int ew = warp;
+        const int quad = warp & 3;                  // a warp reads the TMEM lanes 32 * (warp id % 4) ...
+        const int part = ew >> 2;                   // ... and this 64-column quarter of every accumulator
+        const int row = quad * 32 + lane;
+        const uint32_t qEmptyL0 = map_to_cta(qEmpty(0), 0), accEmptyL0 = map_to_cta(accEmpty(0), 0);
+        uint32_t bi = 0;
+        for (uint32_t ai = 0;; ai++) {
+            const uint32_t sa = ai & 1u;
+            mbar_wait_cluster(qFull(sa), (ai >> 1) & 1u);
+            const long long w = *reinterpret_cast<volatile long long*>(&workQ[sa]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(qEmptyL0 + 8u * sa);
+            if (w < 0) break;
+            const int pair = (int)(w / mPairs), mt = 2 * (int)(w - (long long)pair * mPairs) + (int)rank;
+            uint32_t best = SENT32, second = SENT32;
+            for (int nt = 0; nt < A.nTiles; nt++, bi++) {
+                const uint32_t acc = bi & 1u;
+                mbar_wait(accFull(acc), (bi >> 1) & 1u);
+                tc_fence_after();
+                const int colBase = nt * TC_N + part * EPI2_COLS;
+                const int valid = A.n - colBase;                       // columns of this quarter that exist
+                const uint32_t taddr = tmemBase + ((uint32_t)(quad * 32) << 16) + acc * TC_N + part * EPI2_COLS;
+                uint32_t bq[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, sq[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll
+                for (int c = 0; c < EPI2_COLS / 32; c++) {
+                    int d[32];
+                    tmem_ld32(taddr + c * 32, d);
+                    tmem_ld_wait();
+                    if (c == EPI2_COLS / 32 - 1) {                     // the accumulator is in registers: hand it back to the leader
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(accEmptyL0 + 8u * acc);
+                    }
+                    if (valid >= c * 32 + 32) {
+                        // four independent (best, second) chains, four steps at a time: keys, then maxima, minima, seconds -- no
+                        // instruction waits on its neighbour's 4-cycle result
+#pragma unroll
+                        for (int k = 0; k < 16; k += 4) {
+                            uint32_t p[4], hi[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const uint32_t C = (uint32_t)(16384 + c * 32 + 2 * (k + u)) | ((uint32_t)(16384 + c * 32 + 2 * (k + u) + 1) << 16);
+                                p[u] = C + (uint32_t)d[2 * (k + u)] * (uint32_t)(-64) + (uint32_t)d[2 * (k + u) + 1] * (uint32_t)(-4194304);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) hi[u] = __vmaxu2(p[u], bq[u]);
+#pragma unroll
+                            for (int u = 0; u < 4; u++) bq[u] = __vminu2(p[u], bq[u]);
+#pragma unroll
+                            for (int u = 0; u < 4; u++) sq[u] = __vminu2(sq[u], hi[u]);
+                        }
+                    } else if (valid > c * 32) {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            const uint32_t C = (uint32_t)(16384 + c * 32 + 2 * k) | ((uint32_t)(16384 + c * 32 + 2 * k + 1) << 16);
+                            uint32_t p = C + (uint32_t)d[2 * k] * (uint32_t)(-64) + (uint32_t)d[2 * k + 1] * (uint32_t)(-4194304);
+                            if (c * 32 + 2 * k >= valid) p |= 0x0000ffffu;
+                            if (c * 32 + 2 * k + 1 >= valid) p |= 0xffff0000u;
+                            { const uint32_t hi = __vmaxu2(p, bq[k & 3]); bq[k & 3] = __vminu2(p, bq[k & 3]); sq[k & 3] = __vminu2(sq[k & 3], hi); }
+                        }
+                    }
+                }
+                // four chains -> one
+                const uint32_t b01 = __vminu2(bq[0], bq[1]), s01 = __vminu2(__vmaxu2(bq[0], bq[1]), __vminu2(sq[0], sq[1]));
+                const uint32_t b23 = __vminu2(bq[2], bq[3]), s23 = __vminu2(__vmaxu2(bq[2], bq[3]), __vminu2(sq[2], sq[3]));
+                const uint32_t bb = __vminu2(b01, b23), ss = __vminu2(__vmaxu2(b01, b23), __vminu2(s01, s23));
+                const uint32_t bl = bb & 0xffffu, bh = bb >> 16, sl = ss & 0xffffu, sh = ss >> 16;
+                const uint32_t kb = min(bl, bh), ks = min(max(bl, bh), min(sl, sh));
+                merge2(best, second, key16_to_32(kb, (uint32_t)colBase), key16_to_32(ks, (uint32_t)colBase));
+            }
+            if (part) sMerge[ai & 1u][part - 1][row] = make_uint2(best, second);
+            asm volatile("bar.sync 1, %0;" :: "n"(EPI2_THREADS) : "memory");
+            if (part == 0) {
+#pragma unroll
+                for (int q = 0; q < EPI2_PARTS - 1; q++) {
+                    const uint2 o = sMerge[ai & 1u][q][row];
+                    merge2(best, second, o.x, o.y);
+                }
+                const int qi = mt * TC_M + row;
+                if (qi < A.n) {
+                    const int bd = (int)(best >> 16), sd = (int)(second >> 16);
+                    const size_t o2 = (size_t)pair * A.n + qi;
+                    int idx = -1;
+                    if (bd <= A.thLow && (float)bd < __fmul_rn(A.nnratio, (float)sd)) idx = (int)(best & 0xffffu);
+                    A.bestIdx[o2] = idx;
+                    if (A.bestDist) A.bestDist[o2] = bd;
+                    if (A.secondDist) A.secondDist[o2] = sd;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(512u) : "memory");
+}
+
 // ---- measured denominator of the knn2 roofline: the same tcgen05.mma shape (kind::i8, M 128, N 256, K 32, operands in
 // SWIZZLE_128B shared memory, cta_group::1) issued back to back with no loads and no epilogue, one CTA per SM
 __global__ void __launch_bounds__(128, 1) k_imma_peak(int iters, int* sink) {
@@ -437,8 +727,24 @@ cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded,
     k.thLow = a.thLow; k.nnratio = a.nnratio;
     k.bestIdx = a.bestIdx; k.bestDist = a.bestDist; k.secondDist = a.secondDist;
     k.workCounter = reinterpret_cast<unsigned long long*>(used + counterOff);
+    if (g_knn2Pair.load(std::memory_order_relaxed) && sms >= 2) {
+        // CTA pairs (cta_group::2): one cluster of two CTAs per TPC, each cluster takes (pair, two query tiles) work items
+        e = OBS_ALLOW_MAX_SMEM(k_knn2_tc_pair);
+        if (e != cudaSuccess) return e;
+        const long long items = (long long)k.nPairs * ((k.mTiles + 1) / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2u * (unsigned)std::min<long long>(items, sms / 2));
+        cfg.blockDim = dim3(TC2_THREADS); cfg.dynamicSmemBytes = TC2_SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, k_knn2_tc_pair, mapA, k);
+    }
     const long long total = (long long)k.nPairs * k.mTiles;
     const unsigned grid = (unsigned)std::min<long long>(total, sms);
     k_knn2_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(mapA, mapB, k);
     return cudaGetLastError();
 }
+
+void knn2_tc_set_cta_pair(bool on) { g_knn2Pair.store(on ? 1 : 0, std::memory_order_relaxed); }

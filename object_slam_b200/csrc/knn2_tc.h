@@ -8,3 +8,4 @@ cudaError_t knn2_tc_peak(double* tops);      // measured int8 tcgen05 throughput
 // expands the keyframes of a.desc that a.pairs names into `expanded` (`used`: nKeyframes scratch bytes) and runs the tcgen05
 // kernel over a.pairs; same outputs as launch_knn2
 cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded, uint8_t* used, cudaStream_t st);
+void knn2_tc_set_cta_pair(bool on);       // tcgen05 kernel with cta_group::2 CTA pairs (default) or one CTA per SM

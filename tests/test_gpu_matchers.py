@@ -208,15 +208,18 @@ def test_knn2_matches_oracle(M):
     M.mfNNratio = 0.8
 
 
-@pytest.mark.parametrize("engine", ["tensor", "popc"])
+@pytest.mark.parametrize("engine", ["tensor", "tensor_single_cta", "popc"])
 def test_knn2_engines_match_oracle(M, engine):
     """The tcgen05 int8 contraction (hamming = (256 - a.b) / 2) and the POPC kernel against the oracle: sizes that are not
     multiples of the 128 x 256 tile, a size below one tile, duplicates (lowest index wins, second best counts duplicates),
     complementary descriptors (distance 256), an all-equal keyframe."""
-    M.set_knn2_engine(M.KNN2_TENSOR if engine == "tensor" else M.KNN2_POPC)
+    from object_slam_b200._capi import lib, check
+    M.set_knn2_engine(M.KNN2_POPC if engine == "popc" else M.KNN2_TENSOR)
+    # "tensor" = CTA pairs (tcgen05.mma.cta_group::2, the default), "tensor_single_cta" = one CTA per SM
+    check(lib().obs_set_option(b"knn2_cta_pair", 0 if engine == "tensor_single_cta" else 1))
     M.mfNNratio = 0.6
     try:
-        for n, seed in ((2000, 11), (333, 12), (129, 13), (257, 14), (70, 15), (1, 16), (1024, 17)):
+        for n, seed in ((2000, 11), (333, 12), (129, 13), (257, 14), (70, 15), (1, 16), (1024, 17), (1900, 20)):
             D = synth.keyframe_descriptors(3, n, seed)
             if n >= 70:
                 D[1, 40] = D[1, 7]                  # duplicate database rows
@@ -245,6 +248,7 @@ def test_knn2_engines_match_oracle(M, engine):
             assert np.array_equal(bi[p], obi) and np.array_equal(bd[p], obd) and np.array_equal(sd[p], osd), (engine, p)
     finally:
         M.set_knn2_engine(M.KNN2_AUTO)
+        check(lib().obs_set_option(b"knn2_cta_pair", 1))
         M.mfNNratio = 0.8
 
 

@@ -1,4 +1,4 @@
-"""Times obs_hamming_knn2 with both engines on one GPU (device-resident inputs, CUDA events) and checks that their
+"""Times obs_hamming_knn2 with the POPC engine and both tensor-core variants on one GPU (device-resident inputs, CUDA events) and checks that their
 outputs are identical.  Usage: python tools/knn2_probe.py [keyframes] [window] [n_desc]"""
 import ctypes as C
 import json
@@ -29,8 +29,9 @@ P = pairs.shape[0]
 M = ORBmatcher(0.6, True, device=0)
 out = {}
 res = {}
-for name, eng in (("popc", M.KNN2_POPC), ("tensor", M.KNN2_TENSOR)):
+for name, eng, pair in (("popc", M.KNN2_POPC, 1), ("tensor", M.KNN2_TENSOR, 0), ("tensor_cta_pair", M.KNN2_TENSOR, 1)):
     M.set_knn2_engine(eng)
+    check(lib().obs_set_option(b"knn2_cta_pair", pair))
     bi = torch.empty((P, N), dtype=torch.int32, device=dev)
     bd = torch.empty((P, N), dtype=torch.int32, device=dev)
     sd = torch.empty((P, N), dtype=torch.int32, device=dev)
@@ -51,7 +52,7 @@ for name, eng in (("popc", M.KNN2_POPC), ("tensor", M.KNN2_TENSOR)):
     ms = e0.elapsed_time(e1) / reps
     out[name] = {"ms": ms, "T_dist_per_s": P * N * N / (ms * 1e-3) / 1e12}
     res[name] = (bi.cpu().numpy(), bd.cpu().numpy(), sd.cpu().numpy())
-same = all(np.array_equal(a, b) for a, b in zip(res["popc"], res["tensor"]))
+same = all(np.array_equal(a, b) and np.array_equal(a, c) for a, b, c in zip(res["popc"], res["tensor"], res["tensor_cta_pair"]))
 out["identical"] = bool(same)
 out["config"] = {"keyframes": K, "window": Wn, "n_desc": N, "pairs": int(P), "matches": int((res["popc"][0] >= 0).sum())}
 if not same:
