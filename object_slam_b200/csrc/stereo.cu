@@ -29,9 +29,10 @@ __device__ __forceinline__ int hamming256(const uint32_t* a, const uint4 b0, con
 
 // Row table of the right keypoints (:716-733) as a CSR: rowStart[H+1], rowIdx[...].  One CTA per frame.
 // The order inside a row does not matter here: ties are broken by the keypoint index in the match kernel.
-__global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ StereoArgs A) {
+constexpr int SR_THREADS = 1024;       // one CTA per frame on the critical path of a live frame: as many threads as a CTA takes
+__global__ void __launch_bounds__(SR_THREADS) k_stereo_rows(const __grid_constant__ StereoArgs A) {
     extern __shared__ int sRow[];                 // H + 1 counters, then cursors
-    __shared__ int sWarp[9];
+    __shared__ int sWarp[SR_THREADS / 32 + 1];
     pdl_entry();
     const Geom& g = A.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.x;
@@ -42,9 +43,9 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
     int* rowStart = A.rowStart + (size_t)img * (g.h + 1);
     uint2* rowIdx = A.rowIdx + (size_t)img * A.rowIdxCap;
 
-    for (int i = tid; i <= H; i += 256) sRow[i] = 0;
+    for (int i = tid; i <= H; i += SR_THREADS) sRow[i] = 0;
     __syncthreads();
-    for (int i = tid; i < nR; i += 256) {
+    for (int i = tid; i < nR; i += SR_THREADS) {
         const float y = kpR[i * 7 + 1];
         const int oct = reinterpret_cast<const int*>(kpR)[i * 7 + 5];
         const float r = __fmul_rn(2.0f, g.lv[oct].scale);
@@ -53,9 +54,9 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
         for (int yi = minr; yi <= maxr; yi++) atomicAdd(&sRow[yi], 1);
     }
     __syncthreads();
-    // exclusive scan of the H row counts (chunks of 256)
+    // exclusive scan of the H row counts (chunks of SR_THREADS)
     int carry = 0;
-    for (int base = 0; base < H; base += 256) {
+    for (int base = 0; base < H; base += SR_THREADS) {
         const int i = base + tid;
         const int v = i < H ? sRow[i] : 0;
         int incl = v;
@@ -64,12 +65,12 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
         if (lane == 31) sWarp[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            const int w = lane < 8 ? sWarp[lane] : 0;
+            const int w = sWarp[lane];
             int wi = w;
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-            if (lane < 8) sWarp[lane] = wi - w;
-            if (lane == 7) sWarp[8] = wi;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            sWarp[lane] = wi - w;
+            if (lane == 31) sWarp[32] = wi;
         }
         __syncthreads();
         if (i < H) {
@@ -77,12 +78,12 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Ste
             sRow[i] = ex;                           // becomes the fill cursor
             rowStart[i] = ex;
         }
-        carry += sWarp[8];
+        carry += sWarp[32];
         __syncthreads();
     }
     if (tid == 0) rowStart[H] = carry;
     __syncthreads();
-    for (int i = tid; i < nR; i += 256) {
+    for (int i = tid; i < nR; i += SR_THREADS) {
         const float y = kpR[i * 7 + 1];
         const int oct = reinterpret_cast<const int*>(kpR)[i * 7 + 5];
         const float r = __fmul_rn(2.0f, g.lv[oct].scale);
@@ -247,9 +248,32 @@ __global__ void __launch_bounds__(ST_WARPS * 32, ST_MINCTAS) k_stereo_match(cons
     }
 }
 
-// median of the accepted SADs (element [m/2] of the sorted list, :867) and the outlier cut
+// median of the accepted SADs (element [m/2] of the sorted list, :867) and the outlier cut.  The k-th smallest of the 16-bit
+// values (SAD <= 121 * 510 < 65536) is selected by two 256-bin histograms -- high byte, then low byte inside the selected bin --
+// each followed by one block scan: six barriers instead of the fifty of a bit-by-bit radix selection (the kernel is one CTA per
+// frame and sits on the critical path of a live frame).
+__device__ __forceinline__ void select_bin(int* hist, int* sWarp, int* sSel, int k, int tid) {
+    // thread t owns bin t: exclusive prefix over the 256 bins, the bin whose range holds rank k publishes (bin, rank inside the bin)
+    const int lane = tid & 31, warp = tid >> 5;
+    const int v = hist[tid];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) sWarp[warp] = incl;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) if (w < warp) base += sWarp[w];
+    const int excl = base + incl - v;
+    if (k >= excl && k < excl + v) { sSel[0] = tid; sSel[1] = k - excl; }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) k_stereo_filter(const __grid_constant__ StereoArgs A) {
-    __shared__ int sCnt[2];
+    __shared__ int hist[256];
+    __shared__ int sWarp[8];
+    __shared__ int sSel[2];
+    __shared__ int sCnt;
     pdl_entry();
     const int tid = threadIdx.x, img = blockIdx.x;
     const int cap = A.g.kpCap;
@@ -258,32 +282,30 @@ __global__ void __launch_bounds__(256) k_stereo_filter(const __grid_constant__ S
     float* uRightOut = A.uRight + (size_t)img * cap;
     float* depthOut = A.depth + (size_t)img * cap;
 
-    if (tid == 0) { sCnt[0] = 0; sCnt[1] = 0; }
+    hist[tid] = 0;
+    if (tid == 0) sCnt = 0;
     __syncthreads();
     int mine = 0;
-    for (int i = tid; i < nL; i += 256) mine += sad[i] >= 0;
-    if (mine) atomicAdd(&sCnt[0], mine);
-    __syncthreads();
-    const int m = sCnt[0];
-    if (m == 0) return;                          // the reference indexes an empty vector here (undefined); nothing to filter
-    // radix selection of the k-th smallest (k = m/2, 0-based) over 16-bit values (SAD <= 121*510 < 65536)
-    int k = m / 2;
-    uint32_t prefix = 0;
-    for (int bit = 15; bit >= 0; bit--) {
-        __syncthreads();
-        if (tid == 0) sCnt[1] = 0;
-        __syncthreads();
-        int c0 = 0;
-        for (int i = tid; i < nL; i += 256) {
-            const int s = sad[i];
-            if (s >= 0 && ((uint32_t)s >> (bit + 1)) == (prefix >> (bit + 1)) && !(((uint32_t)s >> bit) & 1)) c0++;
-        }
-        if (c0) atomicAdd(&sCnt[1], c0);
-        __syncthreads();
-        const int zeros = sCnt[1];
-        if (k >= zeros) { k -= zeros; prefix |= 1u << bit; }
+    for (int i = tid; i < nL; i += 256) {
+        const int s = sad[i];
+        if (s >= 0) { mine++; atomicAdd(&hist[(s >> 8) & 255], 1); }
     }
-    const float median = (float)(int)prefix;
+    if (mine) atomicAdd(&sCnt, mine);
+    __syncthreads();
+    const int m = sCnt;
+    if (m == 0) return;                          // the reference indexes an empty vector here (undefined); nothing to filter
+    select_bin(hist, sWarp, sSel, m / 2, tid);
+    const int hiByte = sSel[0], kIn = sSel[1];
+    __syncthreads();
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < nL; i += 256) {
+        const int s = sad[i];
+        if (s >= 0 && (s >> 8) == hiByte) atomicAdd(&hist[s & 255], 1);
+    }
+    __syncthreads();
+    select_bin(hist, sWarp, sSel, kIn, tid);
+    const float median = (float)((hiByte << 8) | sSel[0]);
     const float thDist = __fmul_rn(1.5f * 1.4f, median);
     for (int i = tid; i < nL; i += 256) {
         const int s = sad[i];
@@ -299,7 +321,7 @@ cudaError_t launch_stereo(const StereoArgs& a, int nimg, cudaStream_t st) {
         cudaError_t e = OBS_ALLOW_MAX_SMEM(k_stereo_rows);
         if (e != cudaSuccess) return e;
     }
-    cudaError_t le = launch_k(pdl_enabled(), k_stereo_rows, dim3(nimg), dim3(256), smemRows, st, a);
+    cudaError_t le = launch_k(pdl_enabled(), k_stereo_rows, dim3(nimg), dim3(SR_THREADS), smemRows, st, a);
     if (le != cudaSuccess) return le;
     dim3 grid((a.g.kpCap + ST_WARPS - 1) / ST_WARPS, nimg);
     le = launch_k(pdl_enabled(), k_stereo_match, grid, dim3(ST_WARPS * 32), 0, st, a);
