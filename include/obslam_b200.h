@@ -178,7 +178,8 @@ int obs_stereo_frames(obs_extractor* left, obs_extractor* right, const obs_stere
  *              successor at entry -- griddepcontrol.launch_dependents -- and waits for its predecessor's results with
  *              griddepcontrol.wait), so launch latency and prologues overlap the predecessor's tail;
  *   "graphs" = 1: obs_stereo_frames_submit replays a CUDA graph once it has seen the same buffers, shape and parameters twice
- *              (one cudaGraphLaunch instead of ~60 runtime calls per stereo frame; up to 8 argument sets per handle pair).
+ *              (one cudaGraphLaunch instead of ~60 runtime calls per stereo frame; up to 8 argument sets per handle pair;
+ *              inside the graph the kernels are joined by ordinary graph edges).
  *   "knn2_cta_pair" = 1: the tensor-core engine of obs_hamming_knn2 runs as CTA pairs (tcgen05.mma.cta_group::2: two SMs share every
  *              database tile, csrc/knn2_tc.cu k_knn2_tc_pair); 0: one CTA per SM (k_knn2_tc).
  * Results are identical either way.  Returns OBS_ERR_INVALID for an unknown name. */

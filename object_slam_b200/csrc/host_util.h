@@ -30,6 +30,7 @@ inline cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 
 }
 bool pdl_enabled();                 // process-wide switches (obs_set_option "pdl" / "graphs"), default on
 void set_pdl_enabled(bool on);
+void set_capturing(bool on);       // this thread is inside a stream capture: launch_k drops the PDL attribute
 bool graphs_enabled();
 void set_graphs_enabled(bool on);
 extern std::atomic<unsigned long long> g_allocEpoch;     // bumped by every device (re)allocation: captured graphs hold raw pointers
