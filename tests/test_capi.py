@@ -62,3 +62,14 @@ def test_argument_validation_without_gpu():
     n = C.c_int(5)
     # a null / empty image returns 0 keypoints like the reference's early return (ORBextractor.cc:1046)
     assert L.obs_extract(None, None, 0, 0, 0, None, None, 0, C.byref(n)) == _capi.OBS_OK and n.value == 0
+
+
+def test_launch_options_without_gpu():
+    """obs_set_option only flips process-wide launch switches: known names are accepted (and restored), unknown ones rejected."""
+    L = _capi.lib()
+    for name in (b"pdl", b"graphs", b"knn2_cta_pair"):
+        assert L.obs_set_option(name, 0) == _capi.OBS_OK
+        assert L.obs_set_option(name, 1) == _capi.OBS_OK
+    assert L.obs_set_option(b"no_such_option", 1) == _capi.OBS_ERR_INVALID
+    assert b"unknown option" in L.obs_last_error()
+    assert L.obs_set_option(None, 1) == _capi.OBS_ERR_INVALID
