@@ -23,7 +23,10 @@ namespace {
 #define QT_NT 512
 #endif
 constexpr int QT_THREADS = QT_NT;
-constexpr int QT_SMEM_KEYS = 4096;       // problems with at most this many candidates keep keys + node ids in shared memory
+#ifndef QT_KEYS
+#define QT_KEYS 4096
+#endif
+constexpr int QT_SMEM_KEYS = QT_KEYS;       // problems with at most this many candidates keep keys + node ids in shared memory
 
 struct Smem {
     // carve-up of the dynamic shared memory block for node capacity nc
