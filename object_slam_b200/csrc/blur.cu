@@ -26,7 +26,7 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-// Tiled kernel: a CTA stages the 128 x 128 tile plus its 3-pixel apron in shared memory (aligned 128-bit loads; rows
+// Tiled kernel: a CTA stages the 128 x 128 tile plus its 3-pixel apron in shared memory (16-byte cp.async copies, all in flight at once; rows
 // and columns outside the level are reflected while staging, so the filter loop has no border case), then a
 // thread owns a 4-pixel column strip of a 32-row band and walks down the rows: 3 LDS, 8 IDP.4A for the four
 // horizontal sums, rows paired as u16x2, 4 IDP.2A per output pixel over an 8-row register window.

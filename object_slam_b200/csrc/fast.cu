@@ -13,7 +13,7 @@
 // so one suppression pass serves both thresholds.
 //
 // Shape of the kernel (issue-bound work, so it is organised around instructions per pixel):
-//   * one CTA owns a run of up to 8 cells of one cell row and stages their window with 128-bit loads;
+//   * one CTA owns a run of up to 8 cells of one cell row and stages their window with 16-byte cp.async copies, every row in flight at once;
 //   * pass 1 tests 8 pixels per lane with byte-SIMD |a-b| (VABSDIFF4) against the four compass ring
 //     pixels (a necessary condition for a 9-arc), leaves one bit per pixel in a bitmap, and pass 1b
 //     expands the bitmap into a dense queue of pixels;
@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(FT_THREADS, FT_MINCTAS) k_fast_cells(const __g
     const int cLo = X0 + 3 - xa, cHi = X1 - 3 - xa;       // interior columns in tile coordinates
     const int rLo = 3, rHi = shh - 3;                     // interior rows
 
-    // ---- stage the window (128-bit loads, 16 lanes per row), clear the maps, build the column tables
+    // ---- stage the window (16-byte cp.async copies, 16 lanes per row, all rows requested before anything is waited for), clear the maps,
+    // build the column tables
     {
         int pitch;
         const uint8_t* base = level_ptr(p, g, img, level, pitch);

@@ -1,6 +1,6 @@
 // K8 -- stereo matching.  Replaces Frame::ComputeStereoMatches (src/Frame.cc:706-880).
 //
-//   k_stereo_rows  : one CTA per frame builds the reference's row table (:716-733) as a CSR in HBM:
+//   k_stereo_rows  : one CTA per frame builds the reference's row table (:716-733) as a CSR in HBM (entries carry x, octave and index):
 //     right keypoint i is listed under every row of its band [floor(y-r), ceil(y+r)], r = 2*scale[octave].
 //   k_stereo_match : one warp per left keypoint scans the candidates of row int(vL), keeps those whose
 //     octave is within +-1 and whose x lies in [uL-maxD, uL-minD] (:773-778), and takes the smallest
@@ -9,7 +9,7 @@
 //     distance is < 75 the warp refines it with the 11x11 centre-subtracted SAD slid over +-5 px on
 //     the keypoint's pyramid level (:802-832), fits the parabola (:838-845) and converts to
 //     disparity / depth (:848-862).
-//   k_stereo_filter: one CTA per frame: median of the accepted SADs by 16-bit radix selection and
+//   k_stereo_filter: one CTA per frame: median of the accepted SADs by a two-level 256-bin histogram selection and
 //     the 1.5*1.4*median outlier cut (:866-879).
 // All float expressions are evaluated with individually rounded binary32 operations.
 #include "kernels.h"
