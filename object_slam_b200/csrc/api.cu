@@ -338,6 +338,8 @@ void build_geometry(obs_extractor* e, int w, int h) {
     e->hXtab.assign(std::max(xt, 1), ResizeTap{0, 0, 0});
     e->hYtab.assign(std::max(yt, 1), ResizeTap{0, 0, 0});
     for (int l = 1; l < nl; l++) {
+        g.lv[l].rsScaleX = 1.0 / ((double)g.lv[l].w / g.lv[l - 1].w);          // as in resize_taps
+        g.lv[l].rsScaleY = 1.0 / ((double)g.lv[l].h / g.lv[l - 1].h);
         resize_taps(g.lv[l - 1].w, g.lv[l].w, true, e->hXtab.data() + g.lv[l].xtab);
         resize_taps(g.lv[l - 1].h, g.lv[l].h, false, e->hYtab.data() + g.lv[l].ytab);
         resize_tile_geometry(g.lv[l - 1], g.lv[l], e->hXtab.data() + g.lv[l].xtab, e->hYtab.data() + g.lv[l].ytab);

@@ -30,6 +30,8 @@ struct LevelGeom {
     int blurEdgeBase;    // first border-strip work item of this level
     int rsPitch;         // resize of this level from the previous one: shared-memory row pitch of the staged source
     int rsRows;          //   tile (0 = taps too far apart for the tiled kernel) and its row capacity
+    double rsScaleX, rsScaleY;   // resize from the previous level: source step per destination pixel, exactly the doubles the host built the
+                         //   tap tables with (a CTA derives its source footprint from them without a dependent table load)
     float scale;         // mvScaleFactor[level]
     float invScale;      // mvInvScaleFactor[level]
     float patchSize;     // (float)(int)(31 * scale), :838

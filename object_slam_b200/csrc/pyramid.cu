@@ -155,6 +155,14 @@ __device__ __forceinline__ void hrow_tile(const uint8_t* row, int shift, const u
 // One 128 x 64 output tile of level `level` of image `img`.  CHAIN: the source level may have been written by another CTA of
 // the same cluster moments ago (k_resize_chain), so it is read through L2 (ld.global.cg) instead of the non-coherent path, and the
 // function ends with a barrier because the caller reuses the shared buffers for its next tile.
+// source index of destination index d (OpenCV resize INTER_LINEAR: floor((d + 0.5) * scale - 0.5) on the float value, x clamped)
+__device__ __forceinline__ int tap_ofs(int d, double sc, bool isX, int ssize) {
+    const float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, sc), 0.5);
+    int s = __float2int_rd(f);
+    if (isX) { if (s < 0) s = 0; if (s >= ssize - 1) s = ssize - 1; }
+    return s;
+}
+
 template <bool CHAIN>
 __device__ __forceinline__ void resize_tile_body(const Geom& g, const PyrPtrs& p, const ResizeTap* __restrict__ xtab,
                                                  const ResizeTap* __restrict__ ytab, int level, int img, int tileX, int tileY,
@@ -169,8 +177,11 @@ __device__ __forceinline__ void resize_tile_body(const Geom& g, const PyrPtrs& p
     int spitch, dpitch;
     const uint8_t* src = level_ptr(p, g, img, level - 1, spitch);
     uint8_t* dst = const_cast<uint8_t*>(level_ptr(p, g, img, level, dpitch));
-    const int xs0 = xt[tx0].ofs & ~15, xs1 = xt[tx0 + tw - 1].ofs + 1;
-    const int ys0 = min(max(yt[ty0].ofs, 0), S.h - 1), ys1 = min(max(yt[ty0 + th - 1].ofs + 1, 0), S.h - 1);
+    // source footprint of the tile from the same arithmetic the host built the tap tables with (api.cu resize_taps) -- no table
+    // load in front of the copies
+    const int xs0 = tap_ofs(tx0, D.rsScaleX, true, S.w) & ~15, xs1 = tap_ofs(tx0 + tw - 1, D.rsScaleX, true, S.w) + 1;
+    const int ys0 = min(max(tap_ofs(ty0, D.rsScaleY, false, S.h), 0), S.h - 1);
+    const int ys1 = min(max(tap_ofs(ty0 + th - 1, D.rsScaleY, false, S.h) + 1, 0), S.h - 1);
     const int pitch = D.rsPitch;
     auto ld = [](const uint4* q) { return CHAIN ? __ldcg(q) : __ldg(q); };
     {
