@@ -539,6 +539,7 @@ def main():
     ap.add_argument("--window", type=int, default=8, help="knn2: every keyframe is matched against the +-window neighbours")
     ap.add_argument("--gather-chunks", type=int, default=4, help="knn2: chunks of the all-gather (matching overlaps the later chunks)")
     ap.add_argument("--knn2-engine", default="auto", choices=["auto", "tensor", "popc"])
+    ap.add_argument("--knn2-cta-pair", type=int, default=1, choices=[0, 1], help="knn2 tensor engine: CTA pairs (cta_group::2) or one CTA per SM")
     ap.add_argument("--map-points", type=int, default=20000, help="projection: map points per frame")
     ap.add_argument("--total-frames", type=int, default=32768, help="extract: frames of the whole offline job (configs[3]), sharded over the GPUs")
     ap.add_argument("--pool", type=int, default=512, help="extract: distinct synthetic frames (seed = global frame index mod pool)")

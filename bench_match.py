@@ -644,6 +644,7 @@ def measure_knn2(args, ctx, ClockSampler):
     best = torch.empty((max(P, 1), NDESC), dtype=torch.int32, device=dev)
     M = ORBmatcher(RATIO, True, device=local_rank)
     M.set_knn2_engine({"auto": M.KNN2_AUTO, "tensor": M.KNN2_TENSOR, "popc": M.KNN2_POPC}[args.knn2_engine])
+    check(lib().obs_set_option(b"knn2_cta_pair", int(getattr(args, "knn2_cta_pair", 1))))
     tensor = args.knn2_engine != "popc"
     mstream = M.stream
     comm = None

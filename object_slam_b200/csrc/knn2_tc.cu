@@ -2,22 +2,23 @@
 // (the candidate loop of ORBmatcher::SearchByBoW, /root/reference/src/ORBmatcher.cc:205-226, on
 // DescriptorDistance, :1647-1663) as an exact integer GEMM.
 //
-// With every descriptor bit b stored as the int8 value 1 - 2b, the dot product of two 256-element rows is
-//     a . b = (#equal bits) - (#different bits) = 256 - 2 * hamming(a, b),
-// so hamming = (256 - a.b) / 2, exact in the int32 accumulators of tcgen05.mma kind::i8 (|a.b| <= 256).
+// With every descriptor bit b stored as the int8 value 8 * (1 - 2b), the dot product of two 256-element rows is
+//     a . b = 64 * ((#equal bits) - (#different bits)) = 64 * (256 - 2 * hamming(a, b)),
+// exact in the int32 accumulators of tcgen05.mma kind::i8 (|a.b| <= 16384).
 //
-//   k_knn2_expand   bits -> +-1 int8 rows of 256 bytes (one pass over the descriptor sets per call)
-//   k_knn2_tc       persistent, one CTA per SM, warp specialised:
-//       warp 0      TMA producer: query tile (128 rows) and database tiles (256 rows) as two 128-byte swizzle atoms each
+//   k_knn2_expand   bits -> +-8 int8 rows of 256 bytes (one pass over the descriptor sets per call), so a.b = 64 * (256 - 2 hamming)
+//   k_knn2_tc_pair / k_knn2_tc   persistent, warp specialised (CTA pairs with tcgen05.mma.cta_group::2, or one CTA per SM):
+//       warps 0-15  epilogue.  Every accumulator column is PRE-LOADED (tcgen05.st ... unpack::16b) with 16384 + 63 - (column in the
+//                   warp's 64-column part); the MMAs accumulate onto it, so a finished column holds the 16-bit key
+//                   V = 128 * (256 - dist) + 63 - column, and tcgen05.ld ... pack::16b returns two keys per register with no
+//                   arithmetic.  The running (best, second best) of every 16-bit lane is three packed VIMNMX.U16x2 per register --
+//                   1.5 ALU instructions per distance and nothing else.  Keys are distinct, so the two largest keys are the
+//                   reference's best / second best under its strict-< first-wins update; parts, tiles and threads merge exactly.
+//       warp 16     TMA producer: query tile (128 rows) and database tiles as 128-byte swizzle atoms
 //                   (cp.async.bulk.tensor.3d on a [keyframe][descriptor][256 B] tensor map, SWIZZLE_128B; rows past the end
 //                   of a keyframe are zero-filled by the TMA unit)
-//       warp 1      TMEM allocation; one lane issues 8 x tcgen05.mma.cta_group::1.kind::i8 (M 128, N 256, K 32) per database
-//                   tile into one of two 256-column accumulators and commits to the mbarriers of the pipeline
-//       warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns; thread = one query row and one 128-column half of the tile.
-//                   Distances become 16-bit keys dist << 7 | column-in-half, two per register (two IMAD), and the running
-//                   (best, second best) of every 16-bit lane is three packed VIMNMX.U16x2 per register -- 1.5 ALU
-//                   instructions per distance.  Keys are distinct, so the two smallest keys are the reference's best / second
-//                   best under its strict-< first-wins update; halves, tiles and the two threads of a row merge exactly.
+//       warp 17     TMEM allocation; one lane issues 8 x tcgen05.mma.kind::i8 (K 32 each) per database tile into one of two
+//                   256-column accumulators and commits to the mbarriers of the pipeline
 // The POPC kernel (matcher.cu k_knn2) remains the path for tiny descriptor sets; obs_hamming_knn2 picks per call.
 #include "matcher.h"
 #include "knn2_tc.h"
@@ -38,8 +39,9 @@ constexpr int A_ATOM_BYTES = TC_M * ATOM_B;       // 16 KB
 constexpr int B_ATOM_BYTES = TC_N * ATOM_B;       // 32 KB
 constexpr int A_BYTES = 2 * A_ATOM_BYTES;         // 32 KB
 constexpr int B_BYTES = 2 * B_ATOM_BYTES;         // 64 KB
-constexpr int TC_THREADS = 320;
-constexpr int EPI_THREADS = 256;
+constexpr int EPI2_PARTS = 4;                     // epilogue warps per TMEM lane quarter: each takes 256 / 4 accumulator columns
+constexpr int EPI2_COLS = TC_N / EPI2_PARTS;
+constexpr int EPI2_THREADS = 128 * EPI2_PARTS, TC2_THREADS = 64 + EPI2_THREADS;
 constexpr uint32_t SENT32 = (256u << 16) | 0xffffu;
 constexpr size_t TC_SMEM = 2 * A_BYTES + 2 * B_BYTES + 1024;
 
@@ -97,10 +99,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 // ---- bits -> +-1 int8 -------------------------------------------------------------------------------------------------
-// thread = 16 descriptor bits -> 16 bytes; bit k of the descriptor (bit k%8 of byte k/8) becomes element k: 0 -> +1, 1 -> -1
+// thread = 16 descriptor bits -> 16 bytes; bit k of the descriptor (bit k%8 of byte k/8) becomes element k: 0 -> +8, 1 -> -8.
+// (+-8 instead of +-1: a.b = 64 * (256 - 2 * hamming), so the six low bits of an accumulator are free for a column index -- the
+// CTA-pair kernel lets the tensor core add the MMA result onto pre-stored (bias + column) constants and reads finished keys.)
 __device__ __forceinline__ uint32_t expand4(uint32_t b) {
     const uint32_t x = (b * 0x00204081u) & 0x01010101u;       // bit i of b -> byte i
-    return x * 0xfeu + 0x01010101u;                             // 1 -> 0xff (-1), 0 -> 0x01 (+1)
+    return x * 0xf0u + 0x08080808u;                             // 1 -> 0xf8 (-8), 0 -> 0x08 (+8)
 }
 // only the keyframes a pair of this call names are expanded: k_knn2_mark flags them, one CTA per flagged keyframe expands it
 __global__ void __launch_bounds__(256) k_knn2_mark(const int2* __restrict__ pairs, int nPairs, int nKeyframes, uint8_t* __restrict__ used) {
@@ -121,9 +125,9 @@ __global__ void __launch_bounds__(256) k_knn2_expand(const uint16_t* __restrict_
 }
 
 // ---- epilogue helpers ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t key16_to_32(uint32_t k16, uint32_t colBase) {
-    const uint32_t dist = k16 >> 7;
-    return dist > 256u ? SENT32 : ((dist << 16) | (colBase + (k16 & 127u)));
+// accumulator key V = 128 * (256 - dist) + 63 - column-in-part, 0 = nothing (masked column / no candidate: distance 256)
+__device__ __forceinline__ uint32_t vkey_to_32(uint32_t v, uint32_t colBase) {
+    return v == 0u ? SENT32 : (((256u - (v >> 7)) << 16) | (colBase + 63u - (v & 127u)));
 }
 __device__ __forceinline__ void merge2(uint32_t& best, uint32_t& second, uint32_t b, uint32_t s) {
     const uint32_t hi = max(best, b);
@@ -138,188 +142,6 @@ struct Knn2TcArgs {
     int* bestIdx; int* bestDist; int* secondDist;
     unsigned long long* workCounter;      // zeroed before the launch: next (pair, query tile) work item
 };
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_knn2_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Knn2TcArgs A) {
-    extern __shared__ uint8_t smemRaw[];
-    __shared__ __align__(8) uint64_t bars[16];     // aFull[2] aEmpty[2] bFull[2] bEmpty[2] accFull[2] accEmpty[2] qFull[2] qEmpty[2]
-    __shared__ long long workQ[2];                 // work items handed from the producer to the MMA and epilogue warps (-1 = done)
-    __shared__ uint32_t tmemBaseS;
-    __shared__ uint2 sMerge[2][TC_M];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t base = (smem_u32(smemRaw) + 1023u) & ~1023u;
-    const uint32_t sA0 = base, sB0 = base + 2 * A_BYTES;
-    const uint32_t bar0 = smem_u32(bars);
-    auto aFull = [&](int s) { return bar0 + 8u * (0 + s); };
-    auto aEmpty = [&](int s) { return bar0 + 8u * (2 + s); };
-    auto bFull = [&](int s) { return bar0 + 8u * (4 + s); };
-    auto bEmpty = [&](int s) { return bar0 + 8u * (6 + s); };
-    auto accFull = [&](int s) { return bar0 + 8u * (8 + s); };
-    auto accEmpty = [&](int s) { return bar0 + 8u * (10 + s); };
-    auto qFull = [&](int s) { return bar0 + 8u * (12 + s); };
-    auto qEmpty = [&](int s) { return bar0 + 8u * (14 + s); };
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; s++) {
-            mbar_init(aFull(s), 1); mbar_init(aEmpty(s), 1);
-            mbar_init(bFull(s), 1); mbar_init(bEmpty(s), 1);
-            mbar_init(accFull(s), 1); mbar_init(accEmpty(s), EPI_THREADS / 32);
-            mbar_init(qFull(s), 1); mbar_init(qEmpty(s), 1 + EPI_THREADS / 32);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmemBaseS)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmemBase = tmemBaseS;
-
-    const long long total = (long long)A.nPairs * A.mTiles;
-    if (warp == 0) {
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" :: "l"(&mapA) : "memory");
-            asm volatile("prefetch.tensormap [%0];" :: "l"(&mapB) : "memory");
-            // Work items come from a global counter, not from a fixed stride: a CTA that starts late (its SM was held by another
-            // kernel, e.g. NCCL's while the descriptor gather is in flight) simply takes fewer of them.
-            uint32_t bi = 0;
-            for (uint32_t ai = 0;; ai++) {
-                const uint32_t sa = ai & 1u;
-                mbar_wait(qEmpty(sa), ((ai >> 1) & 1u) ^ 1u);
-                long long w = (long long)atomicAdd(A.workCounter, 1ull);
-                if (w >= total) w = -1;
-                workQ[sa] = w;
-                mbar_arrive(qFull(sa));
-                if (w < 0) break;
-                const int pair = (int)(w / A.mTiles), mt = (int)(w - (long long)pair * A.mTiles);
-                const int2 pr = A.pairs[pair];
-                mbar_wait(aEmpty(sa), ((ai >> 1) & 1u) ^ 1u);
-                mbar_expect_tx(aFull(sa), A_BYTES);
-                tma_load_3d(sA0 + sa * A_BYTES, &mapA, 0, mt * TC_M, pr.x, aFull(sa));
-                tma_load_3d(sA0 + sa * A_BYTES + A_ATOM_BYTES, &mapA, ATOM_B, mt * TC_M, pr.x, aFull(sa));
-                for (int nt = 0; nt < A.nTiles; nt++, bi++) {
-                    const uint32_t sb = bi & 1u;
-                    mbar_wait(bEmpty(sb), ((bi >> 1) & 1u) ^ 1u);
-                    mbar_expect_tx(bFull(sb), B_BYTES);
-                    tma_load_3d(sB0 + sb * B_BYTES, &mapB, 0, nt * TC_N, pr.y, bFull(sb));
-                    tma_load_3d(sB0 + sb * B_BYTES + B_ATOM_BYTES, &mapB, ATOM_B, nt * TC_N, pr.y, bFull(sb));
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t bi = 0;
-            for (uint32_t ai = 0;; ai++) {
-                const uint32_t sa = ai & 1u;
-                mbar_wait(qFull(sa), (ai >> 1) & 1u);
-                const long long w = *reinterpret_cast<volatile long long*>(&workQ[sa]);
-                mbar_arrive(qEmpty(sa));
-                if (w < 0) break;
-                mbar_wait(aFull(sa), (ai >> 1) & 1u);
-                for (int nt = 0; nt < A.nTiles; nt++, bi++) {
-                    const uint32_t sb = bi & 1u, ph = (bi >> 1) & 1u;
-                    mbar_wait(accEmpty(sb), ph ^ 1u);
-                    mbar_wait(bFull(sb), ph);
-                    tc_fence_after();
-                    const uint32_t d = tmemBase + sb * TC_N;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const uint32_t ka = (uint32_t)(k >> 2) * A_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
-                        const uint32_t kb = (uint32_t)(k >> 2) * B_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
-                        umma_i8(d, umma_desc(sA0 + sa * A_BYTES + ka), umma_desc(sB0 + sb * B_BYTES + kb), IDESC_I8, k != 0);
-                    }
-                    umma_commit(bEmpty(sb));        // the database stage is free once these MMAs have read it
-                    umma_commit(accFull(sb));       // ... and the accumulator is complete
-                }
-                umma_commit(aEmpty(sa));
-            }
-        }
-    } else {
-        const int ew = warp - 2;
-        const int quad = warp & 3;                  // a warp reads the TMEM lanes 32 * (warp id % 4) ...
-        const int half = ew >> 2;                   // ... and this 128-column half of every accumulator
-        const int row = quad * 32 + lane;
-        uint32_t bi = 0;
-        for (uint32_t ai = 0;; ai++) {
-            const uint32_t sa = ai & 1u;
-            mbar_wait(qFull(sa), (ai >> 1) & 1u);
-            const long long w = *reinterpret_cast<volatile long long*>(&workQ[sa]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(qEmpty(sa));
-            if (w < 0) break;
-            const int pair = (int)(w / A.mTiles), mt = (int)(w - (long long)pair * A.mTiles);
-            uint32_t best = SENT32, second = SENT32;
-            for (int nt = 0; nt < A.nTiles; nt++, bi++) {
-                const uint32_t sb = bi & 1u;
-                mbar_wait(accFull(sb), (bi >> 1) & 1u);
-                tc_fence_after();
-                const int colBase = nt * TC_N + half * 128;
-                const int valid = A.n - colBase;                       // columns of this half that exist
-                const uint32_t taddr = tmemBase + ((uint32_t)(quad * 32) << 16) + sb * TC_N + half * 128;
-                uint32_t b0 = 0xffffffffu, s0 = 0xffffffffu, b1 = 0xffffffffu, s1 = 0xffffffffu;
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    int d[32];
-                    tmem_ld32(taddr + c * 32, d);
-                    tmem_ld_wait();
-                    if (c == 3) {                                      // the accumulator is in registers: hand it back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(accEmpty(sb));
-                    }
-                    if (valid >= c * 32 + 32) {
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            const uint32_t C = (uint32_t)(16384 + c * 32 + 2 * k) | ((uint32_t)(16384 + c * 32 + 2 * k + 1) << 16);
-                            const uint32_t p = C + (uint32_t)d[2 * k] * (uint32_t)(-64) + (uint32_t)d[2 * k + 1] * (uint32_t)(-4194304);
-                            if (k & 1) { const uint32_t hi = __vmaxu2(p, b1); b1 = __vminu2(p, b1); s1 = __vminu2(s1, hi); }
-                            else       { const uint32_t hi = __vmaxu2(p, b0); b0 = __vminu2(p, b0); s0 = __vminu2(s0, hi); }
-                        }
-                    } else if (valid > c * 32) {
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            const uint32_t C = (uint32_t)(16384 + c * 32 + 2 * k) | ((uint32_t)(16384 + c * 32 + 2 * k + 1) << 16);
-                            uint32_t p = C + (uint32_t)d[2 * k] * (uint32_t)(-64) + (uint32_t)d[2 * k + 1] * (uint32_t)(-4194304);
-                            if (c * 32 + 2 * k >= valid) p |= 0x0000ffffu;
-                            if (c * 32 + 2 * k + 1 >= valid) p |= 0xffff0000u;
-                            if (k & 1) { const uint32_t hi = __vmaxu2(p, b1); b1 = __vminu2(p, b1); s1 = __vminu2(s1, hi); }
-                            else       { const uint32_t hi = __vmaxu2(p, b0); b0 = __vminu2(p, b0); s0 = __vminu2(s0, hi); }
-                        }
-                    }
-                }
-                // two accumulators -> one, 16-bit lanes -> one, half-tile keys -> global keys
-                const uint32_t bb = __vminu2(b0, b1), ss = __vminu2(__vmaxu2(b0, b1), __vminu2(s0, s1));
-                const uint32_t bl = bb & 0xffffu, bh = bb >> 16, sl = ss & 0xffffu, sh = ss >> 16;
-                const uint32_t kb = min(bl, bh), ks = min(max(bl, bh), min(sl, sh));
-                merge2(best, second, key16_to_32(kb, (uint32_t)colBase), key16_to_32(ks, (uint32_t)colBase));
-            }
-            // the two threads of a row (column halves) meet in shared memory
-            if (half == 1) sMerge[ai & 1u][row] = make_uint2(best, second);
-            asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
-            if (half == 0) {
-                const uint2 o = sMerge[ai & 1u][row];
-                merge2(best, second, o.x, o.y);
-                const int qi = mt * TC_M + row;
-                if (qi < A.n) {
-                    const int bd = (int)(best >> 16), sd = (int)(second >> 16);
-                    const size_t o2 = (size_t)pair * A.n + qi;
-                    int idx = -1;
-                    if (bd <= A.thLow && (float)bd < __fmul_rn(A.nnratio, (float)sd)) idx = (int)(best & 0xffffu);
-                    A.bestIdx[o2] = idx;
-                    if (A.bestDist) A.bestDist[o2] = bd;
-                    if (A.secondDist) A.secondDist[o2] = sd;
-                }
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(512u) : "memory");
-}
 
 // ---- CTA-pair variant (cta_group::2) -------------------------------------------------------------------------------------
 // k_knn2_tc pulls every 64 KB database tile through L2 for ONE 128-row query tile: ~53 B per cycle per SM, more than L2 delivers
@@ -336,9 +158,6 @@ constexpr int B2_ATOM_BYTES = 128 * ATOM_B;        // 128 database rows x 128 by
 constexpr int B2_BYTES = 2 * B2_ATOM_BYTES;        // 32 KB: this CTA's half of a database tile
 constexpr int B2_STAGES = 4;
 constexpr size_t TC2_SMEM = 2 * A_BYTES + B2_STAGES * B2_BYTES + 1024;
-constexpr int EPI2_PARTS = 4;                     // epilogue warps per TMEM lane quarter: each takes 256 / 4 accumulator columns
-constexpr int EPI2_COLS = TC_N / EPI2_PARTS;
-constexpr int EPI2_THREADS = 128 * EPI2_PARTS, TC2_THREADS = 64 + EPI2_THREADS;
 constexpr uint32_t IDESC_I8_PAIR = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -380,6 +199,123 @@ __device__ __forceinline__ void umma_i8_pair(uint32_t tmemD, uint64_t da, uint64
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {       // arrives on the barrier at this offset in BOTH CTAs
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+// ---- epilogue of both tensor-core kernels (16 warps: warp w reads the TMEM lanes 32 * (w % 4) and the 64-column part w / 4 of every
+// accumulator).  qEmptyL0 / accEmptyL0: shared::cluster addresses of the barriers the MMA lane waits on (the leader CTA's in a pair).
+template <bool PAIR>
+__device__ __forceinline__ void knn2_epilogue(const Knn2TcArgs& A, uint32_t tmemBase, int warp, int lane, uint32_t rank, int itemsPerPair,
+                                              uint32_t qFull0, uint32_t qEmptyL0, uint32_t accFull0, uint32_t accEmptyL0,
+                                              const long long* workQ, uint2 (*sMerge)[EPI2_PARTS - 1][TC_M]) {
+    const int ew = warp;
+    const int quad = warp & 3;                  // a warp reads the TMEM lanes 32 * (warp id % 4) ...
+    const int part = ew >> 2;                   // ... and this 64-column quarter of every accumulator
+    const int row = quad * 32 + lane;
+    // The accumulator columns of this thread's part are pre-loaded with  16384 + 63 - (column in part)  (tcgen05.st ...
+    // unpack::16b: one register per two columns, zero extended); the MMAs ADD 64 a.b = 16384 - 128 dist, so a finished column holds
+    //     V = 128 * (256 - dist) + 63 - column      (0 <= V < 32832: larger = closer, then the lower column)
+    // and tcgen05.ld ... pack::16b returns two such keys per register with no arithmetic at all.  Best / second best are the two
+    // LARGEST keys of every 16-bit lane: three packed VIMNMX per register.
+    uint32_t cst[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) cst[j] = (uint32_t)(16384 + 63 - 2 * j) | ((uint32_t)(16384 + 63 - (2 * j + 1)) << 16);
+    const uint32_t tpart = tmemBase + ((uint32_t)(quad * 32) << 16) + part * EPI2_COLS;
+    auto store_constants = [&](uint32_t taddr) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x32.unpack::16b.b32 [%0], "
+                     "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                     "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                     :: "r"(taddr), "r"(cst[0]), "r"(cst[1]), "r"(cst[2]), "r"(cst[3]), "r"(cst[4]), "r"(cst[5]), "r"(cst[6]), "r"(cst[7]),
+                        "r"(cst[8]), "r"(cst[9]), "r"(cst[10]), "r"(cst[11]), "r"(cst[12]), "r"(cst[13]), "r"(cst[14]), "r"(cst[15]),
+                        "r"(cst[16]), "r"(cst[17]), "r"(cst[18]), "r"(cst[19]), "r"(cst[20]), "r"(cst[21]), "r"(cst[22]), "r"(cst[23]),
+                        "r"(cst[24]), "r"(cst[25]), "r"(cst[26]), "r"(cst[27]), "r"(cst[28]), "r"(cst[29]), "r"(cst[30]), "r"(cst[31])
+                     : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    };
+    // both accumulators start out holding the constants; the first arrive on accEmpty is that release
+    for (uint32_t acc = 0; acc < 2; acc++) {
+        store_constants(tpart + acc * TC_N);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(accEmptyL0 + 8u * acc);
+    }
+    uint32_t bi = 0;
+    for (uint32_t ai = 0;; ai++) {
+        const uint32_t sa = ai & 1u;
+        if (PAIR) mbar_wait_cluster(qFull0 + 8u * sa, (ai >> 1) & 1u); else mbar_wait(qFull0 + 8u * sa, (ai >> 1) & 1u);
+        const long long w = *reinterpret_cast<const volatile long long*>(&workQ[sa]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(qEmptyL0 + 8u * sa);
+        if (w < 0) break;
+        const int pair = (int)(w / itemsPerPair), it = (int)(w - (long long)pair * itemsPerPair), mt = PAIR ? 2 * it + (int)rank : it;
+        uint32_t best = SENT32, second = SENT32;
+        for (int nt = 0; nt < A.nTiles; nt++, bi++) {
+            const uint32_t acc = bi & 1u;
+            mbar_wait(accFull0 + 8u * acc, (bi >> 1) & 1u);
+            tc_fence_after();
+            const int colBase = nt * TC_N + part * EPI2_COLS;
+            const int valid = A.n - colBase;                       // columns of this part that exist
+            uint32_t v[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                         : "r"(tpart + acc * TC_N) : "memory");
+            tmem_ld_wait();
+            // the keys are in registers: put the constants back and hand the accumulator to the leader's MMA lane
+            store_constants(tpart + acc * TC_N);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(accEmptyL0 + 8u * acc);
+            if (valid <= 0) continue;
+            if (valid < EPI2_COLS) {                               // ragged end of the keyframe: columns past it (zero rows) drop to key 0
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    if (2 * j >= valid) v[j] &= 0xffff0000u;
+                    if (2 * j + 1 >= valid) v[j] &= 0x0000ffffu;
+                }
+            }
+            uint32_t bq[4] = {0u, 0u, 0u, 0u}, sq[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                uint32_t lo[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) lo[u] = __vminu2(v[j + u], bq[u]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) bq[u] = __vmaxu2(v[j + u], bq[u]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) sq[u] = __vmaxu2(sq[u], lo[u]);
+            }
+            // four chains -> one, 16-bit lanes -> one, part keys -> global (dist << 16 | column) keys
+            const uint32_t b01 = __vmaxu2(bq[0], bq[1]), s01 = __vmaxu2(__vminu2(bq[0], bq[1]), __vmaxu2(sq[0], sq[1]));
+            const uint32_t b23 = __vmaxu2(bq[2], bq[3]), s23 = __vmaxu2(__vminu2(bq[2], bq[3]), __vmaxu2(sq[2], sq[3]));
+            const uint32_t bb = __vmaxu2(b01, b23), ss = __vmaxu2(__vminu2(b01, b23), __vmaxu2(s01, s23));
+            const uint32_t bl = bb & 0xffffu, bh = bb >> 16, sl = ss & 0xffffu, sh = ss >> 16;
+            const uint32_t kb = max(bl, bh), ks = max(min(bl, bh), max(sl, sh));
+            merge2(best, second, vkey_to_32(kb, (uint32_t)colBase), vkey_to_32(ks, (uint32_t)colBase));
+        }
+        if (part) sMerge[ai & 1u][part - 1][row] = make_uint2(best, second);
+        asm volatile("bar.sync 1, %0;" :: "n"(EPI2_THREADS) : "memory");
+        if (part == 0) {
+#pragma unroll
+            for (int q = 0; q < EPI2_PARTS - 1; q++) {
+                const uint2 o = sMerge[ai & 1u][q][row];
+                merge2(best, second, o.x, o.y);
+            }
+            const int qi = mt * TC_M + row;
+            if (qi < A.n) {
+                const int bd = (int)(best >> 16), sd = (int)(second >> 16);
+                const size_t o2 = (size_t)pair * A.n + qi;
+                int idx = -1;
+                if (bd <= A.thLow && (float)bd < __fmul_rn(A.nnratio, (float)sd)) idx = (int)(best & 0xffffu);
+                A.bestIdx[o2] = idx;
+                if (A.bestDist) A.bestDist[o2] = bd;
+                if (A.secondDist) A.secondDist[o2] = sd;
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(TC2_THREADS, 1)
@@ -491,7 +427,7 @@ k_knn2_tc_pair(const __grid_constant__ CUtensorMap mapT, const __grid_constant__
                 for (int nt = 0; nt < A.nTiles; nt++, bi++) {
                     const uint32_t sb = bi % B2_STAGES, pb = (bi / B2_STAGES) & 1u;
                     const uint32_t acc = bi & 1u, pacc = (bi >> 1) & 1u;
-                    mbar_wait(accEmpty(acc), pacc ^ 1u);
+                    mbar_wait(accEmpty(acc), pacc);          // phase u = the accumulator holds its constants for use u (phase 0: the initial store)
                     mbar_wait(bFull(sb), pb);
                     tc_fence_after();
                     const uint32_t d = tmemBase + acc * TC_N;
@@ -499,7 +435,7 @@ k_knn2_tc_pair(const __grid_constant__ CUtensorMap mapT, const __grid_constant__
                     for (int k = 0; k < 8; k++) {
                         const uint32_t ka = (uint32_t)(k >> 2) * A_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
                         const uint32_t kb = (uint32_t)(k >> 2) * B2_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
-                        umma_i8_pair(d, umma_desc(sA0 + sa * A_BYTES + ka), umma_desc(sB0 + sb * B2_BYTES + kb), IDESC_I8_PAIR, k != 0);
+                        umma_i8_pair(d, umma_desc(sA0 + sa * A_BYTES + ka), umma_desc(sB0 + sb * B2_BYTES + kb), IDESC_I8_PAIR, 1u);   // onto the stored constants
                     }
                     umma_commit_pair(bEmpty(sb));       // both CTAs' database stages are free once these MMAs have read them
                     umma_commit_pair(accFull(acc));     // ... and both accumulators are complete
@@ -508,101 +444,123 @@ k_knn2_tc_pair(const __grid_constant__ CUtensorMap mapT, const __grid_constant__
             }
         }
     } else {
-        const int ew = warp;
-        const int quad = warp & 3;                  // a warp reads the TMEM lanes 32 * (warp id % 4) ...
-        const int part = ew >> 2;                   // ... and this 64-column quarter of every accumulator
-        const int row = quad * 32 + lane;
-        const uint32_t qEmptyL0 = map_to_cta(qEmpty(0), 0), accEmptyL0 = map_to_cta(accEmpty(0), 0);
-        uint32_t bi = 0;
-        for (uint32_t ai = 0;; ai++) {
-            const uint32_t sa = ai & 1u;
-            mbar_wait_cluster(qFull(sa), (ai >> 1) & 1u);
-            const long long w = *reinterpret_cast<volatile long long*>(&workQ[sa]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(qEmptyL0 + 8u * sa);
-            if (w < 0) break;
-            const int pair = (int)(w / mPairs), mt = 2 * (int)(w - (long long)pair * mPairs) + (int)rank;
-            uint32_t best = SENT32, second = SENT32;
-            for (int nt = 0; nt < A.nTiles; nt++, bi++) {
-                const uint32_t acc = bi & 1u;
-                mbar_wait(accFull(acc), (bi >> 1) & 1u);
-                tc_fence_after();
-                const int colBase = nt * TC_N + part * EPI2_COLS;
-                const int valid = A.n - colBase;                       // columns of this quarter that exist
-                const uint32_t taddr = tmemBase + ((uint32_t)(quad * 32) << 16) + acc * TC_N + part * EPI2_COLS;
-                uint32_t bq[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, sq[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-#pragma unroll
-                for (int c = 0; c < EPI2_COLS / 32; c++) {
-                    int d[32];
-                    tmem_ld32(taddr + c * 32, d);
-                    tmem_ld_wait();
-                    if (c == EPI2_COLS / 32 - 1) {                     // the accumulator is in registers: hand it back to the leader
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(accEmptyL0 + 8u * acc);
-                    }
-                    if (valid >= c * 32 + 32) {
-                        // four independent (best, second) chains, four steps at a time: keys, then maxima, minima, seconds -- no
-                        // instruction waits on its neighbour's 4-cycle result
-#pragma unroll
-                        for (int k = 0; k < 16; k += 4) {
-                            uint32_t p[4], hi[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const uint32_t C = (uint32_t)(16384 + c * 32 + 2 * (k + u)) | ((uint32_t)(16384 + c * 32 + 2 * (k + u) + 1) << 16);
-                                p[u] = C + (uint32_t)d[2 * (k + u)] * (uint32_t)(-64) + (uint32_t)d[2 * (k + u) + 1] * (uint32_t)(-4194304);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; u++) hi[u] = __vmaxu2(p[u], bq[u]);
-#pragma unroll
-                            for (int u = 0; u < 4; u++) bq[u] = __vminu2(p[u], bq[u]);
-#pragma unroll
-                            for (int u = 0; u < 4; u++) sq[u] = __vminu2(sq[u], hi[u]);
-                        }
-                    } else if (valid > c * 32) {
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            const uint32_t C = (uint32_t)(16384 + c * 32 + 2 * k) | ((uint32_t)(16384 + c * 32 + 2 * k + 1) << 16);
-                            uint32_t p = C + (uint32_t)d[2 * k] * (uint32_t)(-64) + (uint32_t)d[2 * k + 1] * (uint32_t)(-4194304);
-                            if (c * 32 + 2 * k >= valid) p |= 0x0000ffffu;
-                            if (c * 32 + 2 * k + 1 >= valid) p |= 0xffff0000u;
-                            { const uint32_t hi = __vmaxu2(p, bq[k & 3]); bq[k & 3] = __vminu2(p, bq[k & 3]); sq[k & 3] = __vminu2(sq[k & 3], hi); }
-                        }
-                    }
-                }
-                // four chains -> one
-                const uint32_t b01 = __vminu2(bq[0], bq[1]), s01 = __vminu2(__vmaxu2(bq[0], bq[1]), __vminu2(sq[0], sq[1]));
-                const uint32_t b23 = __vminu2(bq[2], bq[3]), s23 = __vminu2(__vmaxu2(bq[2], bq[3]), __vminu2(sq[2], sq[3]));
-                const uint32_t bb = __vminu2(b01, b23), ss = __vminu2(__vmaxu2(b01, b23), __vminu2(s01, s23));
-                const uint32_t bl = bb & 0xffffu, bh = bb >> 16, sl = ss & 0xffffu, sh = ss >> 16;
-                const uint32_t kb = min(bl, bh), ks = min(max(bl, bh), min(sl, sh));
-                merge2(best, second, key16_to_32(kb, (uint32_t)colBase), key16_to_32(ks, (uint32_t)colBase));
-            }
-            if (part) sMerge[ai & 1u][part - 1][row] = make_uint2(best, second);
-            asm volatile("bar.sync 1, %0;" :: "n"(EPI2_THREADS) : "memory");
-            if (part == 0) {
-#pragma unroll
-                for (int q = 0; q < EPI2_PARTS - 1; q++) {
-                    const uint2 o = sMerge[ai & 1u][q][row];
-                    merge2(best, second, o.x, o.y);
-                }
-                const int qi = mt * TC_M + row;
-                if (qi < A.n) {
-                    const int bd = (int)(best >> 16), sd = (int)(second >> 16);
-                    const size_t o2 = (size_t)pair * A.n + qi;
-                    int idx = -1;
-                    if (bd <= A.thLow && (float)bd < __fmul_rn(A.nnratio, (float)sd)) idx = (int)(best & 0xffffu);
-                    A.bestIdx[o2] = idx;
-                    if (A.bestDist) A.bestDist[o2] = bd;
-                    if (A.secondDist) A.secondDist[o2] = sd;
-                }
-            }
-        }
+        knn2_epilogue<true>(A, tmemBase, warp, lane, rank, mPairs, qFull(0), map_to_cta(qEmpty(0), 0), accFull(0), map_to_cta(accEmpty(0), 0),
+                            workQ, sMerge);
     }
 
     tc_fence_before();
     cluster_sync_all();
     if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(512u) : "memory");
+}
+
+// ---- one CTA per SM (cta_group::1): same pipeline without the peer; every database tile serves one 128-row query tile
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+k_knn2_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Knn2TcArgs A) {
+    extern __shared__ uint8_t smemRaw[];
+    __shared__ __align__(8) uint64_t bars[16];     // aFull[2] aEmpty[2] bFull[2] bEmpty[2] accFull[2] accEmpty[2] qFull[2] qEmpty[2]
+    __shared__ __align__(8) long long workQ[2];    // work items handed from the producer to the MMA and epilogue warps (-1 = done)
+    __shared__ uint32_t tmemBaseS;
+    __shared__ uint2 sMerge[2][EPI2_PARTS - 1][TC_M];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int W_PRODUCER = EPI2_THREADS / 32, W_MMA = W_PRODUCER + 1;      // (the epilogue warps come first, see k_knn2_tc_pair)
+    constexpr uint32_t EPI_WARPS = EPI2_THREADS / 32;
+    const uint32_t base = (smem_u32(smemRaw) + 1023u) & ~1023u;
+    const uint32_t sA0 = base, sB0 = base + 2 * A_BYTES;
+    const uint32_t bar0 = smem_u32(bars);
+    auto aFull = [&](int s) { return bar0 + 8u * (0 + s); };
+    auto aEmpty = [&](int s) { return bar0 + 8u * (2 + s); };
+    auto bFull = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto bEmpty = [&](int s) { return bar0 + 8u * (6 + s); };
+    auto accFull = [&](int s) { return bar0 + 8u * (8 + s); };
+    auto accEmpty = [&](int s) { return bar0 + 8u * (10 + s); };
+    auto qFull = [&](int s) { return bar0 + 8u * (12 + s); };
+    auto qEmpty = [&](int s) { return bar0 + 8u * (14 + s); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; s++) {
+            mbar_init(aFull(s), 1); mbar_init(aEmpty(s), 1);
+            mbar_init(bFull(s), 1); mbar_init(bEmpty(s), 1);
+            mbar_init(accFull(s), 1); mbar_init(accEmpty(s), EPI_WARPS);
+            mbar_init(qFull(s), 1); mbar_init(qEmpty(s), 1 + EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmemBaseS)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmemBase = tmemBaseS;
+
+    const long long total = (long long)A.nPairs * A.mTiles;
+    if (warp == W_PRODUCER) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&mapB) : "memory");
+            // Work items come from a global counter, not from a fixed stride: a CTA that starts late (its SM was held by another
+            // kernel, e.g. NCCL's while the descriptor gather is in flight) simply takes fewer of them.
+            uint32_t bi = 0;
+            for (uint32_t ai = 0;; ai++) {
+                const uint32_t sa = ai & 1u;
+                mbar_wait(qEmpty(sa), ((ai >> 1) & 1u) ^ 1u);
+                long long w = (long long)atomicAdd(A.workCounter, 1ull);
+                if (w >= total) w = -1;
+                workQ[sa] = w;
+                mbar_arrive(qFull(sa));
+                if (w < 0) break;
+                const int pair = (int)(w / A.mTiles), mt = (int)(w - (long long)pair * A.mTiles);
+                const int2 pr = A.pairs[pair];
+                mbar_wait(aEmpty(sa), ((ai >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(aFull(sa), A_BYTES);
+                tma_load_3d(sA0 + sa * A_BYTES, &mapA, 0, mt * TC_M, pr.x, aFull(sa));
+                tma_load_3d(sA0 + sa * A_BYTES + A_ATOM_BYTES, &mapA, ATOM_B, mt * TC_M, pr.x, aFull(sa));
+                for (int nt = 0; nt < A.nTiles; nt++, bi++) {
+                    const uint32_t sb = bi & 1u;
+                    mbar_wait(bEmpty(sb), ((bi >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(bFull(sb), B_BYTES);
+                    tma_load_3d(sB0 + sb * B_BYTES, &mapB, 0, nt * TC_N, pr.y, bFull(sb));
+                    tma_load_3d(sB0 + sb * B_BYTES + B_ATOM_BYTES, &mapB, ATOM_B, nt * TC_N, pr.y, bFull(sb));
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        if (lane == 0) {
+            uint32_t bi = 0;
+            for (uint32_t ai = 0;; ai++) {
+                const uint32_t sa = ai & 1u;
+                mbar_wait(qFull(sa), (ai >> 1) & 1u);
+                const long long w = *reinterpret_cast<volatile long long*>(&workQ[sa]);
+                mbar_arrive(qEmpty(sa));
+                if (w < 0) break;
+                mbar_wait(aFull(sa), (ai >> 1) & 1u);
+                for (int nt = 0; nt < A.nTiles; nt++, bi++) {
+                    const uint32_t sb = bi & 1u, ph = (bi >> 1) & 1u;
+                    mbar_wait(accEmpty(sb), ph);    // phase u = the accumulator holds its constants for use u (phase 0: the initial store)
+                    mbar_wait(bFull(sb), ph);
+                    tc_fence_after();
+                    const uint32_t d = tmemBase + sb * TC_N;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint32_t ka = (uint32_t)(k >> 2) * A_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
+                        const uint32_t kb = (uint32_t)(k >> 2) * B_ATOM_BYTES + (uint32_t)(k & 3) * 32u;
+                        umma_i8(d, umma_desc(sA0 + sa * A_BYTES + ka), umma_desc(sB0 + sb * B_BYTES + kb), IDESC_I8, 1u);   // onto the stored constants
+                    }
+                    umma_commit(bEmpty(sb));        // the database stage is free once these MMAs have read it
+                    umma_commit(accFull(sb));       // ... and the accumulator is complete
+                }
+                umma_commit(aEmpty(sa));
+            }
+        }
+    } else {
+        knn2_epilogue<false>(A, tmemBase, warp, lane, 0u, A.mTiles, qFull(0), qEmpty(0), accFull(0), accEmpty(0), workQ, sMerge);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(512u) : "memory");
 }
 
 // ---- measured denominator of the knn2 roofline: the same tcgen05.mma shape (kind::i8, M 128, N 256, K 32, operands in
@@ -743,7 +701,7 @@ cudaError_t launch_knn2_tc(const Knn2Args& a, int nKeyframes, uint8_t* expanded,
     }
     const long long total = (long long)k.nPairs * k.mTiles;
     const unsigned grid = (unsigned)std::min<long long>(total, sms);
-    k_knn2_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(mapA, mapB, k);
+    k_knn2_tc<<<grid, TC2_THREADS, TC_SMEM, st>>>(mapA, mapB, k);
     return cudaGetLastError();
 }
 
