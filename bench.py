@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: ORB extraction of both eyes + Frame::ComputeStereoMatches on
 KITTI-shape (1241x376, nFeatures=2000) synthetic stereo frames -- and, on the same JSON line, the two
-sharded batch workloads BASELINE.json names: configs[3] (batched offline extraction of 32768 frames) and
-configs[4] (brute-force keyframe-vs-keyframe Hamming matching with the NCCL all-gather of descriptor sets).
+other workloads BASELINE.json names: configs[2] (TUM frames: extraction + SearchByProjection against a 20k-point map), configs[3]
+(batched offline extraction of 32768 frames) and configs[4] (brute-force keyframe-vs-keyframe Hamming matching with the NCCL all-gather of descriptor sets).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
 
@@ -529,7 +529,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=256, help="stereo frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true", help="skip the white-noise stress case")
-    ap.add_argument("--no-sub", action="store_true", help="headline only: skip the configs[3] / configs[4] sub-results")
+    ap.add_argument("--no-sub", action="store_true", help="headline only: skip the configs[2] / configs[3] / configs[4] sub-results")
     ap.add_argument("--e2e-pipelines", type=int, default=3, help="handle pairs the e2e leg keeps in flight from its one host thread")
     ap.add_argument("--workload", default="stereo", choices=["stereo", "knn2", "projection", "bow", "extract"],
                     help="stereo = configs[1] (the headline, with configs[3] and configs[4] as sub-results); knn2 = configs[4] alone; "
@@ -565,6 +565,7 @@ def main():
     sub = {}
     if not args.no_sub:
         # the sharded batch workloads north_star names, measured in the same process group
+        sub["configs[2]"] = bench_match.run_projection(args, ctx.rank, ctx.local_rank, ctx.world, ClockSampler, as_sub=True)
         sub["configs[3]"] = bench_match.measure_extract(args, ctx, ClockSampler)
         sub["configs[4]"] = bench_match.measure_knn2(args, ctx, ClockSampler)
     line = measure_stereo(ctx, args)
