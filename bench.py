@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Benchmark of the north-star path: ORB extraction of both eyes + Frame::ComputeStereoMatches on
-KITTI-shape (1241x376, nFeatures=2000) synthetic stereo frames -- and, on the same JSON line, the two
+KITTI-shape (1241x376, nFeatures=2000) synthetic stereo frames -- and, on the same JSON line, the three
 other workloads BASELINE.json names: configs[2] (TUM frames: extraction + SearchByProjection against a 20k-point map), configs[3]
 (batched offline extraction of 32768 frames) and configs[4] (brute-force keyframe-vs-keyframe Hamming matching with the NCCL all-gather of descriptor sets).
 
