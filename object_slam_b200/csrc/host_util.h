@@ -57,6 +57,7 @@ template <typename T> struct PinBuf {
         if (count <= n) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; n = 0;
+        g_allocEpoch.fetch_add(1, std::memory_order_relaxed);       // captured graphs hold the staging pointers too
         cudaError_t e = cudaMallocHost((void**)&p, count * sizeof(T));
         if (e == cudaSuccess) n = count;
         return e;
