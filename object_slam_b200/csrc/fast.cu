@@ -33,15 +33,6 @@ constexpr int FT_PITCH = 256;          // columns of a staged row
 #endif
 // CTAs per SM the register allocation aims at.  Alone the kernel is ~9 % faster at 5, but the step as a whole (eyes, blur and consecutive
 // batches overlapping on four streams) is 2.4 % faster at 4: the other kernels find room next to it (A/B).
-#ifndef FT_OPT_LOADS
-#define FT_OPT_LOADS 2
-#endif
-#ifndef FT_OPT_QLOOP
-#define FT_OPT_QLOOP 0
-#endif
-#ifndef FT_OPT_NMS
-#define FT_OPT_NMS 0
-#endif
 #ifndef FT_MINCTAS
 #define FT_MINCTAS 4
 #endif
@@ -116,7 +107,6 @@ struct FastShared {
     uint8_t colOK[FT_PITCH];                   // 0x80: the column takes part in the current phase
     int cellAny[FT_MAXCELLS];
     int qCount;
-    int nCorner, nSurvAtStart, cornerOverflow;
     int nSurv;                                 // suppressed keypoints so far; they are listed from the top of the queue downwards
     int overflow;                              // the list ran into the queue (white-noise images): emission walks the bitmap instead
     uint32_t pinTile, pinThr;                  // loop invariants of pass 2, fetched back with volatile loads (see pass 2)
@@ -173,17 +163,6 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
             // (plain PTX: for an atomicAdd under a lane predicate the compiler emits its own warp aggregation, a second scan)
             if (lane == 31 && incl > 0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(smem_u32(&sh.qCount)), "r"(incl) : "memory");
             base = __shfl_sync(0xffffffffu, base, 31);
-#if FT_OPT_QLOOP
-            uint32_t out = smem_u32(Q) + 2u * (unsigned)(base + incl - n);
-            const unsigned e0 = (unsigned)(r << 8) | (unsigned)(l8 << 5);
-            while (acc) {
-                unsigned b;
-                asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(acc));             // index of the highest flag
-                acc ^= 1u << b;
-                asm volatile("st.shared.u16 [%0], %1;" :: "r"(out), "r"(e0 | b) : "memory");
-                out += 2;
-            }
-#else
             uint16_t* out = Q + base + incl - n;
             const unsigned e0 = (unsigned)(r << 8) | (unsigned)(l8 << 5);
             while (acc) {
@@ -192,10 +171,9 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
                 acc ^= 1u << b;
                 *out++ = (uint16_t)(e0 + b);
             }
-#endif
         }
     }
-    if (tid == 0) { sh.pinTile = smem_u32(tile); sh.pinThr = 255u + (unsigned)max(t, 1); sh.nCorner = 0; sh.cornerOverflow = 0; sh.nSurvAtStart = sh.nSurv; }
+    if (tid == 0) { sh.pinTile = smem_u32(tile); sh.pinThr = 255u + (unsigned)max(t, 1); }
     __syncthreads();
 
     // ---- pass 2
@@ -234,32 +212,11 @@ __device__ __forceinline__ void fast_phase(const uint8_t* tile, uint8_t* score, 
             nC += __popc(bal);
         }
     }
-#if FT_OPT_NMS
-    // The corners sit in the warps' own slices, unevenly.  When the queue left room above itself (for the corners and for as many new
-    // survivors, which are listed from the top of the queue downwards) they are gathered there, so that the suppression runs with
-    // full warps whatever the slices held; otherwise (white-noise images) every warp suppresses its own slice.
-    __syncwarp();
-    if (nC > 0) {
-        const int room = (FT_LIST - sh.nSurvAtStart - total) >> 1;
-        int cbase = 0;
-        if (lane == 0) cbase = atomicAdd(&sh.nCorner, nC);
-        cbase = __shfl_sync(0xffffffffu, cbase, 0);
-        if (cbase + nC <= room) { for (int i = lane; i < nC; i += 32) Q[total + cbase + i] = Q[start + i]; }
-        else if (lane == 0) sh.cornerOverflow = 1;
-    }
-#endif
     __syncthreads();
 
     // ---- pass 3
-#if FT_OPT_NMS
-    int nmsLo = start + lane, nmsHi = start + nC, nmsStep = 32;
-    if (!sh.cornerOverflow) { nmsLo = total + tid; nmsHi = total + sh.nCorner; nmsStep = FT_THREADS; }
-    for (int i = nmsLo; i < nmsHi; i += nmsStep) {
-        const int pos = Q[i];
-#else
     for (int i = lane; i < nC; i += 32) {
         const int pos = Q[start + i];
-#endif
         const int c = pos & 255;
         const uint8_t* sc = score + (pos >> 8) * FT_SP + c;
         const int fl = sh.colFlags[c];
@@ -321,7 +278,6 @@ __global__ void __launch_bounds__(FT_THREADS, FT_MINCTAS) k_fast_cells(const __g
         const uint8_t* src = base + (size_t)(Y0 + (tid >> 4)) * pitch + xa + 16 * v;
         const size_t srcStep = (size_t)pitch * (FT_THREADS / 16);
         const bool ld = v < nVec;
-#if FT_OPT_LOADS == 2
         {
             uint32_t tp = smem_u32(tile + (tid >> 4) * FT_SP + 16 * v);
             const uint8_t* sp = src;
@@ -331,30 +287,6 @@ __global__ void __launch_bounds__(FT_THREADS, FT_MINCTAS) k_fast_cells(const __g
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-#elif FT_OPT_LOADS
-        // all loads of a thread are issued before the first store: one DRAM round trip per CTA instead of one per 16 rows
-        constexpr int NLD = (FT_ROWS + FT_THREADS / 16 - 1) / (FT_THREADS / 16);
-        uint4 px[NLD];
-#pragma unroll
-        for (int k = 0; k < NLD; k++) {
-            const int r = (tid >> 4) + k * (FT_THREADS / 16);
-            px[k] = make_uint4(0, 0, 0, 0);
-            if (ld && r < shh) px[k] = __ldg(reinterpret_cast<const uint4*>(src + k * srcStep));
-        }
-#pragma unroll
-        for (int k = 0; k < NLD; k++) {
-            const int r = (tid >> 4) + k * (FT_THREADS / 16);
-            if (r < shh) {
-                *reinterpret_cast<uint4*>(tile + r * FT_SP + 16 * v) = px[k];
-                *reinterpret_cast<uint4*>(score + r * FT_SP + 16 * v) = make_uint4(0, 0, 0, 0);
-            }
-        }
-#else
-        for (int r = tid >> 4; r < shh; r += FT_THREADS / 16, src += srcStep) {
-            if (ld) *reinterpret_cast<uint4*>(tile + r * FT_SP + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src));
-            *reinterpret_cast<uint4*>(score + r * FT_SP + 16 * v) = make_uint4(0, 0, 0, 0);
-        }
-#endif
         static_assert((sizeof(sh.bitmap) + sizeof(sh.rowOfs)) % 16 == 0 && (sizeof(sh.bitmap) + sizeof(sh.rowOfs)) / 16 <= 2 * FT_THREADS, "clear");
         for (int i = tid; i < (int)((sizeof(sh.bitmap) + sizeof(sh.rowOfs)) / 16); i += FT_THREADS)
             reinterpret_cast<uint4*>(&sh.bitmap[0][0])[i] = make_uint4(0, 0, 0, 0);
@@ -369,9 +301,7 @@ __global__ void __launch_bounds__(FT_THREADS, FT_MINCTAS) k_fast_cells(const __g
         sh.colOK[tid] = (tid >= cLo && tid < cHi) ? 0x80 : 0;
         if (tid < FT_MAXCELLS) sh.cellAny[tid] = 0;
         if (tid == 0) { sh.qCount = 0; sh.nSurv = 0; sh.overflow = 0; }
-#if FT_OPT_LOADS == 2
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
     }
     __syncthreads();
 
@@ -436,13 +366,7 @@ __global__ void __launch_bounds__(FT_THREADS, FT_MINCTAS) k_fast_cells(const __g
 
 }  // namespace
 
-#ifndef FT_SMEM_MIN
-#define FT_SMEM_MIN 0
-#endif
-size_t fast_smem_bytes(int tileRows) {
-    const size_t need = (size_t)2 * tileRows * FT_SP + (size_t)FT_LIST * 2;
-    return need < (size_t)FT_SMEM_MIN ? (size_t)FT_SMEM_MIN : need;       // (A/B knob: a larger footprint caps the CTAs per SM)
-}
+size_t fast_smem_bytes(int tileRows) { return (size_t)2 * tileRows * FT_SP + (size_t)FT_LIST * 2; }
 
 cudaError_t fast_prepare(int tileRows) {
     cudaError_t e = OBS_ALLOW_MAX_SMEM(k_fast_cells);
