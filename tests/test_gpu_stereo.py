@@ -167,3 +167,45 @@ def test_stereo_frames_graph_replay_matches_oracle(gpu, frames):
     from object_slam_b200._capi import ObsError
     with pytest.raises(ObsError):
         check(lib().obs_set_option(b"no_such_option", 1))
+
+
+def test_stereo_frames_graph_cache_eviction(gpu):
+    """More distinct argument sets than the handle pair keeps graphs for (8): ten sets of page-locked buffers driven round-robin through
+    obs_stereo_frames for four rounds -- plain enqueue, capture, replay, eviction and re-capture all give the first round's results."""
+    import ctypes as C
+    from object_slam_b200 import _capi
+    from object_slam_b200._capi import StereoIO, check, lib, pinned_empty, KEYPOINT_DTYPE
+    from object_slam_b200.extractor import StereoFrames
+    shape = synth.TUM_SHAPE
+    H, W = shape
+    pipe = StereoFrames(1000, 1.2, 8, 20, 7, (W, H), 1)
+    cap = pipe.cap
+    sets = []
+    for s in range(10):
+        L, R = synth.stereo_pair(shape, 500 + s)
+        b = dict(left=pinned_empty((1, H, W), np.uint8), right=pinned_empty((1, H, W), np.uint8),
+                 kpL=pinned_empty((1, cap), KEYPOINT_DTYPE), dL=pinned_empty((1, cap, 32), np.uint8), nL=pinned_empty((1,), np.int32),
+                 kpR=pinned_empty((1, cap), KEYPOINT_DTYPE), dR=pinned_empty((1, cap, 32), np.uint8), nR=pinned_empty((1,), np.int32),
+                 ur=pinned_empty((1, cap), np.float32), dp=pinned_empty((1, cap), np.float32))
+        b["left"][0] = L
+        b["right"][0] = R
+        a = _capi.addr
+        b["io"] = StereoIO(a(b["left"]), a(b["right"]), a(b["kpL"]), a(b["dL"]), a(b["nL"]), a(b["kpR"]), a(b["dR"]), a(b["nR"]), a(b["ur"]), a(b["dp"]))
+        sets.append(b)
+    first = []
+    for rnd in range(4):
+        for s, b in enumerate(sets):
+            for k in ("kpL", "dL", "ur", "dp"):
+                b[k][:] = 0
+            check(lib().obs_stereo_frames(pipe.eL._h, pipe.eR._h, C.byref(b["io"]), 1, W, H, W, cap, C.c_float(40.0), C.c_float(0.0), C.c_float(525.0)))
+            n = int(b["nL"][0])
+            got = (n, b["kpL"][0, :n].tobytes(), b["dL"][0, :n].tobytes(), b["ur"][0, :n].tobytes(), b["dp"][0, :n].tobytes())
+            if rnd == 0:
+                first.append(got)
+            else:
+                assert got == first[s], (rnd, s)
+    # and the first round itself is the oracle's answer
+    L, R = synth.stereo_pair(shape, 500)
+    our, odp, _ = _oracle_stereo(L, R, 1000, 40.0, 0.0, 525.0)
+    n = first[0][0]
+    assert np.array_equal(np.frombuffer(first[0][3], np.float32), our) and np.array_equal(np.frombuffer(first[0][4], np.float32), odp)
