@@ -1138,8 +1138,8 @@ int obs_stereo_frames_submit(obs_extractor* L, obs_extractor* R, const obs_stere
     if ((rc = set_shape(R, w, h, n_frames, R->stream))) return rc;
     if (cap > L->g.kpCap) return fail(OBS_ERR_INVALID, "cap %d exceeds obs_extractor_max_keypoints (%d)", cap, L->g.kpCap);
     // Steady state of a live front end: the same pinned buffers, shape and parameters call after call.  The second call with one
-    // argument set is captured into a CUDA graph (both eyes' uploads, 2 x 9 kernels with their programmatic-dependency edges, the
-    // stereo kernels, every download), later calls are one cudaGraphLaunch instead of ~60 runtime calls.
+    // argument set is captured into a CUDA graph (both eyes' uploads, 2 x 9 kernels, the stereo kernels, every download; ordinary
+    // graph edges -- the PDL attribute is dropped inside a capture), later calls are one cudaGraphLaunch instead of ~60 runtime calls.
     obs_extractor::StereoGraph key{};
     const void* iov[10] = {io->left, io->right, io->kp_left, io->desc_left, io->n_left, io->kp_right, io->desc_right, io->n_right, io->u_right, io->depth};
     memcpy(key.io, iov, sizeof(iov));
